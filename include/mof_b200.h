@@ -1,0 +1,162 @@
+/* mof_b200.h — C ABI of the B200-native halfway-alignment solver (libmof_b200.so).
+ *
+ * The reference (fabianprada/MeshOpticalFlow) has no plugin/FFI interface: its solver loop is
+ * reached only through process-global statics inside OpticalFlow/OpticalFlow.cpp. This header is the
+ * boundary a maintainer would bind instead; every entry point names the reference code it replaces
+ * (paths relative to the reference root). INTEGRATION.md shows the call-for-call replacement inside
+ * OpticalFlow.cpp.
+ *
+ * Rules: plain pointers and sizes only; every function returns 0 on success or a negative
+ * MOF_E_* code and never throws, exits or prints (mof_last_error gives the reference-style
+ * message); the caller owns every host buffer; the context owns all device memory; one context
+ * per GPU/stream, no hidden globals. Arithmetic is fp64 with int32 indices, like the reference
+ * (_main<double,3>, OpticalFlow.cpp:1115). There is no CPU fallback: without a CUDA device
+ * mof_create fails.
+ */
+#ifndef MOF_B200_H
+#define MOF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOF_OK 0
+#define MOF_E_INVALID -1      /* bad argument / call order */
+#define MOF_E_CUDA -2         /* CUDA runtime error (message has the cudaError string) */
+#define MOF_E_MESH -3         /* non-manifold or open mesh: "[ERROR] Edge is occupied" (FEM.inl:599), "[ERROR] Boundary edge" (FEM.inl:554) */
+#define MOF_E_NOCONVERGE -4   /* PCG hit its iteration cap */
+#define MOF_E_UNSUPPORTED -5  /* a reference mode outside the accelerated path (vfMode 1|2, 6 channels) */
+
+typedef struct mof_ctx mof_ctx;
+
+/* Solver parameters: the reference's command-line flags (OpticalFlow.cpp:56-63) with the defaults of
+ * _main (:1062-1069), plus the PCG controls that replace the direct factorisation. */
+typedef struct mof_params {
+    int iterations;        /* --iterations 10 */
+    double sSmooth;        /* --sSmooth 3e-3 (float literal in the reference) */
+    double sMultiply;      /* --sMultiply 0.25 */
+    double vfSmooth;       /* --vfSmooth 3e-6 (Whitney) */
+    double vMultiply;      /* --vMultiply 1 */
+    double vfSThreshold;   /* --vfSThreshold 1e-8 */
+    double dogWeight;      /* --dogWeight 1 (0 disables the DoG normalisation; 0<w<1 is MOF_E_UNSUPPORTED) */
+    double dogSmooth;      /* --dogSmooth 1e-4 */
+    double flowTol;        /* relative residual ||r||/||b|| of the flow-system PCG, default 1e-8 */
+    double smoothTol;      /* relative residual of the scalar smoothing PCG, default 1e-10 */
+    int maxCgIterations;   /* PCG cap, default 100000 */
+} mof_params;
+
+/* Counters since mof_create / mof_reset_stats. */
+typedef struct mof_stats {
+    long long kernelLaunches;     /* kernels launched by this library */
+    long long flowCgIterations;   /* PCG iterations spent in flow solves (VectorField.h:85) */
+    long long smoothCgIterations; /* PCG iterations spent in smoothing solves (OpticalFlow.cpp:364, :840) */
+    int flowSolves, smoothSolves;
+    double lastFlowResidual;      /* relative residual reached by the last flow solve */
+    double lastSmoothResidual;
+    float flowSolveMs;            /* device time (CUDA events on the context's stream) in flow PCG kernels */
+    float smoothSolveMs;
+    float advectMs;               /* ... in the advection kernels */
+    float setupMs;                /* ... in mof_set_mesh */
+    double flowSpmvBytes;         /* algorithmic bytes of ONE flow-system SpMV: 12*nnz + 4*(n+1) + 16*n */
+    long long flowRows, flowNnz;
+} mof_stats;
+
+void mof_default_params(mof_params* p);
+
+/* One context per GPU; `stream` is a cudaStream_t (NULL = a stream owned by the context). */
+int mof_create(int device, void* stream, mof_ctx** out);
+void mof_destroy(mof_ctx* ctx);
+const char* mof_last_error(const mof_ctx* ctx);
+int mof_set_params(mof_ctx* ctx, const mof_params* p);
+int mof_get_stats(mof_ctx* ctx, mof_stats* out);
+void mof_reset_stats(mof_ctx* ctx);
+int mof_synchronize(mof_ctx* ctx);
+
+/* Mesh setup. Replaces, in WhitneyFlowViewer::Init (OpticalFlow.cpp:787-815, 863-870):
+ *   setMetricFromEmbedding / makeUnitArea / setInverseMetric  FEM.inl:1305-1323, 1283-1291, 1363-1369
+ *   getEdgeXForms                                              FEM.inl:543-614
+ *   scalarMassMatrix(false) / scalarStiffnessMatrix            FEM.inl:1507-1549, 439-496
+ *   triangleArea                                               OpticalFlow.cpp:813-814
+ *   WhitneyVectorField::Init                                   Whitney.inl:28-180
+ * xyz: V x 3 positions; tri: T x 3 vertex indices. Host pointers (the _device variant takes device
+ * pointers valid on the context's stream). Resets signals and flow. */
+int mof_set_mesh(mof_ctx* ctx, const double* xyz, int V, const int* tri, int T);
+int mof_set_mesh_device(mof_ctx* ctx, const double* d_xyz, int V, const int* d_tri, int T);
+
+/* The two signals to align, V x channels each (channels must be 3), as in flowData.signals
+ * (OpticalFlow.cpp:745-751, 772-779), followed by the difference-of-Gaussians normalisation of
+ * OpticalFlow.cpp:822-857 when params.dogWeight > 0. The raw values are kept for
+ * mof_advect_vertices. Resets the flow to zero. */
+int mof_set_signals(mof_ctx* ctx, const double* a, const double* b, int channels);
+int mof_set_signals_device(mof_ctx* ctx, const double* d_a, const double* d_b, int channels);
+
+/* n iterations of UpdateFlow with the weight schedule of IterativeOptimization
+ * (OpticalFlow.cpp:424-474, 1037-1043; VectorField::UpdateOpticalFlow, VectorField.h:46-104). The
+ * schedule continues across calls; mof_set_signals restarts it. */
+int mof_iterate(mof_ctx* ctx, int n);
+
+/* tFlowField (T x 2, OpticalFlow.cpp:280) and the Whitney coefficients (E, VectorField.h:20). */
+int mof_get_flow(mof_ctx* ctx, double* tField);
+int mof_get_coeffs(mof_ctx* ctx, double* coeffs);
+int mof_num_edges(mof_ctx* ctx);
+
+/* InputGeometryData::flow (OpticalFlow.cpp:482-489): the raw signals resampled along -alpha and
+ * 1-alpha of the flow (ResampleSignal, :198-216). outA/outB: V x 3. */
+int mof_advect_vertices(mof_ctx* ctx, double alpha, double* outA, double* outB);
+int mof_advect_vertices_device(mof_ctx* ctx, double alpha, double* d_outA, double* d_outB);
+
+/* Texel variant. mof_set_texture_map uploads what GetTextureSource produced (MeshFlow.inl:411-467):
+ * srcT[W*H] triangle per texel (-1 = uncovered), srcP[W*H][2] barycentric point, triUV[T][6]
+ * per-corner texture coordinates, and the two RGB8 textures (top row first, as PNGReadColor
+ * returns them). mof_advect_texels is InputTextureData::flow (OpticalFlow.cpp:501-515) with
+ * Sample (MeshFlow.inl:66-84): out[s][W*H][3] in the reference's bottom-up texel order; uncovered
+ * texels are set to the vertically flipped input (OpticalFlow.cpp:889). */
+int mof_set_texture_map(mof_ctx* ctx, int W, int H, const int* srcT, const double* srcP, const double* triUV,
+                        const unsigned char* texA, const unsigned char* texB);
+int mof_advect_texels(mof_ctx* ctx, double alpha, int bilinear, double* outA, double* outB);
+
+/* Debug taps for the parity tests. */
+enum {
+    MOF_CSR_SCALAR_MASS = 0,      /* flowData.sMass       V x V  (FEM.inl:1548) */
+    MOF_CSR_SCALAR_STIFFNESS = 1, /* flowData.sStiffness  V x V  (FEM.inl:1549) */
+    MOF_CSR_WHITNEY_SMOOTH = 2,   /* vf->smoothOperator   E x E  (Whitney.inl:179) */
+    MOF_CSR_FLOW_SYSTEM = 3       /* opticalFlowMatrix of the last iteration (VectorField.h:67) */
+};
+/* rows/nnz query, then copy out with columns ascending in every row. */
+int mof_csr_size(mof_ctx* ctx, int which, int* rows, long long* nnz);
+int mof_get_csr(mof_ctx* ctx, int which, int* rowptr, int* col, double* val);
+
+enum {
+    MOF_ARR_METRIC = 0,          /* T x 3 (g00,g01,g11) after makeUnitArea */
+    MOF_ARR_AREA = 1,            /* T */
+    MOF_ARR_OPPOSITE = 2,        /* 3T int32   EdgeXForm::oppositeEdge */
+    MOF_ARR_XFORM_LINEAR = 3,    /* 3T x 4 row-major */
+    MOF_ARR_XFORM_CONSTANT = 4,  /* 3T x 2 */
+    MOF_ARR_REDUCED_EDGE = 5,    /* 3T int32   reducedEdgeIndex (Whitney.inl:33) */
+    MOF_ARR_EXPANDED_EDGE = 6,   /* E int32    expandedEdgeIndex */
+    MOF_ARR_POSITIVE_EDGE = 7,   /* 3T int32   positiveOrientedEdge as 0/1 */
+    MOF_ARR_PROLONGATION = 8,    /* T x 3 x 2  P entries: row 2t+r, k-th edge of t at [t][k][r] (Whitney.inl:80-83) */
+    MOF_ARR_SIGNALS = 9,         /* V x 6      flowData.signals after DoG: (A rgb, B rgb) per vertex */
+    MOF_ARR_SMOOTHED = 10,       /* V x 6      last iteration's smoothed signals (OpticalFlow.cpp:435) */
+    MOF_ARR_RESAMPLED = 11,      /* V x 6      last iteration's resampled signals (:439) */
+    MOF_ARR_DATA_TERM = 12,      /* T x 3      (d00,d01,d11) (:395-421) */
+    MOF_ARR_DATA_RHS = 13,       /* T x 2 */
+    MOF_ARR_FLOW_RHS = 14,       /* E          scaled R*rhs (VectorField.h:53,60) */
+    MOF_ARR_FLOW_SOLUTION = 15   /* E          solution of the last flow system (VectorField.h:85) */
+};
+/* bytes needed for one array (0 if not available yet), then copy out. */
+long long mof_array_bytes(mof_ctx* ctx, int which);
+int mof_get_array(mof_ctx* ctx, int which, void* out);
+
+/* Stand-alone solver entry for tests and profiling: Jacobi-PCG on a caller-supplied SPD CSR system
+ * (host pointers), NRHS = 1. Returns iterations in *iters and the relative residual in *relres. */
+int mof_pcg_solve_csr(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, const double* b, double* x,
+                      double tol, int maxIters, int* iters, double* relres);
+/* Times `reps` launches of the flow-system SpMV kernel (y = A d fused with d.y) on the context's
+ * current flow matrix; returns average ms per launch. Used by bench.py for the roofline line. */
+int mof_time_flow_spmv(mof_ctx* ctx, int reps, float* msPerLaunch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,401 @@
+// C ABI of libmof_b200.so (include/mof_b200.h): argument checking, host<->device staging, call order.
+#include <cstring>
+#include <vector>
+
+#include "mof_internal.cuh"
+
+using namespace mof;
+
+namespace {
+
+// Interleave two V x 3 signals into V x 6 (A rgb, B rgb) and back.
+__global__ void k_interleave(const double* __restrict__ a, const double* __restrict__ b, int V, double* __restrict__ out6) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3ll * V) return;
+    long long v = i / 3, c = i - 3 * v;
+    out6[6 * v + c] = a[i], out6[6 * v + 3 + c] = b[i];
+}
+__global__ void k_deinterleave(const double* __restrict__ in6, int V, double* __restrict__ a, double* __restrict__ b) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3ll * V) return;
+    long long v = i / 3, c = i - 3 * v;
+    a[i] = in6[6 * v + c], b[i] = in6[6 * v + 3 + c];
+}
+
+int require_mesh(mof_ctx* ctx) { return ctx->haveMesh ? MOF_OK : fail(ctx, MOF_E_INVALID, "call mof_set_mesh first"); }
+int require_signals(mof_ctx* ctx) { return ctx->haveSignals ? MOF_OK : fail(ctx, MOF_E_INVALID, "call mof_set_signals first"); }
+
+int finish_mesh(mof_ctx* ctx) {
+    ctx->haveMesh = ctx->haveSignals = ctx->haveFlowSystem = ctx->haveTexture = false;
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    int rc = build_mesh_operators(ctx);
+    if (rc != MOF_OK) return rc;
+    MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    MOF_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    MOF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.setupMs += ms;
+    ctx->stats.flowRows = ctx->E, ctx->stats.flowNnz = ctx->nnzW;
+    ctx->stats.flowSpmvBytes = 12. * (double)ctx->nnzW + 4. * ((double)ctx->E + 1) + 16. * (double)ctx->E;
+    ctx->haveMesh = true;
+    return MOF_OK;
+}
+
+int finish_signals(mof_ctx* ctx) {
+    ctx->haveSignals = false;
+    MOF_TRY(dog_preprocess(ctx));
+    MOF_CUDA(cudaMemsetAsync(ctx->coeffs.p, 0, sizeof(double) * ctx->E, ctx->stream));
+    MOF_CUDA(cudaMemsetAsync(ctx->tfield.p, 0, sizeof(double) * 2 * ctx->T, ctx->stream));
+    ctx->iterationsDone = 0;
+    ctx->curSmooth = ctx->params.sSmooth, ctx->curVf = ctx->params.vfSmooth;
+    ctx->haveSignals = true, ctx->haveFlowSystem = false;
+    return MOF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void mof_default_params(mof_params* p) {
+    if (!p) return;
+    p->iterations = 10;
+    p->sSmooth = (double)3e-3f;       // cmdLineParameter<float>, OpticalFlow.cpp:59, cast to Real at :1062
+    p->sMultiply = (double)0.25f;
+    p->vfSmooth = 3e-6;               // double literal, OpticalFlow.cpp:1067
+    p->vMultiply = (double)1.0f;
+    p->vfSThreshold = (double)1e-8f;
+    p->dogWeight = (double)1.f;
+    p->dogSmooth = (double)(float)1e-4;
+    p->flowTol = 1e-8;
+    p->smoothTol = 1e-10;
+    p->maxCgIterations = 100000;
+}
+
+int mof_create(int device, void* stream, mof_ctx** out) {
+    if (!out) return MOF_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) return MOF_E_CUDA;  // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return MOF_E_CUDA;
+    mof_ctx* ctx = new mof_ctx();
+    ctx->device = device;
+    mof_default_params(&ctx->params);
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MOF_E_CUDA; }
+        ctx->ownStream = true;
+    }
+    if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return MOF_E_CUDA; }
+    *out = ctx;
+    return MOF_OK;
+}
+
+void mof_destroy(mof_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DBuf<double>* dbl[] = {&ctx->pos, &ctx->g, &ctx->area, &ctx->xlin, &ctx->xcst, &ctx->sMass, &ctx->sStiff, &ctx->sSys, &ctx->sDinv, &ctx->P, &ctx->m0, &ctx->m1,
+                           &ctx->wS, &ctx->wA, &ctx->wDinv, &ctx->raw6, &ctx->sig6, &ctx->smoothed6, &ctx->rhs6, &ctx->resampled6, &ctx->tsample6, &ctx->dataD,
+                           &ctx->dataRhs, &ctx->coeffs, &ctx->tfield, &ctx->fb, &ctx->fx, &ctx->scalars, &ctx->pcg.r, &ctx->pcg.d, &ctx->pcg.q, &ctx->pcg.partial,
+                           &ctx->pcg.result, &ctx->dtmp0, &ctx->dtmp1, &ctx->srcP, &ctx->triUV, &ctx->texOut};
+    for (auto* b : dbl) b->release();
+    DBuf<int>* ints[] = {&ctx->tri, &ctx->opp, &ctx->sRowptr, &ctx->sCol, &ctx->sHe, &ctx->reduced, &ctx->expanded, &ctx->positive, &ctx->wRowptr, &ctx->wCol,
+                         &ctx->itmp0, &ctx->itmp1, &ctx->itmp2, &ctx->flags, &ctx->srcT};
+    for (auto* b : ints) b->release();
+    ctx->hashKeys.release(), ctx->tex[0].release(), ctx->tex[1].release();
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* mof_last_error(const mof_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mof_set_params(mof_ctx* ctx, const mof_params* p) {
+    if (!ctx || !p) return MOF_E_INVALID;
+    if (p->dogWeight > 0 && p->dogWeight < 1)
+        return fail(ctx, MOF_E_UNSUPPORTED, "[ERROR] 0<dogWeight<1 selects the reference's 6-channel path (OpticalFlow.cpp:1114), which is outside the accelerated path");
+    if (p->iterations < 0 || !(p->flowTol > 0) || !(p->smoothTol > 0) || p->maxCgIterations < 1) return fail(ctx, MOF_E_INVALID, "bad solver parameters");
+    ctx->params = *p;
+    return MOF_OK;
+}
+
+int mof_get_stats(mof_ctx* ctx, mof_stats* out) {
+    if (!ctx || !out) return MOF_E_INVALID;
+    *out = ctx->stats;
+    return MOF_OK;
+}
+void mof_reset_stats(mof_ctx* ctx) {
+    if (!ctx) return;
+    long long rows = ctx->stats.flowRows, nnz = ctx->stats.flowNnz;
+    double bytes = ctx->stats.flowSpmvBytes;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    ctx->stats.flowRows = rows, ctx->stats.flowNnz = nnz, ctx->stats.flowSpmvBytes = bytes;
+}
+int mof_synchronize(mof_ctx* ctx) {
+    if (!ctx) return MOF_E_INVALID;
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+
+int mof_set_mesh(mof_ctx* ctx, const double* xyz, int V, const int* tri, int T) {
+    if (!ctx) return MOF_E_INVALID;
+    if (!xyz || !tri || V < 3 || T < 1) return fail(ctx, MOF_E_INVALID, "mof_set_mesh: empty mesh");
+    MOF_CUDA(cudaSetDevice(ctx->device));
+    ctx->V = V, ctx->T = T;
+    MOF_CUDA(ctx->pos.alloc(3ull * V));
+    MOF_CUDA(ctx->tri.alloc(3ull * T));
+    MOF_CUDA(cudaMemcpyAsync(ctx->pos.p, xyz, sizeof(double) * 3 * V, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(ctx->tri.p, tri, sizeof(int) * 3 * T, cudaMemcpyHostToDevice, ctx->stream));
+    return finish_mesh(ctx);
+}
+
+int mof_set_mesh_device(mof_ctx* ctx, const double* d_xyz, int V, const int* d_tri, int T) {
+    if (!ctx) return MOF_E_INVALID;
+    if (!d_xyz || !d_tri || V < 3 || T < 1) return fail(ctx, MOF_E_INVALID, "mof_set_mesh_device: empty mesh");
+    MOF_CUDA(cudaSetDevice(ctx->device));
+    ctx->V = V, ctx->T = T;
+    MOF_CUDA(ctx->pos.alloc(3ull * V));
+    MOF_CUDA(ctx->tri.alloc(3ull * T));
+    MOF_CUDA(cudaMemcpyAsync(ctx->pos.p, d_xyz, sizeof(double) * 3 * V, cudaMemcpyDeviceToDevice, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(ctx->tri.p, d_tri, sizeof(int) * 3 * T, cudaMemcpyDeviceToDevice, ctx->stream));
+    return finish_mesh(ctx);
+}
+
+static int set_signals_common(mof_ctx* ctx, const double* a, const double* b, int channels, cudaMemcpyKind kind) {
+    if (!ctx) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    if (!a || !b) return fail(ctx, MOF_E_INVALID, "mof_set_signals: null signal");
+    if (channels != 3) return fail(ctx, MOF_E_UNSUPPORTED, "[ERROR] only 3-channel signals are on the accelerated path (_main<double,3>, OpticalFlow.cpp:1115)");
+    MOF_CUDA(cudaSetDevice(ctx->device));
+    const int V = ctx->V;
+    MOF_CUDA(ctx->raw6.alloc(6ull * V));
+    MOF_CUDA(ctx->dtmp0.reserve(6ull * V));
+    double* sa = ctx->dtmp0.p;
+    double* sb = ctx->dtmp0.p + 3ull * V;
+    MOF_CUDA(cudaMemcpyAsync(sa, a, sizeof(double) * 3 * V, kind, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(sb, b, sizeof(double) * 3 * V, kind, ctx->stream));
+    MOF_LAUNCH(k_interleave, blocks_for(3ll * V, 256), 256, 0, sa, sb, V, ctx->raw6.p);
+    return finish_signals(ctx);
+}
+int mof_set_signals(mof_ctx* ctx, const double* a, const double* b, int channels) { return set_signals_common(ctx, a, b, channels, cudaMemcpyHostToDevice); }
+int mof_set_signals_device(mof_ctx* ctx, const double* a, const double* b, int channels) { return set_signals_common(ctx, a, b, channels, cudaMemcpyDeviceToDevice); }
+
+int mof_iterate(mof_ctx* ctx, int n) {
+    if (!ctx) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    MOF_TRY(require_signals(ctx));
+    MOF_CUDA(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n; i++) {
+        MOF_TRY(update_flow(ctx, ctx->curSmooth, ctx->curVf));
+        // IterativeOptimization, OpticalFlow.cpp:1041-1042
+        ctx->curSmooth *= ctx->params.sMultiply;
+        ctx->curVf = ctx->curVf * ctx->params.vMultiply > ctx->params.vfSThreshold ? ctx->curVf * ctx->params.vMultiply : ctx->curVf;
+        ctx->iterationsDone++;
+    }
+    return MOF_OK;
+}
+
+int mof_num_edges(mof_ctx* ctx) { return ctx && ctx->haveMesh ? ctx->E : -1; }
+
+int mof_get_flow(mof_ctx* ctx, double* tField) {
+    if (!ctx || !tField) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    MOF_CUDA(cudaMemcpyAsync(tField, ctx->tfield.p, sizeof(double) * 2 * ctx->T, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+int mof_get_coeffs(mof_ctx* ctx, double* coeffs) {
+    if (!ctx || !coeffs) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    MOF_CUDA(cudaMemcpyAsync(coeffs, ctx->coeffs.p, sizeof(double) * ctx->E, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+
+static int advect_common(mof_ctx* ctx, double alpha, double* outA, double* outB, cudaMemcpyKind kind) {
+    if (!ctx || !outA || !outB) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    MOF_TRY(require_signals(ctx));
+    MOF_CUDA(cudaSetDevice(ctx->device));
+    const int V = ctx->V;
+    // InputGeometryData::flow, OpticalFlow.cpp:482-489: raw colours, lengths -alpha and 1-alpha
+    MOF_TRY(advect_vertices(ctx, ctx->raw6.p, -alpha, 1. - alpha, ctx->resampled6.p));
+    MOF_CUDA(ctx->dtmp0.reserve(6ull * V));
+    double* sa = ctx->dtmp0.p;
+    double* sb = ctx->dtmp0.p + 3ull * V;
+    MOF_LAUNCH(k_deinterleave, blocks_for(3ll * V, 256), 256, 0, ctx->resampled6.p, V, sa, sb);
+    MOF_CUDA(cudaMemcpyAsync(outA, sa, sizeof(double) * 3 * V, kind, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(outB, sb, sizeof(double) * 3 * V, kind, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+int mof_advect_vertices(mof_ctx* ctx, double alpha, double* outA, double* outB) { return advect_common(ctx, alpha, outA, outB, cudaMemcpyDeviceToHost); }
+int mof_advect_vertices_device(mof_ctx* ctx, double alpha, double* outA, double* outB) { return advect_common(ctx, alpha, outA, outB, cudaMemcpyDeviceToDevice); }
+
+int mof_set_texture_map(mof_ctx* ctx, int W, int H, const int* srcT, const double* srcP, const double* triUV, const unsigned char* texA, const unsigned char* texB) {
+    if (!ctx) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    if (W < 2 || H < 2 || !srcT || !srcP || !triUV || !texA || !texB) return fail(ctx, MOF_E_INVALID, "mof_set_texture_map: bad arguments");
+    MOF_CUDA(cudaSetDevice(ctx->device));
+    size_t n = (size_t)W * H;
+    for (size_t i = 0; i < n; i++)
+        if (srcT[i] < -1 || srcT[i] >= ctx->T) return fail(ctx, MOF_E_INVALID, "mof_set_texture_map: texel refers to a triangle outside the mesh");
+    ctx->texW = W, ctx->texH = H;
+    MOF_CUDA(ctx->srcT.alloc(n));
+    MOF_CUDA(ctx->srcP.alloc(2 * n));
+    MOF_CUDA(ctx->triUV.alloc(6ull * ctx->T));
+    MOF_CUDA(ctx->tex[0].alloc(3 * n));
+    MOF_CUDA(ctx->tex[1].alloc(3 * n));
+    MOF_CUDA(cudaMemcpyAsync(ctx->srcT.p, srcT, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(ctx->srcP.p, srcP, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(ctx->triUV.p, triUV, sizeof(double) * 6 * ctx->T, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(ctx->tex[0].p, texA, 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(ctx->tex[1].p, texB, 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->haveTexture = true;
+    return MOF_OK;
+}
+
+int mof_advect_texels(mof_ctx* ctx, double alpha, int bilinear, double* outA, double* outB) {
+    if (!ctx || !outA || !outB) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    if (!ctx->haveTexture) return fail(ctx, MOF_E_INVALID, "call mof_set_texture_map first");
+    MOF_CUDA(cudaSetDevice(ctx->device));
+    MOF_TRY(advect_texels(ctx, alpha, bilinear));
+    size_t n = (size_t)ctx->texW * ctx->texH;
+    MOF_CUDA(cudaMemcpyAsync(outA, ctx->texOut.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(outB, ctx->texOut.p + 3 * n, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+
+// ------------------------------------------------------------------------------------ debug taps
+
+static int csr_view(mof_ctx* ctx, int which, int* rows, long long* nnz, const int** rowptr, const int** col, const double** val) {
+    MOF_TRY(require_mesh(ctx));
+    switch (which) {
+        case MOF_CSR_SCALAR_MASS: *rows = ctx->V, *nnz = ctx->nnzS, *rowptr = ctx->sRowptr.p, *col = ctx->sCol.p, *val = ctx->sMass.p; return MOF_OK;
+        case MOF_CSR_SCALAR_STIFFNESS: *rows = ctx->V, *nnz = ctx->nnzS, *rowptr = ctx->sRowptr.p, *col = ctx->sCol.p, *val = ctx->sStiff.p; return MOF_OK;
+        case MOF_CSR_WHITNEY_SMOOTH: *rows = ctx->E, *nnz = ctx->nnzW, *rowptr = ctx->wRowptr.p, *col = ctx->wCol.p, *val = ctx->wS.p; return MOF_OK;
+        case MOF_CSR_FLOW_SYSTEM:
+            if (!ctx->haveFlowSystem) return fail(ctx, MOF_E_INVALID, "no flow system yet: call mof_iterate first");
+            *rows = ctx->E, *nnz = ctx->nnzW, *rowptr = ctx->wRowptr.p, *col = ctx->wCol.p, *val = ctx->wA.p;
+            return MOF_OK;
+    }
+    return fail(ctx, MOF_E_INVALID, "unknown CSR id");
+}
+
+int mof_csr_size(mof_ctx* ctx, int which, int* rows, long long* nnz) {
+    if (!ctx || !rows || !nnz) return MOF_E_INVALID;
+    const int *rp, *c;
+    const double* v;
+    return csr_view(ctx, which, rows, nnz, &rp, &c, &v);
+}
+
+int mof_get_csr(mof_ctx* ctx, int which, int* rowptr, int* col, double* val) {
+    if (!ctx || !rowptr || !col || !val) return MOF_E_INVALID;
+    int rows;
+    long long nnz;
+    const int *rp, *c;
+    const double* v;
+    MOF_TRY(csr_view(ctx, which, &rows, &nnz, &rp, &c, &v));
+    MOF_CUDA(cudaMemcpyAsync(rowptr, rp, sizeof(int) * (rows + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(col, c, sizeof(int) * nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(val, v, sizeof(double) * nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+
+static const void* array_view(mof_ctx* ctx, int which, long long* bytes) {
+    const long long V = ctx->V, T = ctx->T, E = ctx->E;
+    *bytes = 0;
+    if (!ctx->haveMesh) return nullptr;
+    switch (which) {
+        case MOF_ARR_METRIC: *bytes = 8 * 3 * T; return ctx->g.p;
+        case MOF_ARR_AREA: *bytes = 8 * T; return ctx->area.p;
+        case MOF_ARR_OPPOSITE: *bytes = 4 * 3 * T; return ctx->opp.p;
+        case MOF_ARR_XFORM_LINEAR: *bytes = 8 * 12 * T; return ctx->xlin.p;
+        case MOF_ARR_XFORM_CONSTANT: *bytes = 8 * 6 * T; return ctx->xcst.p;
+        case MOF_ARR_REDUCED_EDGE: *bytes = 4 * 3 * T; return ctx->reduced.p;
+        case MOF_ARR_EXPANDED_EDGE: *bytes = 4 * E; return ctx->expanded.p;
+        case MOF_ARR_POSITIVE_EDGE: *bytes = 4 * 3 * T; return ctx->positive.p;
+        case MOF_ARR_PROLONGATION: *bytes = 8 * 6 * T; return ctx->P.p;
+        default: break;
+    }
+    if (!ctx->haveSignals) return nullptr;
+    switch (which) {
+        case MOF_ARR_SIGNALS: *bytes = 8 * 6 * V; return ctx->sig6.p;
+        default: break;
+    }
+    if (!ctx->haveFlowSystem) return nullptr;
+    switch (which) {
+        case MOF_ARR_SMOOTHED: *bytes = 8 * 6 * V; return ctx->smoothed6.p;
+        case MOF_ARR_RESAMPLED: *bytes = 8 * 6 * V; return ctx->resampled6.p;
+        case MOF_ARR_DATA_TERM: *bytes = 8 * 3 * T; return ctx->dataD.p;
+        case MOF_ARR_DATA_RHS: *bytes = 8 * 2 * T; return ctx->dataRhs.p;
+        case MOF_ARR_FLOW_RHS: *bytes = 8 * E; return ctx->fb.p;
+        case MOF_ARR_FLOW_SOLUTION: *bytes = 8 * E; return ctx->fx.p;
+        default: break;
+    }
+    return nullptr;
+}
+
+long long mof_array_bytes(mof_ctx* ctx, int which) {
+    if (!ctx) return 0;
+    long long bytes = 0;
+    array_view(ctx, which, &bytes);
+    return bytes;
+}
+
+int mof_get_array(mof_ctx* ctx, int which, void* out) {
+    if (!ctx || !out) return MOF_E_INVALID;
+    long long bytes = 0;
+    const void* src = array_view(ctx, which, &bytes);
+    if (!src || !bytes) return fail(ctx, MOF_E_INVALID, "array not available");
+    MOF_CUDA(cudaMemcpyAsync(out, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+
+int mof_pcg_solve_csr(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, const double* b, double* x, double tol, int maxIters, int* iters,
+                      double* relres) {
+    if (!ctx || n < 1 || !rowptr || !col || !val || !b || !x || !iters || !relres) return MOF_E_INVALID;
+    MOF_CUDA(cudaSetDevice(ctx->device));
+    long long nnz = rowptr[n];
+    DBuf<int> dRow, dCol;
+    DBuf<double> dVal, dB, dX, dInv;
+    int rc = MOF_OK;
+    auto cleanup = [&]() { dRow.release(), dCol.release(), dVal.release(), dB.release(), dX.release(), dInv.release(); };
+    cudaError_t e;
+    if ((e = dRow.alloc(n + 1)) != cudaSuccess || (e = dCol.alloc(nnz)) != cudaSuccess || (e = dVal.alloc(nnz)) != cudaSuccess || (e = dB.alloc(n)) != cudaSuccess ||
+        (e = dX.alloc(n)) != cudaSuccess || (e = dInv.alloc(n)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(ctx, e, "mof_pcg_solve_csr alloc");
+    }
+    cudaMemcpyAsync(dRow.p, rowptr, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dCol.p, col, sizeof(int) * nnz, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dVal.p, val, sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dB.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+    rc = extract_inverse_diagonal(ctx, n, dRow.p, dCol.p, dVal.p, dInv.p);
+    if (rc == MOF_OK) rc = pcg_solve(ctx, n, nnz, dRow.p, dCol.p, dVal.p, dInv.p, dB.p, dX.p, 1, true, tol, maxIters, iters, relres);
+    if (rc == MOF_OK || rc == MOF_E_NOCONVERGE) {
+        cudaMemcpyAsync(x, dX.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cleanup();
+    return rc;
+}
+
+int mof_time_flow_spmv(mof_ctx* ctx, int reps, float* msPerLaunch) {
+    if (!ctx || reps < 1 || !msPerLaunch) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    if (!ctx->haveFlowSystem) return fail(ctx, MOF_E_INVALID, "no flow system yet: call mof_iterate first");
+    MOF_CUDA(cudaSetDevice(ctx->device));
+    MOF_CUDA(ctx->pcg.q.reserve(ctx->E));
+    return time_spmv(ctx, ctx->E, ctx->nnzW, ctx->wRowptr.p, ctx->wCol.p, ctx->wA.p, ctx->fx.p, ctx->pcg.q.p, reps, msPerLaunch);
+}
+
+}  // extern "C"

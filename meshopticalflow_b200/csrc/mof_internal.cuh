@@ -1,0 +1,149 @@
+// Internal declarations shared by the .cu files of libmof_b200.so. Not part of the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/mof_b200.h"
+
+namespace mof {
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count == n && p) return cudaSuccess;
+        release();
+        if (!count) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        else p = nullptr;
+        return e;
+    }
+    // Scratch use: grow-only, keeps the larger allocation.
+    cudaError_t reserve(size_t count) { return (p && count <= n) ? cudaSuccess : alloc(count); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr, n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// Device-side scalar slots (one small buffer, fp64).
+enum ScalarSlot {
+    SC_AREA_SCALE = 0,   // 2 / sum sqrt det g
+    SC_FROB2 = 1,        // ||R D P||_F^2
+    SC_DATA_SCALE = 2,   // 1 / ||R D P||_F
+    SC_STEP_NUM = 3,     // x . b
+    SC_STEP_DEN = 4,     // x . Dt x
+    SC_DOG = 8,          // 8..8+4*6: per channel old avg, old dot, new avg, new dot
+    SC_COUNT = 64
+};
+
+struct PcgWork {
+    DBuf<double> r, d, q;       // [n * nrhs]
+    DBuf<double> partial;       // block partials, 3 banks
+    DBuf<double> result;        // [8]: iterations, relres, converged flag ...
+    int gridBlocks = 0;
+};
+
+}  // namespace mof
+
+struct mof_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    std::string err;
+    mof_params params;
+    mof_stats stats;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    int V = 0, T = 0, E = 0;
+    long long nnzS = 0, nnzW = 0;
+    bool haveMesh = false, haveSignals = false, haveFlowSystem = false, haveTexture = false;
+    int iterationsDone = 0;
+    double curSmooth = 0, curVf = 0;
+
+    // mesh
+    mof::DBuf<double> pos, g, area, xlin, xcst;
+    mof::DBuf<int> tri, opp;
+    // scalar (V x V) operators, one pattern
+    mof::DBuf<int> sRowptr, sCol, sHe;
+    mof::DBuf<double> sMass, sStiff, sSys, sDinv;
+    // Whitney
+    mof::DBuf<int> reduced, expanded, positive, wRowptr, wCol;
+    mof::DBuf<double> P, m0, m1, wS, wA, wDinv;
+    // signals, (A rgb, B rgb) interleaved per vertex
+    mof::DBuf<double> raw6, sig6, smoothed6, rhs6, resampled6, tsample6, dataD, dataRhs;
+    // flow unknowns
+    mof::DBuf<double> coeffs, tfield, fb, fx;
+    mof::DBuf<double> scalars;
+    mof::PcgWork pcg;
+    // scratch
+    mof::DBuf<int> itmp0, itmp1, itmp2, flags;
+    mof::DBuf<unsigned long long> hashKeys;
+    mof::DBuf<double> dtmp0, dtmp1;
+    // texture path
+    int texW = 0, texH = 0;
+    mof::DBuf<int> srcT;
+    mof::DBuf<double> srcP, triUV, texOut;
+    mof::DBuf<unsigned char> tex[2];
+};
+
+namespace mof {
+
+inline int fail(mof_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+inline int cuda_fail(mof_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, MOF_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define MOF_CUDA(call)                                                  \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return mof::cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+#define MOF_TRY(call)             \
+    do {                          \
+        int rc__ = (call);        \
+        if (rc__ != MOF_OK) return rc__; \
+    } while (0)
+
+inline int blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// Counts a kernel launch of ours (mof_stats.kernelLaunches) and checks the launch.
+#define MOF_LAUNCH(kernel, grid, block, smem, ...)                                  \
+    do {                                                                            \
+        kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);              \
+        ctx->stats.kernelLaunches++;                                                \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) return mof::cuda_fail(ctx, e__, #kernel);           \
+    } while (0)
+
+// setup_kernels.cu
+int build_mesh_operators(mof_ctx* ctx);
+int exclusive_scan_int(mof_ctx* ctx, const int* in, int* out, int n, int* total_out_device);
+int reduce_sum(mof_ctx* ctx, const double* in, long long n, double* out_device);
+
+// pcg_kernels.cu
+// Jacobi-PCG on device CSR, NRHS interleaved per row ([n][nrhs]); x holds the initial guess.
+int pcg_solve(mof_ctx* ctx, int n, long long nnz, const int* rowptr, const int* col, const double* val, const double* dinv,
+              const double* b, double* x, int nrhs, bool zeroGuess, double tol, int maxIters, int* itersOut, double* relresOut);
+int extract_inverse_diagonal(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, double* dinv);
+int time_spmv(mof_ctx* ctx, int n, long long nnz, const int* rowptr, const int* col, const double* val, const double* x, double* y, int reps, float* ms);
+
+// flow_kernels.cu
+int dog_preprocess(mof_ctx* ctx);
+int update_flow(mof_ctx* ctx, double sWeight, double vfWeight);
+int advect_vertices(mof_ctx* ctx, const double* in6, double lenA, double lenB, double* out6);
+int advect_texels(mof_ctx* ctx, double alpha, int bilinear);
+
+}  // namespace mof
