@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — 1M-vertex pair alignments/sec on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--level L]
+
+A step is one whole alignment of one signal pair on the synthetic 1 048 578-vertex sphere
+(BASELINE.json configs[2]): mesh-operator assembly, DoG normalisation, 10 UpdateFlow iterations and the
+final halfway advection — what the reference does between loading its inputs and writing its output.
+
+  value   inputs (positions, triangles, both colour signals) already resident in HBM, results left in HBM;
+          timed with CUDA events on the stream the library launches on.
+  e2e     the same step through the host-pointer C ABI (mof_set_mesh / mof_set_signals / mof_iterate /
+          mof_advect_vertices) from pinned host buffers: the host->device copies of the mesh and signals and
+          the device->host read of the advected colours are inside the timed region.
+  N > 1   independent pairs sharded over the ranks (configs[3]), one process per GPU under torchrun, no
+          data-path collective; weak scaling; time = max over ranks.
+  roofline      the PCG's SpMV+dot kernel on the workload's own flow matrix, timed live with CUDA events.
+  cpu_baseline  the reference's own binary (oracle/_ref, built from the unmodified sources) timed on this box's
+                host cores on a bounded sample, rank 0, N=1 only.
+  --impl reference   only the reference arm, same metric/unit/config, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "1M-vertex pair alignments/sec"
+UNIT = "alignments/s"
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "OpticalFlow_ref")
+SAMPLE_LEVEL = 6  # 16 386 vertices: about 10 s of reference CPU work per alignment
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------- reference arm
+
+def reference_sample_inputs(tmp: str):
+    from meshopticalflow_b200 import synthetic
+    v, t = synthetic.octahedron_sphere(SAMPLE_LEVEL)
+    a, b = synthetic.smooth_rgb_pair(v, 0)
+    synthetic.write_ply_colored(os.path.join(tmp, "A.ply"), v, a, t)
+    synthetic.write_ply_colored(os.path.join(tmp, "B.ply"), v, b, t)
+    return v.shape[0]
+
+
+def time_reference_once(tmp: str) -> float:
+    """One alignment of the bounded sample by the reference's CPU implementation, all host threads."""
+    t0 = time.perf_counter()
+    if os.path.exists(REF_BIN):
+        subprocess.check_call([REF_BIN, "--in", "A.ply", "B.ply", "--out", "r.ply"], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    else:  # the oracle port (only when the reference binary could not be built)
+        from meshopticalflow_b200 import synthetic
+        from oracle import mof_oracle as O
+        p = synthetic.read_ply(os.path.join(tmp, "A.ply"))
+        q = synthetic.read_ply(os.path.join(tmp, "B.ply"))
+        v = np.stack([p["vertex"][k] for k in "xyz"], 1).astype(np.float64)
+        ca = np.stack([p["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.float64)
+        cb = np.stack([q["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.float64)
+        O.align_vertices(v, p["face"]["vertex_indices"], ca, cb)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_dict(seconds: float, sample_vertices: int, target_vertices: int):
+    kind = "reference" if os.path.exists(REF_BIN) else "port"
+    cores = os.cpu_count() or 1
+    scale = target_vertices / sample_vertices
+    return {
+        "value": 1.0 / (seconds * scale), "unit": UNIT, "cores": cores if kind == "reference" else 1, "kind": kind,
+        "sample_seconds": seconds, "sample_vertices": sample_vertices,
+        "sample": (f"one full alignment (defaults, 10 iterations) of the level-{SAMPLE_LEVEL} sphere pair ({sample_vertices} vertices) by "
+                   f"{'oracle/_ref/OpticalFlow_ref (unmodified reference, Eigen LDLT/LLT, OpenMP, MKL off)' if kind == 'reference' else 'the oracle port (scipy SuperLU)'}"
+                   f": {seconds:.2f} s; value = 1/(seconds * {scale:.0f}), a LINEAR-in-vertices extrapolation to {target_vertices} vertices — the reference's sparse"
+                   " Cholesky grows superlinearly (SURVEY.md §6: 16k V 1.0 s/it, 108k V 24 s/it, 262k V 83-141 s/it), so this overstates its real 1M-vertex rate"),
+    }
+
+
+def run_reference_arm(args, config):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    with tempfile.TemporaryDirectory() as tmp:
+        nv = reference_sample_inputs(tmp)
+        for _ in range(args.warmup):
+            time_reference_once(tmp)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            time_reference_once(tmp)
+        sec = (time.perf_counter() - t0) / args.steps
+    target = config["vertices"]
+    base = cpu_baseline_dict(sec, nv, target)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------- the GPU arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--level", type=int, default=9, help="octahedron subdivision level of the workload (9 = 1 048 578 vertices)")
+    args = ap.parse_args()
+
+    V = 4 * 4 ** args.level + 2
+    config = {"workload": f"synthetic subdivided-octahedron sphere, {V} vertices / {2 * V - 4} triangles / {3 * V - 6} Whitney unknowns, smooth random RGB "
+                          "per-vertex signals (B = A rotated 4 deg), reference defaults (10 iterations), one pair per GPU per step",
+              "vertices": V, "pairs_per_step": args.gpus, "parallelism": f"independent pairs x{args.gpus} (no communication)",
+              "l2": "inputs larger than L2: each step streams > 1 GB of operators per PCG iteration; no explicit flush", "pcg_tol": 1e-8}
+    if args.impl == "reference":
+        return run_reference_arm(args, config)
+
+    import torch
+
+    from meshopticalflow_b200 import api, sharding, synthetic
+
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device — the GPU arm has no CPU fallback", file=sys.stderr)
+        return 2
+    rank, local_rank, world = sharding.env_rank_world()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    sharding.init_process_group("nccl")
+
+    verts, tris = synthetic.octahedron_sphere(args.level)
+    T = tris.shape[0]
+
+    def pair(seed):
+        a, b = synthetic.smooth_rgb_pair(verts, seed)
+        return a.astype(np.float64), b.astype(np.float64)
+
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        al = api.Aligner(local_rank, stream.cuda_stream)
+        params = api.default_params()
+        al.set_params(params)
+        d_v, d_t = torch.from_numpy(verts).to(dev), torch.from_numpy(tris).to(dev)
+        d_oa, d_ob = torch.empty((V, 3), dtype=torch.float64, device=dev), torch.empty((V, 3), dtype=torch.float64, device=dev)
+        # a few resident pairs, cycled (a new seed every step and every rank)
+        n_sets = 2
+        pairs_h = [pair(rank + world * k) for k in range(n_sets)]
+        pairs_d = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in pairs_h]
+
+        def step_resident(k):
+            da, db = pairs_d[k % n_sets]
+            al.set_mesh_device(d_v.data_ptr(), V, d_t.data_ptr(), T)
+            al.set_signals_device(da.data_ptr(), db.data_ptr(), 3)
+            al.iterate(params.iterations)
+            al.advect_vertices_device(0.5, d_oa.data_ptr(), d_ob.data_ptr())
+
+        # pinned host buffers for the end-to-end arm
+        h_v, h_t = torch.from_numpy(verts).pin_memory(), torch.from_numpy(tris).pin_memory()
+        h_pairs = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs_h]
+        h_oa, h_ob = torch.empty((V, 3), dtype=torch.float64).pin_memory(), torch.empty((V, 3), dtype=torch.float64).pin_memory()
+
+        def step_e2e(k):
+            ha, hb = h_pairs[k % n_sets]
+            al.set_mesh(h_v.numpy(), h_t.numpy())
+            al.set_signals(ha.numpy(), hb.numpy())
+            al.iterate(params.iterations)
+            al.advect_vertices(0.5, h_oa.numpy(), h_ob.numpy())
+            return float(h_oa[0, 0])
+
+        for k in range(args.warmup):
+            step_resident(k)
+        torch.cuda.synchronize(dev)
+        sharding.barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        al.reset_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(args.steps):
+            step_resident(args.warmup + k)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        sharding.barrier()
+        ms_local = e0.elapsed_time(e1)
+        stats = al.stats()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = sharding.max_over_ranks(ms_local, dev)
+
+        # roofline of the dominant kernel on this workload's own flow matrix
+        spmv_ms = al.time_flow_spmv(50)
+        spmv_bytes = stats["flowSpmvBytes"]
+
+        # end to end
+        step_e2e(0)
+        torch.cuda.synchronize(dev)
+        sharding.barrier()
+        e0.record(stream)
+        for k in range(args.steps):
+            step_e2e(1 + k)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        sharding.barrier()
+        e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        al.close()
+
+    if rank != 0:
+        return 0
+    peak, peak_src = measured_peak_gbs()
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_spmv_dot_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    iters = max(stats["flowCgIterations"], 1)
+    line = {
+        "metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "clocks": clocks,
+        "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(V * 3 * 8 + T * 3 * 4 + 2 * V * 3 * 8),
+                "d2h_bytes_per_step": int(2 * V * 3 * 8), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(stats["kernelLaunches"]),
+        "roofline": {"bound": "hbm", "kernel": "k_spmv_dot (phase 1 of the persistent k_pcg<1>: y = A d fused with d.y, flow system CSR fp64/int32)",
+                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "traffic": traffic, "bytes_per_launch": spmv_bytes, "us_per_launch": spmv_ms * 1e3, "rows": stats["flowRows"], "nnz": stats["flowNnz"]},
+        "pcg": {"flow_iterations_per_alignment": stats["flowCgIterations"] / args.steps, "smooth_iterations_per_alignment": stats["smoothCgIterations"] / args.steps,
+                "flow_solve_ms_per_alignment": stats["flowSolveMs"] / args.steps, "smooth_solve_ms_per_alignment": stats["smoothSolveMs"] / args.steps,
+                "us_per_flow_iteration": stats["flowSolveMs"] * 1e3 / iters, "setup_ms_per_alignment": stats["setupMs"] / args.steps,
+                "advect_ms_per_alignment": stats["advectMs"] / args.steps},
+    }
+    if world == 1:
+        with tempfile.TemporaryDirectory() as tmp:
+            nv = reference_sample_inputs(tmp)
+            sec = time_reference_once(tmp)
+        line["cpu_baseline"] = cpu_baseline_dict(sec, nv, V)
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

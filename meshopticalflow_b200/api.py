@@ -202,8 +202,9 @@ class Aligner:
         self._check(self._lib.mof_get_coeffs(self._ctx, _d(out)))
         return out
 
-    def advect_vertices(self, alpha: float = 0.5):
-        a, b = np.empty((self.V, 3)), np.empty((self.V, 3))
+    def advect_vertices(self, alpha: float = 0.5, out_a=None, out_b=None):
+        a = np.empty((self.V, 3)) if out_a is None else out_a
+        b = np.empty((self.V, 3)) if out_b is None else out_b
         self._check(self._lib.mof_advect_vertices(self._ctx, alpha, _d(a), _d(b)))
         return a, b
 

@@ -163,3 +163,61 @@ def read_ply(path: str):
     if "face" in out and "vertex_indices" in out["face"]:
         out["face"]["vertex_indices"] = out["face"]["vertex_indices"].astype(np.int32)
     return out
+
+
+# ------------------------------------------------------------------------- textured test inputs
+
+def uv_torus(nu: int, nv: int, major: float = 0.55, minor: float = 0.45):
+    """Closed torus of nu x nv quads split into triangles, with per-face-corner texture coordinates laid out
+    like the reference's Example/mesh.ply: vertex (i, j) sits at uv ((i+.5)/nu, (j+.5)/nv), so the faces on the
+    two seams span the texture backwards — a good exercise for the rasteriser's first-writer rule
+    (MeshFlow.inl:334). Returns (vertices float32 [V,3], triangles int32 [T,3], tri_uv float32 [T,6])."""
+    i, j = np.meshgrid(np.arange(nu), np.arange(nv), indexing="ij")
+    th, ph = 2 * np.pi * i / nu, 2 * np.pi * j / nv
+    r = major + minor * np.cos(ph)
+    v = np.stack([r * np.cos(th), minor * np.sin(ph), r * np.sin(th)], -1).reshape(-1, 3).astype(np.float32)
+    vid = lambda a, b: (a % nu) * nv + (b % nv)
+    uv = lambda a, b: np.stack([(a % nu + 0.5) / nu, (b % nv + 0.5) / nv], -1)
+    a, b = i.reshape(-1), j.reshape(-1)
+    t1 = np.stack([vid(a, b), vid(a + 1, b), vid(a + 1, b + 1)], 1)
+    t2 = np.stack([vid(a, b), vid(a + 1, b + 1), vid(a, b + 1)], 1)
+    u1 = np.concatenate([uv(a, b), uv(a + 1, b), uv(a + 1, b + 1)], 1)
+    u2 = np.concatenate([uv(a, b), uv(a + 1, b + 1), uv(a, b + 1)], 1)
+    tri = np.concatenate([t1, t2], 0).astype(np.int32)
+    tuv = np.concatenate([u1, u2], 0).astype(np.float32)
+    # orientation: outward normals
+    n = np.cross(v[tri[:, 1]] - v[tri[:, 0]], v[tri[:, 2]] - v[tri[:, 0]])
+    c = v[tri].mean(1)
+    centre = np.stack([major * c[:, 0] / np.hypot(c[:, 0], c[:, 2]), np.zeros(len(c)), major * c[:, 2] / np.hypot(c[:, 0], c[:, 2])], 1)
+    flip = ((c - centre) * n).sum(1) < 0
+    tri[flip] = tri[flip][:, [0, 2, 1]]
+    tuv[flip] = tuv[flip][:, [0, 1, 4, 5, 2, 3]]
+    return v, tri, tuv
+
+
+def smooth_texture_pair(width: int, height: int, seed: int, shift: float = 0.02):
+    """Two uint8 [H,W,3] textures: a smooth periodic random pattern and the same pattern shifted in u and v."""
+    rng = np.random.default_rng(seed)
+    k = rng.integers(1, 4, size=(3, 5, 2)).astype(np.float64)
+    ph = rng.uniform(0, 2 * np.pi, size=(3, 5))
+
+    def img(du, dv):
+        y, x = np.meshgrid((np.arange(height) + 0.5) / height + dv, (np.arange(width) + 0.5) / width + du, indexing="ij")
+        out = np.zeros((height, width, 3))
+        for c in range(3):
+            s = sum(np.sin(2 * np.pi * (k[c, q, 0] * x + k[c, q, 1] * y) + ph[c, q]) for q in range(5))
+            out[..., c] = 127.5 + 127.5 * np.tanh(0.5 * s)
+        return np.rint(out).clip(0, 255).astype(np.uint8)
+
+    return img(0.0, 0.0), img(shift, 0.5 * shift)
+
+
+def write_ply_textured(path: str, vertices: np.ndarray, triangles: np.ndarray, tri_uv: np.ndarray) -> None:
+    """ASCII: float x y z; list uchar int vertex_indices; list uchar float texcoord (like Example/mesh.ply)."""
+    with open(path, "w") as fp:
+        fp.write(f"ply\nformat ascii 1.0\nelement vertex {len(vertices)}\nproperty float x\nproperty float y\nproperty float z\n"
+                 f"element face {len(triangles)}\nproperty list uchar int vertex_indices\nproperty list uchar float texcoord\nend_header\n")
+        for p in vertices:
+            fp.write("%.9g %.9g %.9g \n" % tuple(p))
+        for f, uv in zip(triangles, tri_uv):
+            fp.write("3 %d %d %d 6 %.9g %.9g %.9g %.9g %.9g %.9g \n" % (f[0], f[1], f[2], *uv))

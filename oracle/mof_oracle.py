@@ -489,6 +489,34 @@ def align_vertices(vertices, triangles, col_a, col_b, params: Params | None = No
     return st, (a + b) / 2.0
 
 
+def prepare_texture_mesh(vertices_f32, triangles, tri_uv, e_length_param=float(np.float32(0.006))):
+    """The texture branch of Init up to the signals, OpticalFlow.cpp:704-726: bounding-box diagonal, edge
+    length = float(eLength * diagonal) (:713), Subdivide (:714)."""
+    v = np.ascontiguousarray(vertices_f32, dtype=np.float32)
+    lo, hi = v.astype(np.float64).min(0), v.astype(np.float64).max(0)
+    diagonal = float(np.sqrt(((hi - lo) ** 2).sum()))
+    e_len = float(np.float32(np.float32(e_length_param) * diagonal))
+    if e_len > 0:
+        return subdivide(v, triangles, np.asarray(tri_uv, dtype=np.float32).astype(np.float64), e_len)
+    return v, np.ascontiguousarray(triangles, dtype=np.int32), np.asarray(tri_uv, dtype=np.float64)
+
+
+def align_texture(vertices_f32, triangles, tri_uv, tex_a, tex_b, params: Params | None = None, taps=False, bilinear=True):
+    """--mesh m.ply --in A.png B.png --out r.png (OpticalFlow.cpp:686-751, 818, 1044-1047). Textures are uint8
+    [H,W,3], top row first. Returns (State, dict with srcT, srcP, advected [2][W*H,3], pixels uint8 [H,W,3] as written)."""
+    params = params or Params()
+    v, t, uv = prepare_texture_mesh(vertices_f32, triangles, tri_uv, params.eLength)
+    H, W = tex_a.shape[0], tex_a.shape[1]
+    sig = [sample_texture_to_vertices(t, uv, v.shape[0], tex, bilinear) for tex in (tex_a, tex_b)]
+    st = init(v.astype(np.float64), t, sig[0], sig[1], params)
+    srcT, srcP = texture_source(uv, W, H, params.pad, st.opp, st.lin, st.cst, st.g)
+    iterate(st, params, taps)
+    adv = [advect_texels(W, H, srcT, srcP, st.opp, st.lin, st.cst, st.g, st.tfield, uv, tex, length, bilinear) for tex, length in ((tex_a, -0.5), (tex_b, 0.5))]
+    blended = (adv[0] + adv[1]) / 2.0
+    pixels = to_uchar_png(blended).reshape(H, W, 3)[::-1]  # flipY, OpticalFlow.cpp:131
+    return st, {"vertices": v, "triangles": t, "tri_uv": uv, "srcT": srcT, "srcP": srcP, "advected": adv, "pixels": np.ascontiguousarray(pixels)}
+
+
 def to_uchar_ply(colors):
     """OutputMesh, OpticalFlow.cpp:139-148: float cast, clamp to [0,255], uchar by truncation
     (PlyFile.inl:2309-2313)."""

@@ -1,0 +1,88 @@
+"""Generates the golden fixtures in this directory from the REFERENCE ITSELF.
+
+Runs oracle/_ref/OpticalFlow_ref (the unmodified reference sources compiled by oracle/ref/build_ref.sh;
+needs /root/reference, so this script only works in the build container) with --tap on two small
+seeded inputs and stores inputs + selected reference outputs as compressed .npz:
+
+  sphere3_vertex.npz   --in A.ply B.ply --out r.ply on the 258-vertex octahedron sphere, 10 iterations
+  torus_texture.npz    --mesh m.ply --in A.png B.png --out r.png --eLength 0.08 on a 24x12 uv torus, 48x48 texels
+
+    python tests/golden/make_golden.py
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from meshopticalflow_b200 import synthetic  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "OpticalFlow_ref")
+
+
+def load_taps(d):
+    return {f[:-4]: np.load(os.path.join(d, f)) for f in os.listdir(d) if f.endswith(".npy")}
+
+
+def keep(taps, names, iterations=10, per_iter=("tFlowField",)):
+    out = {n: taps[n] for n in names}
+    for i in range(iterations):
+        for n in per_iter:
+            out["it%02d.%s" % (i, n)] = taps["it%02d.%s" % (i, n)]
+    return out
+
+
+def sphere():
+    from PIL import Image  # noqa: F401  (only to fail early if the harness image lacks it)
+    v, t = synthetic.octahedron_sphere(3)
+    a, b = synthetic.smooth_rgb_pair(v, 0)
+    with tempfile.TemporaryDirectory() as d:
+        synthetic.write_ply_colored(os.path.join(d, "A.ply"), v, a, t)
+        synthetic.write_ply_colored(os.path.join(d, "B.ply"), v, b, t)
+        subprocess.check_call([REF, "--in", "A.ply", "B.ply", "--out", "r.ply", "--tap", "tap"], cwd=d, stdout=subprocess.DEVNULL)
+        taps = load_taps(os.path.join(d, "tap"))
+        out = synthetic.read_ply(os.path.join(d, "r.ply"))
+    data = keep(taps, ["vertices", "triangles", "g", "oppositeEdge", "xform_linear", "xform_constant", "reducedEdgeIndex", "expandedEdgeIndex",
+                       "positiveOrientedEdge", "signals0", "signals1", "advected0", "advected1", "sMass.rowptr", "sMass.col", "sMass.val",
+                       "sStiffness.val", "smoothOperator.rowptr", "smoothOperator.col", "smoothOperator.val", "prolongation.col", "prolongation.val"],
+                per_iter=("tFlowField", "x", "smoothed0", "resampled1", "dataTerm", "rhs"))
+    data["input_vertices_f32"] = v.astype(np.float32)
+    data["input_a"], data["input_b"] = a, b
+    data["output_rgb"] = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "sphere3_vertex.npz"), **data)
+    print("sphere3_vertex.npz", os.path.getsize(os.path.join(HERE, "sphere3_vertex.npz")) // 1024, "KiB")
+
+
+def torus():
+    from PIL import Image
+    v, t, uv = synthetic.uv_torus(24, 12)
+    ta, tb = synthetic.smooth_texture_pair(48, 48, 1)
+    with tempfile.TemporaryDirectory() as d:
+        synthetic.write_ply_textured(os.path.join(d, "m.ply"), v, t, uv)
+        Image.fromarray(ta).save(os.path.join(d, "A.png"))
+        Image.fromarray(np.dstack([tb, np.full(tb.shape[:2], 255, np.uint8)])).save(os.path.join(d, "B.png"))  # RGBA: alpha must be dropped
+        subprocess.check_call([REF, "--mesh", "m.ply", "--in", "A.png", "B.png", "--out", "r.png", "--eLength", "0.08", "--tap", "tap"], cwd=d,
+                              stdout=subprocess.DEVNULL)
+        taps = load_taps(os.path.join(d, "tap"))
+        pixels = np.asarray(Image.open(os.path.join(d, "r.png")))
+        png_a = open(os.path.join(d, "A.png"), "rb").read()
+        png_b = open(os.path.join(d, "B.png"), "rb").read()
+    data = keep(taps, ["vertices", "triangles", "triangleTextures", "oppositeEdge", "signals0", "signals1", "textureSource_tIdx", "textureSource_p",
+                       "advected0", "advected1", "texture0", "texture1"])
+    data["input_vertices_f32"], data["input_triangles"], data["input_uv"] = v, t, uv
+    data["input_tex_a"], data["input_tex_b"] = ta, tb
+    data["png_a"], data["png_b"] = np.frombuffer(png_a, dtype=np.uint8), np.frombuffer(png_b, dtype=np.uint8)
+    data["output_pixels"] = pixels
+    np.savez_compressed(os.path.join(HERE, "torus_texture.npz"), **data)
+    print("torus_texture.npz", os.path.getsize(os.path.join(HERE, "torus_texture.npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    if not os.path.exists(REF):
+        sys.exit("oracle/_ref/OpticalFlow_ref is missing: run oracle/ref/build_ref.sh (needs /root/reference)")
+    sphere()
+    torus()
