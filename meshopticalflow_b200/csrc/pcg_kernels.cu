@@ -17,11 +17,15 @@
 //
 // SpMV, one right-hand side (flow system, ~11 nnz/row): a CTA stages the products val[k]*d[col[k]]
 // of a 256-row tile in shared memory with fully coalesced streaming loads of val/col (each array is
-// touched exactly once), then one thread per row sums its segment in row order. Algorithmic bytes per
+// touched exactly once, evict-first so that the vectors keep the L2), several independent loads in
+// flight per thread, then one thread per row sums its segment in row order. Algorithmic bytes per
 // launch: 12*nnz + 4*(n+1) + 16*n.
-// SpMV, six right-hand sides (scalar smoothing, 7 nnz/row): one thread per row, the six channels of
-// a vertex are adjacent in memory so the matrix is read once for all six.
+// SpMM, six right-hand sides (scalar smoothing, 7 nnz/row): vectors are [n][6] with the six channels of
+// a vertex adjacent; one thread per (row, channel), so the six lanes of a row read val/col as a broadcast
+// and the gathered 48 bytes as one coalesced piece, and every vector phase is a flat coalesced sweep.
 #include <cooperative_groups.h>
+
+#include <cstdlib>
 
 #include "mof_internal.cuh"
 
@@ -46,13 +50,14 @@ struct PcgArgs {
     double* r;
     double* d;
     double* q;
-    double* partial;  // 3 banks x gridDim x (2N)
+    double* partial;  // 3 banks x gridDim x (3N)
     double* result;   // [0] iterations, [1] max relative residual (true), [2] converged
     double tol2;
     int maxIters;
     int zeroGuess;
 };
 
+// Sum of K per-thread values over the CTA, every thread gets the result; fixed order.
 template <int K>
 __device__ __forceinline__ void block_sum(double (&v)[K], double* sh) {
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -73,10 +78,39 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* sh) {
     __syncthreads();
 }
 
+// Q per-thread values that belong to channel (global thread id % N) -> the Q*N per-channel CTA sums
+// (v[q*N + j]), every thread gets them; fixed order. For N == 1 this is block_sum.
+template <int N, int Q>
+__device__ __forceinline__ void channel_sum(const double (&mine)[Q], double (&v)[Q * N], double* sh) {
+    if (N == 1) {
+        double t[Q * N];
+#pragma unroll
+        for (int q = 0; q < Q; q++) t[q] = mine[q];
+        block_sum<Q * N>(t, sh);
+#pragma unroll
+        for (int q = 0; q < Q; q++) v[q] = t[q];
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) sh[q * PCG_T + threadIdx.x] = mine[q];
+    __syncthreads();
+    double s = 0;
+    if (threadIdx.x < Q * N) {
+        int q = threadIdx.x / N, j = threadIdx.x - q * N;
+        int first = (j + N - (int)((blockIdx.x * (unsigned)PCG_T) % N)) % N;
+        for (int t = first; t < PCG_T; t += N) s += sh[q * PCG_T + t];
+    }
+    __syncthreads();
+    if (threadIdx.x < Q * N) sh[threadIdx.x] = s;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < Q * N; k++) v[k] = sh[k];
+    __syncthreads();
+}
+
 // CTA partial -> global; after the grid barrier every CTA folds all partials in the same order.
 template <int K>
-__device__ __forceinline__ void publish(double (&v)[K], double* bank, double* sh) {
-    block_sum<K>(v, sh);
+__device__ __forceinline__ void publish(const double (&v)[K], double* bank) {
     if (threadIdx.x == 0)
 #pragma unroll
         for (int k = 0; k < K; k++) bank[(size_t)blockIdx.x * K + k] = v[k];
@@ -91,49 +125,58 @@ __device__ __forceinline__ void collect(const double* bank, double (&tot)[K], do
     block_sum<K>(tot, sh);
 }
 
-// out = A in (mode 0, dot += in.out) or out = b - A in (mode 1).
 template <int N>
-__device__ __forceinline__ void spmv(const PcgArgs<N>& a, const double* __restrict__ in, double* __restrict__ out, int mode, double (&dot)[N], double* prod) {
-    const int n = a.n;
-    if (N == 1) {
-        int tiles = (n + TILE_ROWS - 1) / TILE_ROWS;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            int r0 = tile * TILE_ROWS, r1 = min(n, r0 + TILE_ROWS);
-            int k0 = a.rowptr[r0], k1 = a.rowptr[r1];
-            int row = r0 + threadIdx.x;
-            double s = 0;
-            if (k1 - k0 <= PROD_CAP) {
-                for (int k = k0 + threadIdx.x; k < k1; k += PCG_T) prod[k - k0] = a.val[k] * in[a.col[k]];
-                __syncthreads();
-                if (row < r1) {
-                    int kb = a.rowptr[row] - k0, ke = a.rowptr[row + 1] - k0;
-                    for (int k = kb; k < ke; k++) s += prod[k];
+__device__ __forceinline__ double pick(const double (&v)[N], int j) {
+    double r = v[0];
+#pragma unroll
+    for (int k = 1; k < N; k++) r = j == k ? v[k] : r;
+    return r;
+}
+
+// One right-hand side: out = A in (mode 0, returns the CTA-local sum of in.out in `dot`) or out = b - A in (mode 1).
+__device__ __forceinline__ void spmv_tiles(const int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                                           const double* __restrict__ b, const double* __restrict__ in, double* __restrict__ out, int mode, double& dot,
+                                           double* prod) {
+    int tiles = (n + TILE_ROWS - 1) / TILE_ROWS;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        int r0 = tile * TILE_ROWS, r1 = min(n, r0 + TILE_ROWS);
+        int k0 = rowptr[r0], k1 = rowptr[r1];
+        int row = r0 + threadIdx.x;
+        double s = 0;
+        if (k1 - k0 <= PROD_CAP) {
+            // Stream val/col (coalesced, each touched once, evict-first), UNROLL independent loads in flight per
+            // thread before the dependent gathers: enough bytes in flight per SM to cover HBM latency.
+            constexpr int UNROLL = 4;
+            for (int kb = k0 + threadIdx.x; kb < k1; kb += UNROLL * PCG_T) {
+                double v[UNROLL], x[UNROLL];
+                int c[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    int k = kb + u * PCG_T;
+                    bool ok = k < k1;
+                    v[u] = ok ? __ldcs(val + k) : 0.;
+                    c[u] = ok ? __ldcs(col + k) : 0;
                 }
-                __syncthreads();
-            } else if (row < r1) {
-                for (int k = a.rowptr[row]; k < a.rowptr[row + 1]; k++) s += a.val[k] * in[a.col[k]];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) x[u] = in[c[u]];
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    int k = kb + u * PCG_T;
+                    if (k < k1) prod[k - k0] = v[u] * x[u];
+                }
             }
+            __syncthreads();
             if (row < r1) {
-                if (mode == 0) out[row] = s, dot[0] += in[row] * s;
-                else out[row] = a.b[row] - s;
+                int kb = rowptr[row] - k0, ke = rowptr[row + 1] - k0;
+                for (int k = kb; k < ke; k++) s += prod[k];
             }
+            __syncthreads();
+        } else if (row < r1) {  // a tile with very long rows: straight from global memory
+            for (int k = rowptr[row]; k < rowptr[row + 1]; k++) s += val[k] * in[col[k]];
         }
-    } else {
-        for (int row = blockIdx.x * PCG_T + threadIdx.x; row < n; row += gridDim.x * PCG_T) {
-            double s[N];
-#pragma unroll
-            for (int j = 0; j < N; j++) s[j] = 0;
-            for (int k = a.rowptr[row]; k < a.rowptr[row + 1]; k++) {
-                double v = a.val[k];
-                const double* src = in + (size_t)a.col[k] * N;
-#pragma unroll
-                for (int j = 0; j < N; j++) s[j] += v * src[j];
-            }
-#pragma unroll
-            for (int j = 0; j < N; j++) {
-                if (mode == 0) out[(size_t)row * N + j] = s[j], dot[j] += in[(size_t)row * N + j] * s[j];
-                else out[(size_t)row * N + j] = a.b[(size_t)row * N + j] - s[j];
-            }
+        if (row < r1) {
+            if (mode == 0) out[row] = s, dot += in[row] * s;
+            else out[row] = b[row] - s;
         }
     }
 }
@@ -142,125 +185,136 @@ template <int N>
 __global__ void __launch_bounds__(PCG_T) k_pcg(PcgArgs<N> a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double prod[N == 1 ? PROD_CAP : 1];
-    __shared__ double sh[3 * N * PCG_NW];
+    __shared__ double sh[N == 1 ? 3 * PCG_NW : 3 * PCG_T];
     const int n = a.n;
     const size_t bankStride = (size_t)gridDim.x * 3 * N;
     double* bank0 = a.partial;
     double* bank1 = a.partial + bankStride;
     double* bank2 = a.partial + 2 * bankStride;
-    const int gtid = blockIdx.x * PCG_T + threadIdx.x, gsz = gridDim.x * PCG_T;
+    // Flat element mapping: element i = row*N + channel. The sweep stride is a multiple of N, so a thread
+    // always works on the same channel j.
+    const size_t total = (size_t)n * N;
+    const size_t g = (size_t)blockIdx.x * PCG_T + threadIdx.x;
+    const size_t G = ((size_t)gridDim.x * PCG_T / N) * N;
+    const bool active = g < G;
+    const int j = (int)(g % N);
 
     double delta[N], bb[N], alpha[N], beta[N];
     bool frozen[N];
-    double dummy[N];
+
+    auto spmv = [&](const double* __restrict__ in, double* __restrict__ out, int mode, double& dot) {
+        if (N == 1) spmv_tiles(n, a.rowptr, a.col, a.val, a.b, in, out, mode, dot, prod);
+        else if (active)
+            for (size_t i = g; i < total; i += G) {
+                int row = (int)(i / N);
+                double s = 0;
+                for (int k = a.rowptr[row]; k < a.rowptr[row + 1]; k++) s += a.val[k] * in[(size_t)a.col[k] * N + j];
+                if (mode == 0) out[i] = s, dot += in[i] * s;
+                else out[i] = a.b[i] - s;
+            }
+    };
 
     // r = b - A x0 (or b), d = Minv r, delta = r.d, bb = b.b
     if (!a.zeroGuess) {
-        spmv<N>(a, a.x, a.r, 1, dummy, prod);
+        double unused = 0;
+        spmv(a.x, a.r, 1, unused);
+        grid.sync();
     }
     {
-        double acc[3 * N];
-#pragma unroll
-        for (int k = 0; k < 3 * N; k++) acc[k] = 0;
-        for (int row = gtid; row < n; row += gsz) {
-            double di = a.dinv[row];
-#pragma unroll
-            for (int j = 0; j < N; j++) {
-                size_t i = (size_t)row * N + j;
-                double bv = a.b[i], rv;
+        double mine[3] = {0, 0, 0}, acc[3 * N];
+        if (active)
+            for (size_t i = g; i < total; i += G) {
+                double di = a.dinv[i / N], bv = a.b[i], rv;
                 if (a.zeroGuess) rv = bv, a.r[i] = bv, a.x[i] = 0;
                 else rv = a.r[i];
                 double s = di * rv;
                 a.d[i] = s;
-                acc[j] += rv * s, acc[N + j] += rv * rv, acc[2 * N + j] += bv * bv;
+                mine[0] += rv * s, mine[1] += rv * rv, mine[2] += bv * bv;
             }
-        }
-        publish<3 * N>(acc, bank0, sh);
+        channel_sum<N, 3>(mine, acc, sh);
+        publish<3 * N>(acc, bank0);
         grid.sync();
         collect<3 * N>(bank0, acc, sh);
 #pragma unroll
-        for (int j = 0; j < N; j++) delta[j] = acc[j], bb[j] = acc[2 * N + j], frozen[j] = !(acc[N + j] > a.tol2 * acc[2 * N + j]);
+        for (int c = 0; c < N; c++) delta[c] = acc[c], bb[c] = acc[2 * N + c], frozen[c] = !(acc[N + c] > a.tol2 * acc[2 * N + c]);
     }
     bool all = true;
 #pragma unroll
-    for (int j = 0; j < N; j++) all = all && frozen[j];
+    for (int c = 0; c < N; c++) all = all && frozen[c];
 
     int it = 0;
     while (!all && it < a.maxIters) {
         // phase 1: q = A d, d.q
-        double dq[N];
+        {
+            double mine[1] = {0}, dq[N];
+            spmv(a.d, a.q, 0, mine[0]);
+            channel_sum<N, 1>(mine, dq, sh);
+            publish<N>(dq, bank1);
+            grid.sync();
+            collect<N>(bank1, dq, sh);
 #pragma unroll
-        for (int j = 0; j < N; j++) dq[j] = 0;
-        spmv<N>(a, a.d, a.q, 0, dq, prod);
-        publish<N>(dq, bank1, sh);
-        grid.sync();
-        collect<N>(bank1, dq, sh);
-#pragma unroll
-        for (int j = 0; j < N; j++) alpha[j] = (!frozen[j] && dq[j] != 0) ? delta[j] / dq[j] : 0.;
-
+            for (int c = 0; c < N; c++) alpha[c] = (!frozen[c] && dq[c] != 0) ? delta[c] / dq[c] : 0.;
+        }
         // phase 2: x, r, fused r.Minv r and r.r
         double acc[2 * N];
-#pragma unroll
-        for (int k = 0; k < 2 * N; k++) acc[k] = 0;
-        for (int row = gtid; row < n; row += gsz) {
-            double di = a.dinv[row];
-#pragma unroll
-            for (int j = 0; j < N; j++) {
-                size_t i = (size_t)row * N + j;
-                double rv = a.r[i] - alpha[j] * a.q[i];
-                a.x[i] += alpha[j] * a.d[i];
-                a.r[i] = rv;
-                acc[j] += rv * (di * rv), acc[N + j] += rv * rv;
-            }
+        {
+            double mine[2] = {0, 0};
+            const double al = pick<N>(alpha, j);
+            if (active)
+                for (size_t i = g; i < total; i += G) {
+                    double di = a.dinv[i / N];
+                    double rv = a.r[i] - al * a.q[i];
+                    a.x[i] += al * a.d[i];
+                    a.r[i] = rv;
+                    mine[0] += rv * (di * rv), mine[1] += rv * rv;
+                }
+            channel_sum<N, 2>(mine, acc, sh);
+            publish<2 * N>(acc, bank2);
+            grid.sync();
+            collect<2 * N>(bank2, acc, sh);
         }
-        publish<2 * N>(acc, bank2, sh);
-        grid.sync();
-        collect<2 * N>(bank2, acc, sh);
         it++;
         all = true;
 #pragma unroll
-        for (int j = 0; j < N; j++) {
-            beta[j] = (!frozen[j] && delta[j] != 0) ? acc[j] / delta[j] : 0.;
-            delta[j] = acc[j];
-            if (!(acc[N + j] > a.tol2 * bb[j])) frozen[j] = true;
-            all = all && frozen[j];
+        for (int c = 0; c < N; c++) {
+            beta[c] = (!frozen[c] && delta[c] != 0) ? acc[c] / delta[c] : 0.;
+            delta[c] = acc[c];
+            if (!(acc[N + c] > a.tol2 * bb[c])) frozen[c] = true;
+            all = all && frozen[c];
         }
         if (all) break;
-
         // phase 3: d = Minv r + beta d
-        for (int row = gtid; row < n; row += gsz) {
-            double di = a.dinv[row];
-#pragma unroll
-            for (int j = 0; j < N; j++) {
-                size_t i = (size_t)row * N + j;
-                a.d[i] = di * a.r[i] + beta[j] * a.d[i];
-            }
+        {
+            const double be = pick<N>(beta, j);
+            if (active)
+                for (size_t i = g; i < total; i += G) a.d[i] = a.dinv[i / N] * a.r[i] + be * a.d[i];
         }
         grid.sync();
     }
 
     // true residual of the returned x: q = b - A x, max_j ||q_j|| / ||b_j||
     grid.sync();
-    spmv<N>(a, a.x, a.q, 1, dummy, prod);
+    {
+        double unused = 0;
+        spmv(a.x, a.q, 1, unused);
+    }
     grid.sync();
     {
-        double acc[N];
-#pragma unroll
-        for (int j = 0; j < N; j++) acc[j] = 0;
-        for (int row = gtid; row < n; row += gsz)
-#pragma unroll
-            for (int j = 0; j < N; j++) {
-                double v = a.q[(size_t)row * N + j];
-                acc[j] += v * v;
+        double mine[1] = {0}, acc[N];
+        if (active)
+            for (size_t i = g; i < total; i += G) {
+                double v = a.q[i];
+                mine[0] += v * v;
             }
-        publish<N>(acc, bank0, sh);
+        channel_sum<N, 1>(mine, acc, sh);
+        publish<N>(acc, bank0);
         grid.sync();
         collect<N>(bank0, acc, sh);
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             double worst = 0;
 #pragma unroll
-            for (int j = 0; j < N; j++) {
-                double rel = bb[j] > 0 ? sqrt(acc[j] / bb[j]) : 0.;
+            for (int c = 0; c < N; c++) {
+                double rel = bb[c] > 0 ? sqrt(acc[c] / bb[c]) : 0.;
                 worst = rel > worst ? rel : worst;
             }
             a.result[0] = (double)it, a.result[1] = worst, a.result[2] = all ? 1. : 0.;
@@ -268,15 +322,31 @@ __global__ void __launch_bounds__(PCG_T) k_pcg(PcgArgs<N> a) {
     }
 }
 
+static int ctas_per_sm_cap() {
+    static int cap = [] {
+        const char* e = getenv("MOF_PCG_CTAS_PER_SM");
+        int v = e ? atoi(e) : 0;
+        return v > 0 ? v : 4;
+    }();
+    return cap;
+}
+
 template <int N>
-static int launch_pcg(mof_ctx* ctx, PcgArgs<N>& args, int* iters, double* relres, bool* converged) {
-    PcgWork& w = ctx->pcg;
+static int pcg_grid(mof_ctx* ctx, int* grid) {
     int perSm = 0, sms = 0;
     MOF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pcg<N>, PCG_T, 0));
     MOF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     if (perSm < 1) return fail(ctx, MOF_E_CUDA, "k_pcg does not fit on an SM");
-    if (perSm > 4) perSm = 4;
-    int grid = perSm * sms;
+    if (perSm > ctas_per_sm_cap()) perSm = ctas_per_sm_cap();
+    *grid = perSm * sms;
+    return MOF_OK;
+}
+
+template <int N>
+static int launch_pcg(mof_ctx* ctx, PcgArgs<N>& args, int* iters, double* relres, bool* converged) {
+    PcgWork& w = ctx->pcg;
+    int grid = 0;
+    MOF_TRY(pcg_grid<N>(ctx, &grid));
     MOF_CUDA(w.partial.reserve((size_t)grid * 3 * 6 * 3));
     MOF_CUDA(w.result.reserve(8));
     args.partial = w.partial.p, args.result = w.result.p;
@@ -350,29 +420,26 @@ int extract_inverse_diagonal(mof_ctx* ctx, int n, const int* rowptr, const int* 
     return MOF_OK;
 }
 
-// The phase-1 kernel on its own, for the roofline line of bench.py and for ncu: y = A x fused with
-// x.y, same tiles, same grid as inside k_pcg.
-__global__ void __launch_bounds__(PCG_T) k_spmv_dot(PcgArgs<1> a, const double* __restrict__ x, double* __restrict__ y) {
+// The phase-1 code on its own, for the roofline line of bench.py and for ncu: y = A x fused with x.y,
+// same tiles, same grid as inside k_pcg<1>.
+__global__ void __launch_bounds__(PCG_T) k_spmv_dot(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                                                    const double* __restrict__ x, double* __restrict__ y, double* __restrict__ partial) {
     __shared__ double prod[PROD_CAP];
     __shared__ double sh[PCG_NW];
     double dot[1] = {0};
-    spmv<1>(a, x, y, 0, dot, prod);
-    publish<1>(dot, a.partial, sh);
+    spmv_tiles(n, rowptr, col, val, nullptr, x, y, 0, dot[0], prod);
+    block_sum<1>(dot, sh);
+    publish<1>(dot, partial);
 }
 
 int time_spmv(mof_ctx* ctx, int n, long long nnz, const int* rowptr, const int* col, const double* val, const double* x, double* y, int reps, float* ms) {
     (void)nnz;
-    int perSm = 0, sms = 0;
-    MOF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pcg<1>, PCG_T, 0));
-    MOF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-    if (perSm > 4) perSm = 4;
-    int grid = perSm * sms;
+    int grid = 0;
+    MOF_TRY(pcg_grid<1>(ctx, &grid));
     MOF_CUDA(ctx->pcg.partial.reserve((size_t)grid * 3 * 6 * 3));
-    PcgArgs<1> args = {};
-    args.n = n, args.rowptr = rowptr, args.col = col, args.val = val, args.partial = ctx->pcg.partial.p;
-    for (int i = 0; i < 3; i++) MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, args, x, y);
+    for (int i = 0; i < 3; i++) MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, n, rowptr, col, val, x, y, ctx->pcg.partial.p);
     MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int i = 0; i < reps; i++) MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, args, x, y);
+    for (int i = 0; i < reps; i++) MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, n, rowptr, col, val, x, y, ctx->pcg.partial.p);
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     MOF_CUDA(cudaEventSynchronize(ctx->ev1));
     float t = 0;
