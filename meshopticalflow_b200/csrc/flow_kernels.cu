@@ -88,8 +88,8 @@ static int smooth_solve(mof_ctx* ctx, double weight, const double* in6, double* 
     int iters = 0;
     double relres = 0;
     MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    int rc = pcg_solve(ctx, V, ctx->nnzS, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, ctx->sDinv.p, ctx->rhs6.p, out6, 6, false, tol, ctx->params.maxCgIterations,
-                       &iters, &relres);
+    int rc = pcg_solve_csr6(ctx, V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, ctx->sDinv.p, ctx->rhs6.p, out6, false, tol, ctx->params.maxCgIterations, &iters,
+                            &relres);
     ctx->stats.smoothCgIterations += iters, ctx->stats.smoothSolves++, ctx->stats.lastSmoothResidual = relres;
     if (rc != MOF_OK) return rc;
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -285,8 +285,8 @@ __global__ void k_data_term(const int* __restrict__ tri, const double* __restric
 // operator (R D P's 5 entries per row are a subset of it); rowSq[e] = sum of squares of the row,
 // for the Frobenius normalisation (:57).
 __global__ void k_flow_rows(const int* __restrict__ expanded, const int* __restrict__ reduced, const int* __restrict__ opp, const double* __restrict__ P,
-                            const double* __restrict__ D, const double* __restrict__ rhs, const int* __restrict__ wRowptr, const int* __restrict__ wCol, int E,
-                            double* __restrict__ wA, double* __restrict__ fb, double* __restrict__ rowSq) {
+                            const double* __restrict__ D, const double* __restrict__ rhs, const int* __restrict__ wRowptr, const int* __restrict__ sliceBase,
+                            const int* __restrict__ wCol, int E, double* __restrict__ wA, double* __restrict__ fb, double* __restrict__ rowSq) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     int h[2] = {expanded[e], 0};
@@ -308,7 +308,9 @@ __global__ void k_flow_rows(const int* __restrict__ expanded, const int* __restr
         bsum += pe0 * rhs[2 * t] + pe1 * rhs[2 * t + 1];
     }
     double sq = 0;
-    for (int k = wRowptr[e]; k < wRowptr[e + 1]; k++) {
+    const int len = wRowptr[e + 1] - wRowptr[e];
+    for (int jj = 0; jj < len; jj++) {
+        const size_t k = sell_pos(sliceBase, e, jj);  // sliced layout: coalesced across the 32 rows of a warp
         int f = wCol[k];
         double v = 0;
         for (int s = 0; s < 2; s++)
@@ -323,14 +325,16 @@ __global__ void k_flow_rows(const int* __restrict__ expanded, const int* __restr
 
 // A = s * (R D P) + w * S, b = s * (R rhs), s = 1/||R D P||_F (VectorField.h:57-67); also the
 // inverse diagonal for the Jacobi preconditioner.
-__global__ void k_flow_finalize(const int* __restrict__ wRowptr, const int* __restrict__ wCol, const double* __restrict__ wS, double weight, int E,
-                                double* __restrict__ scalars, double* __restrict__ wA, double* __restrict__ fb, double* __restrict__ dinv) {
+__global__ void k_flow_finalize(const int* __restrict__ wRowptr, const int* __restrict__ sliceBase, const int* __restrict__ wCol, const double* __restrict__ wS,
+                                double weight, int E, double* __restrict__ scalars, double* __restrict__ wA, double* __restrict__ fb, double* __restrict__ dinv) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     double scale = (double)1. / sqrt(scalars[SC_FROB2]);
     if (e == 0) scalars[SC_DATA_SCALE] = scale;
     double diag = 0;
-    for (int k = wRowptr[e]; k < wRowptr[e + 1]; k++) {
+    const int len = wRowptr[e + 1] - wRowptr[e];
+    for (int jj = 0; jj < len; jj++) {
+        const size_t k = sell_pos(sliceBase, e, jj);
         double v = wA[k] * scale + wS[k] * weight;
         wA[k] = v;
         if (wCol[k] == e) diag += v;
@@ -390,16 +394,17 @@ int update_flow(mof_ctx* ctx, double sWeight, double vfWeight) {
     // system (VectorField.h:51-67)
     MOF_CUDA(ctx->dtmp0.reserve((size_t)(E > T ? E : T)));
     MOF_LAUNCH(k_flow_rows, blocks_for(E, B), B, 0, ctx->expanded.p, ctx->reduced.p, ctx->opp.p, ctx->P.p, ctx->dataD.p, ctx->dataRhs.p, ctx->wRowptr.p,
-               ctx->wCol.p, E, ctx->wA.p, ctx->fb.p, ctx->dtmp0.p);
+               ctx->wSliceBase.p, ctx->wCol.p, E, ctx->wA.p, ctx->fb.p, ctx->dtmp0.p);
     MOF_TRY(reduce_sum(ctx, ctx->dtmp0.p, E, ctx->scalars.p + SC_FROB2));
-    MOF_LAUNCH(k_flow_finalize, blocks_for(E, B), B, 0, ctx->wRowptr.p, ctx->wCol.p, ctx->wS.p, vfWeight, E, ctx->scalars.p, ctx->wA.p, ctx->fb.p, ctx->wDinv.p);
+    MOF_LAUNCH(k_flow_finalize, blocks_for(E, B), B, 0, ctx->wRowptr.p, ctx->wSliceBase.p, ctx->wCol.p, ctx->wS.p, vfWeight, E, ctx->scalars.p, ctx->wA.p,
+               ctx->fb.p, ctx->wDinv.p);
     ctx->haveFlowSystem = true;
     // solve (:85)
     int iters = 0;
     double relres = 0;
     MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    int rc = pcg_solve(ctx, E, ctx->nnzW, ctx->wRowptr.p, ctx->wCol.p, ctx->wA.p, ctx->wDinv.p, ctx->fb.p, ctx->fx.p, 1, true, ctx->params.flowTol,
-                       ctx->params.maxCgIterations, &iters, &relres);
+    int rc = pcg_solve_sell(ctx, E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, ctx->wDinv.p, ctx->fb.p, ctx->fx.p, true, ctx->params.flowTol,
+                            ctx->params.maxCgIterations, &iters, &relres);
     ctx->stats.flowCgIterations += iters, ctx->stats.flowSolves++, ctx->stats.lastFlowResidual = relres;
     if (rc != MOF_OK) return rc;
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -101,7 +101,7 @@ void mof_destroy(mof_ctx* ctx) {
                            &ctx->dataRhs, &ctx->coeffs, &ctx->tfield, &ctx->fb, &ctx->fx, &ctx->scalars, &ctx->pcg.r, &ctx->pcg.d, &ctx->pcg.q, &ctx->pcg.partial,
                            &ctx->pcg.result, &ctx->dtmp0, &ctx->dtmp1, &ctx->srcP, &ctx->triUV, &ctx->texOut};
     for (auto* b : dbl) b->release();
-    DBuf<int>* ints[] = {&ctx->tri, &ctx->opp, &ctx->sRowptr, &ctx->sCol, &ctx->sHe, &ctx->reduced, &ctx->expanded, &ctx->positive, &ctx->wRowptr, &ctx->wCol,
+    DBuf<int>* ints[] = {&ctx->tri, &ctx->opp, &ctx->sRowptr, &ctx->sCol, &ctx->sHe, &ctx->reduced, &ctx->expanded, &ctx->positive, &ctx->wRowptr, &ctx->wSliceBase, &ctx->wCol,
                          &ctx->itmp0, &ctx->itmp1, &ctx->itmp2, &ctx->flags, &ctx->srcT};
     for (auto* b : ints) b->release();
     ctx->hashKeys.release(), ctx->tex[0].release(), ctx->tex[1].release();
@@ -302,10 +302,22 @@ int mof_get_csr(mof_ctx* ctx, int which, int* rowptr, int* col, double* val) {
     const int *rp, *c;
     const double* v;
     MOF_TRY(csr_view(ctx, which, &rows, &nnz, &rp, &c, &v));
-    MOF_CUDA(cudaMemcpyAsync(rowptr, rp, sizeof(int) * (rows + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    MOF_CUDA(cudaMemcpyAsync(col, c, sizeof(int) * nnz, cudaMemcpyDeviceToHost, ctx->stream));
-    MOF_CUDA(cudaMemcpyAsync(val, v, sizeof(double) * nnz, cudaMemcpyDeviceToHost, ctx->stream));
-    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    DBuf<int> tmpCol;
+    DBuf<double> tmpVal;
+    if (which == MOF_CSR_WHITNEY_SMOOTH || which == MOF_CSR_FLOW_SYSTEM) {
+        // the E x E operators live in the sliced layout: unpack to CSR for the caller
+        MOF_CUDA(tmpCol.alloc((size_t)nnz));
+        MOF_CUDA(tmpVal.alloc((size_t)nnz));
+        int rc = sell_to_csr(ctx, rows, rp, ctx->wSliceBase.p, c, v, tmpCol.p, tmpVal.p);
+        if (rc != MOF_OK) { tmpCol.release(), tmpVal.release(); return rc; }
+        c = tmpCol.p, v = tmpVal.p;
+    }
+    cudaError_t e = cudaMemcpyAsync(rowptr, rp, sizeof(int) * (rows + 1), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(col, c, sizeof(int) * nnz, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(val, v, sizeof(double) * nnz, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    tmpCol.release(), tmpVal.release();
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "mof_get_csr copy");
     return MOF_OK;
 }
 
@@ -365,10 +377,13 @@ int mof_pcg_solve_csr(mof_ctx* ctx, int n, const int* rowptr, const int* col, co
     if (!ctx || n < 1 || !rowptr || !col || !val || !b || !x || !iters || !relres) return MOF_E_INVALID;
     MOF_CUDA(cudaSetDevice(ctx->device));
     long long nnz = rowptr[n];
-    DBuf<int> dRow, dCol;
-    DBuf<double> dVal, dB, dX, dInv;
+    DBuf<int> dRow, dCol, sBase, sCol;
+    DBuf<double> dVal, dB, dX, dInv, sVal;
     int rc = MOF_OK;
-    auto cleanup = [&]() { dRow.release(), dCol.release(), dVal.release(), dB.release(), dX.release(), dInv.release(); };
+    auto cleanup = [&]() {
+        dRow.release(), dCol.release(), dVal.release(), dB.release(), dX.release(), dInv.release();
+        sBase.release(), sCol.release(), sVal.release();
+    };
     cudaError_t e;
     if ((e = dRow.alloc(n + 1)) != cudaSuccess || (e = dCol.alloc(nnz)) != cudaSuccess || (e = dVal.alloc(nnz)) != cudaSuccess || (e = dB.alloc(n)) != cudaSuccess ||
         (e = dX.alloc(n)) != cudaSuccess || (e = dInv.alloc(n)) != cudaSuccess) {
@@ -380,7 +395,8 @@ int mof_pcg_solve_csr(mof_ctx* ctx, int n, const int* rowptr, const int* col, co
     cudaMemcpyAsync(dVal.p, val, sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(dB.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
     rc = extract_inverse_diagonal(ctx, n, dRow.p, dCol.p, dVal.p, dInv.p);
-    if (rc == MOF_OK) rc = pcg_solve(ctx, n, nnz, dRow.p, dCol.p, dVal.p, dInv.p, dB.p, dX.p, 1, true, tol, maxIters, iters, relres);
+    if (rc == MOF_OK) rc = csr_to_sell(ctx, n, dRow.p, dCol.p, dVal.p, sBase, sCol, sVal);
+    if (rc == MOF_OK) rc = pcg_solve_sell(ctx, n, sBase.p, sCol.p, sVal.p, dInv.p, dB.p, dX.p, true, tol, maxIters, iters, relres);
     if (rc == MOF_OK || rc == MOF_E_NOCONVERGE) {
         cudaMemcpyAsync(x, dX.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
@@ -395,7 +411,7 @@ int mof_time_flow_spmv(mof_ctx* ctx, int reps, float* msPerLaunch) {
     if (!ctx->haveFlowSystem) return fail(ctx, MOF_E_INVALID, "no flow system yet: call mof_iterate first");
     MOF_CUDA(cudaSetDevice(ctx->device));
     MOF_CUDA(ctx->pcg.q.reserve(ctx->E));
-    return time_spmv(ctx, ctx->E, ctx->nnzW, ctx->wRowptr.p, ctx->wCol.p, ctx->wA.p, ctx->fx.p, ctx->pcg.q.p, reps, msPerLaunch);
+    return time_spmv_sell(ctx, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, ctx->fx.p, ctx->pcg.q.p, reps, msPerLaunch);
 }
 
 }  // extern "C"

@@ -45,6 +45,17 @@ enum ScalarSlot {
     SC_COUNT = 64
 };
 
+// Sliced storage of the E x E Whitney operators (SELL-32): rows are grouped by 32 (one warp), every
+// group is padded to its longest row and stored entry-major, i.e. entry j of row r lives at
+// sliceBase[r / 32] + 32 * j + r % 32. A warp that owns a slice reads 32 consecutive words per entry
+// index with no staging and no barrier, and every thread has all of its row's loads independent and in
+// flight at once. Padding entries carry value 0 and the row's own column.
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__ size_t sell_pos(const int* sliceBase, int row, int j) {
+    return (size_t)sliceBase[row >> 5] + 32 * (size_t)j + (size_t)(row & 31);
+}
+#endif
+
 struct PcgWork {
     DBuf<double> r, d, q;       // [n * nrhs]
     DBuf<double> partial;       // block partials, 3 banks
@@ -64,7 +75,8 @@ struct mof_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     int V = 0, T = 0, E = 0;
-    long long nnzS = 0, nnzW = 0;
+    long long nnzS = 0, nnzW = 0, wPadded = 0;
+    int wSlices = 0;
     bool haveMesh = false, haveSignals = false, haveFlowSystem = false, haveTexture = false;
     int iterationsDone = 0;
     double curSmooth = 0, curVf = 0;
@@ -76,7 +88,7 @@ struct mof_ctx {
     mof::DBuf<int> sRowptr, sCol, sHe;
     mof::DBuf<double> sMass, sStiff, sSys, sDinv;
     // Whitney
-    mof::DBuf<int> reduced, expanded, positive, wRowptr, wCol;
+    mof::DBuf<int> reduced, expanded, positive, wRowptr, wSliceBase, wCol;  // wCol/wS/wA: sliced layout (sell_pos), wPadded entries
     mof::DBuf<double> P, m0, m1, wS, wA, wDinv;
     // signals, (A rgb, B rgb) interleaved per vertex
     mof::DBuf<double> raw6, sig6, smoothed6, rhs6, resampled6, tsample6, dataD, dataRhs;
@@ -134,11 +146,18 @@ int exclusive_scan_int(mof_ctx* ctx, const int* in, int* out, int n, int* total_
 int reduce_sum(mof_ctx* ctx, const double* in, long long n, double* out_device);
 
 // pcg_kernels.cu
-// Jacobi-PCG on device CSR, NRHS interleaved per row ([n][nrhs]); x holds the initial guess.
-int pcg_solve(mof_ctx* ctx, int n, long long nnz, const int* rowptr, const int* col, const double* val, const double* dinv,
-              const double* b, double* x, int nrhs, bool zeroGuess, double tol, int maxIters, int* itersOut, double* relresOut);
+// Jacobi-PCG, one right-hand side, matrix in the sliced layout (sliceBase has ceil(n/32)+1 entries).
+int pcg_solve_sell(mof_ctx* ctx, int n, const int* sliceBase, const int* col, const double* val, const double* dinv, const double* b, double* x, bool zeroGuess,
+                   double tol, int maxIters, int* itersOut, double* relresOut);
+// Jacobi-PCG, six right-hand sides interleaved per row ([n][6]), matrix in CSR; x holds the initial guess.
+int pcg_solve_csr6(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, const double* dinv, const double* b, double* x, bool zeroGuess,
+                   double tol, int maxIters, int* itersOut, double* relresOut);
 int extract_inverse_diagonal(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, double* dinv);
-int time_spmv(mof_ctx* ctx, int n, long long nnz, const int* rowptr, const int* col, const double* val, const double* x, double* y, int reps, float* ms);
+int time_spmv_sell(mof_ctx* ctx, int n, const int* sliceBase, const int* col, const double* val, const double* x, double* y, int reps, float* ms);
+// CSR (device) -> sliced layout; allocates the three outputs. Used by the stand-alone solver entry.
+int csr_to_sell(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, DBuf<int>& sliceBase, DBuf<int>& sCol, DBuf<double>& sVal);
+// sliced layout -> CSR values/columns (rowptr is shared); for the debug taps.
+int sell_to_csr(mof_ctx* ctx, int n, const int* rowptr, const int* sliceBase, const int* sCol, const double* sVal, int* col, double* val);
 
 // flow_kernels.cu
 int dog_preprocess(mof_ctx* ctx);

@@ -6,23 +6,29 @@
 // unused, in LinearSolvers.h:174-238 (SolvePreconditionedCG + DiagonalPreconditioner).
 //
 // Design (B200): the grid is sized to exactly fill the SMs (occupancy x SM count, co-resident), every
-// CTA loops over row tiles, and the three phases of an iteration are separated by grid-wide barriers
-// instead of kernel launches, so a solve of thousands of iterations is one launch with no host
-// round trip. All scalars (alpha, beta, residual norms) are recomputed identically by every CTA from
-// per-CTA partial sums written in a fixed order: bitwise deterministic, no atomics.
+// CTA loops over its share of the rows, and the three phases of an iteration are separated by
+// grid-wide barriers instead of kernel launches, so a solve of thousands of iterations is one launch
+// with no host round trip. All scalars (alpha, beta, residual norms) are recomputed identically by
+// every CTA from per-CTA partial sums written in a fixed order: bitwise deterministic, no atomics.
 //
 //   phase 1   q = A d, fused with d.q                          (the HBM-bound SpMV; see below)
 //   phase 2   x += alpha d ; r -= alpha q ; fused r.Minv r and r.r
 //   phase 3   d = Minv r + beta d
 //
-// SpMV, one right-hand side (flow system, ~11 nnz/row): a CTA stages the products val[k]*d[col[k]]
-// of a 256-row tile in shared memory with fully coalesced streaming loads of val/col (each array is
-// touched exactly once, evict-first so that the vectors keep the L2), several independent loads in
-// flight per thread, then one thread per row sums its segment in row order. Algorithmic bytes per
-// launch: 12*nnz + 4*(n+1) + 16*n.
-// SpMM, six right-hand sides (scalar smoothing, 7 nnz/row): vectors are [n][6] with the six channels of
-// a vertex adjacent; one thread per (row, channel), so the six lanes of a row read val/col as a broadcast
-// and the gathered 48 bytes as one coalesced piece, and every vector phase is a flat coalesced sweep.
+// SpMV, one right-hand side (flow system, ~11 nnz/row): the matrix is stored SLICED (SELL-32, see
+// mof_internal.cuh): a warp owns 32 consecutive rows, lane = row, and entry j of all 32 rows is 32
+// consecutive words, so every val/col load is one fully coalesced 256/128-byte request, touched exactly
+// once (evict-first, the vectors keep the L2), with no shared-memory staging and no barrier; the
+// loads of a row are independent, so each thread keeps a batch of them in flight before the dependent
+// gathers of d[col]. Algorithmic bytes per launch: 12*nnz + 4*(n+1) + 16*n.
+// SpMM, six right-hand sides (scalar smoothing, 7 nnz/row, CSR): vectors are [n][6] with the six
+// channels of a vertex adjacent; one thread per (row, channel), so the six lanes of a row read val/col as
+// a broadcast and the gathered 48 bytes as one coalesced piece, and every vector phase is a flat sweep.
+//
+// Tried and dropped (measured on B200, 3.1M rows): staging 256-row CSR tiles of val*d[col] in shared
+// memory (117 us per SpMV) and feeding those tiles with cp.async.bulk/mbarrier rings of 2-4 stages
+// (127-224 us: the ring's shared memory costs resident warps, and the kernel is bound by the latency of
+// the dependent gathers, not by the streaming loads).
 #include <cooperative_groups.h>
 
 #include <cstdlib>
@@ -35,13 +41,12 @@ namespace mof {
 
 constexpr int PCG_T = 256;           // threads per CTA
 constexpr int PCG_NW = PCG_T / 32;   // warps per CTA
-constexpr int TILE_ROWS = PCG_T;     // rows per SpMV tile
-constexpr int PROD_CAP = 4096;       // staged products per tile (32 KB)
 
 template <int N>
 struct PcgArgs {
     int n;
-    const int* rowptr;
+    const int* rowptr;     // CSR row pointers (N > 1) — unused for N == 1
+    const int* sliceBase;  // sliced layout (N == 1)
     const int* col;
     const double* val;
     const double* dinv;
@@ -133,58 +138,47 @@ __device__ __forceinline__ double pick(const double (&v)[N], int j) {
     return r;
 }
 
-// One right-hand side: out = A in (mode 0, returns the CTA-local sum of in.out in `dot`) or out = b - A in (mode 1).
-__device__ __forceinline__ void spmv_tiles(const int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-                                           const double* __restrict__ b, const double* __restrict__ in, double* __restrict__ out, int mode, double& dot,
-                                           double* prod) {
-    int tiles = (n + TILE_ROWS - 1) / TILE_ROWS;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        int r0 = tile * TILE_ROWS, r1 = min(n, r0 + TILE_ROWS);
-        int k0 = rowptr[r0], k1 = rowptr[r1];
-        int row = r0 + threadIdx.x;
-        double s = 0;
-        if (k1 - k0 <= PROD_CAP) {
-            // Stream val/col (coalesced, each touched once, evict-first), UNROLL independent loads in flight per
-            // thread before the dependent gathers: enough bytes in flight per SM to cover HBM latency.
-            constexpr int UNROLL = 4;
-            for (int kb = k0 + threadIdx.x; kb < k1; kb += UNROLL * PCG_T) {
-                double v[UNROLL], x[UNROLL];
-                int c[UNROLL];
+// One right-hand side, sliced matrix: out = A in (mode 0, adds this thread's share of in.out to `dot`) or
+// out = b - A in (mode 1). Warp = slice of 32 rows, lane = row; the row's entries are summed in column
+// order, so the result does not depend on the launch geometry.
+constexpr int SPMV_BATCH = 6;  // independent (val, col) pairs in flight per thread before the dependent gathers
+__device__ __forceinline__ void spmv_sell(const int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const double* __restrict__ val,
+                                          const double* __restrict__ b, const double* __restrict__ in, double* __restrict__ out, int mode, double& dot) {
+    const int lane = threadIdx.x & 31;
+    const int slices = (n + 31) >> 5;
+    const int warps = gridDim.x * PCG_NW;
+    for (int s = blockIdx.x * PCG_NW + (threadIdx.x >> 5); s < slices; s += warps) {
+        const int base = sliceBase[s];
+        const int len = (sliceBase[s + 1] - base) >> 5;
+        const double* v0 = val + (size_t)base + lane;
+        const int* c0 = col + (size_t)base + lane;
+        const int row = 32 * s + lane;
+        double acc = 0;
+        for (int j0 = 0; j0 < len; j0 += SPMV_BATCH) {
+            double v[SPMV_BATCH], x[SPMV_BATCH];
+            int c[SPMV_BATCH];
 #pragma unroll
-                for (int u = 0; u < UNROLL; u++) {
-                    int k = kb + u * PCG_T;
-                    bool ok = k < k1;
-                    v[u] = ok ? __ldcs(val + k) : 0.;
-                    c[u] = ok ? __ldcs(col + k) : 0;
-                }
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++) x[u] = in[c[u]];
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++) {
-                    int k = kb + u * PCG_T;
-                    if (k < k1) prod[k - k0] = v[u] * x[u];
-                }
+            for (int u = 0; u < SPMV_BATCH; u++) {
+                bool ok = j0 + u < len;
+                v[u] = ok ? __ldcs(v0 + 32 * (size_t)(j0 + u)) : 0.;
+                c[u] = ok ? __ldcs(c0 + 32 * (size_t)(j0 + u)) : 0;
             }
-            __syncthreads();
-            if (row < r1) {
-                int kb = rowptr[row] - k0, ke = rowptr[row + 1] - k0;
-                for (int k = kb; k < ke; k++) s += prod[k];
-            }
-            __syncthreads();
-        } else if (row < r1) {  // a tile with very long rows: straight from global memory
-            for (int k = rowptr[row]; k < rowptr[row + 1]; k++) s += val[k] * in[col[k]];
+#pragma unroll
+            for (int u = 0; u < SPMV_BATCH; u++) x[u] = in[c[u]];
+#pragma unroll
+            for (int u = 0; u < SPMV_BATCH; u++)
+                if (j0 + u < len) acc += v[u] * x[u];
         }
-        if (row < r1) {
-            if (mode == 0) out[row] = s, dot += in[row] * s;
-            else out[row] = b[row] - s;
+        if (row < n) {
+            if (mode == 0) out[row] = acc, dot += in[row] * acc;
+            else out[row] = b[row] - acc;
         }
     }
 }
 
 template <int N>
-__global__ void __launch_bounds__(PCG_T) k_pcg(PcgArgs<N> a) {
+__global__ void __launch_bounds__(PCG_T, N == 1 ? 5 : 3) k_pcg(PcgArgs<N> a) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double prod[N == 1 ? PROD_CAP : 1];
     __shared__ double sh[N == 1 ? 3 * PCG_NW : 3 * PCG_T];
     const int n = a.n;
     const size_t bankStride = (size_t)gridDim.x * 3 * N;
@@ -203,7 +197,7 @@ __global__ void __launch_bounds__(PCG_T) k_pcg(PcgArgs<N> a) {
     bool frozen[N];
 
     auto spmv = [&](const double* __restrict__ in, double* __restrict__ out, int mode, double& dot) {
-        if (N == 1) spmv_tiles(n, a.rowptr, a.col, a.val, a.b, in, out, mode, dot, prod);
+        if (N == 1) spmv_sell(n, a.sliceBase, a.col, a.val, a.b, in, out, mode, dot);
         else if (active)
             for (size_t i = g; i < total; i += G) {
                 int row = (int)(i / N);
@@ -322,11 +316,12 @@ __global__ void __launch_bounds__(PCG_T) k_pcg(PcgArgs<N> a) {
     }
 }
 
+// Tuning knob (read once): cap on the CTAs per SM of the persistent grid.
 static int ctas_per_sm_cap() {
     static int cap = [] {
         const char* e = getenv("MOF_PCG_CTAS_PER_SM");
-        int v = e ? atoi(e) : 0;
-        return v > 0 ? v : 4;
+        int v = e && *e ? atoi(e) : 0;
+        return v > 0 ? v : 8;
     }();
     return cap;
 }
@@ -362,19 +357,16 @@ static int launch_pcg(mof_ctx* ctx, PcgArgs<N>& args, int* iters, double* relres
 }
 
 template <int N>
-static int pcg_solve_n(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, const double* dinv, const double* b, double* x,
-                       bool zeroGuess, double tol, int maxIters, int* itersOut, double* relresOut) {
+static int pcg_run(mof_ctx* ctx, PcgArgs<N>& args, bool zeroGuess, double tol, int maxIters, int* itersOut, double* relresOut) {
     PcgWork& w = ctx->pcg;
-    size_t len = (size_t)n * N;
+    size_t len = (size_t)args.n * N;
     if (w.r.n < len) {
         MOF_CUDA(w.r.alloc(len));
         MOF_CUDA(w.d.alloc(len));
         MOF_CUDA(w.q.alloc(len));
     }
-    PcgArgs<N> args;
-    args.n = n, args.rowptr = rowptr, args.col = col, args.val = val, args.dinv = dinv, args.b = b, args.x = x;
     args.r = w.r.p, args.d = w.d.p, args.q = w.q.p;
-    args.tol2 = tol * tol, args.maxIters = maxIters, args.zeroGuess = zeroGuess ? 1 : 0;
+    args.tol2 = tol * tol, args.zeroGuess = zeroGuess ? 1 : 0;
     int total = 0, iters = 0;
     double relres = 0;
     bool converged = false;
@@ -397,12 +389,18 @@ static int pcg_solve_n(mof_ctx* ctx, int n, const int* rowptr, const int* col, c
     return MOF_OK;
 }
 
-int pcg_solve(mof_ctx* ctx, int n, long long nnz, const int* rowptr, const int* col, const double* val, const double* dinv, const double* b, double* x,
-              int nrhs, bool zeroGuess, double tol, int maxIters, int* itersOut, double* relresOut) {
-    (void)nnz;
-    if (nrhs == 1) return pcg_solve_n<1>(ctx, n, rowptr, col, val, dinv, b, x, zeroGuess, tol, maxIters, itersOut, relresOut);
-    if (nrhs == 6) return pcg_solve_n<6>(ctx, n, rowptr, col, val, dinv, b, x, zeroGuess, tol, maxIters, itersOut, relresOut);
-    return fail(ctx, MOF_E_INVALID, "pcg_solve: nrhs must be 1 or 6");
+int pcg_solve_sell(mof_ctx* ctx, int n, const int* sliceBase, const int* col, const double* val, const double* dinv, const double* b, double* x, bool zeroGuess,
+                   double tol, int maxIters, int* itersOut, double* relresOut) {
+    PcgArgs<1> args = {};
+    args.n = n, args.sliceBase = sliceBase, args.col = col, args.val = val, args.dinv = dinv, args.b = b, args.x = x;
+    return pcg_run<1>(ctx, args, zeroGuess, tol, maxIters, itersOut, relresOut);
+}
+
+int pcg_solve_csr6(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, const double* dinv, const double* b, double* x, bool zeroGuess,
+                   double tol, int maxIters, int* itersOut, double* relresOut) {
+    PcgArgs<6> args = {};
+    args.n = n, args.rowptr = rowptr, args.col = col, args.val = val, args.dinv = dinv, args.b = b, args.x = x;
+    return pcg_run<6>(ctx, args, zeroGuess, tol, maxIters, itersOut, relresOut);
 }
 
 // DiagonalPreconditioner::set, LinearSolvers.h:88-104.
@@ -421,25 +419,23 @@ int extract_inverse_diagonal(mof_ctx* ctx, int n, const int* rowptr, const int* 
 }
 
 // The phase-1 code on its own, for the roofline line of bench.py and for ncu: y = A x fused with x.y,
-// same tiles, same grid as inside k_pcg<1>.
-__global__ void __launch_bounds__(PCG_T) k_spmv_dot(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-                                                    const double* __restrict__ x, double* __restrict__ y, double* __restrict__ partial) {
-    __shared__ double prod[PROD_CAP];
+// same code, same grid as inside k_pcg<1>.
+__global__ void __launch_bounds__(PCG_T, 5) k_spmv_dot(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const double* __restrict__ val,
+                                                       const double* __restrict__ x, double* __restrict__ y, double* __restrict__ partial) {
     __shared__ double sh[PCG_NW];
     double dot[1] = {0};
-    spmv_tiles(n, rowptr, col, val, nullptr, x, y, 0, dot[0], prod);
+    spmv_sell(n, sliceBase, col, val, nullptr, x, y, 0, dot[0]);
     block_sum<1>(dot, sh);
     publish<1>(dot, partial);
 }
 
-int time_spmv(mof_ctx* ctx, int n, long long nnz, const int* rowptr, const int* col, const double* val, const double* x, double* y, int reps, float* ms) {
-    (void)nnz;
+int time_spmv_sell(mof_ctx* ctx, int n, const int* sliceBase, const int* col, const double* val, const double* x, double* y, int reps, float* ms) {
     int grid = 0;
     MOF_TRY(pcg_grid<1>(ctx, &grid));
     MOF_CUDA(ctx->pcg.partial.reserve((size_t)grid * 3 * 6 * 3));
-    for (int i = 0; i < 3; i++) MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, n, rowptr, col, val, x, y, ctx->pcg.partial.p);
+    for (int i = 0; i < 3; i++) MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, n, sliceBase, col, val, x, y, ctx->pcg.partial.p);
     MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int i = 0; i < reps; i++) MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, n, rowptr, col, val, x, y, ctx->pcg.partial.p);
+    for (int i = 0; i < reps; i++) MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, n, sliceBase, col, val, x, y, ctx->pcg.partial.p);
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     MOF_CUDA(cudaEventSynchronize(ctx->ev1));
     float t = 0;

@@ -409,24 +409,58 @@ __global__ void k_whitney_rowsize(const int* __restrict__ tri, const int* __rest
     size[e] = (sRowptr[a + 1] - sRowptr[a] - 1) + (sRowptr[b + 1] - sRowptr[b] - 1) - 1;
 }
 
+// The E x E operators are stored SLICED (SELL-32, mof_internal.cuh): rows in groups of 32, each group
+// padded to its longest row and stored entry-major, so that a warp working on 32 consecutive rows
+// reads 32 consecutive words per entry index. size32[s] = 32 * (longest row of slice s).
+__global__ void k_slice_sizes(const int* __restrict__ rowptr, int n, int slices, int* __restrict__ size32) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > slices) return;
+    int longest = 0;
+    if (s < slices)
+        for (int r = 32 * s; r < min(n, 32 * s + 32); r++) longest = max(longest, rowptr[r + 1] - rowptr[r]);
+    size32[s] = 32 * longest;
+}
+
+// One thread per (padded) row: the real entries, then the padding (column = the row itself, value 0).
 __global__ void k_whitney_fill(const int* __restrict__ tri, const int* __restrict__ expanded, const int* __restrict__ reduced, const int* __restrict__ opp,
-                               const int* __restrict__ sRowptr, const int* __restrict__ sCol, const int* __restrict__ sHe, const int* __restrict__ wRowptr, int E,
-                               int* __restrict__ wCol) {
+                               const int* __restrict__ sRowptr, const int* __restrict__ sCol, const int* __restrict__ sHe, const int* __restrict__ sliceBase, int E,
+                               int slices, int* __restrict__ wCol) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    int h = expanded[e], t = h / 3, j = h - 3 * t;
-    int a = tri[3 * t + (j + 1) % 3], b = tri[3 * t + (j + 2) % 3];
-    int w = wRowptr[e];
-    for (int k = sRowptr[a]; k < sRowptr[a + 1]; k++)
-        if (sHe[k] >= 0) wCol[w++] = reduced[sHe[k]];
-    for (int k = sRowptr[b]; k < sRowptr[b + 1]; k++)
-        if (sHe[k] >= 0 && sCol[k] != a) wCol[w++] = reduced[sHe[k]];
+    if (e >= 32 * slices) return;
+    const int longest = (sliceBase[(e >> 5) + 1] - sliceBase[e >> 5]) >> 5;
+    int j = 0;
+    if (e < E) {
+        int h = expanded[e], t = h / 3, c = h - 3 * t;
+        int a = tri[3 * t + (c + 1) % 3], b = tri[3 * t + (c + 2) % 3];
+        for (int k = sRowptr[a]; k < sRowptr[a + 1]; k++)
+            if (sHe[k] >= 0) wCol[sell_pos(sliceBase, e, j++)] = reduced[sHe[k]];
+        for (int k = sRowptr[b]; k < sRowptr[b + 1]; k++)
+            if (sHe[k] >= 0 && sCol[k] != a) wCol[sell_pos(sliceBase, e, j++)] = reduced[sHe[k]];
+    }
+    for (; j < longest; j++) wCol[sell_pos(sliceBase, e, j)] = e < E ? e : 0;
+}
+
+// Ascending columns within each sliced row (insertion sort over the row's strided entries).
+__global__ void k_sort_rows_sell(const int* __restrict__ rowptr, const int* __restrict__ sliceBase, int rows, int* __restrict__ col) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int len = rowptr[r + 1] - rowptr[r];
+    size_t base = sell_pos(sliceBase, r, 0);
+    for (int i = 1; i < len; i++) {
+        int c = col[base + 32 * (size_t)i], k = i - 1;
+        while (k >= 0 && col[base + 32 * (size_t)k] > c) {
+            col[base + 32 * (size_t)(k + 1)] = col[base + 32 * (size_t)k];
+            k--;
+        }
+        col[base + 32 * (size_t)(k + 1)] = c;
+    }
 }
 
 // InitializeSmoothOperator, Whitney.inl:92-180: S = (d1^T m2 d1 + m1 d0 m0^-1 d0^T m1) / 2, entry by entry.
 __global__ void k_whitney_values(const int* __restrict__ tri, const int* __restrict__ expanded, const int* __restrict__ reduced, const int* __restrict__ positive,
                                  const int* __restrict__ opp, const double* __restrict__ area, const double* __restrict__ m0, const double* __restrict__ m1,
-                                 const int* __restrict__ wRowptr, const int* __restrict__ wCol, int E, double* __restrict__ wS) {
+                                 const int* __restrict__ wRowptr, const int* __restrict__ sliceBase, const int* __restrict__ wCol, int E,
+                                 double* __restrict__ wS) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     int h = expanded[e], t1 = h / 3, j1 = h - 3 * t1, o = opp[h];
@@ -435,7 +469,9 @@ __global__ void k_whitney_values(const int* __restrict__ tri, const int* __restr
     double w1 = 1. / area[t1], w2 = t2 >= 0 ? 1. / area[t2] : 0.;
     double se1 = positive[h] ? 1. : -1., se2 = o >= 0 ? (positive[o] ? 1. : -1.) : 0.;
     double me = m1[e], ia = 1.0 / m0[a], ib = 1.0 / m0[b];
-    for (int k = wRowptr[e]; k < wRowptr[e + 1]; k++) {
+    const int len = wRowptr[e + 1] - wRowptr[e];
+    for (int jj = 0; jj < len; jj++) {
+        const size_t k = sell_pos(sliceBase, e, jj);
         int f = wCol[k];
         double rot = 0;
         for (int q = 0; q < 3; q++) {
@@ -548,15 +584,27 @@ int build_mesh_operators(mof_ctx* ctx) {
     int nnzW = 0;
     MOF_CUDA(cudaMemcpy(&nnzW, ctx->wRowptr.p + E, sizeof(int), cudaMemcpyDeviceToHost));
     ctx->nnzW = nnzW;
-    MOF_CUDA(ctx->wCol.alloc(nnzW));
-    MOF_CUDA(ctx->wS.alloc(nnzW));
-    MOF_CUDA(ctx->wA.alloc(nnzW));
+    // sliced layout: slice sizes -> slice offsets -> padded entry count
+    const int slices = (E + 31) / 32;
+    ctx->wSlices = slices;
+    MOF_CUDA(ctx->itmp0.alloc(slices + 1));
+    MOF_CUDA(ctx->wSliceBase.alloc(slices + 1));
+    MOF_LAUNCH(k_slice_sizes, blocks_for(slices + 1, B), B, 0, ctx->wRowptr.p, E, slices, ctx->itmp0.p);
+    MOF_TRY(exclusive_scan_int(ctx, ctx->itmp0.p, ctx->wSliceBase.p, slices + 1, nullptr));
+    int padded = 0;
+    MOF_CUDA(cudaMemcpy(&padded, ctx->wSliceBase.p + slices, sizeof(int), cudaMemcpyDeviceToHost));
+    ctx->wPadded = padded;
+    MOF_CUDA(ctx->wCol.alloc((size_t)padded));
+    MOF_CUDA(ctx->wS.alloc((size_t)padded));
+    MOF_CUDA(ctx->wA.alloc((size_t)padded));
     MOF_CUDA(ctx->wDinv.alloc(E));
-    MOF_LAUNCH(k_whitney_fill, blocks_for(E, B), B, 0, ctx->tri.p, ctx->expanded.p, ctx->reduced.p, ctx->opp.p, ctx->sRowptr.p, ctx->sCol.p, ctx->sHe.p,
-               ctx->wRowptr.p, E, ctx->wCol.p);
-    MOF_LAUNCH(k_sort_rows, blocks_for(E, B), B, 0, ctx->wRowptr.p, E, ctx->wCol.p, (int*)nullptr);
+    MOF_CUDA(cudaMemsetAsync(ctx->wS.p, 0, sizeof(double) * (size_t)padded, ctx->stream));  // padding entries stay 0 for good
+    MOF_CUDA(cudaMemsetAsync(ctx->wA.p, 0, sizeof(double) * (size_t)padded, ctx->stream));
+    MOF_LAUNCH(k_whitney_fill, blocks_for(32ll * slices, B), B, 0, ctx->tri.p, ctx->expanded.p, ctx->reduced.p, ctx->opp.p, ctx->sRowptr.p, ctx->sCol.p,
+               ctx->sHe.p, ctx->wSliceBase.p, E, slices, ctx->wCol.p);
+    MOF_LAUNCH(k_sort_rows_sell, blocks_for(E, B), B, 0, ctx->wRowptr.p, ctx->wSliceBase.p, E, ctx->wCol.p);
     MOF_LAUNCH(k_whitney_values, blocks_for(E, B), B, 0, ctx->tri.p, ctx->expanded.p, ctx->reduced.p, ctx->positive.p, ctx->opp.p, ctx->area.p, ctx->m0.p,
-               ctx->m1.p, ctx->wRowptr.p, ctx->wCol.p, E, ctx->wS.p);
+               ctx->m1.p, ctx->wRowptr.p, ctx->wSliceBase.p, ctx->wCol.p, E, ctx->wS.p);
 
     MOF_CUDA(cudaMemcpyAsync(hflags, ctx->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
     MOF_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -573,6 +621,58 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_CUDA(ctx->tsample6.alloc(6ull * T));
     MOF_CUDA(cudaMemsetAsync(ctx->coeffs.p, 0, ctx->coeffs.bytes(), ctx->stream));
     MOF_CUDA(cudaMemsetAsync(ctx->tfield.p, 0, ctx->tfield.bytes(), ctx->stream));
+    return MOF_OK;
+}
+
+// ------------------------------------------------------------------ CSR <-> sliced layout conversions
+
+__global__ void k_csr_to_sell(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, const int* __restrict__ sliceBase, int n,
+                              int slices, int* __restrict__ sCol, double* __restrict__ sVal) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= 32 * slices) return;
+    const int longest = (sliceBase[(r >> 5) + 1] - sliceBase[r >> 5]) >> 5;
+    int j = 0;
+    if (r < n)
+        for (int k = rowptr[r]; k < rowptr[r + 1]; k++, j++) {
+            size_t p = sell_pos(sliceBase, r, j);
+            sCol[p] = col[k], sVal[p] = val[k];
+        }
+    for (; j < longest; j++) {
+        size_t p = sell_pos(sliceBase, r, j);
+        sCol[p] = r < n ? r : 0, sVal[p] = 0.;
+    }
+}
+
+__global__ void k_sell_to_csr(const int* __restrict__ rowptr, const int* __restrict__ sliceBase, const int* __restrict__ sCol, const double* __restrict__ sVal, int n,
+                              int* __restrict__ col, double* __restrict__ val) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int j = 0;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; k++, j++) {
+        size_t p = sell_pos(sliceBase, r, j);
+        col[k] = sCol[p], val[k] = sVal[p];
+    }
+}
+
+int csr_to_sell(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, DBuf<int>& sliceBase, DBuf<int>& sCol, DBuf<double>& sVal) {
+    const int slices = (n + 31) / 32, B = 256;
+    DBuf<int> sizes;
+    MOF_CUDA(sizes.alloc(slices + 1));
+    MOF_CUDA(sliceBase.alloc(slices + 1));
+    MOF_LAUNCH(k_slice_sizes, blocks_for(slices + 1, B), B, 0, rowptr, n, slices, sizes.p);
+    int rc = exclusive_scan_int(ctx, sizes.p, sliceBase.p, slices + 1, nullptr);
+    sizes.release();
+    if (rc != MOF_OK) return rc;
+    int padded = 0;
+    MOF_CUDA(cudaMemcpy(&padded, sliceBase.p + slices, sizeof(int), cudaMemcpyDeviceToHost));
+    MOF_CUDA(sCol.alloc((size_t)padded));
+    MOF_CUDA(sVal.alloc((size_t)padded));
+    MOF_LAUNCH(k_csr_to_sell, blocks_for(32ll * slices, B), B, 0, rowptr, col, val, sliceBase.p, n, slices, sCol.p, sVal.p);
+    return MOF_OK;
+}
+
+int sell_to_csr(mof_ctx* ctx, int n, const int* rowptr, const int* sliceBase, const int* sCol, const double* sVal, int* col, double* val) {
+    MOF_LAUNCH(k_sell_to_csr, blocks_for(n, 256), 256, 0, rowptr, sliceBase, sCol, sVal, n, col, val);
     return MOF_OK;
 }
 
