@@ -403,8 +403,26 @@ int update_flow(mof_ctx* ctx, double sWeight, double vfWeight) {
     int iters = 0;
     double relres = 0;
     MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    int rc = pcg_solve_sell(ctx, E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, ctx->wDinv.p, ctx->fb.p, ctx->fx.p, true, ctx->params.flowTol,
-                            ctx->params.maxCgIterations, &iters, &relres);
+    int rc = MOF_OK;
+    if (mg_usable(ctx)) rc = mg_update_values(ctx);  // Galerkin coarse operators of this system; may find it unusable
+    if (rc == MOF_OK) {
+        bool solved = false;
+        if (mg_usable(ctx)) {
+            // multigrid-preconditioned PCG; a stalled solve (a damping estimate that was too optimistic) is not an
+            // error: the Jacobi-preconditioned kernel below always converges
+            int mgIters = 0;
+            int mrc = mg_pcg_solve(ctx, ctx->params.flowTol, std::min(ctx->params.maxCgIterations, 1000), &mgIters, &relres);
+            iters += mgIters;
+            if (mrc == MOF_OK) solved = true;
+            else if (mrc != MOF_E_NOCONVERGE) rc = mrc;
+        }
+        if (rc == MOF_OK && !solved) {
+            int jIters = 0;
+            rc = pcg_solve_sell(ctx, E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, ctx->wDinv.p, ctx->fb.p, ctx->fx.p, true, ctx->params.flowTol,
+                                ctx->params.maxCgIterations, &jIters, &relres);
+            iters += jIters;
+        }
+    }
     ctx->stats.flowCgIterations += iters, ctx->stats.flowSolves++, ctx->stats.lastFlowResidual = relres;
     if (rc != MOF_OK) return rc;
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -30,6 +30,8 @@ int finish_mesh(mof_ctx* ctx) {
     cudaEventRecord(ctx->ev0, ctx->stream);
     int rc = build_mesh_operators(ctx);
     if (rc != MOF_OK) return rc;
+    rc = mg_setup_mesh(ctx);
+    if (rc != MOF_OK) return rc;
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     MOF_CUDA(cudaEventSynchronize(ctx->ev1));
     float ms = 0;
@@ -105,6 +107,7 @@ void mof_destroy(mof_ctx* ctx) {
                          &ctx->itmp0, &ctx->itmp1, &ctx->itmp2, &ctx->flags, &ctx->srcT};
     for (auto* b : ints) b->release();
     ctx->hashKeys.release(), ctx->tex[0].release(), ctx->tex[1].release();
+    mg_destroy(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);

@@ -56,6 +56,8 @@ __host__ __device__ __forceinline__ size_t sell_pos(const int* sliceBase, int ro
 }
 #endif
 
+struct Multigrid;  // multigrid.cu
+
 struct PcgWork {
     DBuf<double> r, d, q;       // [n * nrhs]
     DBuf<double> partial;       // block partials, 3 banks
@@ -96,6 +98,7 @@ struct mof_ctx {
     mof::DBuf<double> coeffs, tfield, fb, fx;
     mof::DBuf<double> scalars;
     mof::PcgWork pcg;
+    mof::Multigrid* mg = nullptr;  // multilevel preconditioner of the flow system
     // scratch
     mof::DBuf<int> itmp0, itmp1, itmp2, flags;
     mof::DBuf<unsigned long long> hashKeys;
@@ -158,6 +161,16 @@ int time_spmv_sell(mof_ctx* ctx, int n, const int* sliceBase, const int* col, co
 int csr_to_sell(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, DBuf<int>& sliceBase, DBuf<int>& sCol, DBuf<double>& sVal);
 // sliced layout -> CSR values/columns (rowptr is shared); for the debug taps.
 int sell_to_csr(mof_ctx* ctx, int n, const int* rowptr, const int* sliceBase, const int* sCol, const double* sVal, int* col, double* val);
+
+// y = A x on the sliced layout with per-CTA partials of x.y (the phase-1 code of the PCG kernel); *partials = CTA count.
+int spmv_dot_launch(mof_ctx* ctx, int n, const int* sliceBase, const int* col, const double* val, const double* x, double* y, double* partial, int* partials);
+
+// multigrid.cu
+int mg_setup_mesh(mof_ctx* ctx);      // per mesh; leaves the preconditioner unusable (Jacobi-PCG stays) when the mesh does not fit
+bool mg_usable(const mof_ctx* ctx);
+int mg_update_values(mof_ctx* ctx);   // per flow system
+int mg_pcg_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double* relresOut);
+void mg_destroy(mof_ctx* ctx);
 
 // flow_kernels.cu
 int dog_preprocess(mof_ctx* ctx);

@@ -429,6 +429,14 @@ __global__ void __launch_bounds__(PCG_T, 5) k_spmv_dot(int n, const int* __restr
     publish<1>(dot, partial);
 }
 
+int spmv_dot_launch(mof_ctx* ctx, int n, const int* sliceBase, const int* col, const double* val, const double* x, double* y, double* partial, int* partials) {
+    static int grid = 0;
+    if (!grid) MOF_TRY(pcg_grid<1>(ctx, &grid));
+    MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, n, sliceBase, col, val, x, y, partial);
+    *partials = grid;
+    return MOF_OK;
+}
+
 int time_spmv_sell(mof_ctx* ctx, int n, const int* sliceBase, const int* col, const double* val, const double* x, double* y, int reps, float* ms) {
     int grid = 0;
     MOF_TRY(pcg_grid<1>(ctx, &grid));
