@@ -102,8 +102,9 @@ __device__ __forceinline__ void channel_sum(const double (&mine)[Q], double (&v)
     double s = 0;
     if (threadIdx.x < Q * N) {
         int q = threadIdx.x / N, j = threadIdx.x - q * N;
-        int first = (j + N - (int)((blockIdx.x * (unsigned)PCG_T) % N)) % N;
-        for (int t = first; t < PCG_T; t += N) s += sh[q * PCG_T + t];
+        // a CTA owns whole rows (thread t <-> local row t / N, channel t % N), so every channel is summed over the same
+        // rows in the same order: identical right-hand sides give bitwise identical solutions
+        for (int t = j; t < (PCG_T / N) * N; t += N) s += sh[q * PCG_T + t];
     }
     __syncthreads();
     if (threadIdx.x < Q * N) sh[threadIdx.x] = s;
@@ -188,10 +189,11 @@ __global__ void __launch_bounds__(PCG_T, N == 1 ? 5 : 3) k_pcg(PcgArgs<N> a) {
     // Flat element mapping: element i = row*N + channel. The sweep stride is a multiple of N, so a thread
     // always works on the same channel j.
     const size_t total = (size_t)n * N;
-    const size_t g = (size_t)blockIdx.x * PCG_T + threadIdx.x;
-    const size_t G = ((size_t)gridDim.x * PCG_T / N) * N;
-    const bool active = g < G;
-    const int j = (int)(g % N);
+    constexpr int OWNED = (PCG_T / N) * N;  // threads of a CTA that own an element (whole rows per CTA)
+    const size_t g = (size_t)blockIdx.x * OWNED + threadIdx.x;
+    const size_t G = (size_t)gridDim.x * OWNED;
+    const bool active = threadIdx.x < OWNED;
+    const int j = (int)(threadIdx.x % N);
 
     double delta[N], bb[N], alpha[N], beta[N];
     bool frozen[N];
