@@ -4,6 +4,8 @@
 // smoothing solve uses, so one matrix read serves all six channels and a triangle corner is one
 // 48-byte fetch. Per-triangle quantities (walk samples, data term) are written once by one thread
 // and combined by gathers in a fixed order: no atomics, deterministic.
+#include <algorithm>
+
 #include "mof_internal.cuh"
 
 namespace mof {
@@ -88,8 +90,21 @@ static int smooth_solve(mof_ctx* ctx, double weight, const double* in6, double* 
     int iters = 0;
     double relres = 0;
     MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    int rc = pcg_solve_csr6(ctx, V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, ctx->sDinv.p, ctx->rhs6.p, out6, false, tol, ctx->params.maxCgIterations, &iters,
+    int rc = MOF_OK;
+    bool solved = false;
+    if (mg_scalar_usable(ctx)) rc = mg_scalar_update(ctx);
+    if (rc == MOF_OK && mg_scalar_usable(ctx)) {
+        // multigrid-preconditioned PCG over the six channels at once; a stalled solve falls through to Jacobi-PCG
+        int mrc = mg_scalar_solve(ctx, ctx->rhs6.p, out6, tol, std::min(ctx->params.maxCgIterations, 400), &iters, &relres);
+        if (mrc == MOF_OK) solved = true;
+        else if (mrc != MOF_E_NOCONVERGE) rc = mrc;
+    }
+    if (rc == MOF_OK && !solved) {
+        int jIters = 0;
+        rc = pcg_solve_csr6(ctx, V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, ctx->sDinv.p, ctx->rhs6.p, out6, false, tol, ctx->params.maxCgIterations, &jIters,
                             &relres);
+        iters += jIters;
+    }
     ctx->stats.smoothCgIterations += iters, ctx->stats.smoothSolves++, ctx->stats.lastSmoothResidual = relres;
     if (rc != MOF_OK) return rc;
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -404,14 +419,14 @@ int update_flow(mof_ctx* ctx, double sWeight, double vfWeight) {
     double relres = 0;
     MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc = MOF_OK;
-    if (mg_usable(ctx)) rc = mg_update_values(ctx);  // Galerkin coarse operators of this system; may find it unusable
+    if (mg_flow_usable(ctx)) rc = mg_flow_update(ctx);  // Galerkin coarse operators of this system; may find it unusable
     if (rc == MOF_OK) {
         bool solved = false;
-        if (mg_usable(ctx)) {
+        if (mg_flow_usable(ctx)) {
             // multigrid-preconditioned PCG; a stalled solve (a damping estimate that was too optimistic) is not an
             // error: the Jacobi-preconditioned kernel below always converges
             int mgIters = 0;
-            int mrc = mg_pcg_solve(ctx, ctx->params.flowTol, std::min(ctx->params.maxCgIterations, 1000), &mgIters, &relres);
+            int mrc = mg_flow_solve(ctx, ctx->params.flowTol, std::min(ctx->params.maxCgIterations, 1000), &mgIters, &relres);
             iters += mgIters;
             if (mrc == MOF_OK) solved = true;
             else if (mrc != MOF_E_NOCONVERGE) rc = mrc;

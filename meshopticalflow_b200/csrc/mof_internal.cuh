@@ -98,7 +98,8 @@ struct mof_ctx {
     mof::DBuf<double> coeffs, tfield, fb, fx;
     mof::DBuf<double> scalars;
     mof::PcgWork pcg;
-    mof::Multigrid* mg = nullptr;  // multilevel preconditioner of the flow system
+    mof::Multigrid* mg = nullptr;   // multilevel preconditioner of the flow system
+    mof::Multigrid* mgs = nullptr;  // ... and of the scalar smoothing systems
     // scratch
     mof::DBuf<int> itmp0, itmp1, itmp2, flags;
     mof::DBuf<unsigned long long> hashKeys;
@@ -166,11 +167,14 @@ int sell_to_csr(mof_ctx* ctx, int n, const int* rowptr, const int* sliceBase, co
 int spmv_dot_launch(mof_ctx* ctx, int n, const int* sliceBase, const int* col, const double* val, const double* x, double* y, double* partial, int* partials);
 
 // multigrid.cu
-int mg_setup_mesh(mof_ctx* ctx);      // per mesh; leaves the preconditioner unusable (Jacobi-PCG stays) when the mesh does not fit
-bool mg_usable(const mof_ctx* ctx);
-int mg_update_values(mof_ctx* ctx);   // per flow system
-int mg_pcg_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double* relresOut);
+int mg_setup_mesh(mof_ctx* ctx);      // per mesh, both hierarchies; leaves one unusable (Jacobi-PCG stays) when the mesh does not fit
 void mg_destroy(mof_ctx* ctx);
+bool mg_flow_usable(const mof_ctx* ctx);
+int mg_flow_update(mof_ctx* ctx);     // per flow system: coarse operators of the current wA
+int mg_flow_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double* relresOut);   // wA fx = fb
+bool mg_scalar_usable(const mof_ctx* ctx);
+int mg_scalar_update(mof_ctx* ctx);   // per scalar system: coarse operators of the current sSys (sDinv = its inverse diagonal)
+int mg_scalar_solve(mof_ctx* ctx, const double* b6, double* x6, double tol, int maxIters, int* itersOut, double* relresOut);  // x6 = initial guess
 
 // flow_kernels.cu
 int dog_preprocess(mof_ctx* ctx);
