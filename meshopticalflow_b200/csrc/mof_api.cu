@@ -8,6 +8,15 @@ using namespace mof;
 
 namespace {
 
+// Every C-ABI call that touches the device starts with one of these: selects the context's GPU and makes its stream
+// the one device buffers are allocated on and freed in (stream-ordered pool, see DBuf).
+struct StreamScope {
+    explicit StreamScope(mof_ctx* c) {
+        cudaSetDevice(c->device);
+        alloc_stream() = c->stream;
+    }
+};
+
 // Interleave two V x 3 signals into V x 6 (A rgb, B rgb) and back.
 __global__ void k_interleave(const double* __restrict__ a, const double* __restrict__ b, int V, double* __restrict__ out6) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,13 +99,19 @@ int mof_create(int device, void* stream, mof_ctx** out) {
         ctx->ownStream = true;
     }
     if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return MOF_E_CUDA; }
+    // keep freed blocks in the stream-ordered pool instead of handing them back to the driver at every synchronisation
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     *out = ctx;
     return MOF_OK;
 }
 
 void mof_destroy(mof_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    StreamScope scope(ctx);
     cudaStreamSynchronize(ctx->stream);
     DBuf<double>* dbl[] = {&ctx->pos, &ctx->g, &ctx->area, &ctx->xlin, &ctx->xcst, &ctx->sMass, &ctx->sStiff, &ctx->sSys, &ctx->sDinv, &ctx->P, &ctx->m0, &ctx->m1,
                            &ctx->wS, &ctx->wA, &ctx->wDinv, &ctx->raw6, &ctx->sig6, &ctx->smoothed6, &ctx->rhs6, &ctx->resampled6, &ctx->tsample6, &ctx->dataD,
@@ -108,6 +123,7 @@ void mof_destroy(mof_ctx* ctx) {
     for (auto* b : ints) b->release();
     ctx->hashKeys.release(), ctx->tex[0].release(), ctx->tex[1].release();
     mg_destroy(ctx);
+    cudaStreamSynchronize(ctx->stream);  // the frees above are stream-ordered
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
@@ -146,7 +162,7 @@ int mof_synchronize(mof_ctx* ctx) {
 int mof_set_mesh(mof_ctx* ctx, const double* xyz, int V, const int* tri, int T) {
     if (!ctx) return MOF_E_INVALID;
     if (!xyz || !tri || V < 3 || T < 1) return fail(ctx, MOF_E_INVALID, "mof_set_mesh: empty mesh");
-    MOF_CUDA(cudaSetDevice(ctx->device));
+    StreamScope scope(ctx);
     ctx->V = V, ctx->T = T;
     MOF_CUDA(ctx->pos.alloc(3ull * V));
     MOF_CUDA(ctx->tri.alloc(3ull * T));
@@ -158,7 +174,7 @@ int mof_set_mesh(mof_ctx* ctx, const double* xyz, int V, const int* tri, int T) 
 int mof_set_mesh_device(mof_ctx* ctx, const double* d_xyz, int V, const int* d_tri, int T) {
     if (!ctx) return MOF_E_INVALID;
     if (!d_xyz || !d_tri || V < 3 || T < 1) return fail(ctx, MOF_E_INVALID, "mof_set_mesh_device: empty mesh");
-    MOF_CUDA(cudaSetDevice(ctx->device));
+    StreamScope scope(ctx);
     ctx->V = V, ctx->T = T;
     MOF_CUDA(ctx->pos.alloc(3ull * V));
     MOF_CUDA(ctx->tri.alloc(3ull * T));
@@ -172,7 +188,7 @@ static int set_signals_common(mof_ctx* ctx, const double* a, const double* b, in
     MOF_TRY(require_mesh(ctx));
     if (!a || !b) return fail(ctx, MOF_E_INVALID, "mof_set_signals: null signal");
     if (channels != 3) return fail(ctx, MOF_E_UNSUPPORTED, "[ERROR] only 3-channel signals are on the accelerated path (_main<double,3>, OpticalFlow.cpp:1115)");
-    MOF_CUDA(cudaSetDevice(ctx->device));
+    StreamScope scope(ctx);
     const int V = ctx->V;
     MOF_CUDA(ctx->raw6.alloc(6ull * V));
     MOF_CUDA(ctx->dtmp0.reserve(6ull * V));
@@ -190,7 +206,7 @@ int mof_iterate(mof_ctx* ctx, int n) {
     if (!ctx) return MOF_E_INVALID;
     MOF_TRY(require_mesh(ctx));
     MOF_TRY(require_signals(ctx));
-    MOF_CUDA(cudaSetDevice(ctx->device));
+    StreamScope scope(ctx);
     for (int i = 0; i < n; i++) {
         MOF_TRY(update_flow(ctx, ctx->curSmooth, ctx->curVf));
         // IterativeOptimization, OpticalFlow.cpp:1041-1042
@@ -222,7 +238,7 @@ static int advect_common(mof_ctx* ctx, double alpha, double* outA, double* outB,
     if (!ctx || !outA || !outB) return MOF_E_INVALID;
     MOF_TRY(require_mesh(ctx));
     MOF_TRY(require_signals(ctx));
-    MOF_CUDA(cudaSetDevice(ctx->device));
+    StreamScope scope(ctx);
     const int V = ctx->V;
     // InputGeometryData::flow, OpticalFlow.cpp:482-489: raw colours, lengths -alpha and 1-alpha
     MOF_TRY(advect_vertices(ctx, ctx->raw6.p, -alpha, 1. - alpha, ctx->resampled6.p));
@@ -242,7 +258,7 @@ int mof_set_texture_map(mof_ctx* ctx, int W, int H, const int* srcT, const doubl
     if (!ctx) return MOF_E_INVALID;
     MOF_TRY(require_mesh(ctx));
     if (W < 2 || H < 2 || !srcT || !srcP || !triUV || !texA || !texB) return fail(ctx, MOF_E_INVALID, "mof_set_texture_map: bad arguments");
-    MOF_CUDA(cudaSetDevice(ctx->device));
+    StreamScope scope(ctx);
     size_t n = (size_t)W * H;
     for (size_t i = 0; i < n; i++)
         if (srcT[i] < -1 || srcT[i] >= ctx->T) return fail(ctx, MOF_E_INVALID, "mof_set_texture_map: texel refers to a triangle outside the mesh");
@@ -266,7 +282,7 @@ int mof_advect_texels(mof_ctx* ctx, double alpha, int bilinear, double* outA, do
     if (!ctx || !outA || !outB) return MOF_E_INVALID;
     MOF_TRY(require_mesh(ctx));
     if (!ctx->haveTexture) return fail(ctx, MOF_E_INVALID, "call mof_set_texture_map first");
-    MOF_CUDA(cudaSetDevice(ctx->device));
+    StreamScope scope(ctx);
     MOF_TRY(advect_texels(ctx, alpha, bilinear));
     size_t n = (size_t)ctx->texW * ctx->texH;
     MOF_CUDA(cudaMemcpyAsync(outA, ctx->texOut.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -305,6 +321,7 @@ int mof_get_csr(mof_ctx* ctx, int which, int* rowptr, int* col, double* val) {
     const int *rp, *c;
     const double* v;
     MOF_TRY(csr_view(ctx, which, &rows, &nnz, &rp, &c, &v));
+    StreamScope scope(ctx);
     DBuf<int> tmpCol;
     DBuf<double> tmpVal;
     if (which == MOF_CSR_WHITNEY_SMOOTH || which == MOF_CSR_FLOW_SYSTEM) {
@@ -378,7 +395,7 @@ int mof_get_array(mof_ctx* ctx, int which, void* out) {
 int mof_pcg_solve_csr(mof_ctx* ctx, int n, const int* rowptr, const int* col, const double* val, const double* b, double* x, double tol, int maxIters, int* iters,
                       double* relres) {
     if (!ctx || n < 1 || !rowptr || !col || !val || !b || !x || !iters || !relres) return MOF_E_INVALID;
-    MOF_CUDA(cudaSetDevice(ctx->device));
+    StreamScope scope(ctx);
     long long nnz = rowptr[n];
     DBuf<int> dRow, dCol, sBase, sCol;
     DBuf<double> dVal, dB, dX, dInv, sVal;
@@ -412,7 +429,7 @@ int mof_time_flow_spmv(mof_ctx* ctx, int reps, float* msPerLaunch) {
     if (!ctx || reps < 1 || !msPerLaunch) return MOF_E_INVALID;
     MOF_TRY(require_mesh(ctx));
     if (!ctx->haveFlowSystem) return fail(ctx, MOF_E_INVALID, "no flow system yet: call mof_iterate first");
-    MOF_CUDA(cudaSetDevice(ctx->device));
+    StreamScope scope(ctx);
     MOF_CUDA(ctx->pcg.q.reserve(ctx->E));
     return time_spmv_sell(ctx, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, ctx->fx.p, ctx->pcg.q.p, reps, msPerLaunch);
 }

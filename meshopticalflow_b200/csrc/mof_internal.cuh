@@ -12,6 +12,14 @@ namespace mof {
 
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
+// Device buffers come from CUDA's stream-ordered pool (cudaMallocAsync / cudaFreeAsync on the context's stream, release
+// threshold raised in mof_create): re-running the setup for a new mesh or pair re-uses the pool's memory without
+// device-wide synchronisation. The stream is the one of the C-ABI call in progress (set by StreamScope in mof_api.cu).
+inline cudaStream_t& alloc_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
+
 template <class T>
 struct DBuf {
     T* p = nullptr;
@@ -20,7 +28,7 @@ struct DBuf {
         if (count == n && p) return cudaSuccess;
         release();
         if (!count) return cudaSuccess;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), alloc_stream());
         if (e == cudaSuccess) n = count;
         else p = nullptr;
         return e;
@@ -28,7 +36,7 @@ struct DBuf {
     // Scratch use: grow-only, keeps the larger allocation.
     cudaError_t reserve(size_t count) { return (p && count <= n) ? cudaSuccess : alloc(count); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, alloc_stream());
         p = nullptr, n = 0;
     }
     size_t bytes() const { return n * sizeof(T); }

@@ -23,6 +23,9 @@ def main():
     al.set_mesh(v, t)
     print("set_mesh %.3fs E=%d" % (time.time() - t0, al.num_edges), flush=True)
     t0 = time.time()
+    al.set_mesh(v, t)
+    print("set_mesh again (steady state) %.3fs, setupMs so far %.1f" % (time.time() - t0, al.stats()["setupMs"]), flush=True)
+    t0 = time.time()
     al.set_signals(ca, cb)
     s = al.stats()
     print("set_signals %.3fs smoothIters=%d" % (time.time() - t0, s["smoothCgIterations"]), flush=True)
