@@ -45,11 +45,22 @@ constexpr int COARSEST_CELLS = 64;
 template <int K>
 __host__ __device__ __forceinline__ size_t blk(int N, int I, int slot, int k) { return ((size_t)slot * K + k) * (size_t)N + I; }
 
+// The cycle is a preconditioner: it only has to be a fixed symmetric positive definite operator close to the inverse,
+// so it runs in single precision (matrix copies, level vectors) and moves half the bytes; the PCG recurrence around
+// it, its SpMV, dot products and the true-residual check stay in fp64. The Galerkin sums and block inverses are
+// computed in fp64 and rounded once.
+#ifdef MOF_MG_FP64
+using creal = double;
+#else
+using creal = float;
+#endif
+
 struct MgLevel {
     int gridLevel = 0, N = 0;
     DBuf<int> code, nbr, parent, firstChild;   // firstChild: children (ids on the finer level) of each node, N+1 entries
-    DBuf<double> blocks, binv;                 // [27][K][N], [K][N]
-    DBuf<double> r, z, t;                      // [N][D]
+    DBuf<double> blocks;                       // [27][K][N], setup precision
+    DBuf<creal> cblocks, binv;                 // cycle copies: [27][K][N], [K][N]
+    DBuf<creal> r, z, t;                       // [N][D]
     double omega = 0.6;
 };
 
@@ -65,10 +76,13 @@ struct Multigrid {
     int K = 0;                      // number of coarse levels
     std::vector<MgLevel> lev;       // lev[0] = level 1 (finest aggregates)
     DBuf<double> evec;              // FLOW: edge vectors [E][3]
+    DBuf<creal> cevec;              // ... in cycle precision
     DBuf<int> agg, aggPtr, aggList; // aggregate of every fine unknown; members of every aggregate, ascending
     DBuf<signed char> slotOf;       // per matrix entry: stencil slot at level 1 (-1 for padding)
-    DBuf<double> cinv;              // dense inverse on the coarsest level
-    DBuf<double> fz, fz2, ft, fr, fp, fq;   // fine-level vectors of the cycle and of PCG, nFine * nrhs each
+    DBuf<creal> cinv;               // dense inverse on the coarsest level
+    DBuf<creal> fval, fdinv;        // fine matrix values (layout of wA / sSys) and inverse diagonal in cycle precision
+    DBuf<creal> fz, fz2, ft;        // fine-level vectors of the cycle, nFine * nrhs each
+    DBuf<double> fr, fp, fq;        // ... and of PCG
     DBuf<double> partial, scal;
     double omega0 = 0.6;
     int gamma = 1, gammaLevels = 0; // gamma coarse corrections on the first gammaLevels coarse levels (W-cycle knob)
@@ -328,7 +342,7 @@ __global__ void k_coarsen_blocks(const int* __restrict__ firstChild, const int* 
 // block is rank deficient and the directions with eigenvalue < 1e-8 * largest are simply not smoothed (they prolong
 // to ~0 on the edges anyway). An explicit cofactor inverse of such a block is NOT good enough: its error in the
 // well-conditioned directions scales with the condition number and the smoother stops being positive definite.
-__global__ void k_block_pinv(const double* __restrict__ blocks, int N, double* __restrict__ binv) {
+__global__ void k_block_pinv(const double* __restrict__ blocks, int N, creal* __restrict__ binv) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= N) return;
     double m[9];
@@ -363,78 +377,32 @@ __global__ void k_block_pinv(const double* __restrict__ blocks, int N, double* _
         for (int r = 0; r < 3; r++)
             for (int c = 0; c < 3; c++) inv[3 * r + c] += il * Vm[3 * r + e] * Vm[3 * c + e];
     }
-    for (int k = 0; k < 9; k++) binv[(size_t)k * N + I] = inv[k];
+    for (int k = 0; k < 9; k++) binv[(size_t)k * N + I] = (creal)inv[k];
 }
-__global__ void k_scalar_inv(const double* __restrict__ blocks, int N, double* __restrict__ binv) {
+__global__ void k_scalar_inv(const double* __restrict__ blocks, int N, creal* __restrict__ binv) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= N) return;
     double w = blocks[blk<1>(N, I, SLOT_CENTER, 0)];
-    binv[I] = w > 0 ? 1. / w : 0.;
+    binv[I] = (creal)(w > 0 ? 1. / w : 0.);
+}
+// fp64 -> cycle precision (matrix values, inverse diagonals, coarse coefficients, edge vectors)
+__global__ void k_to_creal(const double* __restrict__ src, long long n, creal* __restrict__ dst) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = (creal)src[i];
 }
 
 // ------------------------------------------------------------------------------------- cycle kernels
 
 // z = omega * dinv[row] * r, flat over nrhs interleaved right-hand sides
-__global__ void k_fine_presmooth(const double* __restrict__ r, const double* __restrict__ dinv, double omega, long long len, int nrhs, double* __restrict__ z) {
+template <class TZ>
+__global__ void k_fine_presmooth(const double* __restrict__ r, const creal* __restrict__ dinv, double omega, long long len, int nrhs, TZ* __restrict__ z) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < len) z[i] = omega * dinv[i / nrhs] * r[i];
+    if (i < len) z[i] = (TZ)(omega * (double)dinv[i / nrhs] * r[i]);
 }
 
-// FLOW: sliced SpMV (warp = slice, lane = row), as in pcg_kernels.cu. mode 1: out = b - A in ;
-// mode 2: out = in + omega * dinv * (b - A in)  (one damped Jacobi sweep).
-constexpr int BATCH = 6;
-__global__ void __launch_bounds__(B) k_fine_apply_flow(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const double* __restrict__ val,
-                                                      const double* __restrict__ b, const double* __restrict__ dinv, double omega, const double* __restrict__ in,
-                                                      double* __restrict__ out, int mode) {
-    const int lane = threadIdx.x & 31;
-    const int slices = (n + 31) >> 5;
-    const int warps = gridDim.x * (B / 32);
-    for (int s = blockIdx.x * (B / 32) + (threadIdx.x >> 5); s < slices; s += warps) {
-        const int base = sliceBase[s];
-        const int len = (sliceBase[s + 1] - base) >> 5;
-        const double* v0 = val + (size_t)base + lane;
-        const int* c0 = col + (size_t)base + lane;
-        const int row = 32 * s + lane;
-        double acc = 0;
-        for (int j0 = 0; j0 < len; j0 += BATCH) {
-            double v[BATCH], x[BATCH];
-            int c[BATCH];
-#pragma unroll
-            for (int u = 0; u < BATCH; u++) {
-                bool ok = j0 + u < len;
-                v[u] = ok ? __ldcs(v0 + 32 * (size_t)(j0 + u)) : 0.;
-                c[u] = ok ? __ldcs(c0 + 32 * (size_t)(j0 + u)) : 0;
-            }
-#pragma unroll
-            for (int u = 0; u < BATCH; u++) x[u] = in[c[u]];
-#pragma unroll
-            for (int u = 0; u < BATCH; u++)
-                if (j0 + u < len) acc += v[u] * x[u];
-        }
-        if (row < n) {
-            if (mode == 1) out[row] = b[row] - acc;
-            else out[row] = in[row] + omega * dinv[row] * (b[row] - acc);
-        }
-    }
-}
-// SCALAR: CSR with six interleaved right-hand sides, one thread per (row, channel). mode 0: out = A in with the CTA's
-// partial of in.out ; modes 1, 2 as above.
-__global__ void __launch_bounds__(B) k_fine_apply_scalar(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
-                                                        const double* __restrict__ b, const double* __restrict__ dinv, double omega, const double* __restrict__ in,
-                                                        double* __restrict__ out, int mode, double* __restrict__ partial) {
+// Sum of one value per thread over the CTA, in a fixed order; thread 0 stores it.
+__device__ __forceinline__ void cta_partial(double v, double* __restrict__ partial) {
     __shared__ double sh[B];
-    const long long len = 6ll * n;
-    double dot = 0;
-    for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < len; i += (long long)gridDim.x * B) {
-        const int row = (int)(i / 6), c = (int)(i - 6ll * row);
-        double acc = 0;
-        for (int k = rowptr[row]; k < rowptr[row + 1]; k++) acc += val[k] * in[6 * (size_t)col[k] + c];
-        if (mode == 0) out[i] = acc, dot += in[i] * acc;
-        else if (mode == 1) out[i] = b[i] - acc;
-        else out[i] = in[i] + omega * dinv[row] * (b[i] - acc);
-    }
-    if (mode != 0) return;
-    sh[threadIdx.x] = dot;
+    sh[threadIdx.x] = v;
     __syncthreads();
     for (int o = B / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
@@ -443,15 +411,87 @@ __global__ void __launch_bounds__(B) k_fine_apply_scalar(int n, const int* __res
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
+// FLOW: sliced SpMV (warp = slice, lane = row), as in pcg_kernels.cu. TV = precision of the matrix copy, TX = of the
+// vectors; b is always the fp64 right-hand side (the PCG residual inside a cycle).
+//   mode 1: out = b - A in
+//   mode 2: out = in + omega * dinv * (b - A in)  (one damped Jacobi sweep); with `partial`, also the CTA's part of b.out
+constexpr int BATCH = 6;
+template <class TV, class TX>
+__global__ void __launch_bounds__(B) k_fine_apply_flow(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const TV* __restrict__ val,
+                                                      const double* __restrict__ b, const creal* __restrict__ dinv, double omega, const TX* __restrict__ in,
+                                                      TX* __restrict__ out, int mode, double* __restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int slices = (n + 31) >> 5;
+    const int warps = gridDim.x * (B / 32);
+    double dot = 0;
+    for (int s = blockIdx.x * (B / 32) + (threadIdx.x >> 5); s < slices; s += warps) {
+        const int base = sliceBase[s];
+        const int len = (sliceBase[s + 1] - base) >> 5;
+        const TV* v0 = val + (size_t)base + lane;
+        const int* c0 = col + (size_t)base + lane;
+        const int row = 32 * s + lane;
+        TX acc = 0;
+        for (int j0 = 0; j0 < len; j0 += BATCH) {
+            TV v[BATCH];
+            TX x[BATCH];
+            int c[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                bool ok = j0 + u < len;
+                v[u] = ok ? __ldcs(v0 + 32 * (size_t)(j0 + u)) : (TV)0;
+                c[u] = ok ? __ldcs(c0 + 32 * (size_t)(j0 + u)) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) x[u] = in[c[u]];
+#pragma unroll
+            for (int u = 0; u < BATCH; u++)
+                if (j0 + u < len) acc += (TX)v[u] * x[u];
+        }
+        if (row < n) {
+            const double bv = b[row];
+            if (mode == 1) out[row] = (TX)(bv - (double)acc);
+            else {
+                TX o = (TX)((double)in[row] + omega * (double)dinv[row] * (bv - (double)acc));
+                out[row] = o;
+                dot += bv * (double)o;
+            }
+        }
+    }
+    if (mode == 2 && partial) cta_partial(dot, partial);
+}
+// SCALAR: CSR with six interleaved right-hand sides, one thread per (row, channel). mode 0: out = A in with the CTA's
+// partial of in.out ; modes 1, 2 as above.
+template <class TV, class TX>
+__global__ void __launch_bounds__(B) k_fine_apply_scalar(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const TV* __restrict__ val,
+                                                        const double* __restrict__ b, const creal* __restrict__ dinv, double omega, const TX* __restrict__ in,
+                                                        TX* __restrict__ out, int mode, double* __restrict__ partial) {
+    const long long len = 6ll * n;
+    double dot = 0;
+    for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < len; i += (long long)gridDim.x * B) {
+        const int row = (int)(i / 6), c = (int)(i - 6ll * row);
+        TX acc = 0;
+        for (int k = rowptr[row]; k < rowptr[row + 1]; k++) acc += (TX)val[k] * in[6 * (size_t)col[k] + c];
+        if (mode == 0) out[i] = acc, dot += (double)in[i] * (double)acc;
+        else if (mode == 1) out[i] = (TX)(b[i] - (double)acc);
+        else {
+            const double bv = b[i];
+            TX o = (TX)((double)in[i] + omega * (double)dinv[row] * (bv - (double)acc));
+            out[i] = o;
+            dot += bv * (double)o;
+        }
+    }
+    if (mode == 0 || (mode == 2 && partial)) cta_partial(dot, partial);
+}
+
 // FLOW restriction: rc[I] = sum over the edges of aggregate I of v_e * r_e (P1^T r). One warp per aggregate.
-__global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const double* __restrict__ evec, const double* __restrict__ r, int N,
-                                double* __restrict__ rc) {
+__global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ evec, const creal* __restrict__ r, int N,
+                                creal* __restrict__ rc) {
     int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (I >= N) return;
-    double a0 = 0, a1 = 0, a2 = 0;
+    creal a0 = 0, a1 = 0, a2 = 0;
     for (int q = aggPtr[I] + lane; q < aggPtr[I + 1]; q += 32) {
         int e = aggList[q];
-        double re = r[e];
+        creal re = r[e];
         a0 += evec[3 * (size_t)e] * re, a1 += evec[3 * (size_t)e + 1] * re, a2 += evec[3 * (size_t)e + 2] * re;
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -460,52 +500,52 @@ __global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __res
     if (lane == 0) rc[3 * (size_t)I] = a0, rc[3 * (size_t)I + 1] = a1, rc[3 * (size_t)I + 2] = a2;
 }
 // FLOW prolongation: z_e += v_e . zc[agg(e)]
-__global__ void k_prolong_flow(const int* __restrict__ agg, const double* __restrict__ evec, const double* __restrict__ zc, int E, double* __restrict__ z) {
+__global__ void k_prolong_flow(const int* __restrict__ agg, const creal* __restrict__ evec, const creal* __restrict__ zc, int E, creal* __restrict__ z) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    const double* c = zc + 3 * (size_t)agg[e];
+    const creal* c = zc + 3 * (size_t)agg[e];
     z[e] += evec[3 * (size_t)e] * c[0] + evec[3 * (size_t)e + 1] * c[1] + evec[3 * (size_t)e + 2] * c[2];
 }
 // SCALAR restriction / prolongation: sums and copies per channel. One thread per (cell, channel) / (vertex, channel).
-__global__ void k_restrict_scalar(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const double* __restrict__ r, int N, double* __restrict__ rc) {
+__global__ void k_restrict_scalar(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ r, int N, creal* __restrict__ rc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 6 * N) return;
     int I = i / 6, c = i - 6 * I;
-    double a = 0;
+    creal a = 0;
     for (int q = aggPtr[I]; q < aggPtr[I + 1]; q++) a += r[6 * (size_t)aggList[q] + c];
     rc[i] = a;
 }
-__global__ void k_prolong_scalar(const int* __restrict__ agg, const double* __restrict__ zc, int V, double* __restrict__ z) {
+__global__ void k_prolong_scalar(const int* __restrict__ agg, const creal* __restrict__ zc, int V, creal* __restrict__ z) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 6ll * V) return;
     long long v = i / 6;
     z[i] += zc[6 * (size_t)agg[v] + (i - 6 * v)];
 }
 
-__device__ __forceinline__ void mat3_vec(const double* m, const double* v, double* out) {
+__device__ __forceinline__ void mat3_vec(const creal* m, const creal* v, creal* out) {
     out[0] = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
     out[1] = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
     out[2] = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
 }
 // Applies the diagonal (pseudo-)inverse of cell I to the D values in `v`.
 template <int K, int D>
-__device__ __forceinline__ void apply_binv(const double* __restrict__ binv, int N, int I, const double* v, double* out) {
+__device__ __forceinline__ void apply_binv(const creal* __restrict__ binv, int N, int I, const creal* v, creal* out) {
     if (K == 9) {
-        double m[9];
+        creal m[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) m[k] = binv[(size_t)k * N + I];
         mat3_vec(m, v, out);
     } else {
-        double w = binv[I];
+        creal w = binv[I];
 #pragma unroll
         for (int c = 0; c < D; c++) out[c] = w * v[c];
     }
 }
 template <int K, int D>
-__global__ void k_coarse_presmooth(const double* __restrict__ binv, const double* __restrict__ r, double omega, int N, double* __restrict__ z) {
+__global__ void k_coarse_presmooth(const creal* __restrict__ binv, const creal* __restrict__ r, creal omega, int N, creal* __restrict__ z) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= N) return;
-    double v[D], o[D];
+    creal v[D], o[D];
 #pragma unroll
     for (int c = 0; c < D; c++) v[c] = r[(size_t)D * I + c];
     apply_binv<K, D>(binv, N, I, v, o);
@@ -516,25 +556,25 @@ __global__ void k_coarse_presmooth(const double* __restrict__ binv, const double
 // (32 consecutive cells), so every coefficient component is read as 32 consecutive words and all 27 slots of a cell
 // are in flight at once; the 27 partial products are then summed in slot order by the first warp.
 template <int K, int D>
-__global__ void __launch_bounds__(27 * 32) k_coarse_apply(const double* __restrict__ blocks, const int* __restrict__ nbr, const double* __restrict__ binv,
-                                                         const double* __restrict__ r, const double* __restrict__ z, double omega, int N, int mode,
-                                                         double* __restrict__ out) {
-    __shared__ double part[27][32][D];
+__global__ void __launch_bounds__(27 * 32) k_coarse_apply(const creal* __restrict__ blocks, const int* __restrict__ nbr, const creal* __restrict__ binv,
+                                                         const creal* __restrict__ r, const creal* __restrict__ z, creal omega, int N, int mode,
+                                                         creal* __restrict__ out) {
+    __shared__ creal part[27][32][D];
     const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int I = blockIdx.x * 32 + lane;
-    double o[D];
+    creal o[D];
 #pragma unroll
     for (int c = 0; c < D; c++) o[c] = 0;
     if (I < N) {
         int J = nbr[I * 27 + slot];
         if (J >= 0) {
             if (K == 9) {
-                double m[9];
+                creal m[9];
 #pragma unroll
                 for (int k = 0; k < 9; k++) m[k] = blocks[blk<9>(N, I, slot, k)];
                 mat3_vec(m, z + 3 * (size_t)J, o);
             } else {
-                double w = blocks[blk<1>(N, I, slot, 0)];
+                creal w = blocks[blk<1>(N, I, slot, 0)];
 #pragma unroll
                 for (int c = 0; c < D; c++) o[c] = w * z[(size_t)D * J + c];
             }
@@ -544,7 +584,7 @@ __global__ void __launch_bounds__(27 * 32) k_coarse_apply(const double* __restri
     for (int c = 0; c < D; c++) part[slot][lane][c] = o[c];
     __syncthreads();
     if (slot != 0 || I >= N) return;
-    double res[D];
+    creal res[D];
 #pragma unroll
     for (int c = 0; c < D; c++) res[c] = 0;
     for (int s = 0; s < 27; s++)
@@ -556,33 +596,33 @@ __global__ void __launch_bounds__(27 * 32) k_coarse_apply(const double* __restri
 #pragma unroll
         for (int c = 0; c < D; c++) out[(size_t)D * I + c] = res[c];
     } else {
-        double u[D];
+        creal u[D];
         apply_binv<K, D>(binv, N, I, res, u);
 #pragma unroll
         for (int c = 0; c < D; c++) out[(size_t)D * I + c] = z[(size_t)D * I + c] + omega * u[c];
     }
 }
 template <int D>
-__global__ void k_restrict_coarse(const int* __restrict__ firstChild, const double* __restrict__ rFine, int Ncoarse, double* __restrict__ rc) {
+__global__ void k_restrict_coarse(const int* __restrict__ firstChild, const creal* __restrict__ rFine, int Ncoarse, creal* __restrict__ rc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D * Ncoarse) return;
     int Ip = i / D, c = i - D * Ip;
-    double a = 0;
+    creal a = 0;
     for (int I = firstChild[Ip]; I < firstChild[Ip + 1]; I++) a += rFine[(size_t)D * I + c];
     rc[i] = a;
 }
 template <int D>
-__global__ void k_prolong_coarse(const int* __restrict__ parent, const double* __restrict__ zc, int N, double* __restrict__ z) {
+__global__ void k_prolong_coarse(const int* __restrict__ parent, const creal* __restrict__ zc, int N, creal* __restrict__ z) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D * N) return;
     z[i] += zc[(size_t)D * parent[i / D] + i % D];
 }
 // z = M r on the coarsest level: M is n x n, r and z are [n][C]
-__global__ void k_dense_apply(const double* __restrict__ m, const double* __restrict__ r, int n, int C, double* __restrict__ z) {
+__global__ void k_dense_apply(const creal* __restrict__ m, const creal* __restrict__ r, int n, int C, creal* __restrict__ z) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * C) return;
     int row = i / C, c = i - C * row;
-    double s = 0;
+    creal s = 0;
     for (int k = 0; k < n; k++) s += m[(size_t)row * n + k] * r[(size_t)k * C + c];
     z[i] = s;
 }
@@ -591,10 +631,11 @@ __global__ void k_dense_apply(const double* __restrict__ m, const double* __rest
 
 enum { S_RZ = 0, S_PQ = 1, S_ALPHA = 2, S_BETA = 3, S_RR = 4, S_BB = 5, S_RZNEW = 6 };
 
-__global__ void k_dot_partial(const double* __restrict__ a, const double* __restrict__ b, long long n, double* __restrict__ partial) {
+template <class TA, class TB>
+__global__ void k_dot_partial(const TA* __restrict__ a, const TB* __restrict__ b, long long n, double* __restrict__ partial) {
     __shared__ double sh[B];
     double s = 0;
-    for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < n; i += (long long)gridDim.x * B) s += a[i] * b[i];
+    for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < n; i += (long long)gridDim.x * B) s += (double)a[i] * (double)b[i];
     sh[threadIdx.x] = s;
     __syncthreads();
     for (int o = B / 2; o > 0; o >>= 1) {
@@ -624,9 +665,9 @@ __global__ void k_fold(const double* __restrict__ partial, int np, int slot, dou
         }
     }
 }
-// x += alpha p ; r -= alpha q ; partial(r.r)
+// x += alpha p ; r -= alpha q ; partial(r.r) ; and the cycle's pre-smoothing of the new residual, z = omega * dinv * r
 __global__ void k_update_xr(const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ scal, long long n, double* __restrict__ x,
-                            double* __restrict__ r, double* __restrict__ partial) {
+                            double* __restrict__ r, double* __restrict__ partial, const creal* __restrict__ dinv, double omega, int nrhs, creal* __restrict__ z) {
     __shared__ double sh[B];
     const double alpha = scal[S_ALPHA];
     double s = 0;
@@ -634,6 +675,7 @@ __global__ void k_update_xr(const double* __restrict__ p, const double* __restri
         double rv = r[i] - alpha * q[i];
         x[i] += alpha * p[i];
         r[i] = rv;
+        z[i] = (creal)(omega * (double)dinv[i / nrhs] * rv);
         s += rv * rv;
     }
     sh[threadIdx.x] = s;
@@ -644,31 +686,33 @@ __global__ void k_update_xr(const double* __restrict__ p, const double* __restri
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
-__global__ void k_direction(const double* __restrict__ z, const double* __restrict__ scal, long long n, int first, double* __restrict__ p) {
+__global__ void k_direction(const creal* __restrict__ z, const double* __restrict__ scal, long long n, int first, double* __restrict__ p) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = first ? z[i] : z[i] + scal[S_BETA] * p[i];
+    if (i < n) p[i] = first ? (double)z[i] : (double)z[i] + scal[S_BETA] * p[i];
 }
 // Power iteration support (spectral radius of Minv A per level, for the Jacobi damping).
-__global__ void k_pseudo_random(long long n, double* __restrict__ v) {
+__global__ void k_pseudo_random(long long n, creal* __restrict__ v) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned h = (unsigned)i * 2654435761u + 12345u;
     h ^= h >> 15, h *= 2246822519u, h ^= h >> 13;
-    v[i] = (double)(h & 0xffff) / 32768. - 1.;
+    v[i] = (creal)((double)(h & 0xffff) / 32768. - 1.);
 }
-__global__ void k_normalise(const double* __restrict__ t, const double* __restrict__ scal, int slot, long long n, double* __restrict__ v) {
+__global__ void k_normalise(const creal* __restrict__ t, const double* __restrict__ scal, int slot, long long n, creal* __restrict__ v) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s = scal[slot];
-    v[i] = s > 0 ? t[i] / sqrt(s) : 0.;
+    v[i] = (creal)(s > 0 ? (double)t[i] / sqrt(s) : 0.);
 }
 
 void release_mg(Multigrid* mg) {
     if (!mg) return;
     for (MgLevel& l : mg->lev) {
-        l.code.release(), l.nbr.release(), l.parent.release(), l.firstChild.release(), l.blocks.release(), l.binv.release(), l.r.release(), l.z.release(), l.t.release();
+        l.code.release(), l.nbr.release(), l.parent.release(), l.firstChild.release(), l.blocks.release(), l.cblocks.release(), l.binv.release(), l.r.release(),
+            l.z.release(), l.t.release();
     }
-    mg->evec.release(), mg->agg.release(), mg->aggPtr.release(), mg->aggList.release(), mg->slotOf.release(), mg->cinv.release();
+    mg->evec.release(), mg->cevec.release(), mg->agg.release(), mg->aggPtr.release(), mg->aggList.release(), mg->slotOf.release(), mg->cinv.release();
+    mg->fval.release(), mg->fdinv.release();
     mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release();
     if (mg->hostRR) cudaFreeHost(mg->hostRR);
     delete mg;
@@ -737,6 +781,7 @@ int build_octree(mof_ctx* ctx, Multigrid& mg, const double* pts, int n, double m
         MOF_CUDA(lv.code.alloc(lv.N));
         MOF_CUDA(lv.nbr.alloc(27ull * lv.N));
         MOF_CUDA(lv.blocks.alloc(27ull * Kc * lv.N));
+        MOF_CUDA(lv.cblocks.alloc(27ull * Kc * lv.N));
         MOF_CUDA(lv.binv.alloc((size_t)Kc * lv.N));
         MOF_CUDA(lv.r.alloc((size_t)D * lv.N));
         MOF_CUDA(lv.z.alloc((size_t)D * lv.N));
@@ -784,8 +829,14 @@ int alloc_common(mof_ctx* ctx, Multigrid& mg) {
     MOF_CUDA(mg.fr.alloc(len));
     MOF_CUDA(mg.fp.alloc(len));
     MOF_CUDA(mg.fq.alloc(len));
+    MOF_CUDA(mg.fval.alloc(mg.kind == MG_FLOW ? (size_t)ctx->wPadded : (size_t)ctx->nnzS));
+    MOF_CUDA(mg.fdinv.alloc((size_t)mg.nFine));
     const int nc = (mg.kind == MG_FLOW ? 3 : 1) * mg.lev.back().N;
     MOF_CUDA(mg.cinv.alloc((size_t)nc * nc));
+    if (mg.kind == MG_FLOW) {
+        MOF_CUDA(mg.cevec.alloc(3ull * mg.nFine));
+        MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, mg.evec.p, 3ll * mg.nFine, mg.cevec.p);
+    }
     return MOF_OK;
 }
 
@@ -873,25 +924,37 @@ bool mg_scalar_usable(const mof_ctx* ctx) { return ctx->mgs && ctx->mgs->usable;
 
 namespace {
 
-// Fine-level operator of a hierarchy: out = b - A in (mode 1) or one damped Jacobi sweep (mode 2).
-int fine_apply(mof_ctx* ctx, Multigrid& mg, const double* b, double omega, const double* in, double* out, int mode) {
-    const int grid = kSMs * 8;
+constexpr int FINE_GRID = kSMs * 8;
+
+// Fine-level operator of a hierarchy inside the cycle (cycle-precision matrix copy and vectors, fp64 right-hand side):
+// out = b - A in (mode 1) or one damped Jacobi sweep (mode 2, optionally with the partials of b.out in mg.partial).
+int fine_apply(mof_ctx* ctx, Multigrid& mg, const double* b, double omega, const creal* in, creal* out, int mode, bool withDot = false) {
+    double* partial = withDot ? mg.partial.p : nullptr;
     if (mg.kind == MG_FLOW)
-        MOF_LAUNCH(k_fine_apply_flow, grid, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, b, ctx->wDinv.p, omega, in, out, mode);
+        MOF_LAUNCH((k_fine_apply_flow<creal, creal>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, partial);
     else
-        MOF_LAUNCH(k_fine_apply_scalar, grid, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, b, ctx->sDinv.p, omega, in, out, mode, mg.partial.p);
+        MOF_LAUNCH((k_fine_apply_scalar<creal, creal>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, partial);
     return MOF_OK;
 }
-const double* fine_dinv(mof_ctx* ctx, Multigrid& mg) { return mg.kind == MG_FLOW ? ctx->wDinv.p : ctx->sDinv.p; }
+// out = b - A in with the fp64 matrix (initial and true residuals of PCG)
+int fine_residual(mof_ctx* ctx, Multigrid& mg, const double* b, const double* in, double* out) {
+    if (mg.kind == MG_FLOW)
+        MOF_LAUNCH((k_fine_apply_flow<double, double>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, b, (const creal*)nullptr, 0., in, out, 1,
+                   (double*)nullptr);
+    else
+        MOF_LAUNCH((k_fine_apply_scalar<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, b, (const creal*)nullptr, 0., in, out, 1,
+                   (double*)nullptr);
+    return MOF_OK;
+}
 
 template <int K, int D>
-int coarse_apply(mof_ctx* ctx, MgLevel& lv, double omega, int mode, double* out) {
-    k_coarse_apply<K, D><<<blocks_for(lv.N, 32), 27 * 32, 0, ctx->stream>>>(lv.blocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, omega, lv.N, mode, out);
+int coarse_apply(mof_ctx* ctx, MgLevel& lv, double omega, int mode, creal* out) {
+    k_coarse_apply<K, D><<<blocks_for(lv.N, 32), 27 * 32, 0, ctx->stream>>>(lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out);
     ctx->stats.kernelLaunches++;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MOF_OK : cuda_fail(ctx, e, "k_coarse_apply");
 }
-int coarse_apply(mof_ctx* ctx, Multigrid& mg, MgLevel& lv, double omega, int mode, double* out) {
+int coarse_apply(mof_ctx* ctx, Multigrid& mg, MgLevel& lv, double omega, int mode, creal* out) {
     return mg.kind == MG_FLOW ? coarse_apply<9, 3>(ctx, lv, omega, mode, out) : coarse_apply<1, 6>(ctx, lv, omega, mode, out);
 }
 
@@ -913,27 +976,28 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
     // cycle positive definite; should an estimate ever be too low, PCG stalls and the caller falls back to Jacobi-PCG.
     const int powerIts = 10;
     {
-        MOF_CUDA(cudaMemsetAsync(mg.ft.p, 0, sizeof(double) * len, ctx->stream));
+        MOF_CUDA(cudaMemsetAsync(mg.fq.p, 0, sizeof(double) * len, ctx->stream));  // the zero right-hand side
         MOF_LAUNCH(k_pseudo_random, blocks_for((long long)len, B), B, 0, (long long)len, mg.fz.p);
         for (int it = 0; it <= powerIts; it++) {
-            MOF_LAUNCH(k_dot_partial, NBLK, B, 0, mg.fz.p, mg.fz.p, (long long)len, mg.partial.p);
+            MOF_LAUNCH((k_dot_partial<creal, creal>), NBLK, B, 0, mg.fz.p, mg.fz.p, (long long)len, mg.partial.p);
             MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, 16, mg.scal.p);
             if (it == powerIts) break;
             MOF_LAUNCH(k_normalise, blocks_for((long long)len, B), B, 0, mg.fz.p, mg.scal.p, 16, (long long)len, mg.fz.p);
-            MOF_TRY(fine_apply(ctx, mg, mg.ft.p, -1., mg.fz.p, mg.fz2.p, 2));
+            MOF_TRY(fine_apply(ctx, mg, mg.fq.p, -1., mg.fz.p, mg.fz2.p, 2));
             std::swap(mg.fz.p, mg.fz2.p);
         }
     }
     for (int l = 0; l < mg.K; l++) {
         MgLevel& lv = mg.lev[l];
+        MOF_LAUNCH(k_to_creal, kSMs * 4, B, 0, lv.blocks.p, (long long)lv.blocks.n, lv.cblocks.p);
         if (mg.kind == MG_FLOW) MOF_LAUNCH(k_block_pinv, blocks_for(lv.N, B), B, 0, lv.blocks.p, lv.N, lv.binv.p);
         else MOF_LAUNCH(k_scalar_inv, blocks_for(lv.N, B), B, 0, lv.blocks.p, lv.N, lv.binv.p);
         if (l == mg.K - 1) break;
         const long long nd = (long long)D * lv.N;
-        MOF_CUDA(cudaMemsetAsync(lv.r.p, 0, sizeof(double) * nd, ctx->stream));
+        MOF_CUDA(cudaMemsetAsync(lv.r.p, 0, sizeof(creal) * nd, ctx->stream));
         MOF_LAUNCH(k_pseudo_random, blocks_for(nd, B), B, 0, nd, lv.z.p);
         for (int it = 0; it <= powerIts; it++) {
-            MOF_LAUNCH(k_dot_partial, NBLK, B, 0, lv.z.p, lv.z.p, nd, mg.partial.p);
+            MOF_LAUNCH((k_dot_partial<creal, creal>), NBLK, B, 0, lv.z.p, lv.z.p, nd, mg.partial.p);
             MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, 17 + l, mg.scal.p);
             if (it == powerIts) break;
             MOF_LAUNCH(k_normalise, blocks_for(nd, B), B, 0, lv.z.p, mg.scal.p, 17 + l, nd, lv.z.p);
@@ -1013,7 +1077,8 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
             for (int k = i; k < nc; k++) s += Li[(size_t)k * nc + i] * Li[(size_t)k * nc + j];
             M[(size_t)i * nc + j] = M[(size_t)j * nc + i] = s;
         }
-    MOF_CUDA(cudaMemcpyAsync(mg.cinv.p, M.data(), sizeof(double) * (size_t)nc * nc, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<creal> Mc(M.begin(), M.end());
+    MOF_CUDA(cudaMemcpyAsync(mg.cinv.p, Mc.data(), sizeof(creal) * (size_t)nc * nc, cudaMemcpyHostToDevice, ctx->stream));
     MOF_CUDA(cudaStreamSynchronize(ctx->stream));
     return MOF_OK;
 }
@@ -1028,8 +1093,8 @@ int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
         return MOF_OK;
     }
     MgLevel& up = mg.lev[l + 1];
-    if (flow) MOF_LAUNCH((k_coarse_presmooth<9, 3>), blocks_for(lv.N, B), B, 0, lv.binv.p, lv.r.p, lv.omega, lv.N, lv.z.p);
-    else MOF_LAUNCH((k_coarse_presmooth<1, 6>), blocks_for(lv.N, B), B, 0, lv.binv.p, lv.r.p, lv.omega, lv.N, lv.z.p);
+    if (flow) MOF_LAUNCH((k_coarse_presmooth<9, 3>), blocks_for(lv.N, B), B, 0, lv.binv.p, lv.r.p, (creal)lv.omega, lv.N, lv.z.p);
+    else MOF_LAUNCH((k_coarse_presmooth<1, 6>), blocks_for(lv.N, B), B, 0, lv.binv.p, lv.r.p, (creal)lv.omega, lv.N, lv.z.p);
     for (int g = 0; g < (l < mg.gammaLevels ? mg.gamma : 1); g++) {
         MOF_TRY(coarse_apply(ctx, mg, lv, lv.omega, 1, lv.t.p));
         if (flow) {
@@ -1047,28 +1112,29 @@ int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
     return MOF_OK;
 }
 
-// z = cycle(r) on the fine level; result in mg.fz.
-int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r) {
+// z = cycle(r) on the fine level; result in mg.fz, and the FINE_GRID partials of r.z in mg.partial. With `presmoothed`
+// the first sweep from a zero guess (z = omega0 * dinv * r) is already in mg.fz (k_update_xr leaves it there).
+int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed) {
     const long long len = (long long)mg.fineLen();
     MgLevel& l1 = mg.lev[0];
-    MOF_LAUNCH(k_fine_presmooth, blocks_for(len, B), B, 0, r, fine_dinv(ctx, mg), mg.omega0, len, mg.nrhs, mg.fz.p);
+    if (!presmoothed) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r, mg.fdinv.p, mg.omega0, len, mg.nrhs, mg.fz.p);
     MOF_TRY(fine_apply(ctx, mg, r, mg.omega0, mg.fz.p, mg.ft.p, 1));
-    if (mg.kind == MG_FLOW) MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.evec.p, mg.ft.p, l1.N, l1.r.p);
+    if (mg.kind == MG_FLOW) MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.r.p);
     else MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.r.p);
     MOF_TRY(coarse_cycle(ctx, mg, 0));
-    if (mg.kind == MG_FLOW) MOF_LAUNCH(k_prolong_flow, blocks_for(mg.nFine, B), B, 0, mg.agg.p, mg.evec.p, l1.z.p, mg.nFine, mg.fz.p);
+    if (mg.kind == MG_FLOW) MOF_LAUNCH(k_prolong_flow, blocks_for(mg.nFine, B), B, 0, mg.agg.p, mg.cevec.p, l1.z.p, mg.nFine, mg.fz.p);
     else MOF_LAUNCH(k_prolong_scalar, blocks_for(len, B), B, 0, mg.agg.p, l1.z.p, mg.nFine, mg.fz.p);
-    MOF_TRY(fine_apply(ctx, mg, r, mg.omega0, mg.fz.p, mg.fz2.p, 2));
+    MOF_TRY(fine_apply(ctx, mg, r, mg.omega0, mg.fz.p, mg.fz2.p, 2, true));
     std::swap(mg.fz.p, mg.fz2.p);
     return MOF_OK;
 }
 
-// q = A p with per-CTA partials of p.q; *np = number of partials
+// q = A p (fp64) with per-CTA partials of p.q; *np = number of partials
 int apply_dot(mof_ctx* ctx, Multigrid& mg, const double* p, double* q, int* np) {
     if (mg.kind == MG_FLOW) return spmv_dot_launch(ctx, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, p, q, mg.partial.p, np);
-    const int grid = kSMs * 8;
-    MOF_LAUNCH(k_fine_apply_scalar, grid, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, (const double*)nullptr, ctx->sDinv.p, 0., p, q, 0, mg.partial.p);
-    *np = grid;
+    MOF_LAUNCH((k_fine_apply_scalar<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, (const double*)nullptr, (const creal*)nullptr, 0., p,
+               q, 0, mg.partial.p);
+    *np = FINE_GRID;
     return MOF_OK;
 }
 
@@ -1084,10 +1150,10 @@ int mg_pcg(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGue
         MOF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * len, ctx->stream));
         MOF_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * len, cudaMemcpyDeviceToDevice, ctx->stream));
     } else
-        MOF_TRY(fine_apply(ctx, mg, b, 0., x, r, 1));
-    MOF_LAUNCH(k_dot_partial, NBLK, B, 0, b, b, len, mg.partial.p);
+        MOF_TRY(fine_residual(ctx, mg, b, x, r));
+    MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, b, b, len, mg.partial.p);
     MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, S_BB, mg.scal.p);
-    MOF_LAUNCH(k_dot_partial, NBLK, B, 0, r, r, len, mg.partial.p);
+    MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, r, r, len, mg.partial.p);
     MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, S_RR, mg.scal.p);
     double h2[2] = {0, 0};
     MOF_CUDA(cudaMemcpyAsync(h2, mg.scal.p + S_RR, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1102,23 +1168,21 @@ int mg_pcg(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGue
     int it = 0;
     for (int attempt = 0; attempt < 4 && rr > tol * tol * bb; attempt++) {
         // (re)start: z = M r, p = z, rz = r.z
-        MOF_TRY(fine_cycle(ctx, mg, r));
-        MOF_LAUNCH(k_dot_partial, NBLK, B, 0, r, mg.fz.p, len, mg.partial.p);
-        MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, S_RZ, mg.scal.p);
+        MOF_TRY(fine_cycle(ctx, mg, r, false));
+        MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, FINE_GRID, S_RZ, mg.scal.p);
         MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 1, p);
-        // One PCG iteration is ~60 small dependent launches (most of them on the tiny coarse levels): capture TWO
+        // One PCG iteration is ~55 small dependent launches (most of them on the tiny coarse levels): capture TWO
         // iterations once as a CUDA graph and replay it (the ping-pong buffers of the cycle are back in place after an
         // even number of cycles). The residual norms of both iterations land in pinned host memory.
         auto iteration = [&](int slot) -> int {
             int np = 0;
             MOF_TRY(apply_dot(ctx, mg, p, q, &np));
             MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, np, S_PQ, mg.scal.p);
-            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p, q, mg.scal.p, len, x, r, mg.partial.p);
+            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p, q, mg.scal.p, len, x, r, mg.partial.p, mg.fdinv.p, mg.omega0, mg.nrhs, mg.fz.p);
             MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, S_RR, mg.scal.p);
             MOF_CUDA(cudaMemcpyAsync(mg.hostRR + slot, mg.scal.p + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            MOF_TRY(fine_cycle(ctx, mg, r));
-            MOF_LAUNCH(k_dot_partial, NBLK, B, 0, r, mg.fz.p, len, mg.partial.p);
-            MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, S_RZNEW, mg.scal.p);
+            MOF_TRY(fine_cycle(ctx, mg, r, true));
+            MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, FINE_GRID, S_RZNEW, mg.scal.p);
             MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 0, p);
             return MOF_OK;
         };
@@ -1153,8 +1217,8 @@ int mg_pcg(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGue
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) return cuda_fail(ctx, ce, "cudaGraphLaunch(mg iteration)");
         // true residual of x
-        MOF_TRY(fine_apply(ctx, mg, b, 0., x, r, 1));
-        MOF_LAUNCH(k_dot_partial, NBLK, B, 0, r, r, len, mg.partial.p);
+        MOF_TRY(fine_residual(ctx, mg, b, x, r));
+        MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, r, r, len, mg.partial.p);
         MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, S_RR, mg.scal.p);
         MOF_CUDA(cudaMemcpyAsync(&rr, mg.scal.p + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         MOF_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1178,6 +1242,8 @@ int mg_flow_update(mof_ctx* ctx) {
     MgLevel& l1 = mg.lev[0];
     MOF_LAUNCH(k_level1_flow, blocks_for(27ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, ctx->wRowptr.p, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, mg.slotOf.p, mg.evec.p,
                l1.nbr.p, l1.N, l1.blocks.p);
+    MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->wA.p, ctx->wPadded, mg.fval.p);
+    MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->wDinv.p, (long long)ctx->E, mg.fdinv.p);
     return finish_values(ctx, mg);
 }
 int mg_flow_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double* relresOut) {
@@ -1190,6 +1256,8 @@ int mg_scalar_update(mof_ctx* ctx) {
     Multigrid& mg = *ctx->mgs;
     MgLevel& l1 = mg.lev[0];
     MOF_LAUNCH(k_level1_scalar, blocks_for(27ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, ctx->sRowptr.p, ctx->sSys.p, mg.slotOf.p, l1.nbr.p, l1.N, l1.blocks.p);
+    MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->sSys.p, ctx->nnzS, mg.fval.p);
+    MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->sDinv.p, (long long)ctx->V, mg.fdinv.p);
     return finish_values(ctx, mg);
 }
 int mg_scalar_solve(mof_ctx* ctx, const double* b6, double* x6, double tol, int maxIters, int* itersOut, double* relresOut) {
