@@ -254,6 +254,7 @@ def main():
         step_e2e(0)
         torch.cuda.synchronize(dev)
         sharding.barrier()
+        al.reset_stats()
         e0.record(stream)
         for k in range(args.steps):
             step_e2e(1 + k)
@@ -261,6 +262,7 @@ def main():
         torch.cuda.synchronize(dev)
         sharding.barrier()
         e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        e2e_stats = al.stats()
         al.close()
 
     if rank != 0:
@@ -280,9 +282,12 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "clocks": clocks,
         "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(V * 3 * 8 + T * 3 * 4 + 2 * V * 3 * 8),
-                "d2h_bytes_per_step": int(2 * V * 3 * 8), "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": int(2 * V * 3 * 8), "ms_per_step": e2e_ms / args.steps,
+                "flow_solve_ms_per_alignment": e2e_stats["flowSolveMs"] / args.steps, "smooth_solve_ms_per_alignment": e2e_stats["smoothSolveMs"] / args.steps,
+                "setup_ms_per_alignment": e2e_stats["setupMs"] / args.steps, "advect_ms_per_alignment": e2e_stats["advectMs"] / args.steps,
+                "flow_iterations_per_alignment": e2e_stats["flowCgIterations"] / args.steps},
         "gpu_launches": int(stats["kernelLaunches"]),
-        "roofline": {"bound": "hbm", "kernel": "k_spmv_dot (phase 1 of the persistent k_pcg<1>: y = A d fused with d.y, flow system CSR fp64/int32)",
+        "roofline": {"bound": "hbm", "kernel": "k_spmv_dot (the fp64 SpMV of the flow PCG, y = A d fused with d.y; flow system in the sliced SELL-32 layout, fp64 values / int32 columns)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "traffic": traffic, "bytes_per_launch": spmv_bytes, "us_per_launch": spmv_ms * 1e3, "rows": stats["flowRows"], "nnz": stats["flowNnz"]},
         "pcg": {"flow_iterations_per_alignment": stats["flowCgIterations"] / args.steps, "smooth_iterations_per_alignment": stats["smoothCgIterations"] / args.steps,

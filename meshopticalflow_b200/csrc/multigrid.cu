@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(B) k_fine_apply_scalar(int n, const int* __res
     for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < len; i += (long long)gridDim.x * B) {
         const int row = (int)(i / 6), c = (int)(i - 6ll * row);
         TX acc = 0;
+        // (an explicit batch of 8 predicated loads per row was measured: 86 us against 57 us for this plain loop)
         for (int k = rowptr[row]; k < rowptr[row + 1]; k++) acc += (TX)val[k] * in[6 * (size_t)col[k] + c];
         if (mode == 0) out[i] = acc, dot += (double)in[i] * (double)acc;
         else if (mode == 1) out[i] = (TX)(b[i] - (double)acc);
@@ -481,45 +482,6 @@ __global__ void __launch_bounds__(B) k_fine_apply_scalar(int n, const int* __res
         }
     }
     if (mode == 0 || (mode == 2 && partial)) cta_partial(dot, partial);
-}
-
-// FLOW restriction: rc[I] = sum over the edges of aggregate I of v_e * r_e (P1^T r). One warp per aggregate.
-__global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ evec, const creal* __restrict__ r, int N,
-                                creal* __restrict__ rc) {
-    int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (I >= N) return;
-    creal a0 = 0, a1 = 0, a2 = 0;
-    for (int q = aggPtr[I] + lane; q < aggPtr[I + 1]; q += 32) {
-        int e = aggList[q];
-        creal re = r[e];
-        a0 += evec[3 * (size_t)e] * re, a1 += evec[3 * (size_t)e + 1] * re, a2 += evec[3 * (size_t)e + 2] * re;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o), a1 += __shfl_xor_sync(0xffffffffu, a1, o), a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (lane == 0) rc[3 * (size_t)I] = a0, rc[3 * (size_t)I + 1] = a1, rc[3 * (size_t)I + 2] = a2;
-}
-// FLOW prolongation: z_e += v_e . zc[agg(e)]
-__global__ void k_prolong_flow(const int* __restrict__ agg, const creal* __restrict__ evec, const creal* __restrict__ zc, int E, creal* __restrict__ z) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    const creal* c = zc + 3 * (size_t)agg[e];
-    z[e] += evec[3 * (size_t)e] * c[0] + evec[3 * (size_t)e + 1] * c[1] + evec[3 * (size_t)e + 2] * c[2];
-}
-// SCALAR restriction / prolongation: sums and copies per channel. One thread per (cell, channel) / (vertex, channel).
-__global__ void k_restrict_scalar(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ r, int N, creal* __restrict__ rc) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 6 * N) return;
-    int I = i / 6, c = i - 6 * I;
-    creal a = 0;
-    for (int q = aggPtr[I]; q < aggPtr[I + 1]; q++) a += r[6 * (size_t)aggList[q] + c];
-    rc[i] = a;
-}
-__global__ void k_prolong_scalar(const int* __restrict__ agg, const creal* __restrict__ zc, int V, creal* __restrict__ z) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 6ll * V) return;
-    long long v = i / 6;
-    z[i] += zc[6 * (size_t)agg[v] + (i - 6 * v)];
 }
 
 __device__ __forceinline__ void mat3_vec(const creal* m, const creal* v, creal* out) {
@@ -541,75 +503,147 @@ __device__ __forceinline__ void apply_binv(const creal* __restrict__ binv, int N
         for (int c = 0; c < D; c++) out[c] = w * v[c];
     }
 }
-template <int K, int D>
-__global__ void k_coarse_presmooth(const creal* __restrict__ binv, const creal* __restrict__ r, creal omega, int N, creal* __restrict__ z) {
-    int I = blockIdx.x * blockDim.x + threadIdx.x;
+
+// Every restriction also performs the first smoothing sweep of the level it lands on (from a zero guess):
+// zc = omega * Binv * rc.
+// FLOW restriction: rc[I] = sum over the edges of aggregate I of v_e * r_e (P1^T r). One warp per aggregate.
+__global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ evec, const creal* __restrict__ r, int N,
+                                const creal* __restrict__ binv, creal omega, creal* __restrict__ rc, creal* __restrict__ zc) {
+    int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (I >= N) return;
-    creal v[D], o[D];
-#pragma unroll
-    for (int c = 0; c < D; c++) v[c] = r[(size_t)D * I + c];
-    apply_binv<K, D>(binv, N, I, v, o);
-#pragma unroll
-    for (int c = 0; c < D; c++) z[(size_t)D * I + c] = omega * o[c];
+    creal a0 = 0, a1 = 0, a2 = 0;
+    for (int q = aggPtr[I] + lane; q < aggPtr[I + 1]; q += 32) {
+        int e = aggList[q];
+        creal re = r[e];
+        a0 += evec[3 * (size_t)e] * re, a1 += evec[3 * (size_t)e + 1] * re, a2 += evec[3 * (size_t)e + 2] * re;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o), a1 += __shfl_xor_sync(0xffffffffu, a1, o), a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+        creal v[3] = {a0, a1, a2}, o[3];
+        apply_binv<9, 3>(binv, N, I, v, o);
+        for (int c = 0; c < 3; c++) rc[3 * (size_t)I + c] = v[c], zc[3 * (size_t)I + c] = omega * o[c];
+    }
 }
-// mode 1: out = r - A z ; mode 2: out = z + omega * Binv (r - A z). CTA = 27 warps: warp = stencil slot, lane = cell
-// (32 consecutive cells), so every coefficient component is read as 32 consecutive words and all 27 slots of a cell
-// are in flight at once; the 27 partial products are then summed in slot order by the first warp.
+// FLOW prolongation: z_e += v_e . zc[agg(e)]
+__global__ void k_prolong_flow(const int* __restrict__ agg, const creal* __restrict__ evec, const creal* __restrict__ zc, int E, creal* __restrict__ z) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const creal* c = zc + 3 * (size_t)agg[e];
+    z[e] += evec[3 * (size_t)e] * c[0] + evec[3 * (size_t)e + 1] * c[1] + evec[3 * (size_t)e + 2] * c[2];
+}
+// SCALAR restriction / prolongation: sums and copies per channel. One thread per (cell, channel) / (vertex, channel).
+__global__ void k_restrict_scalar(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ r, int N, const creal* __restrict__ binv,
+                                  creal omega, creal* __restrict__ rc, creal* __restrict__ zc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6 * N) return;
+    int I = i / 6, c = i - 6 * I;
+    creal a = 0;
+    for (int q = aggPtr[I]; q < aggPtr[I + 1]; q++) a += r[6 * (size_t)aggList[q] + c];
+    rc[i] = a;
+    zc[i] = omega * binv[I] * a;
+}
+__global__ void k_prolong_scalar(const int* __restrict__ agg, const creal* __restrict__ zc, int V, creal* __restrict__ z) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6ll * V) return;
+    long long v = i / 6;
+    z[i] += zc[6 * (size_t)agg[v] + (i - 6 * v)];
+}
+
+// Coarse operator of a level. mode 1: out = r - A z ; mode 2: out = z + omega * Binv (r - A z). With `zc`, z stands for
+// z + (prolongation of zc), i.e. the coarse correction is added on the fly while gathering (z itself is not written).
+// CTA = 32 consecutive cells x 9 warps, a warp handling three stencil slots of those cells (lane = cell): every
+// coefficient component is read as 32 consecutive words, a thread has its three slots' loads in flight at once, and the
+// small CTAs (288 threads) let seven of them overlap on an SM. The nine partial sums per (cell, component) are then
+// added in warp order by 32*D threads, which also apply the block inverse.
+constexpr int CA_WARPS = 9, CA_SLOTS = 3;
 template <int K, int D>
-__global__ void __launch_bounds__(27 * 32) k_coarse_apply(const creal* __restrict__ blocks, const int* __restrict__ nbr, const creal* __restrict__ binv,
-                                                         const creal* __restrict__ r, const creal* __restrict__ z, creal omega, int N, int mode,
-                                                         creal* __restrict__ out) {
-    __shared__ creal part[27][32][D];
-    const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(CA_WARPS * 32) k_coarse_apply(const creal* __restrict__ blocks, const int* __restrict__ nbr, const creal* __restrict__ binv,
+                                                               const creal* __restrict__ r, const creal* __restrict__ z, creal omega, int N, int mode,
+                                                               creal* __restrict__ out, const int* __restrict__ parent, const creal* __restrict__ zc) {
+    __shared__ creal part[CA_WARPS][32 * D];
+    __shared__ creal resS[32 * D];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int I = blockIdx.x * 32 + lane;
     creal o[D];
 #pragma unroll
     for (int c = 0; c < D; c++) o[c] = 0;
     if (I < N) {
-        int J = nbr[I * 27 + slot];
-        if (J >= 0) {
+        int J[CA_SLOTS];
+#pragma unroll
+        for (int u = 0; u < CA_SLOTS; u++) J[u] = nbr[I * 27 + CA_SLOTS * w + u];
+#pragma unroll
+        for (int u = 0; u < CA_SLOTS; u++) {
+            if (J[u] < 0) continue;
+            const int slot = CA_SLOTS * w + u;
+            creal zj[D];
+#pragma unroll
+            for (int c = 0; c < D; c++) zj[c] = z[(size_t)D * J[u] + c];
+            if (zc) {
+                const creal* up = zc + (size_t)D * parent[J[u]];
+#pragma unroll
+                for (int c = 0; c < D; c++) zj[c] += up[c];
+            }
             if (K == 9) {
-                creal m[9];
+                creal m[9], t[3];
 #pragma unroll
                 for (int k = 0; k < 9; k++) m[k] = blocks[blk<9>(N, I, slot, k)];
-                mat3_vec(m, z + 3 * (size_t)J, o);
-            } else {
-                creal w = blocks[blk<1>(N, I, slot, 0)];
+                mat3_vec(m, zj, t);
 #pragma unroll
-                for (int c = 0; c < D; c++) o[c] = w * z[(size_t)D * J + c];
+                for (int c = 0; c < 3; c++) o[c] += t[c];
+            } else {
+                creal wgt = blocks[blk<1>(N, I, slot, 0)];
+#pragma unroll
+                for (int c = 0; c < D; c++) o[c] += wgt * zj[c];
             }
         }
     }
 #pragma unroll
-    for (int c = 0; c < D; c++) part[slot][lane][c] = o[c];
+    for (int c = 0; c < D; c++) part[w][lane * D + c] = o[c];
     __syncthreads();
-    if (slot != 0 || I >= N) return;
-    creal res[D];
+    const int t = threadIdx.x;
+    const int ln = t / D, c = t - D * ln;
+    const int Ic = blockIdx.x * 32 + ln;
+    const bool live = t < 32 * D && Ic < N;
+    creal s = 0;
+    if (live) {
 #pragma unroll
-    for (int c = 0; c < D; c++) res[c] = 0;
-    for (int s = 0; s < 27; s++)
-#pragma unroll
-        for (int c = 0; c < D; c++) res[c] += part[s][lane][c];
-#pragma unroll
-    for (int c = 0; c < D; c++) res[c] = r[(size_t)D * I + c] - res[c];
-    if (mode == 1) {
-#pragma unroll
-        for (int c = 0; c < D; c++) out[(size_t)D * I + c] = res[c];
-    } else {
-        creal u[D];
-        apply_binv<K, D>(binv, N, I, res, u);
-#pragma unroll
-        for (int c = 0; c < D; c++) out[(size_t)D * I + c] = z[(size_t)D * I + c] + omega * u[c];
+        for (int q = 0; q < CA_WARPS; q++) s += part[q][t];
+        s = r[(size_t)D * Ic + c] - s;
+        if (mode == 1) out[(size_t)D * Ic + c] = s;
+        else if (K == 9) resS[t] = s;
     }
+    if (mode == 1) return;
+    if (K == 9) __syncthreads();
+    if (!live) return;
+    creal u;
+    if (K == 9) {
+        u = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) u += binv[(size_t)(3 * c + k) * N + Ic] * resS[ln * D + k];
+    } else
+        u = binv[Ic] * s;
+    creal zi = z[(size_t)D * Ic + c];
+    if (zc) zi += zc[(size_t)D * parent[Ic] + c];
+    out[(size_t)D * Ic + c] = zi + omega * u;
 }
-template <int D>
-__global__ void k_restrict_coarse(const int* __restrict__ firstChild, const creal* __restrict__ rFine, int Ncoarse, creal* __restrict__ rc) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= D * Ncoarse) return;
-    int Ip = i / D, c = i - D * Ip;
-    creal a = 0;
-    for (int I = firstChild[Ip]; I < firstChild[Ip + 1]; I++) a += rFine[(size_t)D * I + c];
-    rc[i] = a;
+// Restriction between coarse levels (children of a cell are contiguous) with the first sweep of the coarser level.
+// One thread per coarse cell.
+template <int K, int D>
+__global__ void k_restrict_coarse(const int* __restrict__ firstChild, const creal* __restrict__ rFine, int Ncoarse, const creal* __restrict__ binv, creal omega,
+                                  creal* __restrict__ rc, creal* __restrict__ zc) {
+    int Ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (Ip >= Ncoarse) return;
+    creal a[D], o[D];
+#pragma unroll
+    for (int c = 0; c < D; c++) a[c] = 0;
+    for (int I = firstChild[Ip]; I < firstChild[Ip + 1]; I++)
+#pragma unroll
+        for (int c = 0; c < D; c++) a[c] += rFine[(size_t)D * I + c];
+    apply_binv<K, D>(binv, Ncoarse, Ip, a, o);
+#pragma unroll
+    for (int c = 0; c < D; c++) rc[(size_t)D * Ip + c] = a[c], zc[(size_t)D * Ip + c] = omega * o[c];
 }
 template <int D>
 __global__ void k_prolong_coarse(const int* __restrict__ parent, const creal* __restrict__ zc, int N, creal* __restrict__ z) {
@@ -617,14 +651,42 @@ __global__ void k_prolong_coarse(const int* __restrict__ parent, const creal* __
     if (i >= D * N) return;
     z[i] += zc[(size_t)D * parent[i / D] + i % D];
 }
-// z = M r on the coarsest level: M is n x n, r and z are [n][C]
-__global__ void k_dense_apply(const creal* __restrict__ m, const creal* __restrict__ r, int n, int C, creal* __restrict__ z) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * C) return;
-    int row = i / C, c = i - C * row;
-    creal s = 0;
-    for (int k = 0; k < n; k++) s += m[(size_t)row * n + k] * r[(size_t)k * C + c];
-    z[i] = s;
+// Coarsest level: restriction into shared memory (every CTA repeats it, it is tiny), then z = M r with the dense inverse
+// M (n x n, row-major): one warp per row, lanes across the columns. r and z are flat [n * C] = [cells][D].
+constexpr int DENSE_MAX = 6 * 2 * COARSEST_CELLS;
+constexpr int DENSE_CTAS = 8;
+template <int D>
+__global__ void __launch_bounds__(B) k_dense_restrict_apply(const int* __restrict__ firstChild, const creal* __restrict__ rFine, const creal* __restrict__ m, int n,
+                                                           creal* __restrict__ z) {
+    constexpr int C = D == 3 ? 1 : 6;  // FLOW: n = 3 * cells, one right-hand side; SCALAR: n = cells, six
+    __shared__ creal r[DENSE_MAX];
+    const int total = n * C;  // = D * cells
+    for (int i = threadIdx.x; i < total; i += B) {
+        int Ip = i / D, c = i - D * Ip;
+        creal a = 0;
+        if (firstChild)
+            for (int I = firstChild[Ip]; I < firstChild[Ip + 1]; I++) a += rFine[(size_t)D * I + c];
+        else a = rFine[i];  // single-level hierarchy: already restricted
+        r[i] = a;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * (B / 32) + (threadIdx.x >> 5); row < n; row += gridDim.x * (B / 32)) {
+        creal acc[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) acc[c] = 0;
+        for (int k = lane; k < n; k += 32) {
+            const creal mv = m[(size_t)row * n + k];
+#pragma unroll
+            for (int c = 0; c < C; c++) acc[c] += mv * r[k * C + c];
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++)
+            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        if (lane == 0)
+#pragma unroll
+            for (int c = 0; c < C; c++) z[row * C + c] = acc[c];
+    }
 }
 
 // ------------------------------------------------------------------------------------- PCG kernels
@@ -947,15 +1009,17 @@ int fine_residual(mof_ctx* ctx, Multigrid& mg, const double* b, const double* in
     return MOF_OK;
 }
 
+// `zc` (with the level's parent table) = a coarse correction still to be added to lv.z, see k_coarse_apply.
 template <int K, int D>
-int coarse_apply(mof_ctx* ctx, MgLevel& lv, double omega, int mode, creal* out) {
-    k_coarse_apply<K, D><<<blocks_for(lv.N, 32), 27 * 32, 0, ctx->stream>>>(lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out);
+int coarse_apply(mof_ctx* ctx, MgLevel& lv, double omega, int mode, creal* out, const creal* zc) {
+    k_coarse_apply<K, D><<<blocks_for(lv.N, 32), CA_WARPS * 32, 0, ctx->stream>>>(lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out,
+                                                                          zc ? lv.parent.p : nullptr, zc);
     ctx->stats.kernelLaunches++;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MOF_OK : cuda_fail(ctx, e, "k_coarse_apply");
 }
-int coarse_apply(mof_ctx* ctx, Multigrid& mg, MgLevel& lv, double omega, int mode, creal* out) {
-    return mg.kind == MG_FLOW ? coarse_apply<9, 3>(ctx, lv, omega, mode, out) : coarse_apply<1, 6>(ctx, lv, omega, mode, out);
+int coarse_apply(mof_ctx* ctx, Multigrid& mg, MgLevel& lv, double omega, int mode, creal* out, const creal* zc = nullptr) {
+    return mg.kind == MG_FLOW ? coarse_apply<9, 3>(ctx, lv, omega, mode, out, zc) : coarse_apply<1, 6>(ctx, lv, omega, mode, out, zc);
 }
 
 // Value-dependent part, once per system: coarser Galerkin levels, inverses, damping factors, dense coarsest inverse.
@@ -1083,31 +1147,33 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
     return MOF_OK;
 }
 
-// One cycle on the coarse hierarchy: lev[l].r in, lev[l].z out.
+// One cycle on the coarse hierarchy below level l: lev[l].r and the pre-smoothed lev[l].z in (the restriction kernels
+// leave both), lev[l].z out. Launches per level: residual, restriction (+ first sweep of the next level, or the dense
+// solve on the coarsest), post-smoothing (which adds the coarse correction while gathering).
 int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
     MgLevel& lv = mg.lev[l];
     const bool flow = mg.kind == MG_FLOW;
-    if (l == mg.K - 1) {
-        const int n = (flow ? 3 : 1) * lv.N, C = flow ? 1 : 6;
-        MOF_LAUNCH(k_dense_apply, blocks_for(n * C, 128), 128, 0, mg.cinv.p, lv.r.p, n, C, lv.z.p);
-        return MOF_OK;
-    }
+    if (l == mg.K - 1) return MOF_OK;  // solved by the restriction that filled it
     MgLevel& up = mg.lev[l + 1];
-    if (flow) MOF_LAUNCH((k_coarse_presmooth<9, 3>), blocks_for(lv.N, B), B, 0, lv.binv.p, lv.r.p, (creal)lv.omega, lv.N, lv.z.p);
-    else MOF_LAUNCH((k_coarse_presmooth<1, 6>), blocks_for(lv.N, B), B, 0, lv.binv.p, lv.r.p, (creal)lv.omega, lv.N, lv.z.p);
-    for (int g = 0; g < (l < mg.gammaLevels ? mg.gamma : 1); g++) {
+    const bool upDense = l + 1 == mg.K - 1;
+    const int passes = l < mg.gammaLevels ? mg.gamma : 1;
+    for (int g = 0; g < passes; g++) {
         MOF_TRY(coarse_apply(ctx, mg, lv, lv.omega, 1, lv.t.p));
-        if (flow) {
-            MOF_LAUNCH(k_restrict_coarse<3>, blocks_for(3ll * up.N, B), B, 0, up.firstChild.p, lv.t.p, up.N, up.r.p);
-            MOF_TRY(coarse_cycle(ctx, mg, l + 1));
-            MOF_LAUNCH(k_prolong_coarse<3>, blocks_for(3ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p);
-        } else {
-            MOF_LAUNCH(k_restrict_coarse<6>, blocks_for(6ll * up.N, B), B, 0, up.firstChild.p, lv.t.p, up.N, up.r.p);
-            MOF_TRY(coarse_cycle(ctx, mg, l + 1));
-            MOF_LAUNCH(k_prolong_coarse<6>, blocks_for(6ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p);
+        if (upDense) {
+            const int n = (flow ? 3 : 1) * up.N;
+            if (flow) MOF_LAUNCH(k_dense_restrict_apply<3>, DENSE_CTAS, B, 0, up.firstChild.p, lv.t.p, mg.cinv.p, n, up.z.p);
+            else MOF_LAUNCH(k_dense_restrict_apply<6>, DENSE_CTAS, B, 0, up.firstChild.p, lv.t.p, mg.cinv.p, n, up.z.p);
+        } else if (flow)
+            MOF_LAUNCH((k_restrict_coarse<9, 3>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, (creal)up.omega, up.r.p, up.z.p);
+        else
+            MOF_LAUNCH((k_restrict_coarse<1, 6>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, (creal)up.omega, up.r.p, up.z.p);
+        MOF_TRY(coarse_cycle(ctx, mg, l + 1));
+        if (g + 1 < passes) {  // W-cycle: the correction has to be in z before the next residual
+            if (flow) MOF_LAUNCH(k_prolong_coarse<3>, blocks_for(3ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p);
+            else MOF_LAUNCH(k_prolong_coarse<6>, blocks_for(6ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p);
         }
     }
-    MOF_TRY(coarse_apply(ctx, mg, lv, lv.omega, 2, lv.t.p));
+    MOF_TRY(coarse_apply(ctx, mg, lv, lv.omega, 2, lv.t.p, up.z.p));
     std::swap(lv.z.p, lv.t.p);
     return MOF_OK;
 }
@@ -1119,8 +1185,16 @@ int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed) {
     MgLevel& l1 = mg.lev[0];
     if (!presmoothed) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r, mg.fdinv.p, mg.omega0, len, mg.nrhs, mg.fz.p);
     MOF_TRY(fine_apply(ctx, mg, r, mg.omega0, mg.fz.p, mg.ft.p, 1));
-    if (mg.kind == MG_FLOW) MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.r.p);
-    else MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.r.p);
+    if (mg.kind == MG_FLOW)
+        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p);
+    else
+        MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p);
+    if (mg.K == 1) {  // the aggregates are already the coarsest level
+        const bool flow = mg.kind == MG_FLOW;
+        const int n = (flow ? 3 : 1) * l1.N;
+        if (flow) MOF_LAUNCH(k_dense_restrict_apply<3>, DENSE_CTAS, B, 0, (const int*)nullptr, l1.r.p, mg.cinv.p, n, l1.z.p);
+        else MOF_LAUNCH(k_dense_restrict_apply<6>, DENSE_CTAS, B, 0, (const int*)nullptr, l1.r.p, mg.cinv.p, n, l1.z.p);
+    }
     MOF_TRY(coarse_cycle(ctx, mg, 0));
     if (mg.kind == MG_FLOW) MOF_LAUNCH(k_prolong_flow, blocks_for(mg.nFine, B), B, 0, mg.agg.p, mg.cevec.p, l1.z.p, mg.nFine, mg.fz.p);
     else MOF_LAUNCH(k_prolong_scalar, blocks_for(len, B), B, 0, mg.agg.p, l1.z.p, mg.nFine, mg.fz.p);
