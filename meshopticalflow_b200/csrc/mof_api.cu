@@ -37,10 +37,13 @@ int require_signals(mof_ctx* ctx) { return ctx->haveSignals ? MOF_OK : fail(ctx,
 int finish_mesh(mof_ctx* ctx) {
     ctx->haveMesh = ctx->haveSignals = ctx->haveFlowSystem = ctx->haveTexture = false;
     cudaEventRecord(ctx->ev0, ctx->stream);
+    PhaseTimer pt(ctx);
     int rc = build_mesh_operators(ctx);
     if (rc != MOF_OK) return rc;
+    pt.mark("mesh operators (total)");
     rc = mg_setup_mesh(ctx);
     if (rc != MOF_OK) return rc;
+    pt.mark("multigrid hierarchies (total)");
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     MOF_CUDA(cudaEventSynchronize(ctx->ev1));
     float ms = 0;
@@ -99,6 +102,7 @@ int mof_create(int device, void* stream, mof_ctx** out) {
         ctx->ownStream = true;
     }
     if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return MOF_E_CUDA; }
+    if (cudaHostAlloc((void**)&ctx->pinned, 64 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return MOF_E_CUDA; }
     // keep freed blocks in the stream-ordered pool instead of handing them back to the driver at every synchronisation
     cudaMemPool_t pool = nullptr;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
@@ -126,6 +130,7 @@ void mof_destroy(mof_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);  // the frees above are stream-ordered
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ownStream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -3,7 +3,9 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/mof_b200.h"
@@ -83,6 +85,7 @@ struct mof_ctx {
     mof_params params;
     mof_stats stats;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double* pinned = nullptr;  // 64 doubles of page-locked host memory, allocated once (cudaHostAlloc / cudaFreeHost cost up to 0.4 s)
 
     int V = 0, T = 0, E = 0;
     long long nnzS = 0, nnzW = 0, wPadded = 0;
@@ -142,6 +145,33 @@ inline int cuda_fail(mof_ctx* c, cudaError_t e, const char* what) {
     } while (0)
 
 inline int blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// Host read of device values AFTER everything queued on the context's stream. (The context's stream is non-blocking:
+// a plain cudaMemcpy on the legacy default stream would not be ordered against it.)
+template <class T>
+inline cudaError_t read_back(mof_ctx* ctx, T* host, const T* dev, size_t count = 1) {
+    cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(T) * count, cudaMemcpyDeviceToHost, ctx->stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(ctx->stream);
+}
+
+// MOF_VERBOSE_SETUP=1: wall-clock of the set-up phases on stderr (each mark synchronises the stream).
+struct PhaseTimer {
+    mof_ctx* ctx;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer(mof_ctx* c) : ctx(c) {
+        const char* e = getenv("MOF_VERBOSE_SETUP");
+        on = e && *e && *e != '0';
+        if (on) cudaStreamSynchronize(ctx->stream), t0 = std::chrono::steady_clock::now();
+    }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[setup] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 // Counts a kernel launch of ours (mof_stats.kernelLaunches) and checks the launch.
 #define MOF_LAUNCH(kernel, grid, block, smem, ...)                                  \

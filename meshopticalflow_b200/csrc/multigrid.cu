@@ -86,7 +86,7 @@ struct Multigrid {
     DBuf<double> partial, scal;
     double omega0 = 0.6;
     int gamma = 1, gammaLevels = 0; // gamma coarse corrections on the first gammaLevels coarse levels (W-cycle knob)
-    double* hostRR = nullptr;       // pinned: residual norms of the two iterations of one graph replay
+    double* hostRR = nullptr;       // pinned (a slice of ctx->pinned): residual norms of the two iterations of one graph replay
     std::vector<double> hostBlocks, hostDense;
     std::vector<int> hostNbr;
     int comps() const { return kind == MG_FLOW ? 9 : 1; }     // K
@@ -776,7 +776,6 @@ void release_mg(Multigrid* mg) {
     mg->evec.release(), mg->cevec.release(), mg->agg.release(), mg->aggPtr.release(), mg->aggList.release(), mg->slotOf.release(), mg->cinv.release();
     mg->fval.release(), mg->fdinv.release();
     mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release();
-    if (mg->hostRR) cudaFreeHost(mg->hostRR);
     delete mg;
 }
 
@@ -820,7 +819,7 @@ int build_octree(mof_ctx* ctx, Multigrid& mg, const double* pts, int n, double m
     int rc = levelRanks(probe, -1);
     if (rc != MOF_OK) { freeAll(); return rc; }
     int nProbe = 0;
-    MOF_CUDA(cudaMemcpy(&nProbe, rank[probe].p + (1ll << (3 * probe)), sizeof(int), cudaMemcpyDeviceToHost));
+    MOF_CUDA(read_back(ctx, &nProbe, rank[probe].p + (1ll << (3 * probe))));
     occ[probe].release(), rank[probe].release();
     int L1 = probe + (int)std::lround(std::log((double)n / ((double)target * std::max(nProbe, 1))) / std::log(4.0));
     L1 = std::max(2, std::min(Lmax, L1));
@@ -829,7 +828,7 @@ int build_octree(mof_ctx* ctx, Multigrid& mg, const double* pts, int n, double m
         if (rc != MOF_OK) { freeAll(); return rc; }
     }
     std::vector<int> counts(L1 + 1, 0);
-    for (int L = L1; L >= 1; L--) MOF_CUDA(cudaMemcpy(&counts[L], rank[L].p + (1ll << (3 * L)), sizeof(int), cudaMemcpyDeviceToHost));
+    for (int L = L1; L >= 1; L--) MOF_CUDA(read_back(ctx, &counts[L], rank[L].p + (1ll << (3 * L))));
     int Lc = L1;
     while (Lc > 1 && counts[Lc] > COARSEST_CELLS) Lc--;
     if (counts[Lc] > 2 * COARSEST_CELLS) { freeAll(); return MOF_OK; }
@@ -909,7 +908,7 @@ Multigrid* new_mg(mof_ctx* ctx, MgKind kind, int nFine, int* rcOut) {
     mg->gammaLevels = std::max(0, env_int("MOF_MG_GAMMA_LEVELS", 0));
     cudaError_t e = mg->partial.alloc(8192);  // per-CTA partials: NBLK of ours, or the persistent-grid size of k_spmv_dot
     if (e == cudaSuccess) e = mg->scal.alloc(64);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&mg->hostRR, 8 * sizeof(double), cudaHostAllocDefault);
+    mg->hostRR = ctx->pinned + (kind == MG_FLOW ? 0 : 8);
     *rcOut = e == cudaSuccess ? MOF_OK : cuda_fail(ctx, e, "multigrid workspace");
     return mg;
 }
@@ -923,7 +922,9 @@ void mg_destroy(mof_ctx* ctx) {
 
 // Mesh-dependent part of both hierarchies.
 int mg_setup_mesh(mof_ctx* ctx) {
+    PhaseTimer pt(ctx);
     mg_destroy(ctx);
+    pt.mark("  release old hierarchies");
     const int E = ctx->E, V = ctx->V;
     int rc = MOF_OK;
     ctx->mg = new_mg(ctx, MG_FLOW, E, &rc);
@@ -962,6 +963,7 @@ int mg_setup_mesh(mof_ctx* ctx) {
     }
     emid.release();
     if (rc != MOF_OK) return rc;
+    pt.mark("  flow hierarchy");
 
     if (env_int("MOF_SCALAR_MG", 1)) {
         rc = build_octree(ctx, ms, ctx->pos.p, V, maxEdge, env_int("MOF_MG_TARGET_SCALAR", 14));
@@ -978,6 +980,7 @@ int mg_setup_mesh(mof_ctx* ctx) {
             }
         }
     }
+    pt.mark("  scalar hierarchy");
     return rc;
 }
 

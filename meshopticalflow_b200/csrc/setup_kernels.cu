@@ -500,6 +500,7 @@ static unsigned next_pow2(unsigned long long x) {
 
 int build_mesh_operators(mof_ctx* ctx) {
     const int V = ctx->V, T = ctx->T, nH = 3 * T, B = 256;
+    PhaseTimer pt(ctx);
     MOF_CUDA(ctx->g.alloc(3ull * T));
     MOF_CUDA(ctx->area.alloc(T));
     MOF_CUDA(ctx->opp.alloc(nH));
@@ -520,6 +521,7 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_TRY(reduce_sum(ctx, ctx->dtmp0.p, T, ctx->scalars.p + SC_AREA_SCALE));
     MOF_LAUNCH(k_metric_scale, blocks_for(T, B), B, 0, ctx->g.p, ctx->area.p, T, ctx->scalars.p + SC_AREA_SCALE);
 
+    pt.mark("  metric, unit area");
     // a3: opposite half-edges through an open-addressing table, then the edge transforms
     unsigned cap = next_pow2(2ull * nH + 16);
     MOF_CUDA(ctx->hashKeys.alloc(cap));
@@ -534,6 +536,7 @@ int build_mesh_operators(mof_ctx* ctx) {
     if (hflags[1]) return fail(ctx, MOF_E_MESH, "[ERROR] Boundary edge (TriangleMesh::unfold)");
     MOF_LAUNCH(k_edge_xforms, blocks_for(nH, B), B, 0, ctx->g.p, ctx->opp.p, nH, ctx->xlin.p, ctx->xcst.p);
 
+    pt.mark("  half-edges, edge transforms");
     // a4: V x V pattern (diagonal + one entry per outgoing half-edge), sorted, then values
     MOF_CUDA(ctx->itmp1.alloc(V + 1));
     MOF_CUDA(ctx->sRowptr.alloc(V + 1));
@@ -542,7 +545,7 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_LAUNCH(k_count_outgoing, blocks_for(nH, B), B, 0, ctx->tri.p, nH, ctx->itmp1.p);
     MOF_TRY(exclusive_scan_int(ctx, ctx->itmp1.p, ctx->sRowptr.p, V + 1, nullptr));
     int nnzS = 0;
-    MOF_CUDA(cudaMemcpy(&nnzS, ctx->sRowptr.p + V, sizeof(int), cudaMemcpyDeviceToHost));
+    MOF_CUDA(read_back(ctx, &nnzS, ctx->sRowptr.p + V));
     ctx->nnzS = nnzS;
     MOF_CUDA(ctx->sCol.alloc(nnzS));
     MOF_CUDA(ctx->sHe.alloc(nnzS));
@@ -555,6 +558,7 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_LAUNCH(k_sort_rows, blocks_for(V, B), B, 0, ctx->sRowptr.p, V, ctx->sCol.p, ctx->sHe.p);
     MOF_LAUNCH(k_scalar_values, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sHe.p, ctx->opp.p, ctx->g.p, V, ctx->sMass.p, ctx->sStiff.p, ctx->flags.p);
 
+    pt.mark("  scalar operators");
     // a6: Whitney dof numbering
     MOF_CUDA(ctx->itmp0.alloc(nH + 1));
     MOF_CUDA(ctx->itmp2.alloc(nH + 1));
@@ -563,7 +567,7 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_LAUNCH(k_first_flags, blocks_for(nH + 1, B), B, 0, ctx->opp.p, nH, ctx->itmp0.p);
     MOF_TRY(exclusive_scan_int(ctx, ctx->itmp0.p, ctx->itmp2.p, nH + 1, nullptr));
     int E = 0;
-    MOF_CUDA(cudaMemcpy(&E, ctx->itmp2.p + nH, sizeof(int), cudaMemcpyDeviceToHost));
+    MOF_CUDA(read_back(ctx, &E, ctx->itmp2.p + nH));
     ctx->E = E;
     MOF_CUDA(ctx->expanded.alloc(E));
     MOF_LAUNCH(k_numbering, blocks_for(nH, B), B, 0, ctx->opp.p, ctx->itmp0.p, ctx->itmp2.p, nH, ctx->reduced.p, ctx->expanded.p, ctx->positive.p);
@@ -572,6 +576,7 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_CUDA(ctx->P.alloc(6ull * T));
     MOF_LAUNCH(k_prolongation, blocks_for(T, B), B, 0, ctx->g.p, ctx->positive.p, T, ctx->P.p);
 
+    pt.mark("  numbering, prolongation");
     // a8: smooth operator
     MOF_CUDA(ctx->m0.alloc(V));
     MOF_CUDA(ctx->m1.alloc(E));
@@ -582,7 +587,7 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_LAUNCH(k_whitney_rowsize, blocks_for(E + 1, B), B, 0, ctx->tri.p, ctx->expanded.p, ctx->sRowptr.p, E, ctx->itmp1.p);
     MOF_TRY(exclusive_scan_int(ctx, ctx->itmp1.p, ctx->wRowptr.p, E + 1, nullptr));
     int nnzW = 0;
-    MOF_CUDA(cudaMemcpy(&nnzW, ctx->wRowptr.p + E, sizeof(int), cudaMemcpyDeviceToHost));
+    MOF_CUDA(read_back(ctx, &nnzW, ctx->wRowptr.p + E));
     ctx->nnzW = nnzW;
     // sliced layout: slice sizes -> slice offsets -> padded entry count
     const int slices = (E + 31) / 32;
@@ -592,7 +597,7 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_LAUNCH(k_slice_sizes, blocks_for(slices + 1, B), B, 0, ctx->wRowptr.p, E, slices, ctx->itmp0.p);
     MOF_TRY(exclusive_scan_int(ctx, ctx->itmp0.p, ctx->wSliceBase.p, slices + 1, nullptr));
     int padded = 0;
-    MOF_CUDA(cudaMemcpy(&padded, ctx->wSliceBase.p + slices, sizeof(int), cudaMemcpyDeviceToHost));
+    MOF_CUDA(read_back(ctx, &padded, ctx->wSliceBase.p + slices));
     ctx->wPadded = padded;
     MOF_CUDA(ctx->wCol.alloc((size_t)padded));
     MOF_CUDA(ctx->wS.alloc((size_t)padded));
@@ -611,6 +616,7 @@ int build_mesh_operators(mof_ctx* ctx) {
     if (hflags[4]) return fail(ctx, MOF_E_MESH, "[ERROR] vertex without a triangle (singular mass matrix)");
     ctx->itmp0.release(), ctx->itmp1.release(), ctx->itmp2.release(), ctx->dtmp0.release();
 
+    pt.mark("  Whitney operator");
     // flow-side buffers
     MOF_CUDA(ctx->coeffs.alloc(E));
     MOF_CUDA(ctx->tfield.alloc(2ull * T));
@@ -664,7 +670,7 @@ int csr_to_sell(mof_ctx* ctx, int n, const int* rowptr, const int* col, const do
     sizes.release();
     if (rc != MOF_OK) return rc;
     int padded = 0;
-    MOF_CUDA(cudaMemcpy(&padded, sliceBase.p + slices, sizeof(int), cudaMemcpyDeviceToHost));
+    MOF_CUDA(read_back(ctx, &padded, sliceBase.p + slices));
     MOF_CUDA(sCol.alloc((size_t)padded));
     MOF_CUDA(sVal.alloc((size_t)padded));
     MOF_LAUNCH(k_csr_to_sell, blocks_for(32ll * slices, B), B, 0, rowptr, col, val, sliceBase.p, n, slices, sCol.p, sVal.p);
