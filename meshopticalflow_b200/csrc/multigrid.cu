@@ -511,6 +511,7 @@ __global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __res
                                 const creal* __restrict__ binv, creal omega, creal* __restrict__ rc, creal* __restrict__ zc) {
     int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (I >= N) return;
+    const creal bk = lane < 9 ? binv[(size_t)lane * N + I] : (creal)0;  // the cell's block inverse, fetched alongside the sums
     creal a0 = 0, a1 = 0, a2 = 0;
     for (int q = aggPtr[I] + lane; q < aggPtr[I + 1]; q += 32) {
         int e = aggList[q];
@@ -520,9 +521,12 @@ __global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __res
     for (int o = 16; o > 0; o >>= 1) {
         a0 += __shfl_xor_sync(0xffffffffu, a0, o), a1 += __shfl_xor_sync(0xffffffffu, a1, o), a2 += __shfl_xor_sync(0xffffffffu, a2, o);
     }
+    creal m[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) m[k] = __shfl_sync(0xffffffffu, bk, k);
     if (lane == 0) {
         creal v[3] = {a0, a1, a2}, o[3];
-        apply_binv<9, 3>(binv, N, I, v, o);
+        mat3_vec(m, v, o);
         for (int c = 0; c < 3; c++) rc[3 * (size_t)I + c] = v[c], zc[3 * (size_t)I + c] = omega * o[c];
     }
 }
@@ -553,64 +557,84 @@ __global__ void k_prolong_scalar(const int* __restrict__ agg, const creal* __res
 
 // Coarse operator of a level. mode 1: out = r - A z ; mode 2: out = z + omega * Binv (r - A z). With `zc`, z stands for
 // z + (prolongation of zc), i.e. the coarse correction is added on the fly while gathering (z itself is not written).
-// CTA = 32 consecutive cells x 9 warps, a warp handling three stencil slots of those cells (lane = cell): every
-// coefficient component is read as 32 consecutive words, a thread has its three slots' loads in flight at once, and the
-// small CTAs (288 threads) let seven of them overlap on an SM. The nine partial sums per (cell, component) are then
-// added in warp order by 32*D threads, which also apply the block inverse.
-constexpr int CA_WARPS = 9, CA_SLOTS = 3;
-template <int K, int D>
-__global__ void __launch_bounds__(CA_WARPS * 32) k_coarse_apply(const creal* __restrict__ blocks, const int* __restrict__ nbr, const creal* __restrict__ binv,
-                                                               const creal* __restrict__ r, const creal* __restrict__ z, creal omega, int N, int mode,
-                                                               creal* __restrict__ out, const int* __restrict__ parent, const creal* __restrict__ zc) {
-    __shared__ creal part[CA_WARPS][32 * D];
+// CTA = 32 consecutive cells x (27 / SLOTS) warps, a warp handling SLOTS stencil slots of those cells (lane = cell): every
+// coefficient component is read as 32 consecutive words and all of a thread's loads are issued before the first use
+// (a missing neighbour reads the cell itself against an all-zero coefficient, so there is no branch). SLOTS = 3 on the
+// large levels: 288-thread CTAs, seven of which overlap on an SM; SLOTS = 1 on the small, latency-bound ones. The
+// partial sums per (cell, component) are then added in warp order by 32*D threads, which also apply the block inverse.
+template <int K, int D, int SLOTS>
+__global__ void __launch_bounds__(27 / SLOTS * 32) k_coarse_apply(const creal* __restrict__ blocks, const int* __restrict__ nbr, const creal* __restrict__ binv,
+                                                                 const creal* __restrict__ r, const creal* __restrict__ z, creal omega, int N, int mode,
+                                                                 creal* __restrict__ out, const int* __restrict__ parent, const creal* __restrict__ zc) {
+    constexpr int WARPS = 27 / SLOTS;
+    __shared__ creal part[WARPS][32 * D];
     __shared__ creal resS[32 * D];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int I = blockIdx.x * 32 + lane;
+    // operands of the finishing step (thread t finishes component c of cell Ic), fetched ahead of the barrier
+    const int t = threadIdx.x;
+    const int ln = t / D, c = t - D * ln;
+    const int Ic = blockIdx.x * 32 + ln;
+    const bool live = t < 32 * D && Ic < N;
+    creal rv = 0, zi = 0, bi[3] = {0, 0, 0};
+    if (live) {
+        rv = r[(size_t)D * Ic + c];
+        if (mode == 2) {
+            zi = z[(size_t)D * Ic + c];
+            if (zc) zi += zc[(size_t)D * parent[Ic] + c];
+            if (K == 9) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) bi[k] = binv[(size_t)(3 * c + k) * N + Ic];
+            } else
+                bi[0] = binv[Ic];
+        }
+    }
     creal o[D];
 #pragma unroll
-    for (int c = 0; c < D; c++) o[c] = 0;
+    for (int c2 = 0; c2 < D; c2++) o[c2] = 0;
     if (I < N) {
-        int J[CA_SLOTS];
+        int J[SLOTS], P[SLOTS];
+        creal m[SLOTS][K], zj[SLOTS][D];
 #pragma unroll
-        for (int u = 0; u < CA_SLOTS; u++) J[u] = nbr[I * 27 + CA_SLOTS * w + u];
+        for (int u = 0; u < SLOTS; u++) J[u] = nbr[I * 27 + SLOTS * w + u];
 #pragma unroll
-        for (int u = 0; u < CA_SLOTS; u++) {
-            if (J[u] < 0) continue;
-            const int slot = CA_SLOTS * w + u;
-            creal zj[D];
+        for (int u = 0; u < SLOTS; u++)
 #pragma unroll
-            for (int c = 0; c < D; c++) zj[c] = z[(size_t)D * J[u] + c];
-            if (zc) {
-                const creal* up = zc + (size_t)D * parent[J[u]];
+            for (int k = 0; k < K; k++) m[u][k] = blocks[blk<K>(N, I, SLOTS * w + u, k)];
 #pragma unroll
-                for (int c = 0; c < D; c++) zj[c] += up[c];
-            }
+        for (int u = 0; u < SLOTS; u++) {
+            J[u] = J[u] < 0 ? I : J[u];
+            P[u] = zc ? parent[J[u]] : 0;
+#pragma unroll
+            for (int c = 0; c < D; c++) zj[u][c] = z[(size_t)D * J[u] + c];
+        }
+        if (zc) {
+#pragma unroll
+            for (int u = 0; u < SLOTS; u++)
+#pragma unroll
+                for (int c = 0; c < D; c++) zj[u][c] += zc[(size_t)D * P[u] + c];
+        }
+#pragma unroll
+        for (int u = 0; u < SLOTS; u++) {
             if (K == 9) {
-                creal m[9], t[3];
-#pragma unroll
-                for (int k = 0; k < 9; k++) m[k] = blocks[blk<9>(N, I, slot, k)];
-                mat3_vec(m, zj, t);
+                creal t[3];
+                mat3_vec(m[u], zj[u], t);
 #pragma unroll
                 for (int c = 0; c < 3; c++) o[c] += t[c];
             } else {
-                creal wgt = blocks[blk<1>(N, I, slot, 0)];
 #pragma unroll
-                for (int c = 0; c < D; c++) o[c] += wgt * zj[c];
+                for (int c = 0; c < D; c++) o[c] += m[u][0] * zj[u][c];
             }
         }
     }
 #pragma unroll
     for (int c = 0; c < D; c++) part[w][lane * D + c] = o[c];
     __syncthreads();
-    const int t = threadIdx.x;
-    const int ln = t / D, c = t - D * ln;
-    const int Ic = blockIdx.x * 32 + ln;
-    const bool live = t < 32 * D && Ic < N;
     creal s = 0;
     if (live) {
 #pragma unroll
-        for (int q = 0; q < CA_WARPS; q++) s += part[q][t];
-        s = r[(size_t)D * Ic + c] - s;
+        for (int q = 0; q < WARPS; q++) s += part[q][t];
+        s = rv - s;
         if (mode == 1) out[(size_t)D * Ic + c] = s;
         else if (K == 9) resS[t] = s;
     }
@@ -621,11 +645,9 @@ __global__ void __launch_bounds__(CA_WARPS * 32) k_coarse_apply(const creal* __r
     if (K == 9) {
         u = 0;
 #pragma unroll
-        for (int k = 0; k < 3; k++) u += binv[(size_t)(3 * c + k) * N + Ic] * resS[ln * D + k];
+        for (int k = 0; k < 3; k++) u += bi[k] * resS[ln * D + k];
     } else
-        u = binv[Ic] * s;
-    creal zi = z[(size_t)D * Ic + c];
-    if (zc) zi += zc[(size_t)D * parent[Ic] + c];
+        u = bi[0] * s;
     out[(size_t)D * Ic + c] = zi + omega * u;
 }
 // Restriction between coarse levels (children of a cell are contiguous) with the first sweep of the coarser level.
@@ -1015,8 +1037,12 @@ int fine_residual(mof_ctx* ctx, Multigrid& mg, const double* b, const double* in
 // `zc` (with the level's parent table) = a coarse correction still to be added to lv.z, see k_coarse_apply.
 template <int K, int D>
 int coarse_apply(mof_ctx* ctx, MgLevel& lv, double omega, int mode, creal* out, const creal* zc) {
-    k_coarse_apply<K, D><<<blocks_for(lv.N, 32), CA_WARPS * 32, 0, ctx->stream>>>(lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out,
-                                                                          zc ? lv.parent.p : nullptr, zc);
+    if (lv.N >= 16384)
+        k_coarse_apply<K, D, 3><<<blocks_for(lv.N, 32), 9 * 32, 0, ctx->stream>>>(lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out,
+                                                                              zc ? lv.parent.p : nullptr, zc);
+    else
+        k_coarse_apply<K, D, 1><<<blocks_for(lv.N, 32), 27 * 32, 0, ctx->stream>>>(lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out,
+                                                                               zc ? lv.parent.p : nullptr, zc);
     ctx->stats.kernelLaunches++;
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MOF_OK : cuda_fail(ctx, e, "k_coarse_apply");
