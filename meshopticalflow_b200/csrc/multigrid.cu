@@ -84,6 +84,7 @@ struct Multigrid {
     DBuf<creal> fz, fz2, ft;        // fine-level vectors of the cycle, nFine * nrhs each
     DBuf<double> fr, fp, fq;        // ... and of PCG
     DBuf<double> partial, scal;
+    DBuf<unsigned> counter;         // arrival counter of the last-CTA folds (self-resetting)
     double omega0 = 0.6;
     int gamma = 1, gammaLevels = 0; // gamma coarse corrections on the first gammaLevels coarse levels (W-cycle knob)
     double* hostRR = nullptr;       // pinned (a slice of ctx->pinned): residual norms of the two iterations of one graph replay
@@ -399,17 +400,65 @@ __global__ void k_fine_presmooth(const double* __restrict__ r, const creal* __re
     if (i < len) z[i] = (TZ)(omega * (double)dinv[i / nrhs] * r[i]);
 }
 
-// Sum of one value per thread over the CTA, in a fixed order; thread 0 stores it.
-__device__ __forceinline__ void cta_partial(double v, double* __restrict__ partial) {
+// Slots of the PCG scalars (mg.scal).
+enum { S_RZ = 0, S_PQ = 1, S_ALPHA = 2, S_BETA = 3, S_RR = 4, S_BB = 5, S_RZNEW = 6 };
+
+// One CTA (all B threads): adds `np` per-CTA partials in index order into scal[slot] and derives the PCG scalar that
+// depends on it.
+__device__ __forceinline__ void fold_partials(const double* partial, int np, int slot, double* scal) {
+    __shared__ double shf[B];
+    double s = 0;
+    for (int i = threadIdx.x; i < np; i += B) s += __ldcg(partial + i);
+    shf[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = B / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) shf[threadIdx.x] += shf[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double v = shf[0];
+        scal[slot] = v;
+        if (slot == S_PQ) scal[S_ALPHA] = v != 0 ? scal[S_RZ] / v : 0.;
+        if (slot == S_RZNEW) {
+            scal[S_BETA] = scal[S_RZ] != 0 ? v / scal[S_RZ] : 0.;
+            scal[S_RZ] = v;
+        }
+    }
+}
+// Sum of one value per thread over the CTA, in a fixed order; thread 0 stores it in partial[blockIdx.x]. With slot >= 0
+// the last CTA of the grid to arrive (a self-resetting counter) also folds all the partials — in index order, so the
+// result does not depend on which CTA that is — which saves a one-CTA launch on the critical path.
+__device__ __forceinline__ void cta_partial(double v, double* partial, int slot = -1, double* scal = nullptr, unsigned* counter = nullptr) {
     __shared__ double sh[B];
+    __shared__ bool last;
     sh[threadIdx.x] = v;
     __syncthreads();
     for (int o = B / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = sh[0];
+        if (slot >= 0) {
+            __threadfence();
+            last = atomicAdd(counter, 1u) == gridDim.x - 1;
+        }
+    }
+    if (slot < 0) return;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    fold_partials(partial, (int)gridDim.x, slot, scal);
+    if (threadIdx.x == 0) *counter = 0;
 }
+
+// Where a kernel's reduction goes: per-CTA partials (nullptr: none) and, with slot >= 0, the fold by the last CTA.
+struct Fold {
+    double* partial;
+    int slot;
+    double* scal;
+    unsigned* counter;
+};
 
 // FLOW: sliced SpMV (warp = slice, lane = row), as in pcg_kernels.cu. TV = precision of the matrix copy, TX = of the
 // vectors; b is always the fp64 right-hand side (the PCG residual inside a cycle).
@@ -417,9 +466,9 @@ __device__ __forceinline__ void cta_partial(double v, double* __restrict__ parti
 //   mode 2: out = in + omega * dinv * (b - A in)  (one damped Jacobi sweep); with `partial`, also the CTA's part of b.out
 constexpr int BATCH = 6;
 template <class TV, class TX>
-__global__ void __launch_bounds__(B) k_fine_apply_flow(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const TV* __restrict__ val,
+__global__ void __launch_bounds__(B, 8) k_fine_apply_flow(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const TV* __restrict__ val,
                                                       const double* __restrict__ b, const creal* __restrict__ dinv, double omega, const TX* __restrict__ in,
-                                                      TX* __restrict__ out, int mode, double* __restrict__ partial) {
+                                                      TX* __restrict__ out, int mode, Fold f) {
     const int lane = threadIdx.x & 31;
     const int slices = (n + 31) >> 5;
     const int warps = gridDim.x * (B / 32);
@@ -457,14 +506,14 @@ __global__ void __launch_bounds__(B) k_fine_apply_flow(int n, const int* __restr
             }
         }
     }
-    if (mode == 2 && partial) cta_partial(dot, partial);
+    if (mode == 2 && f.partial) cta_partial(dot, f.partial, f.slot, f.scal, f.counter);
 }
 // SCALAR: CSR with six interleaved right-hand sides, one thread per (row, channel). mode 0: out = A in with the CTA's
 // partial of in.out ; modes 1, 2 as above.
 template <class TV, class TX>
-__global__ void __launch_bounds__(B) k_fine_apply_scalar(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const TV* __restrict__ val,
+__global__ void __launch_bounds__(B, 8) k_fine_apply_scalar(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const TV* __restrict__ val,
                                                         const double* __restrict__ b, const creal* __restrict__ dinv, double omega, const TX* __restrict__ in,
-                                                        TX* __restrict__ out, int mode, double* __restrict__ partial) {
+                                                        TX* __restrict__ out, int mode, Fold f) {
     const long long len = 6ll * n;
     double dot = 0;
     for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < len; i += (long long)gridDim.x * B) {
@@ -481,7 +530,7 @@ __global__ void __launch_bounds__(B) k_fine_apply_scalar(int n, const int* __res
             dot += bv * (double)o;
         }
     }
-    if (mode == 0 || (mode == 2 && partial)) cta_partial(dot, partial);
+    if (mode == 0 || (mode == 2 && f.partial)) cta_partial(dot, f.partial, f.slot, f.scal, f.counter);
 }
 
 __device__ __forceinline__ void mat3_vec(const creal* m, const creal* v, creal* out) {
@@ -713,8 +762,6 @@ __global__ void __launch_bounds__(B) k_dense_restrict_apply(const int* __restric
 
 // ------------------------------------------------------------------------------------- PCG kernels
 
-enum { S_RZ = 0, S_PQ = 1, S_ALPHA = 2, S_BETA = 3, S_RR = 4, S_BB = 5, S_RZNEW = 6 };
-
 template <class TA, class TB>
 __global__ void k_dot_partial(const TA* __restrict__ a, const TB* __restrict__ b, long long n, double* __restrict__ partial) {
     __shared__ double sh[B];
@@ -729,31 +776,12 @@ __global__ void k_dot_partial(const TA* __restrict__ a, const TB* __restrict__ b
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 // Folds the partials (fixed order) into scal[slot] and derives the PCG scalar that depends on it.
-__global__ void k_fold(const double* __restrict__ partial, int np, int slot, double* __restrict__ scal) {
-    __shared__ double sh[B];
-    double s = 0;
-    for (int i = threadIdx.x; i < np; i += B) s += partial[i];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = B / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        double v = sh[0];
-        scal[slot] = v;
-        if (slot == S_PQ) scal[S_ALPHA] = v != 0 ? scal[S_RZ] / v : 0.;
-        if (slot == S_RZNEW) {
-            scal[S_BETA] = scal[S_RZ] != 0 ? v / scal[S_RZ] : 0.;
-            scal[S_RZ] = v;
-        }
-    }
-}
+__global__ void k_fold(const double* __restrict__ partial, int np, int slot, double* __restrict__ scal) { fold_partials(partial, np, slot, scal); }
 // x += alpha p ; r -= alpha q ; partial(r.r) ; and the cycle's pre-smoothing of the new residual, z = omega * dinv * r
-__global__ void k_update_xr(const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ scal, long long n, double* __restrict__ x,
-                            double* __restrict__ r, double* __restrict__ partial, const creal* __restrict__ dinv, double omega, int nrhs, creal* __restrict__ z) {
-    __shared__ double sh[B];
-    const double alpha = scal[S_ALPHA];
+// (the last CTA folds r.r into scal[S_RR])
+__global__ void k_update_xr(const double* __restrict__ p, const double* __restrict__ q, long long n, double* __restrict__ x, double* __restrict__ r,
+                            const creal* __restrict__ dinv, double omega, int nrhs, creal* __restrict__ z, Fold f) {
+    const double alpha = f.scal[S_ALPHA];
     double s = 0;
     for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < n; i += (long long)gridDim.x * B) {
         double rv = r[i] - alpha * q[i];
@@ -762,13 +790,7 @@ __global__ void k_update_xr(const double* __restrict__ p, const double* __restri
         z[i] = (creal)(omega * (double)dinv[i / nrhs] * rv);
         s += rv * rv;
     }
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = B / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+    cta_partial(s, f.partial, f.slot, f.scal, f.counter);
 }
 __global__ void k_direction(const creal* __restrict__ z, const double* __restrict__ scal, long long n, int first, double* __restrict__ p) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -797,7 +819,7 @@ void release_mg(Multigrid* mg) {
     }
     mg->evec.release(), mg->cevec.release(), mg->agg.release(), mg->aggPtr.release(), mg->aggList.release(), mg->slotOf.release(), mg->cinv.release();
     mg->fval.release(), mg->fdinv.release();
-    mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release();
+    mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release(), mg->counter.release();
     delete mg;
 }
 
@@ -930,6 +952,8 @@ Multigrid* new_mg(mof_ctx* ctx, MgKind kind, int nFine, int* rcOut) {
     mg->gammaLevels = std::max(0, env_int("MOF_MG_GAMMA_LEVELS", 0));
     cudaError_t e = mg->partial.alloc(8192);  // per-CTA partials: NBLK of ours, or the persistent-grid size of k_spmv_dot
     if (e == cudaSuccess) e = mg->scal.alloc(64);
+    if (e == cudaSuccess) e = mg->counter.alloc(4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(mg->counter.p, 0, 4 * sizeof(unsigned), ctx->stream);
     mg->hostRR = ctx->pinned + (kind == MG_FLOW ? 0 : 8);
     *rcOut = e == cudaSuccess ? MOF_OK : cuda_fail(ctx, e, "multigrid workspace");
     return mg;
@@ -1015,22 +1039,35 @@ constexpr int FINE_GRID = kSMs * 8;
 
 // Fine-level operator of a hierarchy inside the cycle (cycle-precision matrix copy and vectors, fp64 right-hand side):
 // out = b - A in (mode 1) or one damped Jacobi sweep (mode 2, optionally with the partials of b.out in mg.partial).
-int fine_apply(mof_ctx* ctx, Multigrid& mg, const double* b, double omega, const creal* in, creal* out, int mode, bool withDot = false) {
-    double* partial = withDot ? mg.partial.p : nullptr;
+// dotSlot >= 0 (mode 2): b.out is reduced into mg.scal[dotSlot] by the same launch.
+// MOF_MG_LASTFOLD=0 goes back to one k_fold launch per reduction (for A/B timing).
+bool last_cta_folds() {
+    static const bool on = env_int("MOF_MG_LASTFOLD", 1) != 0;
+    return on;
+}
+Fold fold_into(Multigrid& mg, int slot) { return Fold{mg.partial.p, last_cta_folds() ? slot : -1, mg.scal.p, mg.counter.p}; }
+int fold_after(mof_ctx* ctx, Multigrid& mg, int np, int slot) {
+    if (!last_cta_folds()) MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, np, slot, mg.scal.p);
+    return MOF_OK;
+}
+constexpr Fold NO_FOLD = {nullptr, -1, nullptr, nullptr};
+
+int fine_apply(mof_ctx* ctx, Multigrid& mg, const double* b, double omega, const creal* in, creal* out, int mode, int dotSlot = -1) {
+    const Fold f = dotSlot >= 0 ? fold_into(mg, dotSlot) : NO_FOLD;
     if (mg.kind == MG_FLOW)
-        MOF_LAUNCH((k_fine_apply_flow<creal, creal>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, partial);
+        MOF_LAUNCH((k_fine_apply_flow<creal, creal>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, f);
     else
-        MOF_LAUNCH((k_fine_apply_scalar<creal, creal>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, partial);
+        MOF_LAUNCH((k_fine_apply_scalar<creal, creal>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, f);
     return MOF_OK;
 }
 // out = b - A in with the fp64 matrix (initial and true residuals of PCG)
 int fine_residual(mof_ctx* ctx, Multigrid& mg, const double* b, const double* in, double* out) {
     if (mg.kind == MG_FLOW)
         MOF_LAUNCH((k_fine_apply_flow<double, double>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, b, (const creal*)nullptr, 0., in, out, 1,
-                   (double*)nullptr);
+                   NO_FOLD);
     else
         MOF_LAUNCH((k_fine_apply_scalar<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, b, (const creal*)nullptr, 0., in, out, 1,
-                   (double*)nullptr);
+                   NO_FOLD);
     return MOF_OK;
 }
 
@@ -1207,9 +1244,9 @@ int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
     return MOF_OK;
 }
 
-// z = cycle(r) on the fine level; result in mg.fz, and the FINE_GRID partials of r.z in mg.partial. With `presmoothed`
-// the first sweep from a zero guess (z = omega0 * dinv * r) is already in mg.fz (k_update_xr leaves it there).
-int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed) {
+// z = cycle(r) on the fine level; result in mg.fz, and r.z folded into mg.scal[rzSlot]. With `presmoothed` the first
+// sweep from a zero guess (z = omega0 * dinv * r) is already in mg.fz (k_update_xr leaves it there).
+int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed, int rzSlot) {
     const long long len = (long long)mg.fineLen();
     MgLevel& l1 = mg.lev[0];
     if (!presmoothed) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r, mg.fdinv.p, mg.omega0, len, mg.nrhs, mg.fz.p);
@@ -1227,18 +1264,24 @@ int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed) {
     MOF_TRY(coarse_cycle(ctx, mg, 0));
     if (mg.kind == MG_FLOW) MOF_LAUNCH(k_prolong_flow, blocks_for(mg.nFine, B), B, 0, mg.agg.p, mg.cevec.p, l1.z.p, mg.nFine, mg.fz.p);
     else MOF_LAUNCH(k_prolong_scalar, blocks_for(len, B), B, 0, mg.agg.p, l1.z.p, mg.nFine, mg.fz.p);
-    MOF_TRY(fine_apply(ctx, mg, r, mg.omega0, mg.fz.p, mg.fz2.p, 2, true));
+    MOF_TRY(fine_apply(ctx, mg, r, mg.omega0, mg.fz.p, mg.fz2.p, 2, rzSlot));
+    MOF_TRY(fold_after(ctx, mg, FINE_GRID, rzSlot));
     std::swap(mg.fz.p, mg.fz2.p);
     return MOF_OK;
 }
 
-// q = A p (fp64) with per-CTA partials of p.q; *np = number of partials
-int apply_dot(mof_ctx* ctx, Multigrid& mg, const double* p, double* q, int* np) {
-    if (mg.kind == MG_FLOW) return spmv_dot_launch(ctx, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, p, q, mg.partial.p, np);
+// q = A p (fp64) with p.q folded into mg.scal[S_PQ] (and alpha derived). FLOW runs the PCG's own SpMV kernel of
+// pcg_kernels.cu (the roofline kernel, left as it is) and folds its partials with one more launch.
+int apply_dot(mof_ctx* ctx, Multigrid& mg, const double* p, double* q) {
+    if (mg.kind == MG_FLOW) {
+        int np = 0;
+        MOF_TRY(spmv_dot_launch(ctx, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, p, q, mg.partial.p, &np));
+        MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, np, S_PQ, mg.scal.p);
+        return MOF_OK;
+    }
     MOF_LAUNCH((k_fine_apply_scalar<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, (const double*)nullptr, (const creal*)nullptr, 0., p,
-               q, 0, mg.partial.p);
-    *np = FINE_GRID;
-    return MOF_OK;
+               q, 0, fold_into(mg, S_PQ));
+    return fold_after(ctx, mg, FINE_GRID, S_PQ);
 }
 
 // PCG with the cycle as preconditioner on the hierarchy's fine system: A x = b. With zeroGuess x starts at 0, otherwise
@@ -1271,21 +1314,17 @@ int mg_pcg(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGue
     int it = 0;
     for (int attempt = 0; attempt < 4 && rr > tol * tol * bb; attempt++) {
         // (re)start: z = M r, p = z, rz = r.z
-        MOF_TRY(fine_cycle(ctx, mg, r, false));
-        MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, FINE_GRID, S_RZ, mg.scal.p);
+        MOF_TRY(fine_cycle(ctx, mg, r, false, S_RZ));
         MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 1, p);
-        // One PCG iteration is ~55 small dependent launches (most of them on the tiny coarse levels): capture TWO
+        // One PCG iteration is ~35 small dependent launches (most of them on the tiny coarse levels): capture TWO
         // iterations once as a CUDA graph and replay it (the ping-pong buffers of the cycle are back in place after an
         // even number of cycles). The residual norms of both iterations land in pinned host memory.
         auto iteration = [&](int slot) -> int {
-            int np = 0;
-            MOF_TRY(apply_dot(ctx, mg, p, q, &np));
-            MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, np, S_PQ, mg.scal.p);
-            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p, q, mg.scal.p, len, x, r, mg.partial.p, mg.fdinv.p, mg.omega0, mg.nrhs, mg.fz.p);
-            MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, S_RR, mg.scal.p);
+            MOF_TRY(apply_dot(ctx, mg, p, q));
+            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p, q, len, x, r, mg.fdinv.p, mg.omega0, mg.nrhs, mg.fz.p, fold_into(mg, S_RR));
+            MOF_TRY(fold_after(ctx, mg, NBLK, S_RR));
             MOF_CUDA(cudaMemcpyAsync(mg.hostRR + slot, mg.scal.p + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            MOF_TRY(fine_cycle(ctx, mg, r, true));
-            MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, FINE_GRID, S_RZNEW, mg.scal.p);
+            MOF_TRY(fine_cycle(ctx, mg, r, true, S_RZNEW));
             MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 0, p);
             return MOF_OK;
         };
