@@ -264,6 +264,7 @@ def main():
         e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
         e2e_stats = al.stats()
         al.close()
+    sharding.shutdown()
 
     if rank != 0:
         return 0

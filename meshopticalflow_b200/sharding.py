@@ -37,6 +37,13 @@ def barrier():
         dist.barrier()
 
 
+def shutdown():
+    """Leaves the process group (no-op for a single process)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def max_over_ranks(value: float, device=None) -> float:
     import torch
     import torch.distributed as dist
