@@ -59,6 +59,7 @@ typedef struct mof_stats {
     float setupMs;                /* ... in mof_set_mesh */
     double flowSpmvBytes;         /* algorithmic bytes of ONE flow-system SpMV: 12*nnz + 4*(n+1) + 16*n */
     long long flowRows, flowNnz;
+    long long haloEntries;        /* partitioned mesh: vector entries this rank receives per halo exchange (0 otherwise) */
 } mof_stats;
 
 void mof_default_params(mof_params* p);
@@ -155,6 +156,16 @@ int mof_pcg_solve_csr(mof_ctx* ctx, int n, const int* rowptr, const int* col, co
 /* Times `reps` launches of the flow-system SpMV kernel (y = A d fused with d.y) on the context's
  * current flow matrix; returns average ms per launch. Used by bench.py for the roofline line. */
 int mof_time_flow_spmv(mof_ctx* ctx, int reps, float* msPerLaunch);
+
+/* ---- one mesh over several GPUs (BASELINE.json configs[4]: "vertex-partitioned, NCCL-over-NVLink halo exchange for
+ * SpMV and allreduce for the CG dot products"). The reference has no counterpart: its solve is one Eigen
+ * factorisation (LinearSolvers.h:360-391). One process per GPU; rank 0 obtains an id, the host side distributes it
+ * (bench.py / the tests use torch.distributed for that), every rank calls mof_dist_init BEFORE mof_set_mesh, and from
+ * then on every rank makes the SAME calls with the SAME inputs: the flow solves are then row-partitioned across the
+ * ranks (halo exchange + all-reduce on the context's stream), everything else is replicated, and every rank ends
+ * with the full result. world == 1 is allowed (same code path, no communication). */
+int mof_dist_unique_id(unsigned char id128[128]);
+int mof_dist_init(mof_ctx* ctx, int world, int rank, const unsigned char id128[128]);
 
 #ifdef __cplusplus
 }

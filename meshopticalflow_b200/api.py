@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "mof_default_params", "mof_create", "mof_destroy", "mof_last_error", "mof_set_params", "mof_get_stats", "mof_reset_stats", "mof_synchronize",
     "mof_set_mesh", "mof_set_mesh_device", "mof_set_signals", "mof_set_signals_device", "mof_iterate", "mof_get_flow", "mof_get_coeffs", "mof_num_edges",
     "mof_advect_vertices", "mof_advect_vertices_device", "mof_set_texture_map", "mof_advect_texels", "mof_csr_size", "mof_get_csr", "mof_array_bytes",
-    "mof_get_array", "mof_pcg_solve_csr", "mof_time_flow_spmv",
+    "mof_get_array", "mof_pcg_solve_csr", "mof_time_flow_spmv", "mof_dist_unique_id", "mof_dist_init",
 ]
 
 
@@ -47,7 +47,7 @@ class Stats(ctypes.Structure):
     _fields_ = [("kernelLaunches", c_longlong), ("flowCgIterations", c_longlong), ("smoothCgIterations", c_longlong), ("flowSolves", c_int),
                 ("smoothSolves", c_int), ("lastFlowResidual", c_double), ("lastSmoothResidual", c_double), ("flowSolveMs", c_float),
                 ("smoothSolveMs", c_float), ("advectMs", c_float), ("setupMs", c_float), ("flowSpmvBytes", c_double), ("flowRows", c_longlong),
-                ("flowNnz", c_longlong)]
+                ("flowNnz", c_longlong), ("haloEntries", c_longlong)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -70,6 +70,10 @@ def load_library():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` (make -C meshopticalflow_b200/csrc)")
+    try:  # libmof_b200.so needs libnccl.so.2: let torch's own copy (if torch is here) be the one both of them bind to
+        import torch  # noqa: F401
+    except ImportError:
+        pass
     lib = ctypes.CDLL(LIB_PATH)
     D, I = POINTER(c_double), POINTER(c_int)
     lib.mof_default_params.argtypes = [POINTER(Params)]
@@ -103,6 +107,8 @@ def load_library():
     lib.mof_get_array.argtypes = [c_void_p, c_int, c_void_p]
     lib.mof_pcg_solve_csr.argtypes = [c_void_p, c_int, I, I, D, D, D, c_double, c_int, I, D]
     lib.mof_time_flow_spmv.argtypes = [c_void_p, c_int, POINTER(c_float)]
+    lib.mof_dist_unique_id.argtypes = [POINTER(c_ubyte)]
+    lib.mof_dist_init.argtypes = [c_void_p, c_int, c_int, POINTER(c_ubyte)]
     _lib = lib
     return lib
 
@@ -113,6 +119,15 @@ def _d(a):
 
 def _i(a):
     return a.ctypes.data_as(POINTER(c_int))
+
+
+def dist_unique_id() -> bytes:
+    """A fresh communicator id (call on ONE rank and broadcast it; see sharding.broadcast_bytes)."""
+    buf = (c_ubyte * 128)()
+    rc = load_library().mof_dist_unique_id(buf)
+    if rc != MOF_OK:
+        raise MofError(rc, "mof_dist_unique_id failed")
+    return bytes(buf)
 
 
 def default_params() -> Params:
@@ -162,6 +177,15 @@ class Aligner:
 
     def synchronize(self):
         self._check(self._lib.mof_synchronize(self._ctx))
+
+    # --- one mesh over several GPUs (no reference counterpart): call before set_mesh, on every rank
+    def dist_init(self, world: int, rank: int, unique_id: bytes):
+        """Joins this context to a `world`-rank communicator: the flow solves of the meshes set afterwards are
+        row-partitioned across the ranks. Every rank must then make the same calls with the same inputs."""
+        if len(unique_id) != 128:
+            raise MofError(MOF_E_INVALID, "the communicator id is 128 bytes (dist_unique_id() on rank 0, broadcast by the caller)")
+        buf = (c_ubyte * 128).from_buffer_copy(unique_id)
+        self._check(self._lib.mof_dist_init(self._ctx, world, rank, buf))
 
     # --- Init (OpticalFlow.cpp:787-871)
     def set_mesh(self, vertices, triangles):

@@ -44,6 +44,9 @@ int finish_mesh(mof_ctx* ctx) {
     rc = mg_setup_mesh(ctx);
     if (rc != MOF_OK) return rc;
     pt.mark("multigrid hierarchies (total)");
+    rc = dist_setup_mesh(ctx);
+    if (rc != MOF_OK) return rc;
+    pt.mark("row blocks and halo lists");
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     MOF_CUDA(cudaEventSynchronize(ctx->ev1));
     float ms = 0;
@@ -120,13 +123,14 @@ void mof_destroy(mof_ctx* ctx) {
     DBuf<double>* dbl[] = {&ctx->pos, &ctx->g, &ctx->area, &ctx->xlin, &ctx->xcst, &ctx->sMass, &ctx->sStiff, &ctx->sSys, &ctx->sDinv, &ctx->P, &ctx->m0, &ctx->m1,
                            &ctx->wS, &ctx->wA, &ctx->wDinv, &ctx->raw6, &ctx->sig6, &ctx->smoothed6, &ctx->rhs6, &ctx->resampled6, &ctx->tsample6, &ctx->dataD,
                            &ctx->dataRhs, &ctx->coeffs, &ctx->tfield, &ctx->fb, &ctx->fx, &ctx->scalars, &ctx->pcg.r, &ctx->pcg.d, &ctx->pcg.q, &ctx->pcg.partial,
-                           &ctx->pcg.result, &ctx->dtmp0, &ctx->dtmp1, &ctx->srcP, &ctx->triUV, &ctx->texOut};
+                           &ctx->pcg.result, &ctx->dtmp0, &ctx->dtmp1, &ctx->dtmp2, &ctx->srcP, &ctx->triUV, &ctx->texOut};
     for (auto* b : dbl) b->release();
     DBuf<int>* ints[] = {&ctx->tri, &ctx->opp, &ctx->sRowptr, &ctx->sCol, &ctx->sHe, &ctx->reduced, &ctx->expanded, &ctx->positive, &ctx->wRowptr, &ctx->wSliceBase, &ctx->wCol,
                          &ctx->itmp0, &ctx->itmp1, &ctx->itmp2, &ctx->flags, &ctx->srcT};
     for (auto* b : ints) b->release();
     ctx->hashKeys.release(), ctx->tex[0].release(), ctx->tex[1].release();
     mg_destroy(ctx);
+    dist_destroy(ctx);
     cudaStreamSynchronize(ctx->stream);  // the frees above are stream-ordered
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -153,15 +157,24 @@ int mof_get_stats(mof_ctx* ctx, mof_stats* out) {
 }
 void mof_reset_stats(mof_ctx* ctx) {
     if (!ctx) return;
-    long long rows = ctx->stats.flowRows, nnz = ctx->stats.flowNnz;
+    long long rows = ctx->stats.flowRows, nnz = ctx->stats.flowNnz, halo = ctx->stats.haloEntries;
     double bytes = ctx->stats.flowSpmvBytes;
     memset(&ctx->stats, 0, sizeof(ctx->stats));
-    ctx->stats.flowRows = rows, ctx->stats.flowNnz = nnz, ctx->stats.flowSpmvBytes = bytes;
+    ctx->stats.flowRows = rows, ctx->stats.flowNnz = nnz, ctx->stats.flowSpmvBytes = bytes, ctx->stats.haloEntries = halo;
 }
 int mof_synchronize(mof_ctx* ctx) {
     if (!ctx) return MOF_E_INVALID;
     MOF_CUDA(cudaStreamSynchronize(ctx->stream));
     return MOF_OK;
+}
+
+int mof_dist_unique_id(unsigned char id128[128]) { return id128 ? dist_unique_id(id128) : MOF_E_INVALID; }
+int mof_dist_init(mof_ctx* ctx, int world, int rank, const unsigned char id128[128]) {
+    if (!ctx) return MOF_E_INVALID;
+    StreamScope scope(ctx);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MOF_E_CUDA, "cudaSetDevice");
+    ctx->haveMesh = ctx->haveSignals = false;  // the partition is built with the mesh
+    return dist_init(ctx, world, rank, id128);
 }
 
 int mof_set_mesh(mof_ctx* ctx, const double* xyz, int V, const int* tri, int T) {

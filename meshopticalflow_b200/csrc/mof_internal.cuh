@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -22,24 +23,31 @@ inline cudaStream_t& alloc_stream() {
     return s;
 }
 
+// A buffer keeps its memory when it is re-sized to something that still fits (n = logical size, cap = allocated):
+// aligning pair after pair re-runs the whole set-up with the same sizes, and handing hundreds of MB back to the pool
+// only to ask for them again lets other allocations carve the block up, after which the pool has to grow — which
+// costs seconds once NCCL has enabled peer access.
 template <class T>
 struct DBuf {
     T* p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap = 0;
     cudaError_t alloc(size_t count) {
-        if (count == n && p) return cudaSuccess;
+        if (p && count <= cap && count > 0) {
+            n = count;
+            return cudaSuccess;
+        }
         release();
         if (!count) return cudaSuccess;
         cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), alloc_stream());
-        if (e == cudaSuccess) n = count;
+        if (e == cudaSuccess) n = cap = count;
         else p = nullptr;
         return e;
     }
-    // Scratch use: grow-only, keeps the larger allocation.
-    cudaError_t reserve(size_t count) { return (p && count <= n) ? cudaSuccess : alloc(count); }
+    // Scratch use: grow-only, the logical size follows the largest request.
+    cudaError_t reserve(size_t count) { return (p && count <= n) ? cudaSuccess : alloc(std::max(count, n)); }
     void release() {
         if (p) cudaFreeAsync(p, alloc_stream());
-        p = nullptr, n = 0;
+        p = nullptr, n = cap = 0;
     }
     size_t bytes() const { return n * sizeof(T); }
 };
@@ -67,6 +75,7 @@ __host__ __device__ __forceinline__ size_t sell_pos(const int* sliceBase, int ro
 #endif
 
 struct Multigrid;  // multigrid.cu
+struct DistState;  // dist.cu
 
 struct PcgWork {
     DBuf<double> r, d, q;       // [n * nrhs]
@@ -111,10 +120,11 @@ struct mof_ctx {
     mof::PcgWork pcg;
     mof::Multigrid* mg = nullptr;   // multilevel preconditioner of the flow system
     mof::Multigrid* mgs = nullptr;  // ... and of the scalar smoothing systems
+    mof::DistState* dist = nullptr; // one mesh over several GPUs (dist.cu); nullptr = single GPU
     // scratch
     mof::DBuf<int> itmp0, itmp1, itmp2, flags;
     mof::DBuf<unsigned long long> hashKeys;
-    mof::DBuf<double> dtmp0, dtmp1;
+    mof::DBuf<double> dtmp0, dtmp1, dtmp2;
     // texture path
     int texW = 0, texH = 0;
     mof::DBuf<int> srcT;
@@ -213,6 +223,20 @@ int mg_flow_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double*
 bool mg_scalar_usable(const mof_ctx* ctx);
 int mg_scalar_update(mof_ctx* ctx);   // per scalar system: coarse operators of the current sSys (sDinv = its inverse diagonal)
 int mg_scalar_solve(mof_ctx* ctx, const double* b6, double* x6, double tol, int maxIters, int* itersOut, double* relresOut);  // x6 = initial guess
+
+// dist.cu — one mesh over several GPUs: row blocks of the flow system, halo exchange, all-reduce (NCCL on ctx->stream)
+int dist_unique_id(unsigned char* id128);
+int dist_init(mof_ctx* ctx, int world, int rank, const unsigned char* id128);
+void dist_destroy(mof_ctx* ctx);
+int dist_setup_mesh(mof_ctx* ctx);                       // per mesh: row blocks and halo index lists from the flow pattern
+bool dist_active(const mof_ctx* ctx);                    // a communicator exists and the mesh has been partitioned
+int dist_world(const mof_ctx* ctx);
+void dist_range(const mof_ctx* ctx, int* s0, int* s1, int* r0, int* r1);  // this rank's slices [s0,s1) and rows [r0,r1)
+int dist_halo_f64(mof_ctx* ctx, double* vec);            // fills the entries of a full-length vector that my rows gather from other ranks
+int dist_halo_f32(mof_ctx* ctx, float* vec);
+int dist_allreduce_f64(mof_ctx* ctx, double* v, int count);
+int dist_allreduce_f32(mof_ctx* ctx, float* v, int count);
+int dist_allgather_rows(mof_ctx* ctx, double* vec);      // every rank's rows to every rank
 
 // flow_kernels.cu
 int dog_preprocess(mof_ctx* ctx);

@@ -464,16 +464,18 @@ struct Fold {
 // vectors; b is always the fp64 right-hand side (the PCG residual inside a cycle).
 //   mode 1: out = b - A in
 //   mode 2: out = in + omega * dinv * (b - A in)  (one damped Jacobi sweep); with `partial`, also the CTA's part of b.out
+// PART (one mesh over several GPUs, dist.cu): only the slices [s0, s1) of this rank, and
+//   mode 0: out = A in with the CTA's part of in.out
 constexpr int BATCH = 6;
-template <class TV, class TX>
+template <class TV, class TX, bool PART = false>
 __global__ void __launch_bounds__(B, 8) k_fine_apply_flow(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const TV* __restrict__ val,
                                                       const double* __restrict__ b, const creal* __restrict__ dinv, double omega, const TX* __restrict__ in,
-                                                      TX* __restrict__ out, int mode, Fold f) {
+                                                      TX* __restrict__ out, int mode, Fold f, int s0 = 0, int s1 = 0) {
     const int lane = threadIdx.x & 31;
-    const int slices = (n + 31) >> 5;
+    const int slices = PART ? s1 : (n + 31) >> 5;
     const int warps = gridDim.x * (B / 32);
     double dot = 0;
-    for (int s = blockIdx.x * (B / 32) + (threadIdx.x >> 5); s < slices; s += warps) {
+    for (int s = (PART ? s0 : 0) + blockIdx.x * (B / 32) + (threadIdx.x >> 5); s < slices; s += warps) {
         const int base = sliceBase[s];
         const int len = (sliceBase[s + 1] - base) >> 5;
         const TV* v0 = val + (size_t)base + lane;
@@ -497,6 +499,11 @@ __global__ void __launch_bounds__(B, 8) k_fine_apply_flow(int n, const int* __re
                 if (j0 + u < len) acc += (TX)v[u] * x[u];
         }
         if (row < n) {
+            if (PART && mode == 0) {
+                out[row] = acc;
+                dot += (double)in[row] * (double)acc;
+                continue;
+            }
             const double bv = b[row];
             if (mode == 1) out[row] = (TX)(bv - (double)acc);
             else {
@@ -506,7 +513,7 @@ __global__ void __launch_bounds__(B, 8) k_fine_apply_flow(int n, const int* __re
             }
         }
     }
-    if (mode == 2 && f.partial) cta_partial(dot, f.partial, f.slot, f.scal, f.counter);
+    if ((mode == 2 || (PART && mode == 0)) && f.partial) cta_partial(dot, f.partial, f.slot, f.scal, f.counter);
 }
 // SCALAR: CSR with six interleaved right-hand sides, one thread per (row, channel). mode 0: out = A in with the CTA's
 // partial of in.out ; modes 1, 2 as above.
@@ -557,13 +564,14 @@ __device__ __forceinline__ void apply_binv(const creal* __restrict__ binv, int N
 // zc = omega * Binv * rc.
 // FLOW restriction: rc[I] = sum over the edges of aggregate I of v_e * r_e (P1^T r). One warp per aggregate.
 __global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ evec, const creal* __restrict__ r, int N,
-                                const creal* __restrict__ binv, creal omega, creal* __restrict__ rc, creal* __restrict__ zc) {
+                                const creal* __restrict__ binv, creal omega, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1) {
     int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (I >= N) return;
     const creal bk = lane < 9 ? binv[(size_t)lane * N + I] : (creal)0;  // the cell's block inverse, fetched alongside the sums
     creal a0 = 0, a1 = 0, a2 = 0;
     for (int q = aggPtr[I] + lane; q < aggPtr[I + 1]; q += 32) {
         int e = aggList[q];
+        if (e < r0 || e >= r1) continue;  // partitioned mesh: this rank's rows only (the partial sums are all-reduced)
         creal re = r[e];
         a0 += evec[3 * (size_t)e] * re, a1 += evec[3 * (size_t)e + 1] * re, a2 += evec[3 * (size_t)e + 2] * re;
     }
@@ -715,6 +723,18 @@ __global__ void k_restrict_coarse(const int* __restrict__ firstChild, const crea
     apply_binv<K, D>(binv, Ncoarse, Ip, a, o);
 #pragma unroll
     for (int c = 0; c < D; c++) rc[(size_t)D * Ip + c] = a[c], zc[(size_t)D * Ip + c] = omega * o[c];
+}
+// z = omega * Binv * r on a level (partitioned mesh: the first sweep of level 1, after the restriction was all-reduced)
+template <int K, int D>
+__global__ void k_level_presmooth(const creal* __restrict__ binv, const creal* __restrict__ r, creal omega, int N, creal* __restrict__ z) {
+    int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= N) return;
+    creal v[D], o[D];
+#pragma unroll
+    for (int c = 0; c < D; c++) v[c] = r[(size_t)D * I + c];
+    apply_binv<K, D>(binv, N, I, v, o);
+#pragma unroll
+    for (int c = 0; c < D; c++) z[(size_t)D * I + c] = omega * o[c];
 }
 template <int D>
 __global__ void k_prolong_coarse(const int* __restrict__ parent, const creal* __restrict__ zc, int N, creal* __restrict__ z) {
@@ -877,6 +897,11 @@ int build_octree(mof_ctx* ctx, Multigrid& mg, const double* pts, int n, double m
     while (Lc > 1 && counts[Lc] > COARSEST_CELLS) Lc--;
     if (counts[Lc] > 2 * COARSEST_CELLS) { freeAll(); return MOF_OK; }
     const int K = L1 - Lc + 1;
+    for (size_t l = K; l < mg.lev.size(); l++) {  // a previous, deeper hierarchy: give the extra levels back
+        MgLevel& o = mg.lev[l];
+        o.code.release(), o.nbr.release(), o.parent.release(), o.firstChild.release(), o.blocks.release(), o.cblocks.release(), o.binv.release(), o.r.release(),
+            o.z.release(), o.t.release();
+    }
     mg.lev.resize(K);
     for (int l = 0; l < K; l++) {
         MgLevel& lv = mg.lev[l];
@@ -945,8 +970,10 @@ int alloc_common(mof_ctx* ctx, Multigrid& mg) {
     return MOF_OK;
 }
 
-Multigrid* new_mg(mof_ctx* ctx, MgKind kind, int nFine, int* rcOut) {
-    Multigrid* mg = new Multigrid();
+// A hierarchy object is kept from mesh to mesh: its buffers are re-sized in place (DBuf keeps memory that still fits).
+Multigrid* new_mg(mof_ctx* ctx, Multigrid* old, MgKind kind, int nFine, int* rcOut) {
+    Multigrid* mg = old ? old : new Multigrid();
+    mg->usable = false, mg->K = 0;
     mg->kind = kind, mg->nFine = nFine, mg->nrhs = kind == MG_FLOW ? 1 : 6;
     mg->gamma = std::max(1, std::min(2, env_int("MOF_MG_GAMMA", 1)));
     mg->gammaLevels = std::max(0, env_int("MOF_MG_GAMMA_LEVELS", 0));
@@ -969,20 +996,18 @@ void mg_destroy(mof_ctx* ctx) {
 // Mesh-dependent part of both hierarchies.
 int mg_setup_mesh(mof_ctx* ctx) {
     PhaseTimer pt(ctx);
-    mg_destroy(ctx);
-    pt.mark("  release old hierarchies");
     const int E = ctx->E, V = ctx->V;
     int rc = MOF_OK;
-    ctx->mg = new_mg(ctx, MG_FLOW, E, &rc);
+    ctx->mg = new_mg(ctx, ctx->mg, MG_FLOW, E, &rc);
     if (rc != MOF_OK) return rc;
-    ctx->mgs = new_mg(ctx, MG_SCALAR, V, &rc);
+    ctx->mgs = new_mg(ctx, ctx->mgs, MG_SCALAR, V, &rc);
     if (rc != MOF_OK) return rc;
     Multigrid& mf = *ctx->mg;
     Multigrid& ms = *ctx->mgs;
     // edge geometry: vectors (FLOW prolongation), midpoints (FLOW octree), longest edge (both)
-    DBuf<double> emid;
+    DBuf<double>& emid = ctx->dtmp2;
     MOF_CUDA(mf.evec.alloc(3ull * E));
-    MOF_CUDA(emid.alloc(3ull * E));
+    MOF_CUDA(emid.reserve(3ull * E));
     MOF_CUDA(ctx->dtmp0.reserve((size_t)E));
     MOF_LAUNCH(k_edge_geometry, blocks_for(E, B), B, 0, ctx->pos.p, ctx->tri.p, ctx->expanded.p, E, mf.evec.p, emid.p, ctx->dtmp0.p);
     MOF_TRY(minmax(ctx, mf, ctx->dtmp0.p, E, 1, 0, 1, mf.scal.p + 6));
@@ -1007,7 +1032,6 @@ int mg_setup_mesh(mof_ctx* ctx) {
             }
         }
     }
-    emid.release();
     if (rc != MOF_OK) return rc;
     pt.mark("  flow hierarchy");
 
@@ -1252,7 +1276,7 @@ int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed, i
     if (!presmoothed) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r, mg.fdinv.p, mg.omega0, len, mg.nrhs, mg.fz.p);
     MOF_TRY(fine_apply(ctx, mg, r, mg.omega0, mg.fz.p, mg.ft.p, 1));
     if (mg.kind == MG_FLOW)
-        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p);
+        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, 0, mg.nFine);
     else
         MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p);
     if (mg.K == 1) {  // the aggregates are already the coarsest level
@@ -1376,6 +1400,155 @@ int mg_pcg(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGue
     return MOF_OK;
 }
 
+// ---------------------------------------------------------------------- one mesh over several GPUs (dist.cu)
+
+inline int dist_halo(mof_ctx* c, float* v) { return dist_halo_f32(c, v); }
+inline int dist_halo(mof_ctx* c, double* v) { return dist_halo_f64(c, v); }
+inline int dist_allreduce(mof_ctx* c, float* v, int n) { return dist_allreduce_f32(c, v, n); }
+inline int dist_allreduce(mof_ctx* c, double* v, int n) { return dist_allreduce_f64(c, v, n); }
+
+// Raw slots of mg.scal for this rank's partial sums (all-reduced in place), and the scalar each one feeds.
+enum { R_PQ = 8, R_RR = 9, R_RZ = 10, R_RZNEW = 11, R_BB = 12 };
+__global__ void k_derive(int raw, double* __restrict__ scal) {
+    const double v = scal[raw];
+    if (raw == R_PQ) scal[S_PQ] = v, scal[S_ALPHA] = v != 0 ? scal[S_RZ] / v : 0.;
+    else if (raw == R_RR) scal[S_RR] = v;
+    else if (raw == R_BB) scal[S_BB] = v;
+    else if (raw == R_RZ) scal[S_RZ] = v;
+    else if (raw == R_RZNEW) scal[S_BETA] = scal[S_RZ] != 0 ? v / scal[S_RZ] : 0., scal[S_RZ] = v;
+}
+
+// The FLOW multigrid-PCG with the fine level row-partitioned over the ranks (zero initial guess). Every rank runs this
+// with the same b; vectors are full length, a rank computes the rows [r0, r1) = slices [s0, s1) of each. Per iteration:
+// three halo exchanges (p in fp64, the cycle's iterate twice in fp32), four all-reduces (p.q, r.r, the level-1
+// restriction, r.z); the coarse levels are replicated. x is complete on every rank at the end.
+int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, double tol, int maxIters, int* itersOut, double* relresOut) {
+    int s0, s1, r0, r1;
+    dist_range(ctx, &s0, &s1, &r0, &r1);
+    const long long len = r1 - r0;
+    const long long full = (long long)mg.fineLen();
+    MgLevel& l1 = mg.lev[0];
+    double* r = mg.fr.p;
+    double* p = mg.fp.p;
+    double* q = mg.fq.p;
+    const Fold partials = {mg.partial.p, -1, mg.scal.p, mg.counter.p};
+    // sum of this rank's partials -> all ranks' sum -> the PCG scalar it feeds
+    auto reduce = [&](int np, int raw) -> int {
+        MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, np, raw, mg.scal.p);
+        MOF_TRY(dist_allreduce(ctx, mg.scal.p + raw, 1));
+        MOF_LAUNCH(k_derive, 1, 1, 0, raw, mg.scal.p);
+        return MOF_OK;
+    };
+    auto spmv = [&](auto tv, auto tx, const auto* val, const double* rhs, double omega, const auto* in, auto* out, int mode, Fold f) -> int {
+        using TV = decltype(tv);
+        using TX = decltype(tx);
+        MOF_LAUNCH((k_fine_apply_flow<TV, TX, true>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, val, rhs, mg.fdinv.p, omega, in, out, mode, f, s0, s1);
+        return MOF_OK;
+    };
+    // z = cycle(r) on my rows (mg.fz), r.z into scal via `rawSlot`
+    auto cycle = [&](bool presmoothed, int rawSlot) -> int {
+        if (!presmoothed && len) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r + r0, mg.fdinv.p + r0, mg.omega0, len, 1, mg.fz.p + r0);
+        MOF_TRY(dist_halo(ctx, mg.fz.p));
+        MOF_TRY(spmv(creal(), creal(), mg.fval.p, r, mg.omega0, mg.fz.p, mg.ft.p, 1, NO_FOLD));
+        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, r0, r1);
+        MOF_TRY(dist_allreduce(ctx, l1.r.p, 3 * l1.N));
+        MOF_LAUNCH((k_level_presmooth<9, 3>), blocks_for(l1.N, B), B, 0, l1.binv.p, l1.r.p, (creal)l1.omega, l1.N, l1.z.p);
+        if (mg.K == 1) MOF_LAUNCH(k_dense_restrict_apply<3>, DENSE_CTAS, B, 0, (const int*)nullptr, l1.r.p, mg.cinv.p, 3 * l1.N, l1.z.p);
+        MOF_TRY(coarse_cycle(ctx, mg, 0));
+        if (len) MOF_LAUNCH(k_prolong_flow, blocks_for(len, B), B, 0, mg.agg.p + r0, mg.cevec.p + 3 * (size_t)r0, l1.z.p, (int)len, mg.fz.p + r0);
+        MOF_TRY(dist_halo(ctx, mg.fz.p));
+        MOF_TRY(spmv(creal(), creal(), mg.fval.p, r, mg.omega0, mg.fz.p, mg.fz2.p, 2, partials));
+        MOF_TRY(reduce(FINE_GRID, rawSlot));
+        std::swap(mg.fz.p, mg.fz2.p);
+        return MOF_OK;
+    };
+
+    MOF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * full, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * full, cudaMemcpyDeviceToDevice, ctx->stream));
+    MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, b + r0, b + r0, len, mg.partial.p);
+    MOF_TRY(reduce(NBLK, R_BB));
+    double bb = 0;
+    MOF_CUDA(read_back(ctx, &bb, mg.scal.p + S_BB));
+    double rr = bb;
+    *itersOut = 0, *relresOut = 0;
+    if (!(bb > 0)) return MOF_OK;
+    int it = 0;
+    long long launchesPerReplay = 0;
+    for (int attempt = 0; attempt < 4 && rr > tol * tol * bb; attempt++) {
+        MOF_TRY(cycle(false, R_RZ));
+        if (len) MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p + r0, mg.scal.p, len, 1, p + r0);
+        auto iteration = [&](int half) -> int {
+            MOF_TRY(dist_halo(ctx, p));
+            MOF_TRY(spmv(double(), double(), ctx->wA.p, (const double*)nullptr, 0., p, q, 0, partials));
+            MOF_TRY(reduce(FINE_GRID, R_PQ));
+            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p + r0, q + r0, len, x + r0, r + r0, mg.fdinv.p + r0, mg.omega0, 1, mg.fz.p + r0, partials);
+            MOF_TRY(reduce(NBLK, R_RR));
+            MOF_CUDA(cudaMemcpyAsync(mg.hostRR + half, mg.scal.p + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            MOF_TRY(cycle(true, R_RZNEW));
+            if (len) MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p + r0, mg.scal.p, len, 0, p + r0);
+            return MOF_OK;
+        };
+        // Two iterations (kernels and NCCL operations alike) captured as one CUDA graph and replayed, as in mg_pcg;
+        // MOF_DIST_GRAPH=0 launches them one by one.
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        if (env_int("MOF_DIST_GRAPH", 1)) {
+            const long long launchesBefore = ctx->stats.kernelLaunches;
+            MOF_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+            int crc = iteration(0);
+            if (crc == MOF_OK) crc = iteration(1);
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            launchesPerReplay = ctx->stats.kernelLaunches - launchesBefore;
+            ctx->stats.kernelLaunches = launchesBefore;
+            if (crc != MOF_OK || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                return crc != MOF_OK ? crc : cuda_fail(ctx, ce, "cudaStreamEndCapture(partitioned iteration)");
+            }
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            if (ce != cudaSuccess) {
+                cudaGraphDestroy(graph);
+                return cuda_fail(ctx, ce, "cudaGraphInstantiate(partitioned iteration)");
+            }
+        }
+        int lrc = MOF_OK;
+        while (it < maxIters) {
+            if (exec) {
+                cudaError_t ce = cudaGraphLaunch(exec, ctx->stream);
+                if (ce != cudaSuccess) { lrc = cuda_fail(ctx, ce, "cudaGraphLaunch(partitioned iteration)"); break; }
+                ctx->stats.kernelLaunches += launchesPerReplay;
+            } else {
+                lrc = iteration(0);
+                if (lrc == MOF_OK) lrc = iteration(1);
+                if (lrc != MOF_OK) break;
+            }
+            cudaError_t se = cudaStreamSynchronize(ctx->stream);
+            if (se != cudaSuccess) { lrc = cuda_fail(ctx, se, "cudaStreamSynchronize(partitioned iteration)"); break; }
+            it += 2;
+            rr = mg.hostRR[1];
+            if (!(mg.hostRR[0] > tol * tol * bb) || !(rr > tol * tol * bb) || !std::isfinite(rr)) break;
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (lrc != MOF_OK) return lrc;
+        // true residual of x
+        MOF_TRY(dist_halo(ctx, x));
+        MOF_TRY(spmv(double(), double(), ctx->wA.p, b, 0., x, r, 1, NO_FOLD));
+        MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, r + r0, r + r0, len, mg.partial.p);
+        MOF_TRY(reduce(NBLK, R_RR));
+        MOF_CUDA(read_back(ctx, &rr, mg.scal.p + S_RR));
+        if (it >= maxIters || !std::isfinite(rr)) break;
+    }
+    MOF_TRY(dist_allgather_rows(ctx, x));
+    *itersOut = it;
+    *relresOut = std::sqrt(rr / bb);
+    if (!std::isfinite(rr) || (!(*relresOut <= tol * 1.0001) && (it >= maxIters || !(*relresOut <= 1e-4)))) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "[ERROR] partitioned multigrid PCG did not reach %g in %d iterations (relative residual %g)", tol, it, *relresOut);
+        return fail(ctx, MOF_E_NOCONVERGE, msg);
+    }
+    return MOF_OK;
+}
+
 }  // namespace
 
 // FLOW: coarse operators of the current wA, then the solve wA x = fb into fx.
@@ -1389,6 +1562,7 @@ int mg_flow_update(mof_ctx* ctx) {
     return finish_values(ctx, mg);
 }
 int mg_flow_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double* relresOut) {
+    if (dist_active(ctx)) return mg_pcg_dist(ctx, *ctx->mg, ctx->fb.p, ctx->fx.p, tol, maxIters, itersOut, relresOut);
     return mg_pcg(ctx, *ctx->mg, ctx->fb.p, ctx->fx.p, true, tol, maxIters, itersOut, relresOut);
 }
 

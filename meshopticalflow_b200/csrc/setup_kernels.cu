@@ -531,7 +531,6 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_LAUNCH(k_he_lookup, blocks_for(nH, B), B, 0, ctx->tri.p, nH, ctx->hashKeys.p, ctx->itmp0.p, cap - 1, ctx->opp.p, ctx->flags.p);
     MOF_CUDA(cudaMemcpyAsync(hflags, ctx->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
     MOF_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->hashKeys.release();
     if (hflags[0]) return fail(ctx, MOF_E_MESH, "[ERROR] Edge is occupied");
     if (hflags[1]) return fail(ctx, MOF_E_MESH, "[ERROR] Boundary edge (TriangleMesh::unfold)");
     MOF_LAUNCH(k_edge_xforms, blocks_for(nH, B), B, 0, ctx->g.p, ctx->opp.p, nH, ctx->xlin.p, ctx->xcst.p);
@@ -614,7 +613,7 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_CUDA(cudaMemcpyAsync(hflags, ctx->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
     MOF_CUDA(cudaStreamSynchronize(ctx->stream));
     if (hflags[4]) return fail(ctx, MOF_E_MESH, "[ERROR] vertex without a triangle (singular mass matrix)");
-    ctx->itmp0.release(), ctx->itmp1.release(), ctx->itmp2.release(), ctx->dtmp0.release();
+    // (the scratch buffers stay allocated for the next mesh)
 
     pt.mark("  Whitney operator");
     // flow-side buffers

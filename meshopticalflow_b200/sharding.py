@@ -37,6 +37,29 @@ def barrier():
         dist.barrier()
 
 
+def broadcast_bytes(payload: bytes | None, size: int, src: int = 0, device=None) -> bytes:
+    """`payload` (given on rank `src`, `size` bytes) to every rank; identity for a single process."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return bytes(payload)
+    rank = dist.get_rank()
+    t = torch.zeros(size, dtype=torch.uint8)
+    if rank == src:
+        t = torch.frombuffer(bytearray(payload), dtype=torch.uint8).clone()
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=src)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def row_blocks(num_slices: int, num_rows: int, world_size: int) -> list[tuple[int, int]]:
+    """Rows [r0, r1) of each rank when `num_slices` 32-row slices are dealt in contiguous blocks (dist.cu uses the same
+    rule: block k starts at slice floor(num_slices * k / world_size))."""
+    starts = [min(num_rows, 32 * (num_slices * k // world_size)) for k in range(world_size)] + [num_rows]
+    return [(starts[k], starts[k + 1]) for k in range(world_size)]
+
+
 def shutdown():
     """Leaves the process group (no-op for a single process)."""
     import torch.distributed as dist
