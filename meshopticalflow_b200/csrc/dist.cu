@@ -1,10 +1,11 @@
-// One mesh over several GPUs (BASELINE.json configs[4]): the rows of the flow system are split into
-// contiguous blocks of 32-row slices, one block per rank (one process per GPU). Everything else — mesh operators,
-// signals, walks, the coarse multigrid levels — is replicated: every rank makes the same calls with the same inputs
-// and holds full-length vectors, of which it computes its own rows. What crosses NVLink, through NCCL on the
+// One mesh over several GPUs (BASELINE.json configs[4]): the rows of the two families of linear systems
+// are split into contiguous blocks, one block per rank (one process per GPU) — the E edge unknowns of the flow system
+// in blocks of 32-row slices, the V vertices of the smoothing systems in equal ranges. Everything else — mesh
+// operators, signals, walks, the coarse multigrid levels — is replicated: every rank makes the same calls with the same
+// inputs and holds full-length vectors, of which it computes its own rows. What crosses NVLink, through NCCL on the
 // context's stream:
 //   * halo exchange before every fine-level SpMV: the entries of the input vector that a rank's rows reference outside
-//     its block (index lists built once per mesh from the matrix pattern, grouped ncclSend/ncclRecv of packed values),
+//     its block (index lists built once per mesh from the matrix patterns, grouped ncclSend/ncclRecv of packed values),
 //   * all-reduce of the PCG dot products and of the level-1 restriction (each rank restricts its own rows),
 //   * one all-gather of the solution at the end of a solve.
 // The communicator is created from an id that the host side broadcasts (torch.distributed does that in bench.py and
@@ -19,16 +20,22 @@
 
 namespace mof {
 
+// Row blocks and halo index lists of one system. kind 0 = FLOW (one value per edge), 1 = SCALAR (six per vertex).
+struct Partition {
+    int width = 1;
+    std::vector<int> rowStart;                                  // world + 1
+    std::vector<int> sendCount, sendOff, recvCount, recvOff;    // per peer, in indices
+    int nSend = 0, nRecv = 0;
+    DBuf<int> sendIdx, recvIdx;
+};
+
 struct DistState {
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
     bool meshReady = false;
-    std::vector<int> sliceStart;            // world + 1
-    std::vector<int> rowStart;              // world + 1
-    std::vector<int> sendCount, sendOff, recvCount, recvOff;  // per peer, in entries
-    int nSend = 0, nRecv = 0;
-    DBuf<int> sendIdx, recvIdx;
-    DBuf<double> sendBuf, recvBuf;          // sized for fp64 entries, reused for fp32
+    std::vector<int> sliceStart;            // FLOW: world + 1 (32-row slices)
+    Partition part[2];
+    DBuf<double> sendBuf, recvBuf;          // sized for the widest exchange in fp64, reused for fp32
 };
 
 namespace {
@@ -41,8 +48,8 @@ namespace {
 
 constexpr int B = 256;
 
-// flags[c] = 1 for every column outside [r0, r1) referenced by the slices [s0, s1)
-__global__ void k_mark_halo(const int* __restrict__ sliceBase, const int* __restrict__ col, int s0, int s1, int r0, int r1, int* __restrict__ flags) {
+// flags[c] = 1 for every column outside [r0, r1) referenced by the slices [s0, s1) of the sliced FLOW pattern ...
+__global__ void k_mark_halo_sell(const int* __restrict__ sliceBase, const int* __restrict__ col, int s0, int s1, int r0, int r1, int* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const int warps = gridDim.x * (blockDim.x >> 5);
     for (int s = s0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < s1; s += warps) {
@@ -54,36 +61,98 @@ __global__ void k_mark_halo(const int* __restrict__ sliceBase, const int* __rest
         }
     }
 }
+// ... and by the rows [r0, r1) of the SCALAR CSR pattern.
+__global__ void k_mark_halo_csr(const int* __restrict__ rowptr, const int* __restrict__ col, int r0, int r1, int* __restrict__ flags) {
+    int v = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= r1) return;
+    for (int k = rowptr[v]; k < rowptr[v + 1]; k++) {
+        int c = col[k];
+        if (c < r0 || c >= r1) flags[c] = 1;
+    }
+}
 __global__ void k_compact(const int* __restrict__ flags, const int* __restrict__ pos, int n, int* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flags[i]) out[pos[i]] = i;
 }
 template <class T>
-__global__ void k_pack(const T* __restrict__ vec, const int* __restrict__ idx, int n, T* __restrict__ buf) {
+__global__ void k_pack(const T* __restrict__ vec, const int* __restrict__ idx, int n, int width, T* __restrict__ buf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) buf[i] = vec[idx[i]];
+    if (i >= n * width) return;
+    int e = i / width, c = i - e * width;
+    buf[i] = vec[(size_t)idx[e] * width + c];
 }
 template <class T>
-__global__ void k_unpack(const T* __restrict__ buf, const int* __restrict__ idx, int n, T* __restrict__ vec) {
+__global__ void k_unpack(const T* __restrict__ buf, const int* __restrict__ idx, int n, int width, T* __restrict__ vec) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) vec[idx[i]] = buf[i];
+    if (i >= n * width) return;
+    int e = i / width, c = i - e * width;
+    vec[(size_t)idx[e] * width + c] = buf[i];
 }
 
 template <class T>
-int halo_exchange(mof_ctx* ctx, T* vec, ncclDataType_t type) {
+int halo_exchange(mof_ctx* ctx, int kind, T* vec, ncclDataType_t type) {
     DistState& d = *ctx->dist;
     if (d.world == 1) return MOF_OK;
+    Partition& p = d.part[kind];
+    const int w = p.width;
     T* sb = (T*)d.sendBuf.p;
     T* rb = (T*)d.recvBuf.p;
-    if (d.nSend) MOF_LAUNCH(k_pack<T>, blocks_for(d.nSend, B), B, 0, vec, d.sendIdx.p, d.nSend, sb);
+    if (p.nSend) MOF_LAUNCH(k_pack<T>, blocks_for((long long)p.nSend * w, B), B, 0, vec, p.sendIdx.p, p.nSend, w, sb);
     MOF_NCCL(ncclGroupStart());
     for (int j = 0; j < d.world; j++) {
         if (j == d.rank) continue;
-        if (d.sendCount[j]) MOF_NCCL(ncclSend(sb + d.sendOff[j], (size_t)d.sendCount[j], type, j, d.comm, ctx->stream));
-        if (d.recvCount[j]) MOF_NCCL(ncclRecv(rb + d.recvOff[j], (size_t)d.recvCount[j], type, j, d.comm, ctx->stream));
+        if (p.sendCount[j]) MOF_NCCL(ncclSend(sb + (size_t)p.sendOff[j] * w, (size_t)p.sendCount[j] * w, type, j, d.comm, ctx->stream));
+        if (p.recvCount[j]) MOF_NCCL(ncclRecv(rb + (size_t)p.recvOff[j] * w, (size_t)p.recvCount[j] * w, type, j, d.comm, ctx->stream));
     }
     MOF_NCCL(ncclGroupEnd());
-    if (d.nRecv) MOF_LAUNCH(k_unpack<T>, blocks_for(d.nRecv, B), B, 0, rb, d.recvIdx.p, d.nRecv, vec);
+    if (p.nRecv) MOF_LAUNCH(k_unpack<T>, blocks_for((long long)p.nRecv * w, B), B, 0, rb, p.recvIdx.p, p.nRecv, w, vec);
+    return MOF_OK;
+}
+
+// Halo lists of one partition whose out-of-block columns have been flagged in ctx->itmp0[0..n).
+int build_lists(mof_ctx* ctx, Partition& p, int n) {
+    DistState& d = *ctx->dist;
+    const int N = d.world;
+    DBuf<int>& flags = ctx->itmp0;
+    DBuf<int>& pos = ctx->itmp1;
+    MOF_TRY(exclusive_scan_int(ctx, flags.p, pos.p, n + 1, nullptr));
+    int H = 0;
+    MOF_CUDA(read_back(ctx, &H, pos.p + n));
+    p.nRecv = H;
+    MOF_CUDA(p.recvIdx.alloc((size_t)std::max(H, 1)));
+    if (H) MOF_LAUNCH(k_compact, blocks_for(n, B), B, 0, flags.p, pos.p, n, p.recvIdx.p);
+    std::vector<int> hIdx((size_t)H);
+    if (H) MOF_CUDA(read_back(ctx, hIdx.data(), p.recvIdx.p, (size_t)H));
+    p.sendCount.assign(N, 0), p.sendOff.assign(N, 0), p.recvCount.assign(N, 0), p.recvOff.assign(N, 0);
+    for (int k = 0, i = 0; k < N; k++) {  // ascending indices: grouped by owner
+        p.recvOff[k] = i;
+        while (i < H && hIdx[i] < p.rowStart[k + 1]) i++;
+        p.recvCount[k] = i - p.recvOff[k];
+    }
+    // who needs how much from whom: row k of the matrix = recvCount of rank k
+    DBuf<int> counts, matrix;
+    MOF_CUDA(counts.alloc(N));
+    MOF_CUDA(matrix.alloc((size_t)N * N));
+    MOF_CUDA(cudaMemcpyAsync(counts.p, p.recvCount.data(), sizeof(int) * N, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_NCCL(ncclAllGather(counts.p, matrix.p, N, ncclInt, d.comm, ctx->stream));
+    std::vector<int> hm((size_t)N * N);
+    MOF_CUDA(read_back(ctx, hm.data(), matrix.p, (size_t)N * N));
+    counts.release(), matrix.release();
+    p.nSend = 0;
+    for (int j = 0; j < N; j++) {
+        p.sendCount[j] = j == d.rank ? 0 : hm[(size_t)j * N + d.rank];
+        p.sendOff[j] = p.nSend;
+        p.nSend += p.sendCount[j];
+    }
+    MOF_CUDA(p.sendIdx.alloc((size_t)std::max(p.nSend, 1)));
+    MOF_NCCL(ncclGroupStart());
+    for (int j = 0; j < N; j++) {
+        if (j == d.rank) continue;
+        if (p.recvCount[j]) MOF_NCCL(ncclSend(p.recvIdx.p + p.recvOff[j], (size_t)p.recvCount[j], ncclInt, j, d.comm, ctx->stream));
+        if (p.sendCount[j]) MOF_NCCL(ncclRecv(p.sendIdx.p + p.sendOff[j], (size_t)p.sendCount[j], ncclInt, j, d.comm, ctx->stream));
+    }
+    MOF_NCCL(ncclGroupEnd());
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
     return MOF_OK;
 }
 
@@ -92,10 +161,10 @@ int halo_exchange(mof_ctx* ctx, T* vec, ncclDataType_t type) {
 bool dist_active(const mof_ctx* ctx) { return ctx->dist && ctx->dist->comm && ctx->dist->meshReady; }
 int dist_world(const mof_ctx* ctx) { return ctx->dist ? ctx->dist->world : 1; }
 
-void dist_range(const mof_ctx* ctx, int* s0, int* s1, int* r0, int* r1) {
+void dist_range(const mof_ctx* ctx, int kind, int* s0, int* s1, int* r0, int* r1) {
     const DistState& d = *ctx->dist;
-    *s0 = d.sliceStart[d.rank], *s1 = d.sliceStart[d.rank + 1];
-    *r0 = d.rowStart[d.rank], *r1 = d.rowStart[d.rank + 1];
+    *s0 = kind == 0 ? d.sliceStart[d.rank] : 0, *s1 = kind == 0 ? d.sliceStart[d.rank + 1] : 0;
+    *r0 = d.part[kind].rowStart[d.rank], *r1 = d.part[kind].rowStart[d.rank + 1];
 }
 
 int dist_unique_id(unsigned char* id128) {
@@ -112,6 +181,7 @@ int dist_init(mof_ctx* ctx, int world, int rank, const unsigned char* id128) {
     ctx->dist = new DistState();
     DistState& d = *ctx->dist;
     d.world = world, d.rank = rank;
+    d.part[0].width = 1, d.part[1].width = 6;
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     MOF_NCCL(ncclCommInitRank(&d.comm, world, id, rank));
@@ -121,7 +191,8 @@ int dist_init(mof_ctx* ctx, int world, int rank, const unsigned char* id128) {
 void dist_destroy(mof_ctx* ctx) {
     if (!ctx->dist) return;
     DistState& d = *ctx->dist;
-    d.sendIdx.release(), d.recvIdx.release(), d.sendBuf.release(), d.recvBuf.release();
+    for (Partition& p : d.part) p.sendIdx.release(), p.recvIdx.release();
+    d.sendBuf.release(), d.recvBuf.release();
     if (d.comm) {
         cudaStreamSynchronize(ctx->stream);
         ncclCommDestroy(d.comm);
@@ -130,82 +201,57 @@ void dist_destroy(mof_ctx* ctx) {
     ctx->dist = nullptr;
 }
 
-// Row blocks and halo lists of the flow matrix (pattern only: once per mesh).
+// Row blocks and halo lists of both systems (patterns only: once per mesh).
 int dist_setup_mesh(mof_ctx* ctx) {
     if (!ctx->dist || !ctx->dist->comm) return MOF_OK;
     DistState& d = *ctx->dist;
     d.meshReady = false;
-    const int N = d.world, E = ctx->E, S = ctx->wSlices;
-    d.sliceStart.assign(N + 1, 0), d.rowStart.assign(N + 1, 0);
+    const int N = d.world, E = ctx->E, V = ctx->V, S = ctx->wSlices;
+    d.sliceStart.assign(N + 1, 0);
+    d.part[0].rowStart.assign(N + 1, 0), d.part[1].rowStart.assign(N + 1, 0);
     for (int k = 0; k <= N; k++) {
         d.sliceStart[k] = (int)((long long)S * k / N);
-        d.rowStart[k] = std::min(E, 32 * d.sliceStart[k]);
+        d.part[0].rowStart[k] = std::min(E, 32 * d.sliceStart[k]);
+        d.part[1].rowStart[k] = (int)((long long)V * k / N);
     }
-    d.rowStart[N] = E;
-    d.sendCount.assign(N, 0), d.sendOff.assign(N, 0), d.recvCount.assign(N, 0), d.recvOff.assign(N, 0);
-    d.nSend = d.nRecv = 0;
+    d.part[0].rowStart[N] = E;
+    for (Partition& p : d.part) {
+        p.sendCount.assign(N, 0), p.sendOff.assign(N, 0), p.recvCount.assign(N, 0), p.recvOff.assign(N, 0);
+        p.nSend = p.nRecv = 0;
+    }
     if (N == 1) {
         d.meshReady = true;
         return MOF_OK;
     }
-    const int s0 = d.sliceStart[d.rank], s1 = d.sliceStart[d.rank + 1], r0 = d.rowStart[d.rank], r1 = d.rowStart[d.rank + 1];
     PhaseTimer pt(ctx);
-    // columns my rows reference outside my block, ascending (so grouped by owner)
-    DBuf<int>& flags = ctx->itmp0;  // scratch of the mesh set-up, free again at this point
-    DBuf<int>& pos = ctx->itmp1;
-    MOF_CUDA(flags.reserve((size_t)E + 1));
-    MOF_CUDA(pos.reserve((size_t)E + 1));
-    MOF_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int) * ((size_t)E + 1), ctx->stream));
-    if (s1 > s0) MOF_LAUNCH(k_mark_halo, kSMs * 8, B, 0, ctx->wSliceBase.p, ctx->wCol.p, s0, s1, r0, r1, flags.p);
-    MOF_TRY(exclusive_scan_int(ctx, flags.p, pos.p, E + 1, nullptr));
-    int H = 0;
-    MOF_CUDA(read_back(ctx, &H, pos.p + E));
-    d.nRecv = H;
-    MOF_CUDA(d.recvIdx.alloc((size_t)std::max(H, 1)));
-    if (H) MOF_LAUNCH(k_compact, blocks_for(E, B), B, 0, flags.p, pos.p, E, d.recvIdx.p);
-    std::vector<int> hIdx((size_t)H);
-    if (H) MOF_CUDA(read_back(ctx, hIdx.data(), d.recvIdx.p, (size_t)H));
-    pt.mark("  halo: columns outside my block");
-    for (int k = 0, i = 0; k < N; k++) {
-        d.recvOff[k] = i;
-        while (i < H && hIdx[i] < d.rowStart[k + 1]) i++;
-        d.recvCount[k] = i - d.recvOff[k];
+    const int n = std::max(E, V);
+    MOF_CUDA(ctx->itmp0.reserve((size_t)n + 1));  // scratch of the mesh set-up, free again at this point
+    MOF_CUDA(ctx->itmp1.reserve((size_t)n + 1));
+    {
+        const int s0 = d.sliceStart[d.rank], s1 = d.sliceStart[d.rank + 1], r0 = d.part[0].rowStart[d.rank], r1 = d.part[0].rowStart[d.rank + 1];
+        MOF_CUDA(cudaMemsetAsync(ctx->itmp0.p, 0, sizeof(int) * ((size_t)E + 1), ctx->stream));
+        if (s1 > s0) MOF_LAUNCH(k_mark_halo_sell, kSMs * 8, B, 0, ctx->wSliceBase.p, ctx->wCol.p, s0, s1, r0, r1, ctx->itmp0.p);
+        MOF_TRY(build_lists(ctx, d.part[0], E));
     }
-    // who needs how much from whom: row k of the matrix = recvCount of rank k
-    DBuf<int> counts, matrix;
-    MOF_CUDA(counts.alloc(N));
-    MOF_CUDA(matrix.alloc((size_t)N * N));
-    MOF_CUDA(cudaMemcpyAsync(counts.p, d.recvCount.data(), sizeof(int) * N, cudaMemcpyHostToDevice, ctx->stream));
-    MOF_NCCL(ncclAllGather(counts.p, matrix.p, N, ncclInt, d.comm, ctx->stream));
-    std::vector<int> hm((size_t)N * N);
-    MOF_CUDA(read_back(ctx, hm.data(), matrix.p, (size_t)N * N));
-    counts.release(), matrix.release();
-    pt.mark("  halo: counts all-gather");
-    for (int j = 0, off = 0; j < N; j++) {
-        d.sendCount[j] = j == d.rank ? 0 : hm[(size_t)j * N + d.rank];
-        d.sendOff[j] = off;
-        off += d.sendCount[j];
-        d.nSend = off;
+    pt.mark("  halo lists of the flow system");
+    {
+        const int r0 = d.part[1].rowStart[d.rank], r1 = d.part[1].rowStart[d.rank + 1];
+        MOF_CUDA(cudaMemsetAsync(ctx->itmp0.p, 0, sizeof(int) * ((size_t)V + 1), ctx->stream));
+        if (r1 > r0) MOF_LAUNCH(k_mark_halo_csr, blocks_for(r1 - r0, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, r0, r1, ctx->itmp0.p);
+        MOF_TRY(build_lists(ctx, d.part[1], V));
     }
-    MOF_CUDA(d.sendIdx.alloc((size_t)std::max(d.nSend, 1)));
-    MOF_NCCL(ncclGroupStart());
-    for (int j = 0; j < N; j++) {
-        if (j == d.rank) continue;
-        if (d.recvCount[j]) MOF_NCCL(ncclSend(d.recvIdx.p + d.recvOff[j], (size_t)d.recvCount[j], ncclInt, j, d.comm, ctx->stream));
-        if (d.sendCount[j]) MOF_NCCL(ncclRecv(d.sendIdx.p + d.sendOff[j], (size_t)d.sendCount[j], ncclInt, j, d.comm, ctx->stream));
-    }
-    MOF_NCCL(ncclGroupEnd());
-    MOF_CUDA(d.sendBuf.alloc((size_t)std::max(d.nSend, 1)));
-    MOF_CUDA(d.recvBuf.alloc((size_t)std::max(d.nRecv, 1)));
-    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
-    pt.mark("  halo: index lists exchange");
-    ctx->stats.haloEntries = d.nRecv;
+    pt.mark("  halo lists of the smoothing systems");
+    size_t most = 1;
+    for (Partition& p : d.part) most = std::max(most, (size_t)std::max(p.nSend, p.nRecv) * p.width);
+    MOF_CUDA(d.sendBuf.reserve(most));
+    MOF_CUDA(d.recvBuf.reserve(most));
+    ctx->stats.haloEntries = d.part[0].nRecv;
     d.meshReady = true;
     return MOF_OK;
 }
 
-int dist_halo_f64(mof_ctx* ctx, double* vec) { return halo_exchange<double>(ctx, vec, ncclDouble); }
-int dist_halo_f32(mof_ctx* ctx, float* vec) { return halo_exchange<float>(ctx, vec, ncclFloat); }
+int dist_halo_f64(mof_ctx* ctx, int kind, double* vec) { return halo_exchange<double>(ctx, kind, vec, ncclDouble); }
+int dist_halo_f32(mof_ctx* ctx, int kind, float* vec) { return halo_exchange<float>(ctx, kind, vec, ncclFloat); }
 
 int dist_allreduce_f64(mof_ctx* ctx, double* v, int count) {
     DistState& d = *ctx->dist;
@@ -221,13 +267,15 @@ int dist_allreduce_f32(mof_ctx* ctx, float* v, int count) {
 }
 
 // Every rank's own rows of `vec` to all ranks (the blocks have different lengths: one broadcast per block, grouped).
-int dist_allgather_rows(mof_ctx* ctx, double* vec) {
+int dist_allgather_rows(mof_ctx* ctx, int kind, double* vec) {
     DistState& d = *ctx->dist;
     if (d.world == 1) return MOF_OK;
+    const Partition& p = d.part[kind];
     MOF_NCCL(ncclGroupStart());
     for (int k = 0; k < d.world; k++) {
-        const int n = d.rowStart[k + 1] - d.rowStart[k];
-        if (n > 0) MOF_NCCL(ncclBroadcast(vec + d.rowStart[k], vec + d.rowStart[k], (size_t)n, ncclDouble, k, d.comm, ctx->stream));
+        const size_t n = (size_t)(p.rowStart[k + 1] - p.rowStart[k]) * p.width;
+        double* at = vec + (size_t)p.rowStart[k] * p.width;
+        if (n > 0) MOF_NCCL(ncclBroadcast(at, at, n, ncclDouble, k, d.comm, ctx->stream));
     }
     MOF_NCCL(ncclGroupEnd());
     return MOF_OK;

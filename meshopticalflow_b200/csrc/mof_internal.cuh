@@ -228,15 +228,16 @@ int mg_scalar_solve(mof_ctx* ctx, const double* b6, double* x6, double tol, int 
 int dist_unique_id(unsigned char* id128);
 int dist_init(mof_ctx* ctx, int world, int rank, const unsigned char* id128);
 void dist_destroy(mof_ctx* ctx);
-int dist_setup_mesh(mof_ctx* ctx);                       // per mesh: row blocks and halo index lists from the flow pattern
+// `kind`: 0 = the flow system (E edge rows, one value each), 1 = the smoothing systems (V vertex rows, six values each)
+int dist_setup_mesh(mof_ctx* ctx);                       // per mesh: row blocks and halo index lists from the two patterns
 bool dist_active(const mof_ctx* ctx);                    // a communicator exists and the mesh has been partitioned
 int dist_world(const mof_ctx* ctx);
-void dist_range(const mof_ctx* ctx, int* s0, int* s1, int* r0, int* r1);  // this rank's slices [s0,s1) and rows [r0,r1)
-int dist_halo_f64(mof_ctx* ctx, double* vec);            // fills the entries of a full-length vector that my rows gather from other ranks
-int dist_halo_f32(mof_ctx* ctx, float* vec);
+void dist_range(const mof_ctx* ctx, int kind, int* s0, int* s1, int* r0, int* r1);  // this rank's rows [r0,r1) (FLOW: = slices [s0,s1))
+int dist_halo_f64(mof_ctx* ctx, int kind, double* vec);  // fills the entries of a full-length vector that my rows gather from other ranks
+int dist_halo_f32(mof_ctx* ctx, int kind, float* vec);
 int dist_allreduce_f64(mof_ctx* ctx, double* v, int count);
 int dist_allreduce_f32(mof_ctx* ctx, float* v, int count);
-int dist_allgather_rows(mof_ctx* ctx, double* vec);      // every rank's rows to every rank
+int dist_allgather_rows(mof_ctx* ctx, int kind, double* vec);  // every rank's rows to every rank
 
 // flow_kernels.cu
 int dog_preprocess(mof_ctx* ctx);

@@ -25,6 +25,7 @@
 // If a mesh does not fit the scheme, or a solve stalls, the callers fall back to the Jacobi-PCG kernel of
 // pcg_kernels.cu.
 #include <cmath>
+#include <type_traits>
 #include <cstdlib>
 #include <vector>
 
@@ -517,13 +518,14 @@ __global__ void __launch_bounds__(B, 8) k_fine_apply_flow(int n, const int* __re
 }
 // SCALAR: CSR with six interleaved right-hand sides, one thread per (row, channel). mode 0: out = A in with the CTA's
 // partial of in.out ; modes 1, 2 as above.
-template <class TV, class TX>
+// PART (one mesh over several GPUs): only the rows [r0, r1) of this rank.
+template <class TV, class TX, bool PART = false>
 __global__ void __launch_bounds__(B, 8) k_fine_apply_scalar(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const TV* __restrict__ val,
                                                         const double* __restrict__ b, const creal* __restrict__ dinv, double omega, const TX* __restrict__ in,
-                                                        TX* __restrict__ out, int mode, Fold f) {
-    const long long len = 6ll * n;
+                                                        TX* __restrict__ out, int mode, Fold f, int r0 = 0, int r1 = 0) {
+    const long long len = PART ? 6ll * r1 : 6ll * n;
     double dot = 0;
-    for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < len; i += (long long)gridDim.x * B) {
+    for (long long i = (PART ? 6ll * r0 : 0ll) + (long long)blockIdx.x * B + threadIdx.x; i < len; i += (long long)gridDim.x * B) {
         const int row = (int)(i / 6), c = (int)(i - 6ll * row);
         TX acc = 0;
         // (an explicit batch of 8 predicated loads per row was measured: 86 us against 57 us for this plain loop)
@@ -596,12 +598,15 @@ __global__ void k_prolong_flow(const int* __restrict__ agg, const creal* __restr
 }
 // SCALAR restriction / prolongation: sums and copies per channel. One thread per (cell, channel) / (vertex, channel).
 __global__ void k_restrict_scalar(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ r, int N, const creal* __restrict__ binv,
-                                  creal omega, creal* __restrict__ rc, creal* __restrict__ zc) {
+                                  creal omega, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 6 * N) return;
     int I = i / 6, c = i - 6 * I;
     creal a = 0;
-    for (int q = aggPtr[I]; q < aggPtr[I + 1]; q++) a += r[6 * (size_t)aggList[q] + c];
+    for (int q = aggPtr[I]; q < aggPtr[I + 1]; q++) {
+        const int v = aggList[q];
+        if (v >= r0 && v < r1) a += r[6 * (size_t)v + c];  // (partitioned mesh: this rank's rows only)
+    }
     rc[i] = a;
     zc[i] = omega * binv[I] * a;
 }
@@ -1278,7 +1283,7 @@ int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed, i
     if (mg.kind == MG_FLOW)
         MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, 0, mg.nFine);
     else
-        MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p);
+        MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, 0, mg.nFine);
     if (mg.K == 1) {  // the aggregates are already the coarsest level
         const bool flow = mg.kind == MG_FLOW;
         const int n = (flow ? 3 : 1) * l1.N;
@@ -1402,8 +1407,8 @@ int mg_pcg(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGue
 
 // ---------------------------------------------------------------------- one mesh over several GPUs (dist.cu)
 
-inline int dist_halo(mof_ctx* c, float* v) { return dist_halo_f32(c, v); }
-inline int dist_halo(mof_ctx* c, double* v) { return dist_halo_f64(c, v); }
+inline int dist_halo(mof_ctx* c, int kind, float* v) { return dist_halo_f32(c, kind, v); }
+inline int dist_halo(mof_ctx* c, int kind, double* v) { return dist_halo_f64(c, kind, v); }
 inline int dist_allreduce(mof_ctx* c, float* v, int n) { return dist_allreduce_f32(c, v, n); }
 inline int dist_allreduce(mof_ctx* c, double* v, int n) { return dist_allreduce_f64(c, v, n); }
 
@@ -1418,14 +1423,19 @@ __global__ void k_derive(int raw, double* __restrict__ scal) {
     else if (raw == R_RZNEW) scal[S_BETA] = scal[S_RZ] != 0 ? v / scal[S_RZ] : 0., scal[S_RZ] = v;
 }
 
-// The FLOW multigrid-PCG with the fine level row-partitioned over the ranks (zero initial guess). Every rank runs this
-// with the same b; vectors are full length, a rank computes the rows [r0, r1) = slices [s0, s1) of each. Per iteration:
-// three halo exchanges (p in fp64, the cycle's iterate twice in fp32), four all-reduces (p.q, r.r, the level-1
-// restriction, r.z); the coarse levels are replicated. x is complete on every rank at the end.
-int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, double tol, int maxIters, int* itersOut, double* relresOut) {
+// The multigrid-PCG of either hierarchy with the fine level row-partitioned over the ranks. Every rank runs this with
+// the same b (and the same initial x unless zeroGuess); vectors are full length, a rank computes the rows [r0, r1) of
+// each (FLOW: = slices [s0, s1); SCALAR: six values per row). Per iteration: three halo exchanges (p in fp64, the
+// cycle's iterate twice in fp32), four all-reduces (p.q, r.r, the level-1 restriction, r.z); the coarse levels are
+// replicated. x is complete on every rank at the end.
+int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGuess, double tol, int maxIters, int* itersOut, double* relresOut) {
+    const bool flow = mg.kind == MG_FLOW;
+    const int kind = flow ? 0 : 1, W = mg.nrhs;
     int s0, s1, r0, r1;
-    dist_range(ctx, &s0, &s1, &r0, &r1);
-    const long long len = r1 - r0;
+    dist_range(ctx, kind, &s0, &s1, &r0, &r1);
+    const int rows = r1 - r0;
+    const size_t e0 = (size_t)r0 * W;          // first element of my rows in a fine vector
+    const long long len = (long long)rows * W;  // ... and their number
     const long long full = (long long)mg.fineLen();
     MgLevel& l1 = mg.lev[0];
     double* r = mg.fr.p;
@@ -1439,53 +1449,75 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, double 
         MOF_LAUNCH(k_derive, 1, 1, 0, raw, mg.scal.p);
         return MOF_OK;
     };
-    auto spmv = [&](auto tv, auto tx, const auto* val, const double* rhs, double omega, const auto* in, auto* out, int mode, Fold f) -> int {
-        using TV = decltype(tv);
-        using TX = decltype(tx);
-        MOF_LAUNCH((k_fine_apply_flow<TV, TX, true>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, val, rhs, mg.fdinv.p, omega, in, out, mode, f, s0, s1);
+    // my rows of the fine operator, on the cycle's fp32 copy (mg.fval) or on the fp64 system matrix
+    const double* sysVal = flow ? ctx->wA.p : ctx->sSys.p;
+    auto spmv = [&](const auto* val, const double* rhs, double omega, const auto* in, auto* out, int mode, Fold f) -> int {
+        using TV = std::remove_cv_t<std::remove_pointer_t<decltype(val)>>;
+        if (flow) MOF_LAUNCH((k_fine_apply_flow<TV, TV, true>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, val, rhs, mg.fdinv.p, omega, in, out, mode, f, s0, s1);
+        else MOF_LAUNCH((k_fine_apply_scalar<TV, TV, true>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, val, rhs, mg.fdinv.p, omega, in, out, mode, f, r0, r1);
         return MOF_OK;
     };
+    const int D = mg.dofs();
     // z = cycle(r) on my rows (mg.fz), r.z into scal via `rawSlot`
     auto cycle = [&](bool presmoothed, int rawSlot) -> int {
-        if (!presmoothed && len) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r + r0, mg.fdinv.p + r0, mg.omega0, len, 1, mg.fz.p + r0);
-        MOF_TRY(dist_halo(ctx, mg.fz.p));
-        MOF_TRY(spmv(creal(), creal(), mg.fval.p, r, mg.omega0, mg.fz.p, mg.ft.p, 1, NO_FOLD));
-        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, r0, r1);
-        MOF_TRY(dist_allreduce(ctx, l1.r.p, 3 * l1.N));
-        MOF_LAUNCH((k_level_presmooth<9, 3>), blocks_for(l1.N, B), B, 0, l1.binv.p, l1.r.p, (creal)l1.omega, l1.N, l1.z.p);
-        if (mg.K == 1) MOF_LAUNCH(k_dense_restrict_apply<3>, DENSE_CTAS, B, 0, (const int*)nullptr, l1.r.p, mg.cinv.p, 3 * l1.N, l1.z.p);
+        if (!presmoothed && len) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r + e0, mg.fdinv.p + r0, mg.omega0, len, W, mg.fz.p + e0);
+        MOF_TRY(dist_halo(ctx, kind, mg.fz.p));
+        MOF_TRY(spmv((const creal*)mg.fval.p, r, mg.omega0, (const creal*)mg.fz.p, mg.ft.p, 1, NO_FOLD));
+        if (flow)
+            MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, r0, r1);
+        else
+            MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, r0, r1);
+        MOF_TRY(dist_allreduce(ctx, l1.r.p, D * l1.N));
+        if (flow) MOF_LAUNCH((k_level_presmooth<9, 3>), blocks_for(l1.N, B), B, 0, l1.binv.p, l1.r.p, (creal)l1.omega, l1.N, l1.z.p);
+        else MOF_LAUNCH((k_level_presmooth<1, 6>), blocks_for(l1.N, B), B, 0, l1.binv.p, l1.r.p, (creal)l1.omega, l1.N, l1.z.p);
+        if (mg.K == 1) {
+            if (flow) MOF_LAUNCH(k_dense_restrict_apply<3>, DENSE_CTAS, B, 0, (const int*)nullptr, l1.r.p, mg.cinv.p, 3 * l1.N, l1.z.p);
+            else MOF_LAUNCH(k_dense_restrict_apply<6>, DENSE_CTAS, B, 0, (const int*)nullptr, l1.r.p, mg.cinv.p, l1.N, l1.z.p);
+        }
         MOF_TRY(coarse_cycle(ctx, mg, 0));
-        if (len) MOF_LAUNCH(k_prolong_flow, blocks_for(len, B), B, 0, mg.agg.p + r0, mg.cevec.p + 3 * (size_t)r0, l1.z.p, (int)len, mg.fz.p + r0);
-        MOF_TRY(dist_halo(ctx, mg.fz.p));
-        MOF_TRY(spmv(creal(), creal(), mg.fval.p, r, mg.omega0, mg.fz.p, mg.fz2.p, 2, partials));
+        if (rows) {
+            if (flow) MOF_LAUNCH(k_prolong_flow, blocks_for(rows, B), B, 0, mg.agg.p + r0, mg.cevec.p + 3 * (size_t)r0, l1.z.p, rows, mg.fz.p + e0);
+            else MOF_LAUNCH(k_prolong_scalar, blocks_for(len, B), B, 0, mg.agg.p + r0, l1.z.p, rows, mg.fz.p + e0);
+        }
+        MOF_TRY(dist_halo(ctx, kind, mg.fz.p));
+        MOF_TRY(spmv((const creal*)mg.fval.p, r, mg.omega0, (const creal*)mg.fz.p, mg.fz2.p, 2, partials));
         MOF_TRY(reduce(FINE_GRID, rawSlot));
         std::swap(mg.fz.p, mg.fz2.p);
         return MOF_OK;
     };
 
-    MOF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * full, ctx->stream));
-    MOF_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * full, cudaMemcpyDeviceToDevice, ctx->stream));
-    MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, b + r0, b + r0, len, mg.partial.p);
+    if (zeroGuess) {
+        MOF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * full, ctx->stream));
+        MOF_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * full, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else  // x is complete on every rank: no exchange needed for the first residual
+        MOF_TRY(spmv(sysVal, b, 0., (const double*)x, r, 1, NO_FOLD));
+    MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, b + e0, b + e0, len, mg.partial.p);
     MOF_TRY(reduce(NBLK, R_BB));
-    double bb = 0;
-    MOF_CUDA(read_back(ctx, &bb, mg.scal.p + S_BB));
-    double rr = bb;
+    MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, r + e0, r + e0, len, mg.partial.p);
+    MOF_TRY(reduce(NBLK, R_RR));
+    double h2[2] = {0, 0};
+    MOF_CUDA(read_back(ctx, h2, mg.scal.p + S_RR, 2));
+    double rr = h2[0];
+    const double bb = h2[1];
     *itersOut = 0, *relresOut = 0;
-    if (!(bb > 0)) return MOF_OK;
+    if (!(bb > 0)) {
+        if (!zeroGuess) MOF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * full, ctx->stream));
+        return MOF_OK;
+    }
     int it = 0;
     long long launchesPerReplay = 0;
     for (int attempt = 0; attempt < 4 && rr > tol * tol * bb; attempt++) {
         MOF_TRY(cycle(false, R_RZ));
-        if (len) MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p + r0, mg.scal.p, len, 1, p + r0);
+        if (len) MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p + e0, mg.scal.p, len, 1, p + e0);
         auto iteration = [&](int half) -> int {
-            MOF_TRY(dist_halo(ctx, p));
-            MOF_TRY(spmv(double(), double(), ctx->wA.p, (const double*)nullptr, 0., p, q, 0, partials));
+            MOF_TRY(dist_halo(ctx, kind, p));
+            MOF_TRY(spmv(sysVal, (const double*)nullptr, 0., (const double*)p, q, 0, partials));
             MOF_TRY(reduce(FINE_GRID, R_PQ));
-            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p + r0, q + r0, len, x + r0, r + r0, mg.fdinv.p + r0, mg.omega0, 1, mg.fz.p + r0, partials);
+            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p + e0, q + e0, len, x + e0, r + e0, mg.fdinv.p + r0, mg.omega0, W, mg.fz.p + e0, partials);
             MOF_TRY(reduce(NBLK, R_RR));
             MOF_CUDA(cudaMemcpyAsync(mg.hostRR + half, mg.scal.p + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             MOF_TRY(cycle(true, R_RZNEW));
-            if (len) MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p + r0, mg.scal.p, len, 0, p + r0);
+            if (len) MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p + e0, mg.scal.p, len, 0, p + e0);
             return MOF_OK;
         };
         // Two iterations (kernels and NCCL operations alike) captured as one CUDA graph and replayed, as in mg_pcg;
@@ -1531,14 +1563,14 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, double 
         if (graph) cudaGraphDestroy(graph);
         if (lrc != MOF_OK) return lrc;
         // true residual of x
-        MOF_TRY(dist_halo(ctx, x));
-        MOF_TRY(spmv(double(), double(), ctx->wA.p, b, 0., x, r, 1, NO_FOLD));
-        MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, r + r0, r + r0, len, mg.partial.p);
+        MOF_TRY(dist_halo(ctx, kind, x));
+        MOF_TRY(spmv(sysVal, b, 0., (const double*)x, r, 1, NO_FOLD));
+        MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, r + e0, r + e0, len, mg.partial.p);
         MOF_TRY(reduce(NBLK, R_RR));
         MOF_CUDA(read_back(ctx, &rr, mg.scal.p + S_RR));
         if (it >= maxIters || !std::isfinite(rr)) break;
     }
-    MOF_TRY(dist_allgather_rows(ctx, x));
+    MOF_TRY(dist_allgather_rows(ctx, kind, x));
     *itersOut = it;
     *relresOut = std::sqrt(rr / bb);
     if (!std::isfinite(rr) || (!(*relresOut <= tol * 1.0001) && (it >= maxIters || !(*relresOut <= 1e-4)))) {
@@ -1562,7 +1594,7 @@ int mg_flow_update(mof_ctx* ctx) {
     return finish_values(ctx, mg);
 }
 int mg_flow_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double* relresOut) {
-    if (dist_active(ctx)) return mg_pcg_dist(ctx, *ctx->mg, ctx->fb.p, ctx->fx.p, tol, maxIters, itersOut, relresOut);
+    if (dist_active(ctx)) return mg_pcg_dist(ctx, *ctx->mg, ctx->fb.p, ctx->fx.p, true, tol, maxIters, itersOut, relresOut);
     return mg_pcg(ctx, *ctx->mg, ctx->fb.p, ctx->fx.p, true, tol, maxIters, itersOut, relresOut);
 }
 
@@ -1577,6 +1609,7 @@ int mg_scalar_update(mof_ctx* ctx) {
     return finish_values(ctx, mg);
 }
 int mg_scalar_solve(mof_ctx* ctx, const double* b6, double* x6, double tol, int maxIters, int* itersOut, double* relresOut) {
+    if (dist_active(ctx)) return mg_pcg_dist(ctx, *ctx->mgs, b6, x6, false, tol, maxIters, itersOut, relresOut);
     return mg_pcg(ctx, *ctx->mgs, b6, x6, false, tol, maxIters, itersOut, relresOut);
 }
 

@@ -65,6 +65,9 @@ def main():
             "ranks_agree": spread == 0.0, "repeatable": same_run, "colour_max_diff": float(max(np.abs(col_a - ref_a).max(), np.abs(col_b - ref_b).max())),
             "flow_solve_ms_partitioned": ms_d, "flow_solve_ms_single_gpu": s_s["flowSolveMs"], "flow_iterations_partitioned": s_d2["flowCgIterations"],
             "flow_iterations_single_gpu": s_s["flowCgIterations"], "halo_entries_rank0": s_d2["haloEntries"], "rows": s_d2["flowRows"],
+            "smooth_solve_ms_partitioned": s_d2["smoothSolveMs"], "smooth_solve_ms_single_gpu": s_s["smoothSolveMs"],
+            "smooth_iterations_partitioned": s_d2["smoothCgIterations"], "smooth_iterations_single_gpu": s_s["smoothCgIterations"],
+            "last_smooth_residual": s_d2["lastSmoothResidual"],
             "last_flow_residual": s_d2["lastFlowResidual"], "wall_s_partitioned": wall_d2, "wall_s_single_gpu": wall_s}
     sharding.barrier()
     if rank == 0:
