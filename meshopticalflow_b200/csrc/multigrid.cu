@@ -340,11 +340,15 @@ __global__ void k_coarsen_blocks(const int* __restrict__ firstChild, const int* 
 }
 
 // FLOW: pseudo-inverse of the diagonal 3x3 block through its eigen-decomposition (cyclic Jacobi rotations, accurate
-// for each eigenvalue separately). Cells on the fringe of the surface hold one or two edges, or coplanar ones: their
-// block is rank deficient and the directions with eigenvalue < 1e-8 * largest are simply not smoothed (they prolong
-// to ~0 on the edges anyway). An explicit cofactor inverse of such a block is NOT good enough: its error in the
-// well-conditioned directions scales with the condition number and the smoother stops being positive definite.
-__global__ void k_block_pinv(const double* __restrict__ blocks, int N, creal* __restrict__ binv) {
+// for each eigenvalue separately). Directions with eigenvalue < relTol * largest are not smoothed on that level:
+//  * cells on the fringe of the surface hold one or two edges, or coplanar ones, and their block is rank deficient;
+//  * inside a cell the surface is nearly flat, so the direction normal to it carries an eigenvalue ~(cell size x
+//    curvature)^2 of the tangential ones (2e-4 at 1M vertices, 1.5e-5 at 16M). Keeping it (relTol 1e-8) makes block
+//    Jacobi badly scaled on large meshes: at 16.8M vertices rho(Binv A) = 4.0 on level 1 and the solve stalls;
+//    with relTol = 1e-3 rho stays at 1.8 on every level and size (and 4M vertices need 164 iterations, not 194).
+// An explicit cofactor inverse of such a block is NOT good enough: its error in the well-conditioned directions scales
+// with the condition number and the smoother stops being positive definite.
+__global__ void k_block_pinv(const double* __restrict__ blocks, int N, double relTol, creal* __restrict__ binv) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= N) return;
     double m[9];
@@ -374,7 +378,7 @@ __global__ void k_block_pinv(const double* __restrict__ blocks, int N, creal* __
     double top = fmax(lam[0], fmax(lam[1], lam[2]));
     double inv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int e = 0; e < 3; e++) {
-        if (!(lam[e] > 1e-8 * top) || !(top > 0)) continue;
+        if (!(lam[e] > relTol * top) || !(top > 0)) continue;
         double il = 1. / lam[e];
         for (int r = 0; r < 3; r++)
             for (int c = 0; c < 3; c++) inv[3 * r + c] += il * Vm[3 * r + e] * Vm[3 * c + e];
@@ -1134,6 +1138,8 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
     // estimated by power iteration on I + Minv A (all eigenvalues of Minv A are positive). omega * rho < 2 keeps the
     // cycle positive definite; should an estimate ever be too low, PCG stalls and the caller falls back to Jacobi-PCG.
     const int powerIts = 10;
+    const char* pinvEnv = getenv("MOF_MG_PINV_TOL");
+    const double pinvTol = pinvEnv && *pinvEnv ? atof(pinvEnv) : 1e-3;
     {
         MOF_CUDA(cudaMemsetAsync(mg.fq.p, 0, sizeof(double) * len, ctx->stream));  // the zero right-hand side
         MOF_LAUNCH(k_pseudo_random, blocks_for((long long)len, B), B, 0, (long long)len, mg.fz.p);
@@ -1149,7 +1155,7 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
     for (int l = 0; l < mg.K; l++) {
         MgLevel& lv = mg.lev[l];
         MOF_LAUNCH(k_to_creal, kSMs * 4, B, 0, lv.blocks.p, (long long)lv.blocks.n, lv.cblocks.p);
-        if (mg.kind == MG_FLOW) MOF_LAUNCH(k_block_pinv, blocks_for(lv.N, B), B, 0, lv.blocks.p, lv.N, lv.binv.p);
+        if (mg.kind == MG_FLOW) MOF_LAUNCH(k_block_pinv, blocks_for(lv.N, B), B, 0, lv.blocks.p, lv.N, pinvTol, lv.binv.p);
         else MOF_LAUNCH(k_scalar_inv, blocks_for(lv.N, B), B, 0, lv.blocks.p, lv.N, lv.binv.p);
         if (l == mg.K - 1) break;
         const long long nd = (long long)D * lv.N;
