@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — 1M-vertex pair alignments/sec on B200 (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--level L]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--level L] [--partitioned]
 
 A step is one whole alignment of one signal pair on the synthetic 1 048 578-vertex sphere
 (BASELINE.json configs[2]): mesh-operator assembly, DoG normalisation, 10 UpdateFlow iterations and the
@@ -14,6 +14,8 @@ final halfway advection — what the reference does between loading its inputs a
           the device->host read of the advected colours are inside the timed region.
   N > 1   independent pairs sharded over the ranks (configs[3]), one process per GPU under torchrun, no
           data-path collective; weak scaling; time = max over ranks.
+          --partitioned (configs[4]): instead, ONE pair per step for the whole job, its linear solves row-partitioned
+          over the ranks (NCCL halo exchange + all-reduce); strong scaling; use with --level 10 / 11.
   roofline      the PCG's SpMV+dot kernel on the workload's own flow matrix, timed live with CUDA events.
   cpu_baseline  the reference's own binary (oracle/_ref, built from the unmodified sources) timed on this box's
                 host cores on a bounded sample, rank 0, N=1 only.
