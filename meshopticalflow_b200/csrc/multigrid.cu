@@ -4,7 +4,7 @@
 //   SCALAR  M + eps*S on the V vertices, six right-hand sides at once   (OpticalFlow.cpp:355, :828)
 // The reference factorises both exactly (Eigen SimplicialLDLT / LLT). An iterative solve with Jacobi needs
 // ~sqrt(cond) iterations (4 500 for the flow system at 3.1M unknowns, 1 900 for the first smoothing solve at 1M
-// vertices); one V-cycle per iteration brings that to ~100 and ~15.
+// vertices); one multigrid cycle per iteration brings that to ~70 and ~15.
 //
 // Construction (aggregation multigrid on an octree; built on the GPU, deterministic):
 //  * Aggregates are the occupied cells of a uniform grid over the unknowns' positions (edge midpoints / vertices);
@@ -18,10 +18,10 @@
 //    operator is a 27-point stencil (of 3x3 blocks / of scalars): no sparse pattern, no SpGEMM. The Galerkin
 //    coefficients are re-summed from the current matrix once per system (they follow the data term / eps); the
 //    octree, neighbour tables and per-entry stencil slots depend on the mesh only.
-//  * V(1,1) cycle with damped Jacobi smoothing (block 3x3 pseudo-inverse on the coarse FLOW levels), damping
-//    1.4 / rho with rho from a power iteration per level, which keeps the cycle symmetric positive definite so
-//    that plain PCG applies. One PCG iteration is ~60 small dependent launches: two iterations are captured as a
-//    CUDA graph and replayed.
+//  * (1,1) cycle — W on the large levels, V on the small ones, see Multigrid::gamma — with damped Jacobi smoothing
+//    (block 3x3 pseudo-inverse on the coarse FLOW levels), damping 1.4 / rho with rho from a power iteration per
+//    level, which keeps the cycle symmetric positive definite so that plain PCG applies. One PCG iteration is 40-70
+//    small dependent launches: two iterations are captured as a CUDA graph and replayed.
 // If a mesh does not fit the scheme, or a solve stalls, the callers fall back to the Jacobi-PCG kernel of
 // pcg_kernels.cu.
 #include <cmath>
@@ -87,7 +87,14 @@ struct Multigrid {
     DBuf<double> partial, scal;
     DBuf<unsigned> counter;         // arrival counter of the last-CTA folds (self-resetting)
     double omega0 = 0.6;
-    int gamma = 1, gammaLevels = 0; // gamma coarse corrections on the first gammaLevels coarse levels (W-cycle knob)
+    // Cycle shape: `gamma` coarse corrections per visit on the first `gammaLevels` coarse levels, one below. Default
+    // (gammaLevels < 0): W (gamma 2) on all but the four (FLOW) / five (SCALAR) coarsest levels — the large levels,
+    // where a second visit halves what PCG has left to do (flow solve at 1M vertices: 68 iterations instead of 108,
+    // 4M: 78 instead of 164, 16.8M: 88 instead of 250) at the cost of kernels that are still bandwidth-bound — and V
+    // on the small latency-bound levels, where a second visit costs as much as on a large one. Measured per level
+    // count; the smoothing systems are better conditioned (most of their solves take ~15 iterations) and want one
+    // W level less.
+    int gamma = 2, gammaLevels = -1;
     double* hostRR = nullptr;       // pinned (a slice of ctx->pinned): residual norms of the two iterations of one graph replay
     std::vector<double> hostBlocks, hostDense;
     std::vector<int> hostNbr;
@@ -984,8 +991,8 @@ Multigrid* new_mg(mof_ctx* ctx, Multigrid* old, MgKind kind, int nFine, int* rcO
     Multigrid* mg = old ? old : new Multigrid();
     mg->usable = false, mg->K = 0;
     mg->kind = kind, mg->nFine = nFine, mg->nrhs = kind == MG_FLOW ? 1 : 6;
-    mg->gamma = std::max(1, std::min(2, env_int("MOF_MG_GAMMA", 1)));
-    mg->gammaLevels = std::max(0, env_int("MOF_MG_GAMMA_LEVELS", 0));
+    mg->gamma = std::max(1, std::min(2, env_int("MOF_MG_GAMMA", 2)));
+    mg->gammaLevels = env_int(kind == MG_FLOW ? "MOF_MG_GAMMA_LEVELS" : "MOF_MG_GAMMA_LEVELS_SCALAR", -1);  // < 0: by depth, see coarse_cycle
     cudaError_t e = mg->partial.alloc(8192);  // per-CTA partials: NBLK of ours, or the persistent-grid size of k_spmv_dot
     if (e == cudaSuccess) e = mg->scal.alloc(64);
     if (e == cudaSuccess) e = mg->counter.alloc(4);
@@ -1257,7 +1264,8 @@ int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
     if (l == mg.K - 1) return MOF_OK;  // solved by the restriction that filled it
     MgLevel& up = mg.lev[l + 1];
     const bool upDense = l + 1 == mg.K - 1;
-    const int passes = l < mg.gammaLevels ? mg.gamma : 1;
+    const int wLevels = mg.gammaLevels >= 0 ? mg.gammaLevels : mg.K - (flow ? 4 : 5);
+    const int passes = l < wLevels ? mg.gamma : 1;
     for (int g = 0; g < passes; g++) {
         MOF_TRY(coarse_apply(ctx, mg, lv, lv.omega, 1, lv.t.p));
         if (upDense) {
