@@ -66,3 +66,20 @@ def test_cli_usage_and_flag_handling():
     assert "6-channel" in r.stderr and r.returncode != 0
     r = _run("--in", "/nonexistent/a.ply", "/nonexistent/b.ply", "--out", "x.ply")
     assert r.returncode != 0 and "Unable to read" in r.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` times the reference's CPU implementation (oracle/_ref, or the oracle port) on a
+    bounded sample and prints one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "1M-vertex pair alignments/sec" and line["unit"] == "alignments/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["vertices"] == 1048578
