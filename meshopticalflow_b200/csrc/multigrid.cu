@@ -25,8 +25,8 @@
 // If a mesh does not fit the scheme, or a solve stalls, the callers fall back to the Jacobi-PCG kernel of
 // pcg_kernels.cu.
 #include <cmath>
-#include <type_traits>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "mof_internal.cuh"
