@@ -25,7 +25,7 @@ extern "C" {
 #define MOF_E_CUDA -2         /* CUDA runtime error (message has the cudaError string) */
 #define MOF_E_MESH -3         /* non-manifold or open mesh: "[ERROR] Edge is occupied" (FEM.inl:599), "[ERROR] Boundary edge" (FEM.inl:554) */
 #define MOF_E_NOCONVERGE -4   /* PCG hit its iteration cap */
-#define MOF_E_UNSUPPORTED -5  /* a reference mode outside the accelerated path (vfMode 1|2, 6 channels) */
+#define MOF_E_UNSUPPORTED -5  /* a combination outside the accelerated path (e.g. a partitioned mesh with vfMode 1|2) */
 
 typedef struct mof_ctx mof_ctx;
 
@@ -35,14 +35,16 @@ typedef struct mof_params {
     int iterations;        /* --iterations 10 */
     double sSmooth;        /* --sSmooth 3e-3 (float literal in the reference) */
     double sMultiply;      /* --sMultiply 0.25 */
-    double vfSmooth;       /* --vfSmooth 3e-6 (Whitney) */
+    double vfSmooth;       /* --vfSmooth: 3e-6 (Whitney), 5e-7 (Conformal), 1e4 (Connection), OpticalFlow.cpp:1067-1069; <= 0 selects the mode's default */
     double vMultiply;      /* --vMultiply 1 */
     double vfSThreshold;   /* --vfSThreshold 1e-8 */
-    double dogWeight;      /* --dogWeight 1 (0 disables the DoG normalisation; 0<w<1 is MOF_E_UNSUPPORTED) */
+    double dogWeight;      /* --dogWeight 1 (0 disables the DoG normalisation; 0<w<1 blends raw and DoG signals as 6 channels, OpticalFlow.cpp:849-855, 1114) */
     double dogSmooth;      /* --dogSmooth 1e-4 */
     double flowTol;        /* relative residual ||r||/||b|| of the flow-system PCG, default 1e-8 */
     double smoothTol;      /* relative residual of the scalar smoothing PCG, default 1e-10 */
     int maxCgIterations;   /* PCG cap, default 100000 */
+    int vfMode;            /* --vfMode 0 Whitney | 1 Conformal | 2 Connection (VectorField.h:3-7); read by mof_set_signals */
+    int cMode;             /* --cMode 0 projected barycentric | 1 barycentric dual | 2 inverse cotangent (Connection.inl:1-5) */
 } mof_params;
 
 /* Counters since mof_create / mof_reset_stats. */
@@ -96,10 +98,13 @@ int mof_set_signals_device(mof_ctx* ctx, const double* d_a, const double* d_b, i
  * schedule continues across calls; mof_set_signals restarts it. */
 int mof_iterate(mof_ctx* ctx, int n);
 
-/* tFlowField (T x 2, OpticalFlow.cpp:280) and the Whitney coefficients (E, VectorField.h:20). */
+/* tFlowField (T x 2, OpticalFlow.cpp:280) and the basis coefficients (VectorField.h:20): mof_num_coeffs of them —
+ * E for Whitney (one per edge), 2V for Conformal ([potential; co-potential], Conformal.inl:14), 2T for Connection
+ * ([2t+r], Connection.inl:25). */
 int mof_get_flow(mof_ctx* ctx, double* tField);
 int mof_get_coeffs(mof_ctx* ctx, double* coeffs);
 int mof_num_edges(mof_ctx* ctx);
+long long mof_num_coeffs(mof_ctx* ctx);
 
 /* InputGeometryData::flow (OpticalFlow.cpp:482-489): the raw signals resampled along -alpha and
  * 1-alpha of the flow (ResampleSignal, :198-216). outA/outB: V x 3. */
@@ -142,8 +147,9 @@ enum {
     MOF_ARR_RESAMPLED = 11,      /* V x 6      last iteration's resampled signals (:439) */
     MOF_ARR_DATA_TERM = 12,      /* T x 3      (d00,d01,d11) (:395-421) */
     MOF_ARR_DATA_RHS = 13,       /* T x 2 */
-    MOF_ARR_FLOW_RHS = 14,       /* E          scaled R*rhs (VectorField.h:53,60) */
-    MOF_ARR_FLOW_SOLUTION = 15   /* E          solution of the last flow system (VectorField.h:85) */
+    MOF_ARR_FLOW_RHS = 14,       /* mof_num_coeffs   scaled R*rhs (VectorField.h:53,60) */
+    MOF_ARR_FLOW_SOLUTION = 15,  /* mof_num_coeffs   solution of the last flow system (VectorField.h:85) */
+    MOF_ARR_SIGNALS_RAW = 16     /* V x 6      6-channel blend only: the (1-w)*raw half of flowData.signals; MOF_ARR_SIGNALS is the w*DoG half */
 };
 /* bytes needed for one array (0 if not available yet), then copy out. */
 long long mof_array_bytes(mof_ctx* ctx, int which);

@@ -19,19 +19,22 @@ MOF_OK, MOF_E_INVALID, MOF_E_CUDA, MOF_E_MESH, MOF_E_NOCONVERGE, MOF_E_UNSUPPORT
 
 CSR_SCALAR_MASS, CSR_SCALAR_STIFFNESS, CSR_WHITNEY_SMOOTH, CSR_FLOW_SYSTEM = range(4)
 (ARR_METRIC, ARR_AREA, ARR_OPPOSITE, ARR_XFORM_LINEAR, ARR_XFORM_CONSTANT, ARR_REDUCED_EDGE, ARR_EXPANDED_EDGE, ARR_POSITIVE_EDGE,
- ARR_PROLONGATION, ARR_SIGNALS, ARR_SMOOTHED, ARR_RESAMPLED, ARR_DATA_TERM, ARR_DATA_RHS, ARR_FLOW_RHS, ARR_FLOW_SOLUTION) = range(16)
+ ARR_PROLONGATION, ARR_SIGNALS, ARR_SMOOTHED, ARR_RESAMPLED, ARR_DATA_TERM, ARR_DATA_RHS, ARR_FLOW_RHS, ARR_FLOW_SOLUTION, ARR_SIGNALS_RAW) = range(17)
+
+VF_WHITNEY, VF_CONFORMAL, VF_CONNECTION = range(3)  # --vfMode, VectorField.h:3-7
 
 _ARRAY_SPEC = {
     ARR_METRIC: (np.float64, 3), ARR_AREA: (np.float64, None), ARR_OPPOSITE: (np.int32, None), ARR_XFORM_LINEAR: (np.float64, 4),
     ARR_XFORM_CONSTANT: (np.float64, 2), ARR_REDUCED_EDGE: (np.int32, None), ARR_EXPANDED_EDGE: (np.int32, None), ARR_POSITIVE_EDGE: (np.int32, None),
     ARR_PROLONGATION: (np.float64, 6), ARR_SIGNALS: (np.float64, 6), ARR_SMOOTHED: (np.float64, 6), ARR_RESAMPLED: (np.float64, 6),
     ARR_DATA_TERM: (np.float64, 3), ARR_DATA_RHS: (np.float64, 2), ARR_FLOW_RHS: (np.float64, None), ARR_FLOW_SOLUTION: (np.float64, None),
+    ARR_SIGNALS_RAW: (np.float64, 6),
 }
 
 # Every symbol include/mof_b200.h declares (the CPU test tier checks the library exports them all).
 EXPORTED_SYMBOLS = [
     "mof_default_params", "mof_create", "mof_destroy", "mof_last_error", "mof_set_params", "mof_get_stats", "mof_reset_stats", "mof_synchronize",
-    "mof_set_mesh", "mof_set_mesh_device", "mof_set_signals", "mof_set_signals_device", "mof_iterate", "mof_get_flow", "mof_get_coeffs", "mof_num_edges",
+    "mof_set_mesh", "mof_set_mesh_device", "mof_set_signals", "mof_set_signals_device", "mof_iterate", "mof_get_flow", "mof_get_coeffs", "mof_num_edges", "mof_num_coeffs",
     "mof_advect_vertices", "mof_advect_vertices_device", "mof_set_texture_map", "mof_advect_texels", "mof_csr_size", "mof_get_csr", "mof_array_bytes",
     "mof_get_array", "mof_pcg_solve_csr", "mof_time_flow_spmv", "mof_dist_unique_id", "mof_dist_init",
 ]
@@ -40,7 +43,7 @@ EXPORTED_SYMBOLS = [
 class Params(ctypes.Structure):
     _fields_ = [("iterations", c_int), ("sSmooth", c_double), ("sMultiply", c_double), ("vfSmooth", c_double), ("vMultiply", c_double),
                 ("vfSThreshold", c_double), ("dogWeight", c_double), ("dogSmooth", c_double), ("flowTol", c_double), ("smoothTol", c_double),
-                ("maxCgIterations", c_int)]
+                ("maxCgIterations", c_int), ("vfMode", c_int), ("cMode", c_int)]
 
 
 class Stats(ctypes.Structure):
@@ -96,6 +99,8 @@ def load_library():
     lib.mof_get_flow.argtypes = [c_void_p, D]
     lib.mof_get_coeffs.argtypes = [c_void_p, D]
     lib.mof_num_edges.argtypes = [c_void_p]
+    lib.mof_num_coeffs.argtypes = [c_void_p]
+    lib.mof_num_coeffs.restype = c_longlong
     lib.mof_advect_vertices.argtypes = [c_void_p, c_double, D, D]
     lib.mof_advect_vertices_device.argtypes = [c_void_p, c_double, c_void_p, c_void_p]
     lib.mof_set_texture_map.argtypes = [c_void_p, c_int, c_int, I, D, D, POINTER(c_ubyte), POINTER(c_ubyte)]
@@ -221,8 +226,13 @@ class Aligner:
         self._check(self._lib.mof_get_flow(self._ctx, _d(out)))
         return out
 
+    @property
+    def num_coeffs(self) -> int:
+        """Unknowns of the flow basis in use: E (Whitney), 2V (Conformal), 2T (Connection)."""
+        return self._lib.mof_num_coeffs(self._ctx)
+
     def coeffs(self):
-        out = np.empty(self.num_edges)
+        out = np.empty(self.num_coeffs)
         self._check(self._lib.mof_get_coeffs(self._ctx, _d(out)))
         return out
 

@@ -79,11 +79,14 @@ __global__ void k_mul(const double* __restrict__ a, const double* __restrict__ b
 
 // ---------------------------------------------------------------- scalar smoothing (a9) and DoG (a5)
 
-static int smooth_solve(mof_ctx* ctx, double weight, const double* in6, double* out6, double tol) {
+// `sameSystem`: the matrix, its inverse diagonal and the multigrid coarse operators are those of the previous call.
+static int smooth_solve(mof_ctx* ctx, double weight, const double* in6, double* out6, double tol, bool sameSystem = false) {
     const int V = ctx->V;
     // sM = sMass + weight * sStiffness (OpticalFlow.cpp:355); b = sMass * x (:363); x0 = the signal itself
-    MOF_LAUNCH(k_axpby, blocks_for(ctx->nnzS, B), B, 0, ctx->sMass.p, ctx->sStiff.p, weight, ctx->nnzS, ctx->sSys.p);
-    MOF_TRY(extract_inverse_diagonal(ctx, V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, ctx->sDinv.p));
+    if (!sameSystem) {
+        MOF_LAUNCH(k_axpby, blocks_for(ctx->nnzS, B), B, 0, ctx->sMass.p, ctx->sStiff.p, weight, ctx->nnzS, ctx->sSys.p);
+        MOF_TRY(extract_inverse_diagonal(ctx, V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, ctx->sDinv.p));
+    }
     MOF_CUDA(ctx->rhs6.reserve(6ull * V));
     MOF_LAUNCH(k_spmv6, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sMass.p, in6, V, ctx->rhs6.p);
     if (out6 != in6) MOF_CUDA(cudaMemcpyAsync(out6, in6, sizeof(double) * 6 * V, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -92,7 +95,7 @@ static int smooth_solve(mof_ctx* ctx, double weight, const double* in6, double* 
     MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     int rc = MOF_OK;
     bool solved = false;
-    if (mg_scalar_usable(ctx)) rc = mg_scalar_update(ctx);
+    if (mg_scalar_usable(ctx) && !sameSystem) rc = mg_scalar_update(ctx);
     if (rc == MOF_OK && mg_scalar_usable(ctx)) {
         // multigrid-preconditioned PCG over the six channels at once; a stalled solve falls through to Jacobi-PCG
         int mrc = mg_scalar_solve(ctx, ctx->rhs6.p, out6, tol, std::min(ctx->params.maxCgIterations, 400), &iters, &relres);
@@ -130,6 +133,12 @@ __global__ void k_dog_finish(const double* __restrict__ x, const double* __restr
     double scale = sqrt(oldVar / newVar);
     out[i] = (x[i] - newAvg) * scale + oldAvg;
 }
+// The Channels == 6 branch, OpticalFlow.cpp:855: raw * (1 - w) and DoG * w side by side (here: in two V x 6 arrays).
+__global__ void k_dog_blend(const double* __restrict__ raw, double w, long long n, double* __restrict__ dog, double* __restrict__ lo) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lo[i] = raw[i] * (1. - w), dog[i] *= w;
+}
 
 // Difference-of-Gaussians normalisation, OpticalFlow.cpp:822-857 (3-channel branch), all six
 // channels at once. getIntegral (FEM.inl:2081-2098) is the dot product with the barycentric
@@ -141,6 +150,12 @@ int dog_preprocess(mof_ctx* ctx) {
     MOF_CUDA(ctx->smoothed6.alloc(6ull * V));
     MOF_CUDA(ctx->resampled6.alloc(6ull * V));
     MOF_CUDA(ctx->rhs6.alloc(6ull * V));
+    ctx->blend = ctx->params.dogWeight > 0 && ctx->params.dogWeight < 1;
+    if (ctx->blend) {
+        MOF_CUDA(ctx->sigLo6.alloc(6ull * V));
+        MOF_CUDA(ctx->smoothedLo6.alloc(6ull * V));
+        MOF_CUDA(ctx->resampledLo6.alloc(6ull * V));
+    }
     if (!(ctx->params.dogWeight > 0)) {
         MOF_CUDA(cudaMemcpyAsync(ctx->sig6.p, ctx->raw6.p, sizeof(double) * 6 * V, cudaMemcpyDeviceToDevice, ctx->stream));
         return MOF_OK;
@@ -156,6 +171,7 @@ int dog_preprocess(mof_ctx* ctx) {
     MOF_TRY(dot6(ctx, x, nullptr, ctx->m0.p, V, sc + 2, 4));
     MOF_TRY(dot6(ctx, x, mb, nullptr, V, sc + 3, 4));
     MOF_LAUNCH(k_dog_finish, blocks_for(6ll * V, B), B, 0, x, sc, V, ctx->sig6.p);
+    if (ctx->blend) MOF_LAUNCH(k_dog_blend, blocks_for(6ll * V, B), B, 0, ctx->raw6.p, ctx->params.dogWeight, 6ll * V, ctx->sig6.p, ctx->sigLo6.p);
     return MOF_OK;
 }
 
@@ -272,22 +288,26 @@ int advect_vertices(mof_ctx* ctx, const double* in6, double lenA, double lenB, d
 
 // SetDataTerm, OpticalFlow.cpp:395-421, with the k<2 right-hand side the optimised reference build
 // computes. D = sum_c gamma gamma^T area, rhs = sum_c gamma meanDiff area.
-__global__ void k_data_term(const int* __restrict__ tri, const double* __restrict__ area, const double* __restrict__ sig6, int T, double* __restrict__ D,
-                            double* __restrict__ rhs) {
+// `lo6` (6-channel blend only, else null): the raw half of the signals, channels 0-2 of the reference's Point<Real,6>.
+__global__ void k_data_term(const int* __restrict__ tri, const double* __restrict__ area, const double* __restrict__ sig6, const double* __restrict__ lo6, int T,
+                            double* __restrict__ D, double* __restrict__ rhs) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
-    const double* v0 = sig6 + (size_t)tri[3 * t] * 6;
-    const double* v1 = sig6 + (size_t)tri[3 * t + 1] * 6;
-    const double* v2 = sig6 + (size_t)tri[3 * t + 2] * 6;
     double ar = area[t];
     double d00 = 0, d01 = 0, d10 = 0, d11 = 0, r0 = 0, r1 = 0;
+    for (int set = lo6 ? 0 : 1; set < 2; set++) {
+        const double* sig = set ? sig6 : lo6;
+        const double* v0 = sig + (size_t)tri[3 * t] * 6;
+        const double* v1 = sig + (size_t)tri[3 * t + 1] * 6;
+        const double* v2 = sig + (size_t)tri[3 * t + 2] * 6;
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        double f0 = (v0[c] + v0[c + 3]) / 2.0, f1 = (v1[c] + v1[c + 3]) / 2.0, f2 = (v2[c] + v2[c + 3]) / 2.0;
-        double meanDiff = ((v0[c] - v0[c + 3]) + (v1[c] - v1[c + 3]) + (v2[c] - v2[c + 3])) / 3;
-        double ga = f1 - f0, gb = f2 - f0;
-        d00 += ga * ga * ar, d01 += ga * gb * ar, d10 += gb * ga * ar, d11 += gb * gb * ar;
-        r0 += ga * meanDiff * ar, r1 += gb * meanDiff * ar;
+        for (int c = 0; c < 3; c++) {
+            double f0 = (v0[c] + v0[c + 3]) / 2.0, f1 = (v1[c] + v1[c + 3]) / 2.0, f2 = (v2[c] + v2[c + 3]) / 2.0;
+            double meanDiff = ((v0[c] - v0[c + 3]) + (v1[c] - v1[c + 3]) + (v2[c] - v2[c + 3])) / 3;
+            double ga = f1 - f0, gb = f2 - f0;
+            d00 += ga * ga * ar, d01 += ga * gb * ar, d10 += gb * ga * ar, d11 += gb * gb * ar;
+            r0 += ga * meanDiff * ar, r1 += gb * meanDiff * ar;
+        }
     }
     (void)d10;
     D[3 * t] = d00, D[3 * t + 1] = d01, D[3 * t + 2] = d11;
@@ -404,8 +424,19 @@ int update_flow(mof_ctx* ctx, double sWeight, double vfWeight) {
         MOF_CUDA(cudaMemcpyAsync(ctx->smoothed6.p, ctx->sig6.p, sizeof(double) * 6 * V, cudaMemcpyDeviceToDevice, ctx->stream));
     // halfway advection of both (:439)
     MOF_TRY(advect_vertices(ctx, smoothed, -0.5, 0.5, ctx->resampled6.p));
+    if (ctx->blend) {
+        // channels 0-2 of the 6-channel signals: the same system, a second solve; the same walks, a second sampling
+        const double* lo = ctx->sigLo6.p;
+        if (sWeight) {
+            MOF_TRY(smooth_solve(ctx, sWeight, ctx->sigLo6.p, ctx->smoothedLo6.p, ctx->params.smoothTol, true));
+            lo = ctx->smoothedLo6.p;
+        }
+        MOF_TRY(advect_vertices(ctx, lo, -0.5, 0.5, ctx->resampledLo6.p));
+    }
     // data term (:470)
-    MOF_LAUNCH(k_data_term, blocks_for(T, B), B, 0, ctx->tri.p, ctx->area.p, ctx->resampled6.p, T, ctx->dataD.p, ctx->dataRhs.p);
+    MOF_LAUNCH(k_data_term, blocks_for(T, B), B, 0, ctx->tri.p, ctx->area.p, ctx->resampled6.p, ctx->blend ? ctx->resampledLo6.p : nullptr, T, ctx->dataD.p,
+               ctx->dataRhs.p);
+    if (vf_active(ctx)) return vf_update_flow(ctx, vfWeight);  // Conformal / Connection basis (vector_fields.cu)
     // system (VectorField.h:51-67)
     MOF_CUDA(ctx->dtmp0.reserve((size_t)(E > T ? E : T)));
     MOF_LAUNCH(k_flow_rows, blocks_for(E, B), B, 0, ctx->expanded.p, ctx->reduced.p, ctx->opp.p, ctx->P.p, ctx->dataD.p, ctx->dataRhs.p, ctx->wRowptr.p,

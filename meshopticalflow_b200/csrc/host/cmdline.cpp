@@ -31,9 +31,10 @@ void show_usage(const char* exe, const Options& d) {
     printf("\t[--dogSmooth <difference of Gaussians smoothing weight>=%g]\n", d.dogSmooth);
     printf("Vector Field Parameters: \n");
     printf("\t[--vfMode <vector field mode >=%d]\n", d.vfMode);
-    printf("\t \t [0] Whitney \n\t \t [1] Conformal (not in this build)\n\t \t [2] Connection (not in this build)\n");
+    printf("\t \t [0] Whitney \n\t \t [1] Conformal \n\t \t [2] Connection \n");
     printf("\t[--cMode <connection mode >=%d]\n", d.cMode);
-    printf("\t[--vfSmooth <vector field smoothing weight>= Whitney -> %g]\n", 3e-6);
+    printf("\t \t [0] Projected baricentric \n\t \t [1] Baricentric dual \n\t \t [2] Inverse cotangents \n");
+    printf("\t[--vfSmooth <vector field smoothing weight>= Whitney -> %g,Conformal -> %g,Connection -> %g]\n", 3e-6, 5e-7, 1e4);
     printf("\t[--vMultiply <vector field weight multiplication factor>=%g]\n", d.vMultiply);
     printf("\t[--vfSThreshold <vector field weight threshold>=%g]\n", d.vfSThreshold);
     printf("Auxiliar Parameters: \n");

@@ -61,12 +61,12 @@ int main(int argc, char* argv[]) {
     }
     if (opt.search <= 0) fprintf(stderr, "[WARNING] Search range must be positive: %g<=0\n", opt.search);
     opt.dogWeight = std::min(1.f, std::max(0.f, opt.dogWeight));
-    if (opt.dogWeight > 0 && opt.dogWeight < 1) {
-        fprintf(stderr, "[ERROR] 0<dogWeight<1 selects the 6-channel blend (OpticalFlow.cpp:1114), which this build does not accelerate\n");
-        return EXIT_FAILURE;
+    if (opt.vfMode < 0 || opt.vfMode > 2) {
+        printf("ERROR: Unsupported vector field! \n");  // OpticalFlow.cpp:867
+        return 0;
     }
-    if (opt.vfMode != 0) {
-        fprintf(stderr, "[ERROR] --vfMode %d: only the Whitney vector field (0) is part of this build\n", opt.vfMode);
+    if (opt.vfMode == 2 && (opt.cMode < 0 || opt.cMode > 2)) {
+        printf("Undefined Connection Mode \n");  // Connection.inl:68
         return EXIT_FAILURE;
     }
     if (!opt.outSet) {
@@ -183,7 +183,9 @@ int main(int argc, char* argv[]) {
     mof_default_params(&params);
     params.iterations = opt.iterations;
     params.sSmooth = (double)opt.sSmooth, params.sMultiply = (double)opt.sMultiply;
-    params.vfSmooth = opt.vfSmoothSet ? (double)opt.vfSmooth : 3e-6;
+    const double vfSmoothDefault[3] = {3e-6, 5e-7, 1e4};  // _main, OpticalFlow.cpp:1064-1069
+    params.vfSmooth = opt.vfSmoothSet ? (double)opt.vfSmooth : vfSmoothDefault[opt.vfMode];
+    params.vfMode = opt.vfMode, params.cMode = opt.cMode;
     params.vMultiply = (double)opt.vMultiply, params.vfSThreshold = (double)opt.vfSThreshold;
     params.dogWeight = (double)opt.dogWeight, params.dogSmooth = (double)opt.dogSmooth;
     params.flowTol = opt.flowTol, params.smoothTol = opt.smoothTol;

@@ -60,11 +60,17 @@ int finish_mesh(mof_ctx* ctx) {
 
 int finish_signals(mof_ctx* ctx) {
     ctx->haveSignals = false;
+    if (ctx->params.vfMode != 0 && dist_active(ctx))
+        return fail(ctx, MOF_E_UNSUPPORTED, "[ERROR] a partitioned mesh (mof_dist_init) supports the Whitney vector field only");
     MOF_TRY(dog_preprocess(ctx));
-    MOF_CUDA(cudaMemsetAsync(ctx->coeffs.p, 0, sizeof(double) * ctx->E, ctx->stream));
+    MOF_TRY(vf_init(ctx));  // VectorField::Init for --vfMode 1|2 (OpticalFlow.cpp:862-871); Whitney was built with the mesh
+    MOF_CUDA(cudaMemsetAsync(ctx->coeffs.p, 0, sizeof(double) * vf_unknowns(ctx), ctx->stream));
     MOF_CUDA(cudaMemsetAsync(ctx->tfield.p, 0, sizeof(double) * 2 * ctx->T, ctx->stream));
     ctx->iterationsDone = 0;
-    ctx->curSmooth = ctx->params.sSmooth, ctx->curVf = ctx->params.vfSmooth;
+    ctx->curSmooth = ctx->params.sSmooth;
+    // _main, OpticalFlow.cpp:1064-1069: the smoothing weight's default depends on the basis
+    const double vfDefault[3] = {3e-6, 5e-7, 1e4};
+    ctx->curVf = ctx->params.vfSmooth > 0 ? ctx->params.vfSmooth : vfDefault[ctx->params.vfMode];
     ctx->haveSignals = true, ctx->haveFlowSystem = false;
     return MOF_OK;
 }
@@ -86,6 +92,8 @@ void mof_default_params(mof_params* p) {
     p->flowTol = 1e-8;
     p->smoothTol = 1e-10;
     p->maxCgIterations = 100000;
+    p->vfMode = 0;                    // WHITNEY_VECTOR_FIELD, OpticalFlow.cpp:58
+    p->cMode = 0;                     // PROJECTED_BARICENTRIC_WEIGHTS
 }
 
 int mof_create(int device, void* stream, mof_ctx** out) {
@@ -123,7 +131,7 @@ void mof_destroy(mof_ctx* ctx) {
     DBuf<double>* dbl[] = {&ctx->pos, &ctx->g, &ctx->area, &ctx->xlin, &ctx->xcst, &ctx->sMass, &ctx->sStiff, &ctx->sSys, &ctx->sDinv, &ctx->P, &ctx->m0, &ctx->m1,
                            &ctx->wS, &ctx->wA, &ctx->wDinv, &ctx->raw6, &ctx->sig6, &ctx->smoothed6, &ctx->rhs6, &ctx->resampled6, &ctx->tsample6, &ctx->dataD,
                            &ctx->dataRhs, &ctx->coeffs, &ctx->tfield, &ctx->fb, &ctx->fx, &ctx->scalars, &ctx->pcg.r, &ctx->pcg.d, &ctx->pcg.q, &ctx->pcg.partial,
-                           &ctx->pcg.result, &ctx->dtmp0, &ctx->dtmp1, &ctx->dtmp2, &ctx->srcP, &ctx->triUV, &ctx->texOut};
+                           &ctx->pcg.result, &ctx->dtmp0, &ctx->dtmp1, &ctx->dtmp2, &ctx->srcP, &ctx->triUV, &ctx->texOut, &ctx->sigLo6, &ctx->smoothedLo6, &ctx->resampledLo6};
     for (auto* b : dbl) b->release();
     DBuf<int>* ints[] = {&ctx->tri, &ctx->opp, &ctx->sRowptr, &ctx->sCol, &ctx->sHe, &ctx->reduced, &ctx->expanded, &ctx->positive, &ctx->wRowptr, &ctx->wSliceBase, &ctx->wCol,
                          &ctx->itmp0, &ctx->itmp1, &ctx->itmp2, &ctx->flags, &ctx->srcT};
@@ -131,6 +139,7 @@ void mof_destroy(mof_ctx* ctx) {
     ctx->hashKeys.release(), ctx->tex[0].release(), ctx->tex[1].release();
     mg_destroy(ctx);
     dist_destroy(ctx);
+    vf_destroy(ctx);
     cudaStreamSynchronize(ctx->stream);  // the frees above are stream-ordered
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -143,8 +152,10 @@ const char* mof_last_error(const mof_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int mof_set_params(mof_ctx* ctx, const mof_params* p) {
     if (!ctx || !p) return MOF_E_INVALID;
-    if (p->dogWeight > 0 && p->dogWeight < 1)
-        return fail(ctx, MOF_E_UNSUPPORTED, "[ERROR] 0<dogWeight<1 selects the reference's 6-channel path (OpticalFlow.cpp:1114), which is outside the accelerated path");
+    if (p->vfMode < 0 || p->vfMode > 2) return fail(ctx, MOF_E_INVALID, "ERROR: Unsupported vector field! ");  // OpticalFlow.cpp:867
+    if (p->vfMode == 2 && (p->cMode < 0 || p->cMode > 2)) return fail(ctx, MOF_E_INVALID, "Undefined Connection Mode ");  // Connection.inl:68
+    if ((p->vfMode != ctx->params.vfMode || p->cMode != ctx->params.cMode || (p->dogWeight != ctx->params.dogWeight)) && ctx->haveSignals)
+        ctx->haveSignals = false;  // the basis and the DoG blend are fixed by mof_set_signals: it has to be called again
     if (p->iterations < 0 || !(p->flowTol > 0) || !(p->smoothTol > 0) || p->maxCgIterations < 1) return fail(ctx, MOF_E_INVALID, "bad solver parameters");
     ctx->params = *p;
     return MOF_OK;
@@ -236,6 +247,7 @@ int mof_iterate(mof_ctx* ctx, int n) {
 }
 
 int mof_num_edges(mof_ctx* ctx) { return ctx && ctx->haveMesh ? ctx->E : -1; }
+long long mof_num_coeffs(mof_ctx* ctx) { return ctx && ctx->haveMesh ? vf_unknowns(ctx) : -1; }
 
 int mof_get_flow(mof_ctx* ctx, double* tField) {
     if (!ctx || !tField) return MOF_E_INVALID;
@@ -247,7 +259,7 @@ int mof_get_flow(mof_ctx* ctx, double* tField) {
 int mof_get_coeffs(mof_ctx* ctx, double* coeffs) {
     if (!ctx || !coeffs) return MOF_E_INVALID;
     MOF_TRY(require_mesh(ctx));
-    MOF_CUDA(cudaMemcpyAsync(coeffs, ctx->coeffs.p, sizeof(double) * ctx->E, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(coeffs, ctx->coeffs.p, sizeof(double) * vf_unknowns(ctx), cudaMemcpyDeviceToHost, ctx->stream));
     MOF_CUDA(cudaStreamSynchronize(ctx->stream));
     return MOF_OK;
 }
@@ -316,6 +328,12 @@ static int csr_view(mof_ctx* ctx, int which, int* rows, long long* nnz, const in
     switch (which) {
         case MOF_CSR_SCALAR_MASS: *rows = ctx->V, *nnz = ctx->nnzS, *rowptr = ctx->sRowptr.p, *col = ctx->sCol.p, *val = ctx->sMass.p; return MOF_OK;
         case MOF_CSR_SCALAR_STIFFNESS: *rows = ctx->V, *nnz = ctx->nnzS, *rowptr = ctx->sRowptr.p, *col = ctx->sCol.p, *val = ctx->sStiff.p; return MOF_OK;
+        case MOF_CSR_FLOW_SYSTEM:
+            if (vf_active(ctx)) return fail(ctx, MOF_E_UNSUPPORTED, "the Conformal / Connection flow systems are applied matrix-free: there is no assembled matrix to return");
+            break;
+        default: break;
+    }
+    switch (which) {
         case MOF_CSR_WHITNEY_SMOOTH: *rows = ctx->E, *nnz = ctx->nnzW, *rowptr = ctx->wRowptr.p, *col = ctx->wCol.p, *val = ctx->wS.p; return MOF_OK;
         case MOF_CSR_FLOW_SYSTEM:
             if (!ctx->haveFlowSystem) return fail(ctx, MOF_E_INVALID, "no flow system yet: call mof_iterate first");
@@ -378,6 +396,10 @@ static const void* array_view(mof_ctx* ctx, int which, long long* bytes) {
     if (!ctx->haveSignals) return nullptr;
     switch (which) {
         case MOF_ARR_SIGNALS: *bytes = 8 * 6 * V; return ctx->sig6.p;
+        case MOF_ARR_SIGNALS_RAW:
+            if (!ctx->blend) return nullptr;
+            *bytes = 8 * 6 * V;
+            return ctx->sigLo6.p;
         default: break;
     }
     if (!ctx->haveFlowSystem) return nullptr;
@@ -386,8 +408,8 @@ static const void* array_view(mof_ctx* ctx, int which, long long* bytes) {
         case MOF_ARR_RESAMPLED: *bytes = 8 * 6 * V; return ctx->resampled6.p;
         case MOF_ARR_DATA_TERM: *bytes = 8 * 3 * T; return ctx->dataD.p;
         case MOF_ARR_DATA_RHS: *bytes = 8 * 2 * T; return ctx->dataRhs.p;
-        case MOF_ARR_FLOW_RHS: *bytes = 8 * E; return ctx->fb.p;
-        case MOF_ARR_FLOW_SOLUTION: *bytes = 8 * E; return ctx->fx.p;
+        case MOF_ARR_FLOW_RHS: *bytes = 8 * vf_unknowns(ctx); return vf_active(ctx) ? vf_rhs(ctx) : ctx->fb.p;
+        case MOF_ARR_FLOW_SOLUTION: *bytes = 8 * vf_unknowns(ctx); return vf_active(ctx) ? vf_solution(ctx) : ctx->fx.p;
         default: break;
     }
     return nullptr;
@@ -447,6 +469,7 @@ int mof_time_flow_spmv(mof_ctx* ctx, int reps, float* msPerLaunch) {
     if (!ctx || reps < 1 || !msPerLaunch) return MOF_E_INVALID;
     MOF_TRY(require_mesh(ctx));
     if (!ctx->haveFlowSystem) return fail(ctx, MOF_E_INVALID, "no flow system yet: call mof_iterate first");
+    if (vf_active(ctx)) return fail(ctx, MOF_E_UNSUPPORTED, "mof_time_flow_spmv times the Whitney flow matrix");
     StreamScope scope(ctx);
     MOF_CUDA(ctx->pcg.q.reserve(ctx->E));
     return time_spmv_sell(ctx, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, ctx->fx.p, ctx->pcg.q.p, reps, msPerLaunch);

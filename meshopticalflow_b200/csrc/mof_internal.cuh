@@ -1,7 +1,13 @@
 // Internal declarations shared by the .cu files of libmof_b200.so. Not part of the C ABI.
 #pragma once
 
+// MOF_HOST_EMULATION (tests/host_emulation, CPU test tier only): the CUDA runtime calls and the launch syntax are
+// replaced by host stand-ins so that whole .cu files can be compiled by g++ and run one "thread" at a time.
+#ifdef MOF_HOST_EMULATION
+#include "emul_cuda_runtime.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -11,9 +17,9 @@
 
 #include "../../include/mof_b200.h"
 
-namespace mof {
+#include "mof_slots.h"
 
-constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+namespace mof {
 
 // Device buffers come from CUDA's stream-ordered pool (cudaMallocAsync / cudaFreeAsync on the context's stream, release
 // threshold raised in mof_create): re-running the setup for a new mesh or pair re-uses the pool's memory without
@@ -52,17 +58,6 @@ struct DBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
-// Device-side scalar slots (one small buffer, fp64).
-enum ScalarSlot {
-    SC_AREA_SCALE = 0,   // 2 / sum sqrt det g
-    SC_FROB2 = 1,        // ||R D P||_F^2
-    SC_DATA_SCALE = 2,   // 1 / ||R D P||_F
-    SC_STEP_NUM = 3,     // x . b
-    SC_STEP_DEN = 4,     // x . Dt x
-    SC_DOG = 8,          // 8..8+4*6: per channel old avg, old dot, new avg, new dot
-    SC_COUNT = 64
-};
-
 // Sliced storage of the E x E Whitney operators (SELL-32): rows are grouped by 32 (one warp), every
 // group is padded to its longest row and stored entry-major, i.e. entry j of row r lives at
 // sliceBase[r / 32] + 32 * j + r % 32. A warp that owns a slice reads 32 consecutive words per entry
@@ -76,6 +71,7 @@ __host__ __device__ __forceinline__ size_t sell_pos(const int* sliceBase, int ro
 
 struct Multigrid;  // multigrid.cu
 struct DistState;  // dist.cu
+struct VfState;    // vector_fields.cu
 
 struct PcgWork {
     DBuf<double> r, d, q;       // [n * nrhs]
@@ -121,6 +117,10 @@ struct mof_ctx {
     mof::Multigrid* mg = nullptr;   // multilevel preconditioner of the flow system
     mof::Multigrid* mgs = nullptr;  // ... and of the scalar smoothing systems
     mof::DistState* dist = nullptr; // one mesh over several GPUs (dist.cu); nullptr = single GPU
+    mof::VfState* vf = nullptr;     // Conformal / Connection basis of the signals in place (vector_fields.cu); nullptr = Whitney
+    // 6-channel blend (0 < dogWeight < 1, OpticalFlow.cpp:849-855): sig6 holds the DoG half (times w), these the raw half (times 1-w)
+    bool blend = false;
+    mof::DBuf<double> sigLo6, smoothedLo6, resampledLo6;
     // scratch
     mof::DBuf<int> itmp0, itmp1, itmp2, flags;
     mof::DBuf<unsigned long long> hashKeys;
@@ -184,6 +184,13 @@ struct PhaseTimer {
 };
 
 // Counts a kernel launch of ours (mof_stats.kernelLaunches) and checks the launch.
+#ifdef MOF_HOST_EMULATION
+#define MOF_LAUNCH(kernel, grid, block, smem, ...)                                  \
+    do {                                                                            \
+        mof_emul::launch((grid), (block), [&] { kernel(__VA_ARGS__); });            \
+        ctx->stats.kernelLaunches++;                                                \
+    } while (0)
+#else
 #define MOF_LAUNCH(kernel, grid, block, smem, ...)                                  \
     do {                                                                            \
         kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);              \
@@ -191,6 +198,7 @@ struct PhaseTimer {
         cudaError_t e__ = cudaGetLastError();                                       \
         if (e__ != cudaSuccess) return mof::cuda_fail(ctx, e__, #kernel);           \
     } while (0)
+#endif
 
 // setup_kernels.cu
 int build_mesh_operators(mof_ctx* ctx);
@@ -238,6 +246,15 @@ int dist_halo_f32(mof_ctx* ctx, int kind, float* vec);
 int dist_allreduce_f64(mof_ctx* ctx, double* v, int count);
 int dist_allreduce_f32(mof_ctx* ctx, float* v, int count);
 int dist_allgather_rows(mof_ctx* ctx, int kind, double* vec);  // every rank's rows to every rank
+
+// vector_fields.cu — the Conformal and Connection bases (--vfMode 1|2): matrix-free block-Jacobi PCG
+int vf_init(mof_ctx* ctx);                 // per signal pair, for ctx->params.vfMode / cMode (mode 0 releases the state)
+void vf_destroy(mof_ctx* ctx);
+bool vf_active(const mof_ctx* ctx);
+long long vf_unknowns(const mof_ctx* ctx);  // E (Whitney), 2V (Conformal) or 2T (Connection)
+const double* vf_rhs(const mof_ctx* ctx);
+const double* vf_solution(const mof_ctx* ctx);
+int vf_update_flow(mof_ctx* ctx, double vfWeight);  // VectorField::UpdateOpticalFlow from ctx->dataD / dataRhs
 
 // flow_kernels.cu
 int dog_preprocess(mof_ctx* ctx);

@@ -1,0 +1,201 @@
+// The Conformal and Connection vector-field bases (--vfMode 1|2, --cMode 0|1|2):
+// same alignment loop, same data term and walks, a different space of flow fields.
+//
+//   Conformal  (include/Src/Conformal.inl)   2V unknowns [a(0..V-1); b(0..V-1)]: the flow of triangle t is
+//              sum_k ginv grad_k a[v_k] + rotGrad_k / sqrt(det g) b[v_k]; smoothness = the bi-Laplacian
+//              K diag(1/m) K / 2 on each half (K = scalar stiffness, m = lumped mass).
+//   Connection (include/Src/Connection.inl)  2T unknowns [2t+r]: one tangent vector per triangle in its own chart
+//              (prolongation = identity); smoothness = sum over edges of l |v_i - L v_ii|^2 in the metric of i,
+//              L the linear part of the edge transform, l one of three edge weights.
+//
+// The reference forms R D P + w S by sparse products and factorises it (VectorField.h:46-104). Here neither
+// system matrix is ever formed: A p is applied from its factors (per-triangle 2x2 data blocks through P, the V x V
+// stiffness CSR twice for the bi-Laplacian, per-triangle 2x2 transport blocks for the connection), which reads
+// less memory than the assembled matrix would (Conformal: a 2-ring pattern of ~19 entries per row, never stored),
+// and the system is solved by PCG with a 2x2 block-Jacobi preconditioner (the (a_v, b_v) pair of a vertex, the
+// two components of a triangle's vector). All reductions are two-stage on fixed grids: deterministic.
+//
+// The Conformal system is singular (constants of either potential are in the null space of P and of K); the
+// right-hand side R rhs is in its range, so CG from a zero guess converges and the flow P x is unique.
+#include "mof_internal.cuh"
+#include "vf_kernels.cuh"
+
+namespace mof {
+
+using namespace vfk;
+
+// ----------------------------------------------------------------------------------------- host
+
+struct VfState {
+    int mode = 0, cMode = 0;
+    long long N = 0;
+    DBuf<double> connDiag, connOff;  // Connection: [T][3], [T][3][4]
+    DBuf<double> minv, blk, w, u;    // Conformal: [V], [V][4], [T][2], [V][2]
+    DBuf<double> binv, b, x, r, z, p, q, partial, sc;
+    void release() {
+        DBuf<double>* all[] = {&connDiag, &connOff, &minv, &blk, &w, &u, &binv, &b, &x, &r, &z, &p, &q, &partial, &sc};
+        for (auto* d : all) d->release();
+    }
+};
+
+void vf_destroy(mof_ctx* ctx) {
+    if (!ctx->vf) return;
+    ctx->vf->release();
+    delete ctx->vf;
+    ctx->vf = nullptr;
+}
+
+bool vf_active(const mof_ctx* ctx) { return ctx->vf && ctx->vf->mode != 0; }
+long long vf_unknowns(const mof_ctx* ctx) { return vf_active(ctx) ? ctx->vf->N : ctx->E; }
+const double* vf_rhs(const mof_ctx* ctx) { return ctx->vf->b.p; }
+const double* vf_solution(const mof_ctx* ctx) { return ctx->vf->x.p; }
+
+// VectorField::Init for the mode in ctx->params (Conformal.inl:12-82, Connection.inl:22-104); mode 0 tears the state down.
+int vf_init(mof_ctx* ctx) {
+    const int mode = ctx->params.vfMode;
+    if (mode == 0) {
+        vf_destroy(ctx);
+        return MOF_OK;
+    }
+    if (!ctx->vf) ctx->vf = new VfState();
+    VfState& s = *ctx->vf;
+    const int V = ctx->V, T = ctx->T;
+    s.mode = mode, s.cMode = ctx->params.cMode;
+    s.N = mode == 1 ? 2ll * V : 2ll * T;
+    MOF_CUDA(s.sc.alloc(S_COUNT));
+    MOF_CUDA(s.partial.alloc(2 * RED));
+    MOF_CUDA(s.binv.alloc(3ull * (s.N / 2)));
+    DBuf<double>* vecs[] = {&s.b, &s.x, &s.r, &s.z, &s.p, &s.q};
+    for (auto* v : vecs) MOF_CUDA(v->alloc((size_t)s.N));
+    if (mode == 1) {
+        MOF_CUDA(s.minv.alloc(V));
+        MOF_CUDA(s.blk.alloc(4ull * V));
+        MOF_CUDA(s.w.alloc(2ull * T));
+        MOF_CUDA(s.u.alloc(2ull * V));
+        // lumped mass = sum of sqrt(det)/6 over the fan = the barycentric vertex area m0 (FEM.inl:474, Conformal.inl:29)
+        MOF_LAUNCH(k_invert, blocks_for(V, B), B, 0, ctx->m0.p, V, s.minv.p);
+    } else {
+        MOF_CUDA(s.connDiag.alloc(3ull * T));
+        MOF_CUDA(s.connOff.alloc(12ull * T));
+        MOF_LAUNCH(k_connection_blocks, blocks_for(T, B), B, 0, ctx->g.p, ctx->area.p, ctx->opp.p, ctx->xlin.p, ctx->xcst.p, s.cMode, T, s.connDiag.p, s.connOff.p);
+    }
+    MOF_CUDA(ctx->coeffs.alloc((size_t)s.N));
+    return MOF_OK;
+}
+
+static int vf_apply(mof_ctx* ctx, double weight, const double* x, double* y) {
+    VfState& s = *ctx->vf;
+    const int V = ctx->V, T = ctx->T;
+    if (s.mode == 1) {
+        MOF_LAUNCH(k_conformal_tri, blocks_for(T, B), B, 0, ctx->tri.p, ctx->g.p, ctx->dataD.p, ctx->scalars.p, x, V, T, s.w.p);
+        MOF_LAUNCH(k_conformal_ku, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sStiff.p, s.minv.p, x, V, s.u.p);
+        MOF_LAUNCH(k_conformal_row, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sHe.p, ctx->sStiff.p, ctx->g.p, s.w.p, s.u.p, weight, V, y);
+    } else
+        MOF_LAUNCH(k_connection_apply, blocks_for(T, B), B, 0, ctx->dataD.p, s.connDiag.p, s.connOff.p, ctx->opp.p, ctx->scalars.p, weight, x, T, y);
+    return MOF_OK;
+}
+
+static int vf_dot(mof_ctx* ctx, const double* a, const double* b, long long n, double* out) {
+    VfState& s = *ctx->vf;
+    MOF_LAUNCH(k_dot_partial, RED, B, 0, a, b, n, s.partial.p);
+    MOF_LAUNCH(k_fold, 1, B, 0, s.partial.p, RED, 1, out, out);
+    return MOF_OK;
+}
+
+// Block-Jacobi PCG on the matrix-free operator, x0 = 0. Convergence is read back every `kCheck` iterations; the TRUE
+// residual b - A x decides, and restarts the recurrence when it has drifted.
+static int vf_pcg(mof_ctx* ctx, double weight, double tol, int maxIters, int* itersOut, double* relresOut) {
+    VfState& s = *ctx->vf;
+    const long long N = s.N, half = N / 2;
+    const int split = s.mode == 1 ? 1 : 0;
+    constexpr int kCheck = 25;
+    double* sc = s.sc.p;
+    MOF_CUDA(cudaMemsetAsync(s.x.p, 0, sizeof(double) * N, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(s.r.p, s.b.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
+    MOF_TRY(vf_dot(ctx, s.b.p, s.b.p, N, sc + S_BB));
+    double bb = 0;
+    MOF_CUDA(read_back(ctx, &bb, sc + S_BB));
+    *itersOut = 0, *relresOut = 0;
+    if (!(bb > 0)) return MOF_OK;  // zero right-hand side: x = 0
+    int iters = 0;
+    double relres = 1;
+    for (int restart = 0; restart < 8; restart++) {
+        int cur = 0;
+        MOF_LAUNCH(k_pcg_start, RED, B, 0, s.binv.p, s.r.p, half, split, s.z.p, s.partial.p);
+        MOF_LAUNCH(k_fold, 1, B, 0, s.partial.p, RED, 2, sc + S_RZ0 + cur, sc + S_RR);
+        MOF_LAUNCH(k_pcg_direction, blocks_for(N, B), B, 0, sc, cur, -1, s.z.p, N, s.p.p);
+        bool converged = false;
+        while (iters < maxIters && !converged) {
+            for (int k = 0; k < kCheck && iters < maxIters; k++, iters++) {
+                MOF_TRY(vf_apply(ctx, weight, s.p.p, s.q.p));
+                MOF_TRY(vf_dot(ctx, s.p.p, s.q.p, N, sc + S_PQ));
+                MOF_LAUNCH(k_pcg_step, RED, B, 0, s.binv.p, sc, S_RZ0 + cur, s.p.p, s.q.p, half, split, s.x.p, s.r.p, s.z.p, s.partial.p);
+                MOF_LAUNCH(k_fold, 1, B, 0, s.partial.p, RED, 2, sc + S_RZ0 + (cur ^ 1), sc + S_RR);
+                MOF_LAUNCH(k_pcg_direction, blocks_for(N, B), B, 0, sc, S_RZ0 + (cur ^ 1), S_RZ0 + cur, s.z.p, N, s.p.p);
+                cur ^= 1;
+            }
+            double rr = 0;
+            MOF_CUDA(read_back(ctx, &rr, sc + S_RR));
+            if (!(rr == rr)) return fail(ctx, MOF_E_NOCONVERGE, "flow PCG (matrix-free) produced a NaN residual");
+            converged = rr <= tol * tol * bb;
+        }
+        // true residual
+        MOF_TRY(vf_apply(ctx, weight, s.x.p, s.q.p));
+        MOF_LAUNCH(k_residual, blocks_for(N, B), B, 0, s.b.p, s.q.p, N, s.r.p);
+        MOF_TRY(vf_dot(ctx, s.r.p, s.r.p, N, sc + S_RR));
+        double rr = 0;
+        MOF_CUDA(read_back(ctx, &rr, sc + S_RR));
+        relres = sqrt(rr / bb);
+        if (relres <= tol || iters >= maxIters) break;
+    }
+    *itersOut = iters, *relresOut = relres;
+    if (!(relres <= tol)) return fail(ctx, MOF_E_NOCONVERGE, "flow PCG (matrix-free) hit its iteration cap");
+    return MOF_OK;
+}
+
+// VectorField::UpdateOpticalFlow, VectorField.h:46-104, from the data term in ctx->dataD / ctx->dataRhs.
+int vf_update_flow(mof_ctx* ctx, double vfWeight) {
+    VfState& s = *ctx->vf;
+    const int V = ctx->V, T = ctx->T;
+    const long long N = s.N;
+    MOF_CUDA(ctx->dtmp0.reserve((size_t)std::max<long long>(N, T)));
+    // ||R D P||_F and the scale (:57)
+    if (s.mode == 1) {
+        MOF_LAUNCH(k_conformal_rows, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sHe.p, ctx->opp.p, ctx->sStiff.p, s.minv.p, ctx->g.p, ctx->dataD.p, V,
+                   ctx->dtmp0.p, s.blk.p);
+        MOF_TRY(reduce_sum(ctx, ctx->dtmp0.p, V, ctx->scalars.p + SC_FROB2));
+    } else {
+        MOF_LAUNCH(k_connection_frob, blocks_for(T, B), B, 0, ctx->dataD.p, T, ctx->dtmp0.p);
+        MOF_TRY(reduce_sum(ctx, ctx->dtmp0.p, T, ctx->scalars.p + SC_FROB2));
+    }
+    MOF_LAUNCH(k_set_scale, 1, 1, 0, ctx->scalars.p);
+    if (s.mode == 1)
+        MOF_LAUNCH(k_conformal_finalize, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sHe.p, ctx->g.p, ctx->dataRhs.p, s.blk.p, ctx->scalars.p, vfWeight, V, s.binv.p,
+                   s.b.p);
+    else
+        MOF_LAUNCH(k_connection_finalize, blocks_for(T, B), B, 0, ctx->dataD.p, ctx->dataRhs.p, s.connDiag.p, ctx->scalars.p, vfWeight, T, s.binv.p, s.b.p);
+    ctx->haveFlowSystem = true;
+    // solve (:85)
+    int iters = 0;
+    double relres = 0;
+    MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = vf_pcg(ctx, vfWeight, ctx->params.flowTol, ctx->params.maxCgIterations, &iters, &relres);
+    ctx->stats.flowCgIterations += iters, ctx->stats.flowSolves++, ctx->stats.lastFlowResidual = relres;
+    if (rc != MOF_OK) return rc;
+    MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    MOF_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    MOF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.flowSolveMs += ms;
+    // optimal step and update (:91-103)
+    MOF_TRY(vf_dot(ctx, s.x.p, s.b.p, N, ctx->scalars.p + SC_STEP_NUM));
+    if (s.mode == 1) MOF_LAUNCH(k_conformal_step_terms, blocks_for(T, B), B, 0, ctx->tri.p, ctx->g.p, ctx->dataD.p, s.x.p, V, T, ctx->dtmp0.p);
+    else MOF_LAUNCH(k_connection_step_terms, blocks_for(T, B), B, 0, ctx->dataD.p, s.x.p, T, ctx->dtmp0.p);
+    MOF_TRY(reduce_sum(ctx, ctx->dtmp0.p, T, ctx->scalars.p + SC_STEP_DEN));
+    MOF_LAUNCH(k_vf_update_coeffs, blocks_for(N, B), B, 0, s.x.p, ctx->scalars.p, N, ctx->coeffs.p);
+    if (s.mode == 1) MOF_LAUNCH(k_conformal_field, blocks_for(T, B), B, 0, ctx->tri.p, ctx->g.p, ctx->coeffs.p, V, T, ctx->tfield.p);
+    else MOF_CUDA(cudaMemcpyAsync(ctx->tfield.p, ctx->coeffs.p, sizeof(double) * 2 * T, cudaMemcpyDeviceToDevice, ctx->stream));
+    return MOF_OK;
+}
+
+}  // namespace mof

@@ -246,6 +246,86 @@ def whitney_smooth_operator(g, triangles, opp, reduced, expanded, positive, nv):
     return S, m0, m1
 
 
+# ------------------------------------------------------ Conformal and Connection bases (--vfMode 1|2)
+
+ROT_GRAD = np.array([[1.0, -1.0], [0.0, 1.0], [-1.0, 0.0]])   # Conformal.inl:56
+EDGE_DIR = np.array([[-1.0, 1.0], [0.0, -1.0], [1.0, 0.0]])   # Connection.inl:35
+
+
+def conformal_field(g, triangles, nv, K):
+    """ConformalVectorField, Conformal.inl:12-82. Unknowns: 2V (a potential and a co-potential per vertex).
+    P (2T x 2V): row 2t+r, entry k = (ginv grad_k)[r] on vertex k, (rotGrad_k)[r]/sqrt(det g) on V + vertex k.
+    S = blockdiag(B, B), B = K diag(1/m) K / 2 with m the LUMPED mass diagonal (sum of sqrt(det)/6, FEM.inl:474)
+    and K the scalar stiffness matrix."""
+    T = g.shape[0]
+    gi = inverse_metric(g)
+    sq = np.sqrt(det(g))
+    t = np.arange(T)
+    rows, cols, vals = [], [], []
+    for k in range(3):
+        pg = np.stack([gi[:, 0] * GRAD[k, 0] + gi[:, 1] * GRAD[k, 1], gi[:, 1] * GRAD[k, 0] + gi[:, 2] * GRAD[k, 1]], 1)
+        for r in range(2):
+            rows.append(2 * t + r), cols.append(triangles[:, k]), vals.append(pg[:, r])
+            rows.append(2 * t + r), cols.append(triangles[:, k] + nv), vals.append(ROT_GRAD[k, r] / sq)
+    P = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(2 * T, 2 * nv)).tocsr()
+    m = np.zeros(nv)
+    np.add.at(m, triangles.reshape(-1), np.repeat(sq / 6.0, 3))
+    Bl = (K @ sp.diags(1.0 / m) @ K) * 0.5
+    S = sp.block_diag([Bl, Bl]).tocsr()
+    S.sort_indices()
+    return P, S
+
+
+def connection_weights(g, opp, lin, cst, mode):
+    """The per-half-edge weight l of ConnectionVectorField::InitializeSmoothOperator, Connection.inl:55-70.
+    mode 0: |edge|^2 / (4 (area_i + area_ii) / 3); 1: ((area_i + area_ii) / 3) / |centroid_i - centroid_ii|^2
+    (the neighbour's centroid unfolded into i's chart); 2: 1 / (cot_i + cot_ii)."""
+    area = triangle_areas(g)
+    h = np.arange(opp.size)
+    i, j = h // 3, h % 3
+    o = opp
+    ii, jj = o // 3, o % 3
+
+    def gdot(gt, a, b):
+        return a[:, 0] * (gt[:, 0] * b[:, 0] + gt[:, 1] * b[:, 1]) + a[:, 1] * (gt[:, 1] * b[:, 0] + gt[:, 2] * b[:, 1])
+
+    if mode == 0:
+        return gdot(g[i], EDGE_DIR[j], EDGE_DIR[j]) / (4.0 * (area[i] + area[ii]) / 3.0)
+    if mode == 1:
+        c = 1.0 / 3
+        xc = np.stack([lin[o, 0] * c + lin[o, 1] * c + cst[o, 0], lin[o, 2] * c + lin[o, 3] * c + cst[o, 1]], 1)
+        d = np.array([c, c])[None] - xc
+        return ((area[i] + area[ii]) / 3.0) / gdot(g[i], d, d)
+    if mode == 2:
+        ci = gdot(g[i], -EDGE_DIR[(j + 1) % 3], EDGE_DIR[(j + 2) % 3]) / (2.0 * area[i])
+        cii = gdot(g[ii], -EDGE_DIR[(jj + 1) % 3], EDGE_DIR[(jj + 2) % 3]) / (2.0 * area[ii])
+        return 1.0 / (ci + cii)
+    raise ValueError("Undefined Connection Mode")
+
+
+def connection_field(g, opp, lin, cst, mode):
+    """ConnectionVectorField, Connection.inl:22-104. Unknowns: 2T (one tangent vector per triangle, in the
+    triangle's chart), P = identity. Row block i of S: sum_j l_j g_i on the diagonal, -l_j g_i L_j towards the
+    neighbour across edge j, L_j = the linear part of the transform from the neighbour's chart into i's."""
+    T = g.shape[0]
+    l = connection_weights(g, opp, lin, cst, mode)
+    h = np.arange(3 * T)
+    i, o = h // 3, opp
+    ii = o // 3
+    G = np.stack([g[:, 0], g[:, 1], g[:, 1], g[:, 2]], 1)  # row-major 2x2
+    Lo = lin[o]
+    X = np.stack([G[i, 0] * Lo[:, 0] + G[i, 1] * Lo[:, 2], G[i, 0] * Lo[:, 1] + G[i, 1] * Lo[:, 3],
+                  G[i, 2] * Lo[:, 0] + G[i, 3] * Lo[:, 2], G[i, 2] * Lo[:, 1] + G[i, 3] * Lo[:, 3]], 1)  # g_i L, row-major
+    rows, cols, vals = [], [], []
+    for r in range(2):
+        for c in range(2):
+            rows.append(2 * i + r), cols.append(2 * i + c), vals.append(l * G[i, 2 * r + c])
+            rows.append(2 * i + r), cols.append(2 * ii + c), vals.append(-l * X[:, 2 * r + c])
+    S = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(2 * T, 2 * T)).tocsr()
+    S.sort_indices()
+    return sp.identity(2 * T, format="csr"), S
+
+
 # -------------------------------------------------------------------------------- solver pieces
 
 def smooth_signal(M, S, signal, weight):
@@ -269,6 +349,11 @@ def dog_preprocess(M, S, g, triangles, signal, weight):
         new_var = float(x @ b) - new_avg * new_avg
         out[:, c] = (x - new_avg) * np.sqrt(old_var / new_var) + old_avg
     return out
+
+
+def dog_blend(signal, dog, weight):
+    """The Channels == 6 branch, OpticalFlow.cpp:849-855: (raw * (1 - w), DoG * w) side by side."""
+    return np.hstack([signal * (1.0 - weight), dog * weight])
 
 
 def data_term(triangles, areas, a, b):
@@ -401,13 +486,19 @@ class Params:
     iterations: int = 10
     sSmooth: float = float(np.float32(3e-3))
     sMultiply: float = 0.25
-    vfSmooth: float = 3e-6
+    vfSmooth: float | None = None   # None = the mode's default, OpticalFlow.cpp:1067-1069
     vMultiply: float = 1.0
     vfSThreshold: float = float(np.float32(1e-8))
     dogWeight: float = 1.0
     dogSmooth: float = float(np.float32(1e-4))
     eLength: float = float(np.float32(0.006))
     pad: int = 2
+    vfMode: int = 0   # 0 Whitney, 1 Conformal, 2 Connection (VectorField.h:3-7); vfSmooth defaults 3e-6 / 5e-7 / 1e4 (:1067-1069)
+    cMode: int = 0    # Connection.inl:1-5
+
+    def __post_init__(self):
+        if self.vfSmooth is None:
+            self.vfSmooth = (3e-6, 5e-7, 1e4)[self.vfMode]
 
 
 @dataclass
@@ -442,13 +533,21 @@ def init(vertices, triangles, sig_a, sig_b, params: Params) -> State:
     M, S = scalar_matrices(g, triangles, nv)
     signals = [np.asarray(sig_a, dtype=np.float64).copy(), np.asarray(sig_b, dtype=np.float64).copy()]
     if params.dogWeight > 0:
-        signals = [dog_preprocess(M, S, g, triangles, s, params.dogSmooth) for s in signals]
+        dog = [dog_preprocess(M, S, g, triangles, s, params.dogSmooth) for s in signals]
+        signals = dog if params.dogWeight >= 1 else [dog_blend(s, d, params.dogWeight) for s, d in zip(signals, dog)]
     reduced, expanded, positive = whitney_numbering(opp)
-    P = whitney_prolongation(g, reduced, positive)
-    Sw, _, _ = whitney_smooth_operator(g, triangles, opp, reduced, expanded, positive, nv)
+    if params.vfMode == 0:
+        P = whitney_prolongation(g, reduced, positive)
+        Sw, _, _ = whitney_smooth_operator(g, triangles, opp, reduced, expanded, positive, nv)
+    elif params.vfMode == 1:
+        P, Sw = conformal_field(g, triangles, nv, S)
+    elif params.vfMode == 2:
+        P, Sw = connection_field(g, opp, lin, cst, params.cMode)
+    else:
+        raise ValueError("ERROR: Unsupported vector field!")
     w = Whitney(reduced, expanded, positive, P, Sw)
     T = triangles.shape[0]
-    return State(vertices, triangles, g, opp, lin, cst, triangle_areas(g), M, S, w, signals, np.zeros(expanded.size), np.zeros((T, 2)))
+    return State(vertices, triangles, g, opp, lin, cst, triangle_areas(g), M, S, w, signals, np.zeros(P.shape[1]), np.zeros((T, 2)))
 
 
 def update_flow(st: State, s_weight, vf_weight, tap_prefix=None):
@@ -466,7 +565,8 @@ def update_flow(st: State, s_weight, vf_weight, tap_prefix=None):
 
 def iterate(st: State, params: Params, taps=False):
     """IterativeOptimization's loop, OpticalFlow.cpp:1037-1043."""
-    sw, vw = params.sSmooth, params.vfSmooth
+    sw = params.sSmooth
+    vw = params.vfSmooth
     for i in range(params.iterations):
         update_flow(st, sw, vw, "it%02d." % i if taps else None)
         sw *= params.sMultiply

@@ -38,6 +38,15 @@ def golden_torus():
     return dict(np.load(os.path.join(GOLDEN, "torus_texture.npz")))
 
 
+@pytest.fixture(scope="session")
+def golden_modes():
+    return dict(np.load(os.path.join(GOLDEN, "sphere3_modes.npz")))
+
+
+# name in tests/golden/sphere3_modes.npz -> (vfMode, cMode)
+VF_MODES = {"conformal": (1, 0), "connection0": (2, 0), "connection1": (2, 1), "connection2": (2, 2)}
+
+
 def csr_from_golden(g, name, shape=None):
     import scipy.sparse as sp
     return sp.csr_matrix((g[name + ".val"], g[name + ".col"], g[name + ".rowptr"]), shape=shape)

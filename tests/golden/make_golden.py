@@ -6,6 +6,8 @@ seeded inputs and stores inputs + selected reference outputs as compressed .npz:
 
   sphere3_vertex.npz   --in A.ply B.ply --out r.ply on the 258-vertex octahedron sphere, 10 iterations
   torus_texture.npz    --mesh m.ply --in A.png B.png --out r.png --eLength 0.08 on a 24x12 uv torus, 48x48 texels
+  sphere3_modes.npz    the 258-vertex sphere again with 4 iterations of --vfMode 1, --vfMode 2 --cMode 0|1|2 (taps) and of
+                       --dogWeight 0.5 (the 6-channel blend: output colours only, the tap build is 3-channel)
 
     python tests/golden/make_golden.py
 """
@@ -81,8 +83,41 @@ def torus():
     print("torus_texture.npz", os.path.getsize(os.path.join(HERE, "torus_texture.npz")) // 1024, "KiB")
 
 
+MODES = {"conformal": ["--vfMode", "1"], "connection0": ["--vfMode", "2"], "connection1": ["--vfMode", "2", "--cMode", "1"],
+         "connection2": ["--vfMode", "2", "--cMode", "2"]}
+
+
+def modes():
+    v, t = synthetic.octahedron_sphere(3)
+    a, b = synthetic.smooth_rgb_pair(v, 0)
+    data = {"input_vertices_f32": v.astype(np.float32), "triangles": t.astype(np.int32), "input_a": a, "input_b": b}
+    with tempfile.TemporaryDirectory() as d:
+        synthetic.write_ply_colored(os.path.join(d, "A.ply"), v, a, t)
+        synthetic.write_ply_colored(os.path.join(d, "B.ply"), v, b, t)
+        for name, flags in MODES.items():
+            subprocess.check_call([REF, "--in", "A.ply", "B.ply", "--out", name + ".ply", "--iterations", "4", "--tap", "tap_" + name] + flags, cwd=d,
+                                  stdout=subprocess.DEVNULL)
+            taps = load_taps(os.path.join(d, "tap_" + name))
+            for k in ("smoothOperator.rowptr", "smoothOperator.col", "smoothOperator.val", "advected0", "advected1"):
+                data[name + "." + k] = taps[k]
+            for i in range(4):
+                data["%s.it%02d.tFlowField" % (name, i)] = taps["it%02d.tFlowField" % i]
+                data["%s.it%02d.coeffs" % (name, i)] = taps["it%02d.coeffs" % i]
+            out = synthetic.read_ply(os.path.join(d, name + ".ply"))
+            data[name + ".output_rgb"] = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.uint8)
+        subprocess.check_call([REF, "--in", "A.ply", "B.ply", "--out", "blend.ply", "--iterations", "4", "--dogWeight", "0.5"], cwd=d, stdout=subprocess.DEVNULL)
+        out = synthetic.read_ply(os.path.join(d, "blend.ply"))
+        data["blend.output_rgb"] = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "sphere3_modes.npz"), **data)
+    print("sphere3_modes.npz", os.path.getsize(os.path.join(HERE, "sphere3_modes.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/OpticalFlow_ref is missing: run oracle/ref/build_ref.sh (needs /root/reference)")
+    if len(sys.argv) > 1 and sys.argv[1] == "modes":
+        modes()
+        sys.exit(0)
     sphere()
     torus()
+    modes()

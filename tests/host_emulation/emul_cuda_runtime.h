@@ -1,0 +1,47 @@
+// TEST INFRASTRUCTURE (CPU tier): host stand-ins for the few CUDA runtime calls and for the kernel-launch syntax that
+// meshopticalflow_b200/csrc uses, so that a .cu file can be compiled by g++ with -DMOF_HOST_EMULATION and its REAL
+// source — kernels and host driver alike — run on the CPU. "Device" memory is malloc'd host memory, streams and events
+// are no-ops (everything is synchronous), and a launch runs the kernel body once per (block, thread) on fibers
+// (ucontext) of one OS thread, __syncthreads() yielding to the next fiber of the block: barrier semantics hold,
+// __shared__ variables (made `static`) are per block because blocks run one after the other.
+#pragma once
+
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __shared__ static
+
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(d, s, bytes); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return cudaSuccess; }
+
+struct EmulDim { unsigned x = 1, y = 1, z = 1; };
+extern EmulDim blockIdx, blockDim, threadIdx, gridDim;
+void __syncthreads();
+
+namespace mof_emul {
+void launch(long long grid, int block, const std::function<void()>& body);
+}

@@ -164,10 +164,10 @@ def test_error_paths(aligner):
         al.set_signals(np.zeros((4, 6)), np.zeros((4, 6)))
     assert e.value.code == api.MOF_E_UNSUPPORTED
     p = api.default_params()
-    p.dogWeight = 0.5
+    p.vfMode = 3  # "ERROR: Unsupported vector field!" (OpticalFlow.cpp:867)
     with pytest.raises(api.MofError) as e:
         al.set_params(p)
-    assert e.value.code == api.MOF_E_UNSUPPORTED
+    assert e.value.code == api.MOF_E_INVALID and "Unsupported vector field" in e.value.message
     col = np.arange(12, dtype=np.float64).reshape(4, 3) * 10
     col_b = col + np.array([[1.0, -2.0, 0.5], [0.0, 1.0, -1.0], [2.0, 0.0, 1.0], [-1.0, 1.0, 0.0]])
     al.set_signals(col, col_b)

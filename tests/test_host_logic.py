@@ -28,6 +28,7 @@ def test_default_params_are_the_reference_defaults():
     assert p.vfSmooth == 3e-6 and p.vMultiply == 1.0 and p.vfSThreshold == float(np.float32(1e-8))
     assert p.dogWeight == 1.0 and p.dogSmooth == float(np.float32(1e-4))
     assert p.flowTol == 1e-8
+    assert p.vfMode == api.VF_WHITNEY and p.cMode == 0
 
 
 def test_no_cpu_fallback():
@@ -57,13 +58,13 @@ def _run(*args):
 def test_cli_usage_and_flag_handling():
     r = _run()
     assert r.returncode == 1 and "Usage" in r.stdout and "--sSmooth" in r.stdout  # missing --in: usage + EXIT_FAILURE (OpticalFlow.cpp:1099-1103)
-    r = _run("--IN", "a.ply", "b.ply", "--bogus", "--out", "x.ply", "--vfMode", "1")
+    r = _run("--IN", "a.ply", "b.ply", "--bogus", "--out", "x.ply", "--vfMode", "3")
     assert "[WARNING] Invalid option: --bogus" in r.stderr  # CmdLineParser.inl:253-256, names are case-insensitive (:247)
-    assert "only the Whitney vector field" in r.stderr and r.returncode != 0
+    assert "ERROR: Unsupported vector field!" in r.stdout and r.returncode == 0  # OpticalFlow.cpp:867-868: printf + return 0 from Init
+    r = _run("--in", "a.ply", "b.ply", "--out", "x.ply", "--vfMode", "2", "--cMode", "7")
+    assert "Undefined Connection Mode" in r.stdout
     r = _run("--in", "a.ply", "b.ply")
     assert "pass --out" in r.stderr and r.returncode != 0
-    r = _run("--in", "a.ply", "b.ply", "--out", "x.ply", "--dogWeight", "0.5")
-    assert "6-channel" in r.stderr and r.returncode != 0
     r = _run("--in", "/nonexistent/a.ply", "/nonexistent/b.ply", "--out", "x.ply")
     assert r.returncode != 0 and "Unable to read" in r.stderr
 

@@ -2,7 +2,9 @@
 reference binary (tests/golden/make_golden.py). This is what pins the oracle on a box without /root/reference."""
 import numpy as np
 
-from conftest import colour_outliers, csr_from_golden, rel, sorted_csr
+import pytest
+
+from conftest import VF_MODES, colour_outliers, csr_from_golden, rel, sorted_csr
 from oracle import mof_oracle as O
 
 
@@ -80,6 +82,43 @@ def test_texture_alignment_matches_reference(golden_torus):
     for s in range(2):
         assert colour_outliers(res["advected"][s], g["advected%d" % s], 1e-6) < 2e-3
     assert colour_outliers(res["pixels"], g["output_pixels"], 1.0) < 2e-3
+
+
+@pytest.mark.parametrize("name", sorted(VF_MODES))
+def test_conformal_and_connection_fields_match_reference(golden_modes, name):
+    """--vfMode 1 | 2 (--cMode 0|1|2): smoothness operator, per-iteration coefficients and flow, output colours."""
+    g = golden_modes
+    vf_mode, c_mode = VF_MODES[name]
+    v, t, a, b = _sphere_inputs(g)
+    params = O.Params(iterations=4, vfMode=vf_mode, cMode=c_mode)
+    assert params.vfSmooth == (3e-6, 5e-7, 1e4)[vf_mode]
+    st = O.init(v, t, a, b, params)
+    n = 2 * v.shape[0] if vf_mode == 1 else 2 * t.shape[0]
+    assert st.coeffs.size == n
+    ref = sorted_csr(csr_from_golden(g, name + ".smoothOperator", (n, n)))
+    ref.sum_duplicates()
+    S = st.whitney.S
+    assert abs(S - ref).max() < 1e-12 * abs(ref).max()
+    assert abs(ref - ref.T).max() < 1e-12 * abs(ref).max()  # what makes CG applicable
+    O.iterate(st, params, taps=True)
+    for i in range(4):
+        assert rel(st.taps["it%02d.tFlowField" % i], g["%s.it%02d.tFlowField" % (name, i)]) < 1e-8, i
+        if vf_mode == 2:  # the Conformal system is singular (constants): coefficients are unique only up to its null space
+            assert rel(st.taps["it%02d.coeffs" % i], g["%s.it%02d.coeffs" % (name, i)]) < 1e-8, i
+    ca, cb = O.advect_vertices(st, a, b)
+    assert np.abs(ca - g[name + ".advected0"]).max() < 1e-6 and np.abs(cb - g[name + ".advected1"]).max() < 1e-6
+    out = O.to_uchar_ply((ca + cb) / 2.0)
+    assert np.abs(out.astype(int) - g[name + ".output_rgb"].astype(int)).max() <= 1
+
+
+def test_six_channel_dog_blend_matches_reference(golden_modes):
+    """0 < dogWeight < 1: _main<double,6> (OpticalFlow.cpp:1114), signals = ((1-w) raw, w DoG)."""
+    g = golden_modes
+    v, t, a, b = _sphere_inputs(g)
+    params = O.Params(iterations=4, dogWeight=0.5)
+    st, blended = O.align_vertices(v, t, a, b, params)
+    assert st.signals[0].shape[1] == 6
+    assert np.abs(O.to_uchar_ply(blended).astype(int) - g["blend.output_rgb"].astype(int)).max() <= 1
 
 
 def test_walk_edge_cases():

@@ -33,3 +33,19 @@ def test_sphere_level4(tmp_path):
     out = synthetic.read_ply(str(tmp_path / "r.ply"))
     rgb = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1)
     assert np.abs(O.to_uchar_ply((ca + cb) / 2.0).astype(int) - rgb.astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("flags,kw", [(["--vfMode", "1"], dict(vfMode=1)), (["--vfMode", "2", "--cMode", "1"], dict(vfMode=2, cMode=1)),
+                                      (["--dogWeight", "0.25"], dict(dogWeight=0.25))])
+def test_other_bases_and_the_dog_blend(tmp_path, flags, kw):
+    """Conformal / Connection fields and the 6-channel blend on the 1026-vertex sphere, whole program."""
+    v, t = synthetic.octahedron_sphere(4)
+    a, b = synthetic.smooth_rgb_pair(v, 5)
+    synthetic.write_ply_colored(str(tmp_path / "A.ply"), v, a, t)
+    synthetic.write_ply_colored(str(tmp_path / "B.ply"), v, b, t)
+    subprocess.check_call([REF_BIN, "--in", "A.ply", "B.ply", "--out", "r.ply", "--iterations", "3"] + flags, cwd=tmp_path, stdout=subprocess.DEVNULL)
+    vf = v.astype(np.float32).astype(np.float64)
+    _, blended = O.align_vertices(vf, t, a.astype(np.float64), b.astype(np.float64), O.Params(iterations=3, **kw))
+    out = synthetic.read_ply(str(tmp_path / "r.ply"))
+    rgb = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1)
+    assert np.abs(O.to_uchar_ply(blended).astype(int) - rgb.astype(int)).max() <= 1
