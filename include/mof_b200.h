@@ -149,7 +149,8 @@ enum {
     MOF_ARR_DATA_RHS = 13,       /* T x 2 */
     MOF_ARR_FLOW_RHS = 14,       /* mof_num_coeffs   scaled R*rhs (VectorField.h:53,60) */
     MOF_ARR_FLOW_SOLUTION = 15,  /* mof_num_coeffs   solution of the last flow system (VectorField.h:85) */
-    MOF_ARR_SIGNALS_RAW = 16     /* V x 6      6-channel blend only: the (1-w)*raw half of flowData.signals; MOF_ARR_SIGNALS is the w*DoG half */
+    MOF_ARR_SIGNALS_RAW = 16,    /* V x 6      6-channel blend only: the (1-w)*raw half of flowData.signals; MOF_ARR_SIGNALS is the w*DoG half */
+    MOF_ARR_RESAMPLED_RAW = 17   /* V x 6      6-channel blend only: that half of the last iteration's resampled signals */
 };
 /* bytes needed for one array (0 if not available yet), then copy out. */
 long long mof_array_bytes(mof_ctx* ctx, int which);

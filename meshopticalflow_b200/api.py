@@ -19,7 +19,8 @@ MOF_OK, MOF_E_INVALID, MOF_E_CUDA, MOF_E_MESH, MOF_E_NOCONVERGE, MOF_E_UNSUPPORT
 
 CSR_SCALAR_MASS, CSR_SCALAR_STIFFNESS, CSR_WHITNEY_SMOOTH, CSR_FLOW_SYSTEM = range(4)
 (ARR_METRIC, ARR_AREA, ARR_OPPOSITE, ARR_XFORM_LINEAR, ARR_XFORM_CONSTANT, ARR_REDUCED_EDGE, ARR_EXPANDED_EDGE, ARR_POSITIVE_EDGE,
- ARR_PROLONGATION, ARR_SIGNALS, ARR_SMOOTHED, ARR_RESAMPLED, ARR_DATA_TERM, ARR_DATA_RHS, ARR_FLOW_RHS, ARR_FLOW_SOLUTION, ARR_SIGNALS_RAW) = range(17)
+ ARR_PROLONGATION, ARR_SIGNALS, ARR_SMOOTHED, ARR_RESAMPLED, ARR_DATA_TERM, ARR_DATA_RHS, ARR_FLOW_RHS, ARR_FLOW_SOLUTION, ARR_SIGNALS_RAW,
+ ARR_RESAMPLED_RAW) = range(18)
 
 VF_WHITNEY, VF_CONFORMAL, VF_CONNECTION = range(3)  # --vfMode, VectorField.h:3-7
 
@@ -28,7 +29,7 @@ _ARRAY_SPEC = {
     ARR_XFORM_CONSTANT: (np.float64, 2), ARR_REDUCED_EDGE: (np.int32, None), ARR_EXPANDED_EDGE: (np.int32, None), ARR_POSITIVE_EDGE: (np.int32, None),
     ARR_PROLONGATION: (np.float64, 6), ARR_SIGNALS: (np.float64, 6), ARR_SMOOTHED: (np.float64, 6), ARR_RESAMPLED: (np.float64, 6),
     ARR_DATA_TERM: (np.float64, 3), ARR_DATA_RHS: (np.float64, 2), ARR_FLOW_RHS: (np.float64, None), ARR_FLOW_SOLUTION: (np.float64, None),
-    ARR_SIGNALS_RAW: (np.float64, 6),
+    ARR_SIGNALS_RAW: (np.float64, 6), ARR_RESAMPLED_RAW: (np.float64, 6),
 }
 
 # Every symbol include/mof_b200.h declares (the CPU test tier checks the library exports them all).

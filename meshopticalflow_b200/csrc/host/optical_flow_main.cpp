@@ -226,6 +226,21 @@ int main(int argc, char* argv[]) {
         Stopwatch t;
         mof_get_stats(ctx, &before);
         if (!mof_ok(ctx, mof_iterate(ctx, 1))) return EXIT_FAILURE;
+        if (opt.debug) {
+            // UpdateFlow's --debug dump (:458-465): the two resampled signals (channels 0-2) as coloured binary meshes
+            std::vector<double> res6(6 * (size_t)V);
+            const bool blend = opt.dogWeight > 0 && opt.dogWeight < 1;
+            if (!mof_ok(ctx, mof_get_array(ctx, blend ? MOF_ARR_RESAMPLED_RAW : MOF_ARR_RESAMPLED, res6.data()))) return EXIT_FAILURE;
+            std::vector<float> xyzf(vertices.begin(), vertices.end()), rgb(3 * (size_t)V);
+            std::string werr;
+            for (int s = 0; s < 2; s++) {
+                for (int v = 0; v < V; v++)
+                    for (int c = 0; c < 3; c++) rgb[3 * (size_t)v + c] = std::min(255.f, std::max(0.f, (float)res6[6 * (size_t)v + 3 * s + c]));
+                char name[64];
+                snprintf(name, sizeof(name), "resampled.%c.%d.ply", s ? 'T' : 'S', i);
+                if (!mof::ply_write_colored_binary(name, xyzf, rgb, triangles, werr)) fprintf(stderr, "[ERROR] %s\n", werr.c_str());
+            }
+        }
         if (opt.verbose) {
             mof_get_stats(ctx, &after);
             printf("\t Signal Smoothing: %.4f(s)\n", (after.smoothSolveMs - before.smoothSolveMs) * 1e-3);

@@ -199,4 +199,26 @@ bool ply_write_colored_ascii(const char* file_name, const std::vector<float>& xy
     return true;
 }
 
+bool ply_write_colored_binary(const char* file_name, const std::vector<float>& xyz, const std::vector<float>& rgb, const std::vector<int>& tri, std::string& err) {
+    FILE* fp = fopen(file_name, "wb");
+    if (!fp) { err = std::string("Failed to open file for writing: ") + file_name; return false; }
+    size_t nv = xyz.size() / 3, nt = tri.size() / 3;
+    fprintf(fp, "ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n", (int)nv);
+    fprintf(fp, "property uchar red\nproperty uchar green\nproperty uchar blue\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n", (int)nt);
+    std::vector<unsigned char> rec(15 * nv);
+    for (size_t i = 0; i < nv; i++) {
+        memcpy(&rec[15 * i], &xyz[3 * i], 12);
+        for (int c = 0; c < 3; c++) rec[15 * i + 12 + c] = (unsigned char)(double)rgb[3 * i + c];
+    }
+    fwrite(rec.data(), 1, rec.size(), fp);
+    rec.resize(13 * nt);
+    for (size_t i = 0; i < nt; i++) {
+        rec[13 * i] = 3;
+        memcpy(&rec[13 * i + 1], &tri[3 * i], 12);
+    }
+    fwrite(rec.data(), 1, rec.size(), fp);
+    fclose(fp);
+    return true;
+}
+
 }  // namespace mof

@@ -25,6 +25,8 @@ bool ply_read(const char* file_name, PlyMesh& mesh, std::string& err);
 // ASCII: float x y z, uchar red green blue, list uchar int vertex_indices; numbers printed "%g " / "%u " /
 // "%d " like write_ascii_item (PlyFile.inl:2117-2160); colours are uchar by truncation (PlyFile.inl:2309-2313).
 bool ply_write_colored_ascii(const char* file_name, const std::vector<float>& xyz, const std::vector<float>& rgb, const std::vector<int>& tri, std::string& err);
+// The same elements as binary_little_endian records (PLY_BINARY_NATIVE on this platform): what --debug writes (OpticalFlow.cpp:458-465).
+bool ply_write_colored_binary(const char* file_name, const std::vector<float>& xyz, const std::vector<float>& rgb, const std::vector<int>& tri, std::string& err);
 
 }  // namespace mof
 

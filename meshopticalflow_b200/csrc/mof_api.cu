@@ -406,6 +406,10 @@ static const void* array_view(mof_ctx* ctx, int which, long long* bytes) {
     switch (which) {
         case MOF_ARR_SMOOTHED: *bytes = 8 * 6 * V; return ctx->smoothed6.p;
         case MOF_ARR_RESAMPLED: *bytes = 8 * 6 * V; return ctx->resampled6.p;
+        case MOF_ARR_RESAMPLED_RAW:
+            if (!ctx->blend) return nullptr;
+            *bytes = 8 * 6 * V;
+            return ctx->resampledLo6.p;
         case MOF_ARR_DATA_TERM: *bytes = 8 * 3 * T; return ctx->dataD.p;
         case MOF_ARR_DATA_RHS: *bytes = 8 * 2 * T; return ctx->dataRhs.p;
         case MOF_ARR_FLOW_RHS: *bytes = 8 * vf_unknowns(ctx); return vf_active(ctx) ? vf_rhs(ctx) : ctx->fb.p;

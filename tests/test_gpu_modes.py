@@ -157,3 +157,32 @@ def test_command_line_flags(tmp_path, golden_modes, flags, name):
     out = synthetic.read_ply(str(tmp_path / "r.ply"))
     rgb = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1).astype(int)
     assert np.abs(rgb - g[name + ".output_rgb"].astype(int)).max() <= 1
+
+
+def test_debug_dumps(tmp_path):
+    """--debug: resampled.S.<i>.ply / resampled.T.<i>.ply per iteration, binary, as UpdateFlow writes them (OpticalFlow.cpp:458-465)."""
+    v, t = synthetic.octahedron_sphere(3)
+    a, b = synthetic.smooth_rgb_pair(v, 0)
+    synthetic.write_ply_colored(str(tmp_path / "A.ply"), v, a, t, True)
+    synthetic.write_ply_colored(str(tmp_path / "B.ply"), v, b, t, True)
+    r = subprocess.run([CLI_BIN, "--in", "A.ply", "B.ply", "--out", "r.ply", "--iterations", "2", "--debug"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    al = api.Aligner(0)
+    try:
+        al.set_mesh(v.astype(np.float32).astype(np.float64), t)
+        al.set_signals(a.astype(np.float64), b.astype(np.float64))
+        for i in range(2):
+            al.iterate(1)
+            res = al.array(api.ARR_RESAMPLED)
+            for s, tag in enumerate("ST"):
+                path = tmp_path / ("resampled.%s.%d.ply" % (tag, i))
+                raw = open(path, "rb").read()
+                assert raw.startswith(b"ply\nformat binary_little_endian 1.0\nelement vertex 258\nproperty float x\n")
+                assert len(raw) == raw.index(b"end_header\n") + 11 + 15 * 258 + 13 * 512
+                out = synthetic.read_ply(str(path))
+                rgb = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1).astype(int)
+                expect = np.clip(res[:, 3 * s:3 * s + 3].astype(np.float32), 0, 255).astype(np.uint8).astype(int)
+                assert np.abs(rgb - expect).max() <= 1
+                assert np.array_equal(out["face"]["vertex_indices"], t)
+    finally:
+        al.close()
