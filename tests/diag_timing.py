@@ -1,5 +1,5 @@
 """Timing/iteration-count probe of the CUDA path on a synthetic sphere (GPU needed; no oracle).
-`python tests/diag_timing.py [level] [iterations]`"""
+`python tests/diag_timing.py [level] [iterations] [vfMode] [cMode] [dogWeight]`"""
 import os
 import sys
 import time
@@ -19,6 +19,13 @@ def main():
     ca, cb = ca.astype(np.float64), cb.astype(np.float64)
     print(f"level {level}: V={v.shape[0]} T={t.shape[0]} (generated in {time.time() - t0:.1f}s)", flush=True)
     al = api.Aligner(0)
+    vf_mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    p = api.default_params()
+    p.vfMode, p.cMode = vf_mode, int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    p.dogWeight = float(sys.argv[5]) if len(sys.argv) > 5 else 1.0
+    p.vfSmooth = 0.0  # the mode's default
+    al.set_params(p)
+    print(f"vfMode {p.vfMode} cMode {p.cMode} dogWeight {p.dogWeight}", flush=True)
     t0 = time.time()
     al.set_mesh(v, t)
     print("set_mesh %.3fs E=%d" % (time.time() - t0, al.num_edges), flush=True)
@@ -41,8 +48,12 @@ def main():
     t0 = time.time()
     a, b = al.advect_vertices(0.5)
     print("final advect %.3fs; mean|A-B| before %.3f after %.3f" % (time.time() - t0, np.abs(ca - cb).mean(), np.abs(a - b).mean()))
-    ms = al.time_flow_spmv(50)
     s = al.stats()
+    if vf_mode != 0:
+        print("unknowns", al.num_coeffs, "stats", s)
+        al.close()
+        return
+    ms = al.time_flow_spmv(50)
     print(f"flow SpMV {ms * 1e3:.1f} us, {s['flowSpmvBytes'] / ms / 1e6:.1f} GB/s algorithmic ({s['flowRows']} rows, {s['flowNnz']} nnz)")
     print("stats", s)
     al.close()
