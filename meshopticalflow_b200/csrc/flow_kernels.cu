@@ -5,6 +5,7 @@
 // 48-byte fetch. Per-triangle quantities (walk samples, data term) are written once by one thread
 // and combined by gathers in a fixed order: no atomics, deterministic.
 #include <algorithm>
+#include <thread>
 
 #include "mof_internal.cuh"
 
@@ -116,6 +117,125 @@ static int smooth_solve(mof_ctx* ctx, double weight, const double* in6, double* 
     MOF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.smoothSolveMs += ms;
     return MOF_OK;
+}
+
+// ---------------------------------------------------- the next smoothing solve, under the flow solve
+//
+// The smoothing systems (M + eps_i S) x = M b depend on the iteration's weight and on the input signals, not on the
+// flow: the solve of iteration i+1 can run while the flow system of iteration i is being solved. Both solvers spend
+// about a third of a PCG iteration in latency-bound launches on the small multigrid levels, which a second stream
+// fills. A worker thread drives the scalar solver on its own stream through a VIEW of the context: a shallow copy
+// that shares the read-only operators, the smoothing-only buffers (sSys, sDinv, rhs6, the scalar hierarchy) and the
+// input signals, and owns what a solve writes besides those (stream, events, counters, Jacobi-PCG work vectors,
+// scratch). The owner joins the worker before it uses the result or changes anything the view reads.
+// MOF_SMOOTH_AHEAD=0 keeps everything on one stream.
+struct SmoothAhead {
+    mof_ctx view;
+    std::thread worker;
+    bool running = false;
+    double weight = 0;
+    int rc = MOF_OK;
+    cudaEvent_t fence = nullptr;  // owner's stream -> view's stream
+    DBuf<double> out6, outLo6;    // results; swapped with smoothed6 / smoothedLo6 when consumed
+};
+
+static bool smooth_ahead_enabled() {  // read per iteration: tests flip it inside one process
+    const char* e = getenv("MOF_SMOOTH_AHEAD");
+    return !(e && *e == '0');
+}
+
+static void smooth_ahead_join(mof_ctx* ctx) {
+    SmoothAhead* a = ctx->ahead;
+    if (!a || !a->running) return;
+    a->worker.join();
+    a->running = false;
+    mof_stats& s = a->view.stats;
+    ctx->stats.kernelLaunches += s.kernelLaunches, ctx->stats.smoothCgIterations += s.smoothCgIterations, ctx->stats.smoothSolves += s.smoothSolves;
+    ctx->stats.smoothSolveMs += s.smoothSolveMs;
+    if (s.smoothSolves) ctx->stats.lastSmoothResidual = s.lastSmoothResidual;
+    memset(&s, 0, sizeof(s));
+}
+
+void smooth_ahead_drain(mof_ctx* ctx) {
+    smooth_ahead_join(ctx);
+    if (ctx->ahead) ctx->ahead->weight = 0, ctx->ahead->rc = MOF_E_INVALID;
+}
+
+void smooth_ahead_destroy(mof_ctx* ctx) {
+    SmoothAhead* a = ctx->ahead;
+    if (!a) return;
+    smooth_ahead_join(ctx);
+    a->out6.release(), a->outLo6.release();
+    // what the view allocated for itself (on its own stream; the shared buffers are the owner's to free)
+    cudaStream_t mine = alloc_stream();
+    alloc_stream() = a->view.stream;
+    a->view.pcg.r.release(), a->view.pcg.d.release(), a->view.pcg.q.release(), a->view.pcg.partial.release(), a->view.pcg.result.release();
+    a->view.dtmp0.release(), a->view.dtmp1.release(), a->view.dtmp2.release();
+    cudaStreamSynchronize(a->view.stream);
+    alloc_stream() = mine;
+    if (a->fence) cudaEventDestroy(a->fence);
+    if (a->view.ev0) cudaEventDestroy(a->view.ev0);
+    if (a->view.ev1) cudaEventDestroy(a->view.ev1);
+    if (a->view.stream) cudaStreamDestroy(a->view.stream);
+    delete a;
+    ctx->ahead = nullptr;
+}
+
+// Starts the smoothing solve(s) of `weight` on the second stream. Failing to start is not an error: the caller's
+// next iteration then solves on its own stream as before.
+static void smooth_ahead_start(mof_ctx* ctx, double weight) {
+    if (!smooth_ahead_enabled() || dist_active(ctx) || !(weight != 0)) return;
+    const size_t V = (size_t)ctx->V;
+    SmoothAhead* a = ctx->ahead;
+    if (!a) {
+        a = new SmoothAhead();
+        bool ok = cudaStreamCreateWithFlags(&a->view.stream, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreate(&a->view.ev0) == cudaSuccess &&
+                  cudaEventCreate(&a->view.ev1) == cudaSuccess && cudaEventCreateWithFlags(&a->fence, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            delete a;
+            return;
+        }
+        memset(&a->view.stats, 0, sizeof(a->view.stats));
+        ctx->ahead = a;
+    }
+    smooth_ahead_join(ctx);
+    if (a->out6.alloc(6 * V) != cudaSuccess || (ctx->blend && a->outLo6.alloc(6 * V) != cudaSuccess)) return;
+    // refresh the view: everything the scalar solver reads, by value (the view never allocates or frees these)
+    mof_ctx& v = a->view;
+    v.device = ctx->device, v.params = ctx->params, v.pinned = ctx->pinned;
+    v.V = ctx->V, v.T = ctx->T, v.E = ctx->E, v.nnzS = ctx->nnzS;
+    v.sRowptr = ctx->sRowptr, v.sCol = ctx->sCol, v.sHe = ctx->sHe, v.sMass = ctx->sMass, v.sStiff = ctx->sStiff, v.sSys = ctx->sSys, v.sDinv = ctx->sDinv, v.rhs6 = ctx->rhs6;
+    v.mgs = ctx->mgs, v.mg = nullptr, v.dist = nullptr, v.vf = nullptr, v.ahead = nullptr;
+    // the view's stream starts after everything queued on the owner's (the signals, the previous smoothing's readers)
+    if (cudaEventRecord(a->fence, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(a->view.stream, a->fence, 0) != cudaSuccess) return;
+    a->weight = weight, a->rc = MOF_OK, a->running = true;
+    const double* in6 = ctx->sig6.p;
+    const double* inLo6 = ctx->blend ? ctx->sigLo6.p : nullptr;
+    double* out6 = a->out6.p;
+    double* outLo6 = a->outLo6.p;
+    const double tol = ctx->params.smoothTol;
+    a->worker = std::thread([a, in6, inLo6, out6, outLo6, weight, tol] {
+        mof_ctx* view = &a->view;
+        int rc = cudaSetDevice(view->device) == cudaSuccess ? MOF_OK : MOF_E_CUDA;
+        alloc_stream() = view->stream;
+        if (rc == MOF_OK) rc = smooth_solve(view, weight, in6, out6, tol, false);
+        if (rc == MOF_OK && inLo6) rc = smooth_solve(view, weight, inLo6, outLo6, tol, true);
+        if (rc == MOF_OK && cudaStreamSynchronize(view->stream) != cudaSuccess) rc = MOF_E_CUDA;
+        a->rc = rc;
+    });
+}
+
+// The owner's side: true if the solves of `weight` were done ahead; their results are then in smoothed6 (/ smoothedLo6).
+static bool smooth_ahead_take(mof_ctx* ctx, double weight) {
+    SmoothAhead* a = ctx->ahead;
+    if (!a) return false;
+    smooth_ahead_join(ctx);
+    const bool hit = a->rc == MOF_OK && a->weight == weight && a->out6.p && (!ctx->blend || a->outLo6.p);
+    a->weight = 0;
+    if (!hit) return false;
+    std::swap(ctx->smoothed6, a->out6);
+    if (ctx->blend) std::swap(ctx->smoothedLo6, a->outLo6);
+    return true;
 }
 
 __global__ void k_sub(const double* a, const double* b, long long n, double* out) {
@@ -417,8 +537,10 @@ int update_flow(mof_ctx* ctx, double sWeight, double vfWeight) {
     const int V = ctx->V, T = ctx->T, E = ctx->E;
     // smoothing of both signals, six channels in one solve (:435)
     const double* smoothed = ctx->sig6.p;
+    bool doneAhead = false;
     if (sWeight) {
-        MOF_TRY(smooth_solve(ctx, sWeight, ctx->sig6.p, ctx->smoothed6.p, ctx->params.smoothTol));
+        doneAhead = smooth_ahead_take(ctx, sWeight);  // solved on the second stream during the previous flow solve?
+        if (!doneAhead) MOF_TRY(smooth_solve(ctx, sWeight, ctx->sig6.p, ctx->smoothed6.p, ctx->params.smoothTol));
         smoothed = ctx->smoothed6.p;
     } else
         MOF_CUDA(cudaMemcpyAsync(ctx->smoothed6.p, ctx->sig6.p, sizeof(double) * 6 * V, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -428,7 +550,7 @@ int update_flow(mof_ctx* ctx, double sWeight, double vfWeight) {
         // channels 0-2 of the 6-channel signals: the same system, a second solve; the same walks, a second sampling
         const double* lo = ctx->sigLo6.p;
         if (sWeight) {
-            MOF_TRY(smooth_solve(ctx, sWeight, ctx->sigLo6.p, ctx->smoothedLo6.p, ctx->params.smoothTol, true));
+            if (!doneAhead) MOF_TRY(smooth_solve(ctx, sWeight, ctx->sigLo6.p, ctx->smoothedLo6.p, ctx->params.smoothTol, true));
             lo = ctx->smoothedLo6.p;
         }
         MOF_TRY(advect_vertices(ctx, lo, -0.5, 0.5, ctx->resampledLo6.p));
@@ -436,6 +558,8 @@ int update_flow(mof_ctx* ctx, double sWeight, double vfWeight) {
     // data term (:470)
     MOF_LAUNCH(k_data_term, blocks_for(T, B), B, 0, ctx->tri.p, ctx->area.p, ctx->resampled6.p, ctx->blend ? ctx->resampledLo6.p : nullptr, T, ctx->dataD.p,
                ctx->dataRhs.p);
+    // the next iteration's smoothing (IterativeOptimization's schedule, OpticalFlow.cpp:1041) runs under this iteration's flow solve
+    if (sWeight && ctx->iterationsDone + 1 < ctx->params.iterations) smooth_ahead_start(ctx, sWeight * ctx->params.sMultiply);
     if (vf_active(ctx)) return vf_update_flow(ctx, vfWeight);  // Conformal / Connection basis (vector_fields.cu)
     // system (VectorField.h:51-67)
     MOF_CUDA(ctx->dtmp0.reserve((size_t)(E > T ? E : T)));

@@ -35,6 +35,7 @@ int require_mesh(mof_ctx* ctx) { return ctx->haveMesh ? MOF_OK : fail(ctx, MOF_E
 int require_signals(mof_ctx* ctx) { return ctx->haveSignals ? MOF_OK : fail(ctx, MOF_E_INVALID, "call mof_set_signals first"); }
 
 int finish_mesh(mof_ctx* ctx) {
+    smooth_ahead_drain(ctx);
     ctx->haveMesh = ctx->haveSignals = ctx->haveFlowSystem = ctx->haveTexture = false;
     cudaEventRecord(ctx->ev0, ctx->stream);
     PhaseTimer pt(ctx);
@@ -60,6 +61,7 @@ int finish_mesh(mof_ctx* ctx) {
 
 int finish_signals(mof_ctx* ctx) {
     ctx->haveSignals = false;
+    smooth_ahead_drain(ctx);
     if (ctx->params.vfMode != 0 && dist_active(ctx))
         return fail(ctx, MOF_E_UNSUPPORTED, "[ERROR] a partitioned mesh (mof_dist_init) supports the Whitney vector field only");
     MOF_TRY(dog_preprocess(ctx));
@@ -127,6 +129,7 @@ int mof_create(int device, void* stream, mof_ctx** out) {
 void mof_destroy(mof_ctx* ctx) {
     if (!ctx) return;
     StreamScope scope(ctx);
+    smooth_ahead_destroy(ctx);
     cudaStreamSynchronize(ctx->stream);
     DBuf<double>* dbl[] = {&ctx->pos, &ctx->g, &ctx->area, &ctx->xlin, &ctx->xcst, &ctx->sMass, &ctx->sStiff, &ctx->sSys, &ctx->sDinv, &ctx->P, &ctx->m0, &ctx->m1,
                            &ctx->wS, &ctx->wA, &ctx->wDinv, &ctx->raw6, &ctx->sig6, &ctx->smoothed6, &ctx->rhs6, &ctx->resampled6, &ctx->tsample6, &ctx->dataD,
@@ -152,6 +155,7 @@ const char* mof_last_error(const mof_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int mof_set_params(mof_ctx* ctx, const mof_params* p) {
     if (!ctx || !p) return MOF_E_INVALID;
+    smooth_ahead_drain(ctx);
     if (p->vfMode < 0 || p->vfMode > 2) return fail(ctx, MOF_E_INVALID, "ERROR: Unsupported vector field! ");  // OpticalFlow.cpp:867
     if (p->vfMode == 2 && (p->cMode < 0 || p->cMode > 2)) return fail(ctx, MOF_E_INVALID, "Undefined Connection Mode ");  // Connection.inl:68
     if ((p->vfMode != ctx->params.vfMode || p->cMode != ctx->params.cMode || (p->dogWeight != ctx->params.dogWeight)) && ctx->haveSignals)
@@ -184,6 +188,7 @@ int mof_dist_init(mof_ctx* ctx, int world, int rank, const unsigned char id128[1
     if (!ctx) return MOF_E_INVALID;
     StreamScope scope(ctx);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, MOF_E_CUDA, "cudaSetDevice");
+    smooth_ahead_drain(ctx);
     ctx->haveMesh = ctx->haveSignals = false;  // the partition is built with the mesh
     return dist_init(ctx, world, rank, id128);
 }

@@ -72,6 +72,7 @@ __host__ __device__ __forceinline__ size_t sell_pos(const int* sliceBase, int ro
 struct Multigrid;  // multigrid.cu
 struct DistState;  // dist.cu
 struct VfState;    // vector_fields.cu
+struct SmoothAhead;  // flow_kernels.cu
 
 struct PcgWork {
     DBuf<double> r, d, q;       // [n * nrhs]
@@ -118,6 +119,7 @@ struct mof_ctx {
     mof::Multigrid* mgs = nullptr;  // ... and of the scalar smoothing systems
     mof::DistState* dist = nullptr; // one mesh over several GPUs (dist.cu); nullptr = single GPU
     mof::VfState* vf = nullptr;     // Conformal / Connection basis of the signals in place (vector_fields.cu); nullptr = Whitney
+    mof::SmoothAhead* ahead = nullptr;  // the NEXT iteration's smoothing solve, running on a second stream under the flow solve
     // 6-channel blend (0 < dogWeight < 1, OpticalFlow.cpp:849-855): sig6 holds the DoG half (times w), these the raw half (times 1-w)
     bool blend = false;
     mof::DBuf<double> sigLo6, smoothedLo6, resampledLo6;
@@ -258,6 +260,8 @@ int vf_update_flow(mof_ctx* ctx, double vfWeight);  // VectorField::UpdateOptica
 
 // flow_kernels.cu
 int dog_preprocess(mof_ctx* ctx);
+void smooth_ahead_drain(mof_ctx* ctx);    // waits for a smoothing solve in flight and drops its result (before anything it reads changes)
+void smooth_ahead_destroy(mof_ctx* ctx);
 int update_flow(mof_ctx* ctx, double sWeight, double vfWeight);
 int advect_vertices(mof_ctx* ctx, const double* in6, double lenA, double lenB, double* out6);
 int advect_texels(mof_ctx* ctx, double alpha, int bilinear);

@@ -286,3 +286,37 @@ def test_million_vertex_properties(aligner):
     al.set_signals(a, b)
     al.iterate(2)
     assert np.array_equal(al.flow(), f1)
+
+
+def test_smoothing_ahead_on_a_second_stream_changes_nothing(monkeypatch):
+    """The next iteration's smoothing solve runs on a second stream (a worker thread) under the flow solve. It is the
+    same computation on the same inputs: with it and without it (MOF_SMOOTH_AHEAD=0) every flow, the smoothed signals
+    and the iteration counts are identical, bit for bit."""
+    v, t = synthetic.octahedron_sphere(7)
+    a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(v, 6))
+    runs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MOF_SMOOTH_AHEAD", mode)
+        al = api.Aligner(0)
+        try:
+            p = api.default_params()
+            p.iterations = 5
+            al.set_params(p)
+            al.set_mesh(v, t)
+            al.set_signals(a, b)
+            flows = []
+            for i in range(5):  # one call per iteration, like the command line
+                al.iterate(1)
+                flows.append(al.flow())
+            smoothed = al.array(api.ARR_SMOOTHED)
+            al.set_signals(b, a)  # a solve in flight or not, new signals start clean
+            al.iterate(5)
+            s = al.stats()
+            runs[mode] = (flows, smoothed, al.flow(), s["smoothCgIterations"], s["flowCgIterations"], s["smoothSolves"])
+        finally:
+            al.close()
+    for x, y in zip(runs["1"][0], runs["0"][0]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(runs["1"][1], runs["0"][1]) and np.array_equal(runs["1"][2], runs["0"][2])
+    assert runs["1"][3:] == runs["0"][3:]
+    assert runs["1"][5] == 2 * (1 + 5)
