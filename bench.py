@@ -177,7 +177,9 @@ def main():
               "vertices": V, "pairs_per_step": 1 if args.partitioned else args.gpus,
               "parallelism": (f"one mesh, flow solves row-partitioned x{args.gpus} (NCCL halo exchange + all-reduce), everything else replicated" if args.partitioned
                               else f"independent pairs x{args.gpus} (no communication)"),
-              "l2": "inputs larger than L2: each step streams > 1 GB of operators per PCG iteration; no explicit flush", "pcg_tol": 1e-8}
+              "l2": "inputs larger than L2: each step streams > 1 GB of operators per PCG iteration; no explicit flush", "pcg_tol": 1e-8,
+              "streams": ("one" if os.environ.get("MOF_SMOOTH_AHEAD", "1") == "0" or args.partitioned
+                          else "two: the next iteration's smoothing solve runs under the flow solve (solve times below overlap)")}
     if args.impl == "reference":
         return run_reference_arm(args, config)
 

@@ -111,7 +111,13 @@ int mof_create(int device, void* stream, mof_ctx** out) {
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     if (stream) ctx->stream = (cudaStream_t)stream;
     else {
-        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MOF_E_CUDA; }
+        // The context's own stream carries the critical path (the flow solves); the smoothing solves that run ahead on a
+        // second stream (flow_kernels.cu) stay at the default, lowest priority and fill what it leaves free.
+        int least = 0, greatest = 0;
+        const char* pe = getenv("MOF_STREAM_PRIORITY");
+        const bool prioritise = !(pe && *pe == '0') && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least;
+        cudaError_t se = prioritise ? cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, greatest) : cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { delete ctx; return MOF_E_CUDA; }
         ctx->ownStream = true;
     }
     if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return MOF_E_CUDA; }

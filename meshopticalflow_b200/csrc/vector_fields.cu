@@ -63,7 +63,7 @@ int vf_init(mof_ctx* ctx) {
     s.mode = mode, s.cMode = ctx->params.cMode;
     s.N = mode == 1 ? 2ll * V : 2ll * T;
     MOF_CUDA(s.sc.alloc(S_COUNT));
-    MOF_CUDA(s.partial.alloc(2 * RED));
+    MOF_CUDA(s.partial.alloc(3 * RED));  // p.q | r.z, r.r
     MOF_CUDA(s.binv.alloc(3ull * (s.N / 2)));
     DBuf<double>* vecs[] = {&s.b, &s.x, &s.r, &s.z, &s.p, &s.q};
     for (auto* v : vecs) MOF_CUDA(v->alloc((size_t)s.N));
@@ -83,15 +83,16 @@ int vf_init(mof_ctx* ctx) {
     return MOF_OK;
 }
 
+// y = A x on the fixed grid, with the partial sums of x . y in s.partial[0..RED).
 static int vf_apply(mof_ctx* ctx, double weight, const double* x, double* y) {
     VfState& s = *ctx->vf;
     const int V = ctx->V, T = ctx->T;
     if (s.mode == 1) {
-        MOF_LAUNCH(k_conformal_tri, blocks_for(T, B), B, 0, ctx->tri.p, ctx->g.p, ctx->dataD.p, ctx->scalars.p, x, V, T, s.w.p);
-        MOF_LAUNCH(k_conformal_ku, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sStiff.p, s.minv.p, x, V, s.u.p);
-        MOF_LAUNCH(k_conformal_row, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sHe.p, ctx->sStiff.p, ctx->g.p, s.w.p, s.u.p, weight, V, y);
+        MOF_LAUNCH(k_conformal_stage1, RED, B, 0, ctx->tri.p, ctx->g.p, ctx->dataD.p, ctx->scalars.p, ctx->sRowptr.p, ctx->sCol.p, ctx->sStiff.p, s.minv.p, x, V, T, s.w.p,
+                   s.u.p);
+        MOF_LAUNCH(k_conformal_row, RED, B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sHe.p, ctx->sStiff.p, ctx->g.p, s.w.p, s.u.p, weight, x, V, y, s.partial.p);
     } else
-        MOF_LAUNCH(k_connection_apply, blocks_for(T, B), B, 0, ctx->dataD.p, s.connDiag.p, s.connOff.p, ctx->opp.p, ctx->scalars.p, weight, x, T, y);
+        MOF_LAUNCH(k_connection_apply, RED, B, 0, ctx->dataD.p, s.connDiag.p, s.connOff.p, ctx->opp.p, ctx->scalars.p, weight, x, T, y, s.partial.p);
     return MOF_OK;
 }
 
@@ -121,17 +122,15 @@ static int vf_pcg(mof_ctx* ctx, double weight, double tol, int maxIters, int* it
     double relres = 1;
     for (int restart = 0; restart < 8; restart++) {
         int cur = 0;
-        MOF_LAUNCH(k_pcg_start, RED, B, 0, s.binv.p, s.r.p, half, split, s.z.p, s.partial.p);
-        MOF_LAUNCH(k_fold, 1, B, 0, s.partial.p, RED, 2, sc + S_RZ0 + cur, sc + S_RR);
-        MOF_LAUNCH(k_pcg_direction, blocks_for(N, B), B, 0, sc, cur, -1, s.z.p, N, s.p.p);
+        double* rzrr = s.partial.p + RED;
+        MOF_LAUNCH(k_pcg_start, RED, B, 0, s.binv.p, s.r.p, half, split, s.z.p, rzrr);
+        MOF_LAUNCH(k_pcg_direction, RED, B, 0, sc, S_RZ0 + cur, -1, rzrr, RED, s.z.p, N, s.p.p);
         bool converged = false;
         while (iters < maxIters && !converged) {
             for (int k = 0; k < kCheck && iters < maxIters; k++, iters++) {
                 MOF_TRY(vf_apply(ctx, weight, s.p.p, s.q.p));
-                MOF_TRY(vf_dot(ctx, s.p.p, s.q.p, N, sc + S_PQ));
-                MOF_LAUNCH(k_pcg_step, RED, B, 0, s.binv.p, sc, S_RZ0 + cur, s.p.p, s.q.p, half, split, s.x.p, s.r.p, s.z.p, s.partial.p);
-                MOF_LAUNCH(k_fold, 1, B, 0, s.partial.p, RED, 2, sc + S_RZ0 + (cur ^ 1), sc + S_RR);
-                MOF_LAUNCH(k_pcg_direction, blocks_for(N, B), B, 0, sc, S_RZ0 + (cur ^ 1), S_RZ0 + cur, s.z.p, N, s.p.p);
+                MOF_LAUNCH(k_pcg_step, RED, B, 0, s.binv.p, sc, S_RZ0 + cur, s.partial.p, RED, s.p.p, s.q.p, half, split, s.x.p, s.r.p, s.z.p, rzrr);
+                MOF_LAUNCH(k_pcg_direction, RED, B, 0, sc, S_RZ0 + (cur ^ 1), S_RZ0 + cur, rzrr, RED, s.z.p, N, s.p.p);
                 cur ^= 1;
             }
             double rr = 0;

@@ -213,80 +213,115 @@ __global__ void k_conformal_finalize(const int* __restrict__ rowptr, const int* 
 }
 
 // ------------------------------------------------------------------------------ operator application
+//
+// The apply kernels run on a FIXED grid of RED CTAs (grid-stride loops) and leave the partial sums of x . (A x) in
+// partial[0..RED): the PCG's p.q costs no launch of its own, and its consumer folds the RED partials itself.
+
+// Sum over the CTA, returned to every thread (fixed order: deterministic).
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[B];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = B / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    double s = sh[0];
+    __syncthreads();
+    return s;
+}
+// Sum of np partials; every CTA that calls it adds them in the same order and gets the same bits.
+__device__ __forceinline__ double fold_partials(const double* __restrict__ partial, int np) {
+    double s = 0;
+    for (int i = threadIdx.x; i < np; i += B) s += partial[i];
+    return block_sum(s);
+}
 
 // Connection: y_t = (s D_t + w Sdiag_t) x_t + w sum_j Soff_tj x_nbr(j).
 __global__ void k_connection_apply(const double* __restrict__ D, const double* __restrict__ diag, const double* __restrict__ off, const int* __restrict__ opp,
-                                   const double* __restrict__ scalars, double weight, const double* __restrict__ x, int T, double* __restrict__ y) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    double s = scalars[SC_DATA_SCALE];
-    double a00 = s * D[3 * t] + weight * diag[3 * t], a01 = s * D[3 * t + 1] + weight * diag[3 * t + 1], a11 = s * D[3 * t + 2] + weight * diag[3 * t + 2];
-    double x0 = x[2 * t], x1 = x[2 * t + 1];
-    double y0 = a00 * x0 + a01 * x1, y1 = a01 * x0 + a11 * x1;
-    double o0 = 0, o1 = 0;
+                                   const double* __restrict__ scalars, double weight, const double* __restrict__ x, int T, double* __restrict__ y,
+                                   double* __restrict__ partial) {
+    const double s = scalars[SC_DATA_SCALE];
+    double dot = 0;
+    for (int t = blockIdx.x * B + threadIdx.x; t < T; t += gridDim.x * B) {
+        double a00 = s * D[3 * t] + weight * diag[3 * t], a01 = s * D[3 * t + 1] + weight * diag[3 * t + 1], a11 = s * D[3 * t + 2] + weight * diag[3 * t + 2];
+        double x0 = x[2 * t], x1 = x[2 * t + 1];
+        double y0 = a00 * x0 + a01 * x1, y1 = a01 * x0 + a11 * x1;
+        double o0 = 0, o1 = 0;
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        int n = opp[3 * t + j] / 3;
-        const double* X = off + 12 * (size_t)t + 4 * j;
-        double n0 = x[2 * n], n1 = x[2 * n + 1];
-        o0 += X[0] * n0 + X[1] * n1, o1 += X[2] * n0 + X[3] * n1;
+        for (int j = 0; j < 3; j++) {
+            int n = opp[3 * t + j] / 3;
+            const double* X = off + 12 * (size_t)t + 4 * j;
+            double n0 = x[2 * n], n1 = x[2 * n + 1];
+            o0 += X[0] * n0 + X[1] * n1, o1 += X[2] * n0 + X[3] * n1;
+        }
+        y0 += weight * o0, y1 += weight * o1;
+        y[2 * t] = y0, y[2 * t + 1] = y1;
+        dot += x0 * y0 + x1 * y1;
     }
-    y[2 * t] = y0 + weight * o0, y[2 * t + 1] = y1 + weight * o1;
+    dot = block_sum(dot);
+    if (!threadIdx.x) partial[blockIdx.x] = dot;
 }
 
-// Conformal, stage 1 (triangles): w_t = s D_t (P x)_t.
-__global__ void k_conformal_tri(const int* __restrict__ tri, const double* __restrict__ g, const double* __restrict__ D, const double* __restrict__ scalars,
-                                const double* __restrict__ x, int V, int T, double* __restrict__ w) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    ConformalP p;
-    conformal_p(g, t, p);
-    double z[2] = {0, 0};
+// Conformal, stage 1, one launch for two independent loops: triangles w_t = s D_t (P x)_t, vertices u = diag(1/m) K x
+// on both halves.
+__global__ void k_conformal_stage1(const int* __restrict__ tri, const double* __restrict__ g, const double* __restrict__ D, const double* __restrict__ scalars,
+                                   const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ stiff, const double* __restrict__ minv,
+                                   const double* __restrict__ x, int V, int T, double* __restrict__ w, double* __restrict__ u) {
+    const double s = scalars[SC_DATA_SCALE];
+    for (int t = blockIdx.x * B + threadIdx.x; t < T; t += gridDim.x * B) {
+        ConformalP p;
+        conformal_p(g, t, p);
+        double z[2] = {0, 0};
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        int v = tri[3 * t + k];
-        double a = x[v], b = x[v + V];
-        z[0] += p.pg[k][0] * a + p.pr[k][0] * b, z[1] += p.pg[k][1] * a + p.pr[k][1] * b;
+        for (int k = 0; k < 3; k++) {
+            int v = tri[3 * t + k];
+            double a = x[v], b = x[v + V];
+            z[0] += p.pg[k][0] * a + p.pr[k][0] * b, z[1] += p.pg[k][1] * a + p.pr[k][1] * b;
+        }
+        const double* Dt = D + 3 * (size_t)t;
+        w[2 * t] = s * (Dt[0] * z[0] + Dt[1] * z[1]), w[2 * t + 1] = s * (Dt[1] * z[0] + Dt[2] * z[1]);
     }
-    double s = scalars ? scalars[SC_DATA_SCALE] : 1.0;
-    const double* Dt = D + 3 * (size_t)t;
-    w[2 * t] = s * (Dt[0] * z[0] + Dt[1] * z[1]), w[2 * t + 1] = s * (Dt[1] * z[0] + Dt[2] * z[1]);
-}
-// Conformal, stage 2 (vertices): u = diag(1/m) K x on both halves.
-__global__ void k_conformal_ku(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ stiff, const double* __restrict__ minv,
-                               const double* __restrict__ x, int V, double* __restrict__ u) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= V) return;
-    double a = 0, b = 0;
-    for (int k = rowptr[v]; k < rowptr[v + 1]; k++) {
-        double kv = stiff[k];
-        int c = col[k];
-        a += kv * x[c], b += kv * x[c + V];
+    for (int v = blockIdx.x * B + threadIdx.x; v < V; v += gridDim.x * B) {
+        double a = 0, b = 0;
+        for (int k = rowptr[v]; k < rowptr[v + 1]; k++) {
+            double kv = stiff[k];
+            int c = col[k];
+            a += kv * x[c], b += kv * x[c + V];
+        }
+        u[2 * (size_t)v] = a * minv[v], u[2 * (size_t)v + 1] = b * minv[v];
     }
-    u[2 * (size_t)v] = a * minv[v], u[2 * (size_t)v + 1] = b * minv[v];
 }
-// Conformal, stage 3 (vertices): y = w/2 K u + P^T w.
+// Conformal, stage 2 (vertices): y = w/2 K u + P^T w, with the partials of x . y.
 __global__ void k_conformal_row(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ he, const double* __restrict__ stiff,
-                                const double* __restrict__ g, const double* __restrict__ w, const double* __restrict__ u, double weight, int V,
-                                double* __restrict__ y) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= V) return;
-    double ka = 0, kb = 0, ya = 0, yb = 0;
-    for (int k = rowptr[v]; k < rowptr[v + 1]; k++) {
-        double kv = stiff[k];
-        int c = col[k];
-        ka += kv * u[2 * (size_t)c], kb += kv * u[2 * (size_t)c + 1];
-        int h = he[k];
-        if (h < 0) continue;
-        int t = h / 3, j = h - 3 * t;
-        double pg[2], pr[2];
-        conformal_corner(g, t, (j + 1) % 3, pg, pr);
-        ya += pg[0] * w[2 * t] + pg[1] * w[2 * t + 1], yb += pr[0] * w[2 * t] + pr[1] * w[2 * t + 1];
+                                const double* __restrict__ g, const double* __restrict__ w, const double* __restrict__ u, double weight, const double* __restrict__ x,
+                                int V, double* __restrict__ y, double* __restrict__ partial) {
+    double dot = 0;
+    for (int v = blockIdx.x * B + threadIdx.x; v < V; v += gridDim.x * B) {
+        double ka = 0, kb = 0, ya = 0, yb = 0;
+        for (int k = rowptr[v]; k < rowptr[v + 1]; k++) {
+            double kv = stiff[k];
+            int c = col[k];
+            ka += kv * u[2 * (size_t)c], kb += kv * u[2 * (size_t)c + 1];
+            int h = he[k];
+            if (h < 0) continue;
+            int t = h / 3, j = h - 3 * t;
+            double pg[2], pr[2];
+            conformal_corner(g, t, (j + 1) % 3, pg, pr);
+            ya += pg[0] * w[2 * t] + pg[1] * w[2 * t + 1], yb += pr[0] * w[2 * t] + pr[1] * w[2 * t + 1];
+        }
+        ya += 0.5 * weight * ka, yb += 0.5 * weight * kb;
+        y[v] = ya, y[v + V] = yb;
+        dot += x[v] * ya + x[v + V] * yb;
     }
-    y[v] = 0.5 * weight * ka + ya, y[v + V] = 0.5 * weight * kb + yb;
+    dot = block_sum(dot);
+    if (!threadIdx.x) partial[blockIdx.x] = dot;
 }
 
 // ------------------------------------------------------------------------------------------ PCG
+//
+// One iteration = apply (above; p.q partials) -> k_pcg_step -> k_pcg_direction, all on RED CTAs. Scalars live in
+// sc[]: r.z alternates between two slots so that no launch reads a slot another CTA of the same launch writes.
 
 // pair i of the unknowns: (2i, 2i+1) interleaved (Connection) or (i, i+half) split (Conformal)
 __device__ __forceinline__ void pair_index(long long i, long long half, int split, long long& i0, long long& i1) {
@@ -294,10 +329,9 @@ __device__ __forceinline__ void pair_index(long long i, long long half, int spli
     else i0 = 2 * i, i1 = 2 * i + 1;
 }
 
-// z = Binv r, partial sums of r.z and r.r (start of a solve or a restart).
+// z = Binv r, partial sums of r.z (out[0..RED)) and r.r (out[RED..2RED)) (start of a solve or a restart).
 __global__ void k_pcg_start(const double* __restrict__ binv, const double* __restrict__ r, long long half, int split, double* __restrict__ z,
-                            double* __restrict__ partial) {
-    __shared__ double sh[2][B];
+                            double* __restrict__ out) {
     double srz = 0, srr = 0;
     for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < half; i += (long long)gridDim.x * B) {
         long long i0, i1;
@@ -308,20 +342,15 @@ __global__ void k_pcg_start(const double* __restrict__ binv, const double* __res
         z[i0] = z0, z[i1] = z1;
         srz += r0 * z0 + r1 * z1, srr += r0 * r0 + r1 * r1;
     }
-    sh[0][threadIdx.x] = srz, sh[1][threadIdx.x] = srr;
-    __syncthreads();
-    for (int o = B / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sh[0][threadIdx.x] += sh[0][threadIdx.x + o], sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
-        __syncthreads();
-    }
-    if (!threadIdx.x) partial[blockIdx.x] = sh[0][0], partial[gridDim.x + blockIdx.x] = sh[1][0];
+    srz = block_sum(srz), srr = block_sum(srr);
+    if (!threadIdx.x) out[blockIdx.x] = srz, out[gridDim.x + blockIdx.x] = srr;
 }
-// alpha = rz / pq; x += alpha p; r -= alpha q; z = Binv r; partial sums of r.z and r.r.
-__global__ void k_pcg_step(const double* __restrict__ binv, const double* __restrict__ sc, int rzSlot, const double* __restrict__ p, const double* __restrict__ q,
-                           long long half, int split, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z, double* __restrict__ partial) {
-    __shared__ double sh[2][B];
-    double pq = sc[S_PQ];
-    double alpha = pq != 0 ? sc[rzSlot] / pq : 0.0;
+// alpha = rz / (sum of the p.q partials); x += alpha p; r -= alpha q; z = Binv r; partial sums of r.z and r.r.
+__global__ void k_pcg_step(const double* __restrict__ binv, const double* __restrict__ sc, int rzSlot, const double* __restrict__ pqPartial, int np,
+                           const double* __restrict__ p, const double* __restrict__ q, long long half, int split, double* __restrict__ x, double* __restrict__ r,
+                           double* __restrict__ z, double* __restrict__ out) {
+    const double pq = fold_partials(pqPartial, np);
+    const double alpha = pq != 0 ? sc[rzSlot] / pq : 0.0;
     double srz = 0, srr = 0;
     for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < half; i += (long long)gridDim.x * B) {
         long long i0, i1;
@@ -334,24 +363,21 @@ __global__ void k_pcg_step(const double* __restrict__ binv, const double* __rest
         z[i0] = z0, z[i1] = z1;
         srz += r0 * z0 + r1 * z1, srr += r0 * r0 + r1 * r1;
     }
-    sh[0][threadIdx.x] = srz, sh[1][threadIdx.x] = srr;
-    __syncthreads();
-    for (int o = B / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sh[0][threadIdx.x] += sh[0][threadIdx.x + o], sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
-        __syncthreads();
-    }
-    if (!threadIdx.x) partial[blockIdx.x] = sh[0][0], partial[gridDim.x + blockIdx.x] = sh[1][0];
+    srz = block_sum(srz), srr = block_sum(srr);
+    if (!threadIdx.x) out[blockIdx.x] = srz, out[gridDim.x + blockIdx.x] = srr;
 }
-// p = z + (rzNew / rzOld) p   (rzOld slot < 0: p = z)
-__global__ void k_pcg_direction(const double* __restrict__ sc, int newSlot, int oldSlot, const double* __restrict__ z, long long n, double* __restrict__ p) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// Folds the r.z / r.r partials (CTA 0 publishes them in sc[newSlot], sc[S_RR]); p = z + (rzNew / rzOld) p, or p = z when
+// oldSlot < 0.
+__global__ void k_pcg_direction(double* __restrict__ sc, int newSlot, int oldSlot, const double* __restrict__ rzrr, int np, const double* __restrict__ z,
+                                long long n, double* __restrict__ p) {
+    const double rzNew = fold_partials(rzrr, np), rr = fold_partials(rzrr + np, np);
     double beta = 0;
     if (oldSlot >= 0) {
         double o = sc[oldSlot];
-        beta = o != 0 ? sc[newSlot] / o : 0.0;
+        beta = o != 0 ? rzNew / o : 0.0;
     }
-    p[i] = z[i] + (oldSlot >= 0 ? beta * p[i] : 0.0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc[newSlot] = rzNew, sc[S_RR] = rr;
+    for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < n; i += (long long)gridDim.x * B) p[i] = z[i] + (oldSlot >= 0 ? beta * p[i] : 0.0);
 }
 __global__ void k_residual(const double* __restrict__ b, const double* __restrict__ ax, long long n, double* __restrict__ r) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
