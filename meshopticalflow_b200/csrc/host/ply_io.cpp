@@ -134,6 +134,7 @@ bool ply_read(const char* file_name, PlyMesh& mesh, std::string& err) {
     if (!sawPly || !done || format < 0) { err = std::string("not a PLY file: ") + file_name; return false; }
 
     mesh = PlyMesh();
+    mesh.format = format;
     Reader rd{bytes.data(), (size_t)size, pos, format};
     for (const Element& el : elements) {
         bool isVertex = el.name == "vertex", isFace = el.name == "face";

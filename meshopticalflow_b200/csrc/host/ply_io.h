@@ -16,6 +16,7 @@ struct PlyMesh {
     std::vector<int> faceIndex;    // concatenated vertex indices
     std::vector<int> uvSize;       // texcoord entries per face (empty if the file has none)
     std::vector<float> uv;         // concatenated texcoord values
+    int format = 0;                // as read: 0 ascii, 1 binary_little_endian, 2 binary_big_endian
     size_t vertexCount() const { return xyz.size() / 3; }
     size_t faceCount() const { return faceSize.size(); }
 };

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # TEST INFRASTRUCTURE ONLY.
-# Builds oracle/_ref/OpticalFlow_ref: the reference's own OpticalFlow.cpp + include/ headers,
+# Builds oracle/_ref/OpticalFlow_ref (and SampleTextureToVertices_ref): the reference's own OpticalFlow.cpp + include/ headers,
 # compiled from where they lie under $MOF_REFERENCE (default /root/reference) with the shipped
 # Makefile's release flags (OpticalFlow/Makefile:6,12), MKL off as shipped (OpticalFlow.cpp:29).
 # No reference source is copied into the repository: the few generated files below live in a
@@ -45,3 +45,8 @@ g++ $CXXFLAGS \
     "$HERE/ref_driver.cpp" "$REPO/meshopticalflow_b200/csrc/host/png_codec.cpp" \
     -o "$OUT/OpticalFlow_ref" -lgomp -lz
 echo "build_ref: built $OUT/OpticalFlow_ref"
+# The sibling tool that makes per-vertex inputs from the texture configuration's files; compiles as it is.
+g++ $CXXFLAGS -I"$HERE/shims" -I"$REPO/meshopticalflow_b200/csrc/host" -I"$REF/include" \
+    "$REF/SampleTextureToVertices/SampleTextureToVertices.cpp" "$REPO/meshopticalflow_b200/csrc/host/png_codec.cpp" \
+    -o "$OUT/SampleTextureToVertices_ref" -lgomp -lz
+echo "build_ref: built $OUT/SampleTextureToVertices_ref"

@@ -6,6 +6,7 @@ seeded inputs and stores inputs + selected reference outputs as compressed .npz:
 
   sphere3_vertex.npz   --in A.ply B.ply --out r.ply on the 258-vertex octahedron sphere, 10 iterations
   torus_texture.npz    --mesh m.ply --in A.png B.png --out r.png --eLength 0.08 on a 24x12 uv torus, 48x48 texels
+  sample_texture_tool.npz  oracle/_ref/SampleTextureToVertices_ref on the uv torus (ascii, subdivided, binary): files in, files out
   sphere3_modes.npz    the 258-vertex sphere again with 4 iterations of --vfMode 1, --vfMode 2 --cMode 0|1|2 (taps) and of
                        --dogWeight 0.5 (the 6-channel blend: output colours only, the tap build is 3-channel)
 
@@ -83,6 +84,33 @@ def torus():
     print("torus_texture.npz", os.path.getsize(os.path.join(HERE, "torus_texture.npz")) // 1024, "KiB")
 
 
+def tool():
+    """SampleTextureToVertices (the sibling tool) on the uv torus: input files and the reference's output files, byte for byte."""
+    from PIL import Image
+    ref_tool = os.path.join(ROOT, "oracle", "_ref", "SampleTextureToVertices_ref")
+    v, t, uv = synthetic.uv_torus(24, 12)
+    ta, _ = synthetic.smooth_texture_pair(48, 48, 1)
+    data = {}
+    with tempfile.TemporaryDirectory() as d:
+        synthetic.write_ply_textured(os.path.join(d, "m.ply"), v, t, uv)
+        with open(os.path.join(d, "mb.ply"), "wb") as fp:  # the same mesh as binary records
+            fp.write((f"ply\nformat binary_little_endian 1.0\nelement vertex {len(v)}\nproperty float x\nproperty float y\nproperty float z\n"
+                      f"element face {len(t)}\nproperty list uchar int vertex_indices\nproperty list uchar float texcoord\nend_header\n").encode())
+            fp.write(np.asarray(v, dtype="<f4").tobytes())
+            rec = np.zeros(len(t), dtype=[("n", "u1"), ("i", "<i4", 3), ("m", "u1"), ("uv", "<f4", 6)])
+            rec["n"], rec["i"], rec["m"], rec["uv"] = 3, t, 6, uv
+            fp.write(rec.tobytes())
+        Image.fromarray(ta).save(os.path.join(d, "A.png"))
+        runs = {"plain": ["--in", "m.ply"], "subdivided": ["--in", "m.ply", "--eLength", "0.08"], "binary": ["--in", "mb.ply", "--eLength", "0.1"]}
+        for name, flags in runs.items():
+            subprocess.check_call([ref_tool, "--texture", "A.png", "--out", name + ".ply"] + flags, cwd=d, stdout=subprocess.DEVNULL)
+            data["out_" + name] = np.frombuffer(open(os.path.join(d, name + ".ply"), "rb").read(), dtype=np.uint8)
+        for f in ("m.ply", "mb.ply", "A.png"):
+            data["in_" + f] = np.frombuffer(open(os.path.join(d, f), "rb").read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "sample_texture_tool.npz"), **data)
+    print("sample_texture_tool.npz", os.path.getsize(os.path.join(HERE, "sample_texture_tool.npz")) // 1024, "KiB")
+
+
 MODES = {"conformal": ["--vfMode", "1"], "connection0": ["--vfMode", "2"], "connection1": ["--vfMode", "2", "--cMode", "1"],
          "connection2": ["--vfMode", "2", "--cMode", "2"]}
 
@@ -115,9 +143,10 @@ def modes():
 if __name__ == "__main__":
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/OpticalFlow_ref is missing: run oracle/ref/build_ref.sh (needs /root/reference)")
-    if len(sys.argv) > 1 and sys.argv[1] == "modes":
-        modes()
+    if len(sys.argv) > 1 and sys.argv[1] in ("modes", "tool"):
+        {"modes": modes, "tool": tool}[sys.argv[1]]()
         sys.exit(0)
     sphere()
     torus()
     modes()
+    tool()
