@@ -80,6 +80,13 @@ __global__ void k_mul(const double* __restrict__ a, const double* __restrict__ b
 
 // ---------------------------------------------------------------- scalar smoothing (a9) and DoG (a5)
 
+int scalar_system_set(mof_ctx* ctx, double eps) {
+    MOF_LAUNCH(k_axpby, blocks_for(ctx->nnzS, B), B, 0, ctx->sMass.p, ctx->sStiff.p, eps, ctx->nnzS, ctx->sSys.p);
+    MOF_TRY(extract_inverse_diagonal(ctx, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, ctx->sDinv.p));
+    if (mg_scalar_usable(ctx)) MOF_TRY(mg_scalar_update(ctx));
+    return MOF_OK;
+}
+
 // `sameSystem`: the matrix, its inverse diagonal and the multigrid coarse operators are those of the previous call.
 static int smooth_solve(mof_ctx* ctx, double weight, const double* in6, double* out6, double tol, bool sameSystem = false) {
     const int V = ctx->V;
@@ -559,7 +566,8 @@ int update_flow(mof_ctx* ctx, double sWeight, double vfWeight) {
     MOF_LAUNCH(k_data_term, blocks_for(T, B), B, 0, ctx->tri.p, ctx->area.p, ctx->resampled6.p, ctx->blend ? ctx->resampledLo6.p : nullptr, T, ctx->dataD.p,
                ctx->dataRhs.p);
     // the next iteration's smoothing (IterativeOptimization's schedule, OpticalFlow.cpp:1041) runs under this iteration's flow solve
-    if (sWeight && ctx->iterationsDone + 1 < ctx->params.iterations) smooth_ahead_start(ctx, sWeight * ctx->params.sMultiply);
+    // (not when the flow solve itself borrows the scalar hierarchy: the Conformal basis' preconditioner)
+    if (sWeight && ctx->iterationsDone + 1 < ctx->params.iterations && !vf_uses_scalar_hierarchy(ctx)) smooth_ahead_start(ctx, sWeight * ctx->params.sMultiply);
     if (vf_active(ctx)) return vf_update_flow(ctx, vfWeight);  // Conformal / Connection basis (vector_fields.cu)
     // system (VectorField.h:51-67)
     MOF_CUDA(ctx->dtmp0.reserve((size_t)(E > T ? E : T)));

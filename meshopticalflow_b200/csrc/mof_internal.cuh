@@ -233,6 +233,7 @@ int mg_flow_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double*
 bool mg_scalar_usable(const mof_ctx* ctx);
 int mg_scalar_update(mof_ctx* ctx);   // per scalar system: coarse operators of the current sSys (sDinv = its inverse diagonal)
 int mg_scalar_solve(mof_ctx* ctx, const double* b6, double* x6, double tol, int maxIters, int* itersOut, double* relresOut);  // x6 = initial guess
+int mg_scalar_cycle(mof_ctx* ctx, const double* r6, double* z6);  // z6 = one cycle applied to r6 (approximate inverse of the current sSys)
 
 // dist.cu — one mesh over several GPUs: row blocks of the flow system, halo exchange, all-reduce (NCCL on ctx->stream)
 int dist_unique_id(unsigned char* id128);
@@ -253,6 +254,7 @@ int dist_allgather_rows(mof_ctx* ctx, int kind, double* vec);  // every rank's r
 int vf_init(mof_ctx* ctx);                 // per signal pair, for ctx->params.vfMode / cMode (mode 0 releases the state)
 void vf_destroy(mof_ctx* ctx);
 bool vf_active(const mof_ctx* ctx);
+bool vf_uses_scalar_hierarchy(const mof_ctx* ctx);  // Conformal with the two-cycle preconditioner: the flow solve re-values sSys and the scalar hierarchy
 long long vf_unknowns(const mof_ctx* ctx);  // E (Whitney), 2V (Conformal) or 2T (Connection)
 const double* vf_rhs(const mof_ctx* ctx);
 const double* vf_solution(const mof_ctx* ctx);
@@ -260,6 +262,7 @@ int vf_update_flow(mof_ctx* ctx, double vfWeight);  // VectorField::UpdateOptica
 
 // flow_kernels.cu
 int dog_preprocess(mof_ctx* ctx);
+int scalar_system_set(mof_ctx* ctx, double eps);  // sSys = M + eps S, its inverse diagonal and (if usable) the scalar hierarchy's coarse operators
 void smooth_ahead_drain(mof_ctx* ctx);    // waits for a smoothing solve in flight and drops its result (before anything it reads changes)
 void smooth_ahead_destroy(mof_ctx* ctx);
 int update_flow(mof_ctx* ctx, double sWeight, double vfWeight);

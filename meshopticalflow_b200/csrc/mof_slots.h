@@ -12,6 +12,7 @@ enum ScalarSlot {
     SC_DATA_SCALE = 2,   // 1 / ||R D P||_F
     SC_STEP_NUM = 3,     // x . b
     SC_STEP_DEN = 4,     // x . Dt x
+    SC_TMP = 5,          // scratch of the call in progress
     SC_DOG = 8,          // 8..8+4*6: per channel old avg, old dot, new avg, new dot
     SC_COUNT = 64
 };

@@ -1689,6 +1689,16 @@ int mg_scalar_update(mof_ctx* ctx) {
     MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->sDinv.p, (long long)ctx->V, mg.fdinv.p);
     return finish_values(ctx, mg);
 }
+// One cycle of the SCALAR hierarchy as an approximate solve of sSys Z = R from a zero guess (six channels, [V][6]): a fixed,
+// symmetric positive definite operator (to the fp32 of the cycle). The coarse operators must be those of the current sSys
+// (mg_scalar_update). A building block for preconditioners outside this file (the Conformal basis, vector_fields.cu).
+int mg_scalar_cycle(mof_ctx* ctx, const double* r6, double* z6) {
+    Multigrid& mg = *ctx->mgs;
+    MOF_TRY(fine_cycle(ctx, mg, r6, false, S_RZ));
+    const long long len = (long long)mg.fineLen();
+    MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 1, z6);
+    return MOF_OK;
+}
 int mg_scalar_solve(mof_ctx* ctx, const double* b6, double* x6, double tol, int maxIters, int* itersOut, double* relresOut) {
     if (dist_active(ctx)) return mg_pcg_dist(ctx, *ctx->mgs, b6, x6, false, tol, maxIters, itersOut, relresOut);
     return mg_pcg(ctx, *ctx->mgs, b6, x6, false, tol, maxIters, itersOut, relresOut);

@@ -358,10 +358,13 @@ __global__ void k_pcg_step(const double* __restrict__ binv, const double* __rest
         x[i0] += alpha * p[i0], x[i1] += alpha * p[i1];
         double r0 = r[i0] - alpha * q[i0], r1 = r[i1] - alpha * q[i1];
         r[i0] = r0, r[i1] = r1;
-        const double* bq = binv + 3 * i;
-        double z0 = bq[0] * r0 + bq[1] * r1, z1 = bq[1] * r0 + bq[2] * r1;
-        z[i0] = z0, z[i1] = z1;
-        srz += r0 * z0 + r1 * z1, srr += r0 * r0 + r1 * r1;
+        if (binv) {  // block-Jacobi; with another preconditioner the caller computes z and the r.z partials afterwards
+            const double* bq = binv + 3 * i;
+            double z0 = bq[0] * r0 + bq[1] * r1, z1 = bq[1] * r0 + bq[2] * r1;
+            z[i0] = z0, z[i1] = z1;
+            srz += r0 * z0 + r1 * z1;
+        }
+        srr += r0 * r0 + r1 * r1;
     }
     srz = block_sum(srz), srr = block_sum(srr);
     if (!threadIdx.x) out[blockIdx.x] = srz, out[gridDim.x + blockIdx.x] = srr;
@@ -379,6 +382,39 @@ __global__ void k_pcg_direction(double* __restrict__ sc, int newSlot, int oldSlo
     if (blockIdx.x == 0 && threadIdx.x == 0) sc[newSlot] = rzNew, sc[S_RR] = rr;
     for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < n; i += (long long)gridDim.x * B) p[i] = z[i] + (oldSlot >= 0 ? beta * p[i] : 0.0);
 }
+// ---- Conformal basis, two-cycle preconditioner: z = kappa C M C r on each half, C = one cycle of the scalar multigrid
+// hierarchy on M + eps K (six-channel layout [V][6]: the two halves ride in channels 0 and 1, the others stay zero).
+__global__ void k_conformal_pack(const double* __restrict__ r, int V, double* __restrict__ r6) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    double* d = r6 + 6 * (size_t)v;
+    d[0] = r[v], d[1] = r[v + V], d[2] = d[3] = d[4] = d[5] = 0;
+}
+__global__ void k_conformal_weight(const double* __restrict__ z6, const double* __restrict__ m0, int V, double* __restrict__ r6) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    double* d = r6 + 6 * (size_t)v;
+    d[0] = m0[v] * z6[6 * (size_t)v], d[1] = m0[v] * z6[6 * (size_t)v + 1], d[2] = d[3] = d[4] = d[5] = 0;
+}
+__global__ void k_conformal_unpack(const double* __restrict__ z6, double kappa, int V, double* __restrict__ z) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    z[v] = kappa * z6[6 * (size_t)v], z[v + V] = kappa * z6[6 * (size_t)v + 1];
+}
+// the diagonal of the stiffness matrix / the trace of a vertex's diagonal block of P^T D P (to balance eps)
+__global__ void k_stiffness_diagonal(const int* __restrict__ rowptr, const int* __restrict__ he, const double* __restrict__ stiff, int V, double* __restrict__ out) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    double d = 0;
+    for (int k = rowptr[v]; k < rowptr[v + 1]; k++)
+        if (he[k] < 0) d = stiff[k];
+    out[v] = d;
+}
+__global__ void k_block_trace(const double* __restrict__ blk, int V, double* __restrict__ out) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < V) out[v] = blk[4 * (size_t)v] + blk[4 * (size_t)v + 2];
+}
+
 __global__ void k_residual(const double* __restrict__ b, const double* __restrict__ ax, long long n, double* __restrict__ r) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) r[i] = b[i] - ax[i];

@@ -186,3 +186,28 @@ def test_debug_dumps(tmp_path):
                 assert np.array_equal(out["face"]["vertex_indices"], t)
     finally:
         al.close()
+
+
+def test_conformal_two_cycle_preconditioner(monkeypatch):
+    """Conformal basis at 16 386 vertices: PCG preconditioned by two cycles of the scalar multigrid hierarchy around the
+    lumped mass (default where the hierarchy exists) against block Jacobi (MOF_CONFORMAL_MG=0): same flow, at least five
+    times fewer iterations, and the smoothing solves that share the hierarchy are undisturbed."""
+    v, t = synthetic.octahedron_sphere(6)
+    a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(v, 8))
+    runs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MOF_CONFORMAL_MG", mode)
+        al = api.Aligner(0)
+        try:
+            al.set_params(_params(2, 1))
+            al.set_mesh(v, t)
+            al.set_signals(a, b)
+            al.iterate(2)
+            s = al.stats()
+            assert s["lastFlowResidual"] <= 1e-8 and s["lastSmoothResidual"] <= 1.01e-10
+            runs[mode] = (al.flow(), s["flowCgIterations"], s["smoothCgIterations"], al.array(api.ARR_SMOOTHED))
+        finally:
+            al.close()
+    assert rel(runs["1"][0], runs["0"][0]) < 1e-5
+    assert runs["1"][1] * 5 < runs["0"][1], (runs["1"][1], runs["0"][1])
+    assert runs["1"][2] == runs["0"][2] and rel(runs["1"][3], runs["0"][3]) < 1e-9

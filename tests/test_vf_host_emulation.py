@@ -41,8 +41,10 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
-@pytest.mark.parametrize("name", sorted(VF_MODES))
-def test_vector_field_source_on_the_host(emul, golden_modes, name):
+@pytest.mark.parametrize("name,hierarchy", [(n, 0) for n in sorted(VF_MODES)] + [("conformal", 1)])
+def test_vector_field_source_on_the_host(emul, golden_modes, name, hierarchy):
+    """hierarchy = 1: the Conformal PCG preconditioned by two "cycles" of the scalar hierarchy around the lumped mass (here a
+    dense solve of M + eps K rounded to fp32 stands in for a cycle) instead of block Jacobi."""
     g = golden_modes
     vf_mode, c_mode = VF_MODES[name]
     v = g["input_vertices_f32"].astype(np.float64)
@@ -63,16 +65,22 @@ def test_vector_field_source_on_the_host(emul, golden_modes, name):
     rhs = np.ascontiguousarray(np.stack([st.taps["it%02d.rhs" % i] for i in range(steps)]))
     outB, outX, outC = np.zeros((steps, N)), np.zeros((steps, N)), np.zeros((steps, N))
     outF, outS = np.zeros((steps, T, 2)), np.zeros(steps)
-    iters, relres = ctypes.c_longlong(), ctypes.c_double()
+    iters, relres, cycles = ctypes.c_longlong(), ctypes.c_double(), ctypes.c_int()
+    Mc = st.M
+    assert np.array_equal(Mc.indptr, S.indptr) and np.array_equal(Mc.indices, S.indices)
     arrs = dict(g=np.ascontiguousarray(st.g), area=np.ascontiguousarray(st.area), opp=np.ascontiguousarray(st.opp, dtype=np.int32), lin=np.ascontiguousarray(st.lin),
                 cst=np.ascontiguousarray(st.cst), tri=np.ascontiguousarray(t, dtype=np.int32), rp=S.indptr.astype(np.int32), col=S.indices.astype(np.int32),
                 val=np.ascontiguousarray(S.data))
     rc = emul.emul_vf_run(V, T, _p(arrs["g"], _D), _p(arrs["area"], _D), _p(arrs["opp"], _I), _p(arrs["lin"], _D), _p(arrs["cst"], _D), _p(arrs["tri"], _I),
-                          _p(arrs["rp"], _I), _p(arrs["col"], _I), _p(he, _I), _p(arrs["val"], _D), _p(m0, _D), vf_mode, c_mode, ctypes.c_double(params.vfSmooth),
+                          _p(arrs["rp"], _I), _p(arrs["col"], _I), _p(he, _I), _p(arrs["val"], _D), _p(np.ascontiguousarray(Mc.data), _D), hierarchy, _p(m0, _D), vf_mode, c_mode, ctypes.c_double(params.vfSmooth),
                           ctypes.c_double(1e-8), steps, _p(D, _D), _p(rhs, _D), _p(outB, _D), _p(outX, _D), _p(outF, _D), _p(outS, _D), _p(outC, _D),
-                          ctypes.byref(iters), ctypes.byref(relres))
+                          ctypes.byref(iters), ctypes.byref(relres), ctypes.byref(cycles))
     assert rc == 0
     assert relres.value <= 1e-8 and iters.value > 0
+    if hierarchy:  # two cycles per iteration (+ the start of each solve), and far fewer iterations than block Jacobi needs (~470 per solve here)
+        assert cycles.value >= 2 * iters.value and iters.value <= 3 * 175, (cycles.value, iters.value)
+    else:
+        assert cycles.value == 0
     P = st.whitney.P
     for i in range(steps):
         A, bvec, Dt, scale = O.flow_system(st.whitney, D[i], rhs[i], params.vfSmooth)
