@@ -78,6 +78,7 @@ int vf_init(mof_ctx* ctx) {
     VfState& s = *ctx->vf;
     const int V = ctx->V, T = ctx->T;
     s.mode = mode, s.cMode = ctx->params.cMode;
+    s.mgPrec = s.mgNow = false;
     s.N = mode == 1 ? 2ll * V : 2ll * T;
     MOF_CUDA(s.sc.alloc(S_COUNT));
     MOF_CUDA(s.partial.alloc(3 * RED));  // p.q | r.z, r.r
