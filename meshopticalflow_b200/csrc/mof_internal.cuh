@@ -63,7 +63,7 @@ struct DBuf {
 // sliceBase[r / 32] + 32 * j + r % 32. A warp that owns a slice reads 32 consecutive words per entry
 // index with no staging and no barrier, and every thread has all of its row's loads independent and in
 // flight at once. Padding entries carry value 0 and the row's own column.
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(MOF_HOST_EMULATION)
 __host__ __device__ __forceinline__ size_t sell_pos(const int* sliceBase, int row, int j) {
     return (size_t)sliceBase[row >> 5] + 32 * (size_t)j + (size_t)(row & 31);
 }

@@ -7,6 +7,7 @@
 
 #include "../../meshopticalflow_b200/csrc/vector_fields.cu"
 
+#ifndef EMUL_WITH_FLOW  // linked alone: stand-ins for what vector_fields.cu calls in other translation units, and the entry point
 // What vector_fields.cu calls in other translation units, stood in for on the host.
 namespace {
 bool g_hierarchy = false;            // "the scalar multigrid hierarchy exists"
@@ -120,3 +121,4 @@ int emul_vf_run(int V, int T, const double* g, const double* area, const int* op
 }
 
 }  // extern "C"
+#endif  // EMUL_WITH_FLOW
