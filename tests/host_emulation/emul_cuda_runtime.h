@@ -56,4 +56,28 @@ void __syncthreads();
 
 namespace mof_emul {
 void launch(long long grid, int block, const std::function<void()>& body);
+unsigned long long shuffle(unsigned long long bits, int srcLane);  // warp-synchronous exchange of 8 bytes
+int lane();
+template <class T>
+inline T shuffle_value(T v, int srcLane) {
+    static_assert(sizeof(T) <= 8, "shuffle of up to 8 bytes");
+    unsigned long long bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    bits = shuffle(bits, srcLane);
+    memcpy(&v, &bits, sizeof(T));
+    return v;
 }
+}  // namespace mof_emul
+
+// warp shuffles (full-warp participation of the live lanes is assumed, as in the kernels of this repository)
+template <class T> inline T __shfl_sync(unsigned, T v, int srcLane, int = 32) { return mof_emul::shuffle_value(v, srcLane); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) { return mof_emul::shuffle_value(v, mof_emul::lane() - (int)d); }
+template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned d, int = 32) { return mof_emul::shuffle_value(v, mof_emul::lane() + (int)d); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return mof_emul::shuffle_value(v, mof_emul::lane() ^ m); }
+// atomics: one OS thread, fibers switch only at synchronisation points
+template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicCAS(T* p, T expected, T desired) { T o = *p; if (o == expected) *p = desired; return o; }
+template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+inline void __threadfence() {}
+inline void __syncwarp(unsigned = 0xffffffffu) {}
