@@ -121,6 +121,31 @@ int mof_set_texture_map(mof_ctx* ctx, int W, int H, const int* srcT, const doubl
                         const unsigned char* texA, const unsigned char* texB);
 int mof_advect_texels(mof_ctx* ctx, double alpha, int bilinear, double* outA, double* outB);
 
+/* The texture configuration's one-time preparation on the device (the reference runs it serially on the CPU; the
+ * outputs are the same, integer for integer and bit for bit: see csrc/texprep_kernels.cu).
+ *
+ * mof_subdivide is Subdivide (MeshFlow.inl:223-232 over _Subdivide :158-220): every side longer than edgeLength is
+ * split at its midpoint, sweep after sweep, until none is left; midpoint vertices are numbered in the order the
+ * reference's scan meets their edges. xyz[V][3] single precision like the reference's PlyVertex<float>, tri[T][3],
+ * triUV[T][6]. Needs no mesh in place; the result stays in the context until mof_get_subdivision copies it out
+ * (xyz[outV][3], tri[outT][3], triUV[outT][6]). edgeLength <= 0 leaves the mesh as it is (OpticalFlow.cpp:714).
+ *
+ * mof_build_texture_map is GetTextureSource (MeshFlow.inl:411-467) for the mesh in place: RasterizeTriangle (:281-337,
+ * first triangle wins except under the rule of :334), padRadius rings of padding (:426-455), RemapSamplePoint through
+ * RiemannianMesh::exp (:340-350, FEM.inl:835-899) over the edge transforms the library built. It installs the map and
+ * the two textures exactly as mof_set_texture_map would. A ray that misses its triangle makes the reference exit
+ * (FEM.inl:889): here MOF_E_MESH with its message, *misses = the number of such texels. mof_get_texture_map reads the
+ * installed map back (srcT[W*H], srcP[W*H][2]).
+ *
+ * mof_sample_textures_to_vertices is SampleTextureToVertices (MeshFlow.inl:252-266, Sample :66-84) of the two installed
+ * textures: outA/outB[V][3], each vertex the mean of its wedges' samples (summed in triangle order). */
+int mof_subdivide(mof_ctx* ctx, const float* xyz, int V, const int* tri, const double* triUV, int T, double edgeLength, int* outV, int* outT);
+int mof_get_subdivision(mof_ctx* ctx, float* xyz, int* tri, double* triUV);
+int mof_build_texture_map(mof_ctx* ctx, int W, int H, int padRadius, const double* triUV, const unsigned char* texA, const unsigned char* texB,
+                          int* misses);
+int mof_get_texture_map(mof_ctx* ctx, int* srcT, double* srcP);
+int mof_sample_textures_to_vertices(mof_ctx* ctx, int bilinear, double* outA, double* outB);
+
 /* Debug taps for the parity tests. */
 enum {
     MOF_CSR_SCALAR_MASS = 0,      /* flowData.sMass       V x V  (FEM.inl:1548) */

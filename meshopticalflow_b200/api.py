@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = [
     "mof_set_mesh", "mof_set_mesh_device", "mof_set_signals", "mof_set_signals_device", "mof_iterate", "mof_get_flow", "mof_get_coeffs", "mof_num_edges", "mof_num_coeffs",
     "mof_advect_vertices", "mof_advect_vertices_device", "mof_set_texture_map", "mof_advect_texels", "mof_csr_size", "mof_get_csr", "mof_array_bytes",
     "mof_get_array", "mof_pcg_solve_csr", "mof_time_flow_spmv", "mof_dist_unique_id", "mof_dist_init",
+    "mof_subdivide", "mof_get_subdivision", "mof_build_texture_map", "mof_get_texture_map", "mof_sample_textures_to_vertices",
 ]
 
 
@@ -106,6 +107,11 @@ def load_library():
     lib.mof_advect_vertices_device.argtypes = [c_void_p, c_double, c_void_p, c_void_p]
     lib.mof_set_texture_map.argtypes = [c_void_p, c_int, c_int, I, D, D, POINTER(c_ubyte), POINTER(c_ubyte)]
     lib.mof_advect_texels.argtypes = [c_void_p, c_double, c_int, D, D]
+    lib.mof_subdivide.argtypes = [c_void_p, POINTER(ctypes.c_float), c_int, I, D, c_int, c_double, I, I]
+    lib.mof_get_subdivision.argtypes = [c_void_p, POINTER(ctypes.c_float), I, D]
+    lib.mof_build_texture_map.argtypes = [c_void_p, c_int, c_int, c_int, D, POINTER(c_ubyte), POINTER(c_ubyte), I]
+    lib.mof_get_texture_map.argtypes = [c_void_p, I, D]
+    lib.mof_sample_textures_to_vertices.argtypes = [c_void_p, c_int, D, D]
     lib.mof_csr_size.argtypes = [c_void_p, c_int, I, POINTER(c_longlong)]
     lib.mof_get_csr.argtypes = [c_void_p, c_int, I, I, D]
     lib.mof_array_bytes.argtypes = [c_void_p, c_int]
@@ -254,6 +260,40 @@ class Aligner:
         tb = np.ascontiguousarray(tex_b, dtype=np.uint8)
         self._tex = (W, H)
         self._check(self._lib.mof_set_texture_map(self._ctx, W, H, _i(srcT), _d(srcP), _d(uv), ta.ctypes.data_as(POINTER(c_ubyte)), tb.ctypes.data_as(POINTER(c_ubyte))))
+
+    # --- the texture configuration's one-time preparation on the device (MeshFlow.inl:158-467)
+    def subdivide(self, vertices_f32, triangles, tri_uv, edge_length: float):
+        """Subdivide: returns (vertices float32 [V',3], triangles int32 [T',3], tri_uv float64 [T',6])."""
+        v = np.ascontiguousarray(vertices_f32, dtype=np.float32)
+        t = np.ascontiguousarray(triangles, dtype=np.int32)
+        uv = np.ascontiguousarray(tri_uv, dtype=np.float64).reshape(-1, 6)
+        nv, nt = c_int(), c_int()
+        self._check(self._lib.mof_subdivide(self._ctx, v.ctypes.data_as(POINTER(ctypes.c_float)), v.shape[0], _i(t), _d(uv), t.shape[0], float(edge_length), byref(nv), byref(nt)))
+        vo, to, uo = np.empty((nv.value, 3), dtype=np.float32), np.empty((nt.value, 3), dtype=np.int32), np.empty((nt.value, 6))
+        self._check(self._lib.mof_get_subdivision(self._ctx, vo.ctypes.data_as(POINTER(ctypes.c_float)), _i(to), _d(uo)))
+        return vo, to, uo
+
+    def build_texture_map(self, W, H, pad, tri_uv, tex_a, tex_b):
+        """GetTextureSource for the mesh in place; installs the map and the textures. Returns (srcT [W*H], srcP [W*H,2])."""
+        uv = np.ascontiguousarray(tri_uv, dtype=np.float64)
+        ta = np.ascontiguousarray(tex_a, dtype=np.uint8)
+        tb = np.ascontiguousarray(tex_b, dtype=np.uint8)
+        self._tex = (W, H)
+        misses = c_int()
+        self._check(self._lib.mof_build_texture_map(self._ctx, W, H, pad, _d(uv), ta.ctypes.data_as(POINTER(c_ubyte)), tb.ctypes.data_as(POINTER(c_ubyte)), byref(misses)))
+        return self.texture_map()
+
+    def texture_map(self):
+        W, H = self._tex
+        srcT, srcP = np.empty(W * H, dtype=np.int32), np.empty((W * H, 2))
+        self._check(self._lib.mof_get_texture_map(self._ctx, _i(srcT), _d(srcP)))
+        return srcT, srcP
+
+    def sample_textures_to_vertices(self, bilinear: bool = True):
+        """SampleTextureToVertices of the two installed textures: (colours A [V,3], colours B [V,3])."""
+        a, b = np.empty((self.V, 3)), np.empty((self.V, 3))
+        self._check(self._lib.mof_sample_textures_to_vertices(self._ctx, 1 if bilinear else 0, _d(a), _d(b)))
+        return a, b
 
     def advect_texels(self, alpha: float = 0.5, bilinear: bool = True):
         W, H = self._tex

@@ -75,6 +75,19 @@ int main(int argc, char* argv[]) {
     }
 
     const bool processTexture = opt.meshSet;
+    // MOF_GPU_TEXPREP=1: the texture configuration's one-time preparation (Subdivide, SampleTextureToVertices,
+    // GetTextureSource) runs on the GPU (csrc/texprep_kernels.cu) instead of in host/texture_prep.cpp; same outputs.
+    const char* gpuPrepEnv = getenv("MOF_GPU_TEXPREP");
+    const bool gpuPrep = processTexture && gpuPrepEnv && *gpuPrepEnv && *gpuPrepEnv != '0';
+    mof_ctx* ctx = nullptr;
+    auto ensure_context = [&]() {
+        if (ctx) return true;
+        if (mof_create(opt.device, nullptr, &ctx) != MOF_OK) {
+            fprintf(stderr, "[ERROR] no usable CUDA device %d (this build has no CPU solver)\n", opt.device);
+            return false;
+        }
+        return true;
+    };
     mof::TexturedMesh tmesh;          // texture configuration
     std::vector<unsigned char> textures[2];
     int tW = 0, tH = 0;
@@ -111,7 +124,15 @@ int main(int argc, char* argv[]) {
             for (int c = 0; c < 3; c++) lo[c] = std::min(lo[c], (double)tmesh.xyz[3 * v + c]), hi[c] = std::max(hi[c], (double)tmesh.xyz[3 * v + c]);
         double diagonal = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
         float eLength = (float)(opt.eLength * diagonal);  // float parameter times double, stored back as float (:713)
-        if (eLength > 0) mof::subdivide(tmesh, (double)eLength);
+        if (eLength > 0 && gpuPrep) {
+            if (!ensure_context()) return EXIT_FAILURE;
+            int newV = 0, newT = 0;
+            if (!mof_ok(ctx, mof_subdivide(ctx, tmesh.xyz.data(), (int)(tmesh.xyz.size() / 3), tmesh.tri.data(), tmesh.uv.data(), (int)nf, (double)eLength, &newV, &newT)))
+                return EXIT_FAILURE;
+            tmesh.xyz.resize(3 * (size_t)newV), tmesh.tri.resize(3 * (size_t)newT), tmesh.uv.resize(6 * (size_t)newT);
+            if (!mof_ok(ctx, mof_get_subdivision(ctx, tmesh.xyz.data(), tmesh.tri.data(), tmesh.uv.data()))) return EXIT_FAILURE;
+        } else if (eLength > 0)
+            mof::subdivide(tmesh, (double)eLength);
         printf("Num vertices %d  \n", (int)(tmesh.xyz.size() / 3));
 
         for (int s = 0; s < 2; s++) {
@@ -130,7 +151,8 @@ int main(int argc, char* argv[]) {
                 return EXIT_FAILURE;
             }
         }
-        for (int s = 0; s < 2; s++) mof::sample_texture_to_vertices(tmesh, textures[s].data(), tW, tH, !opt.nearest, signal[s]);
+        if (!gpuPrep)
+            for (int s = 0; s < 2; s++) mof::sample_texture_to_vertices(tmesh, textures[s].data(), tW, tH, !opt.nearest, signal[s]);
         vertices.assign(tmesh.xyz.begin(), tmesh.xyz.end());
         triangles = tmesh.tri;
     } else {
@@ -174,11 +196,7 @@ int main(int argc, char* argv[]) {
     outXyz.resize(vertices.size());
     for (size_t i = 0; i < vertices.size(); i++) outXyz[i] = (float)vertices[i];
 
-    mof_ctx* ctx = nullptr;
-    if (mof_create(opt.device, nullptr, &ctx) != MOF_OK) {
-        fprintf(stderr, "[ERROR] no usable CUDA device %d (this build has no CPU solver)\n", opt.device);
-        return EXIT_FAILURE;
-    }
+    if (!ensure_context()) return EXIT_FAILURE;
     mof_params params;
     mof_default_params(&params);
     params.iterations = opt.iterations;
@@ -196,7 +214,13 @@ int main(int argc, char* argv[]) {
         if (!mof_ok(ctx, mof_set_mesh(ctx, vertices.data(), V, triangles.data(), T))) return 0;
         if (opt.verbose) printf("Got edge transforms: %.2f (s)\nGot system matrices: %.2f (s)\n", t.elapsed(), 0.);
     }
-    if (processTexture) {
+    if (gpuPrep) {
+        // GetTextureSource (:818) and SampleTextureToVertices (:741-745) on the GPU
+        int misses = 0;
+        if (!mof_ok(ctx, mof_build_texture_map(ctx, tW, tH, opt.pad, tmesh.uv.data(), textures[0].data(), textures[1].data(), &misses))) return misses ? 0 : EXIT_FAILURE;
+        for (int s = 0; s < 2; s++) signal[s].resize(3 * (size_t)V);
+        if (!mof_ok(ctx, mof_sample_textures_to_vertices(ctx, opt.nearest ? 0 : 1, signal[0].data(), signal[1].data()))) return EXIT_FAILURE;
+    } else if (processTexture) {
         // GetTextureSource (:818) on the host, from the edge transforms the GPU just built
         std::vector<int> opp(3 * (size_t)T), srcT;
         std::vector<double> lin(12 * (size_t)T), cst(6 * (size_t)T), srcP;

@@ -146,6 +146,7 @@ void mof_destroy(mof_ctx* ctx) {
                          &ctx->itmp0, &ctx->itmp1, &ctx->itmp2, &ctx->flags, &ctx->srcT};
     for (auto* b : ints) b->release();
     ctx->hashKeys.release(), ctx->tex[0].release(), ctx->tex[1].release();
+    ctx->subXyz.release(), ctx->subTri.release(), ctx->subUv.release();
     mg_destroy(ctx);
     dist_destroy(ctx);
     vf_destroy(ctx);
@@ -328,6 +329,94 @@ int mof_advect_texels(mof_ctx* ctx, double alpha, int bilinear, double* outA, do
     size_t n = (size_t)ctx->texW * ctx->texH;
     MOF_CUDA(cudaMemcpyAsync(outA, ctx->texOut.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
     MOF_CUDA(cudaMemcpyAsync(outB, ctx->texOut.p + 3 * n, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+
+// ---------------------------------------------------- texture-configuration preparation on the device
+
+int mof_subdivide(mof_ctx* ctx, const float* xyz, int V, const int* tri, const double* triUV, int T, double edgeLength, int* outV, int* outT) {
+    if (!ctx) return MOF_E_INVALID;
+    if (!xyz || !tri || !triUV || V < 1 || T < 1 || !outV || !outT) return fail(ctx, MOF_E_INVALID, "mof_subdivide: bad arguments");
+    for (size_t i = 0; i < 3 * (size_t)T; i++)
+        if (tri[i] < 0 || tri[i] >= V) return fail(ctx, MOF_E_INVALID, "[ERROR] triangle refers to a vertex index outside [0,V)");
+    StreamScope scope(ctx);
+    MOF_CUDA(ctx->subXyz.alloc(3ull * V));
+    MOF_CUDA(ctx->subTri.alloc(3ull * T));
+    MOF_CUDA(ctx->subUv.alloc(6ull * T));
+    MOF_CUDA(cudaMemcpyAsync(ctx->subXyz.p, xyz, sizeof(float) * 3 * V, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(ctx->subTri.p, tri, sizeof(int) * 3 * T, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(ctx->subUv.p, triUV, sizeof(double) * 6 * T, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->subV = V, ctx->subT = T;
+    if (edgeLength > 0) MOF_TRY(subdivide_mesh(ctx, edgeLength, nullptr));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    *outV = ctx->subV, *outT = ctx->subT;
+    return MOF_OK;
+}
+
+int mof_get_subdivision(mof_ctx* ctx, float* xyz, int* tri, double* triUV) {
+    if (!ctx) return MOF_E_INVALID;
+    if (!ctx->subV || !ctx->subXyz.p) return fail(ctx, MOF_E_INVALID, "call mof_subdivide first");
+    if (!xyz || !tri || !triUV) return fail(ctx, MOF_E_INVALID, "mof_get_subdivision: bad arguments");
+    StreamScope scope(ctx);
+    MOF_CUDA(cudaMemcpyAsync(xyz, ctx->subXyz.p, sizeof(float) * 3 * ctx->subV, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(tri, ctx->subTri.p, sizeof(int) * 3 * ctx->subT, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(triUV, ctx->subUv.p, sizeof(double) * 6 * ctx->subT, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+
+int mof_build_texture_map(mof_ctx* ctx, int W, int H, int padRadius, const double* triUV, const unsigned char* texA, const unsigned char* texB, int* misses) {
+    if (!ctx) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    if (W < 2 || H < 2 || (long long)W * H > (1ll << 30) || padRadius < 0 || !triUV || !texA || !texB) return fail(ctx, MOF_E_INVALID, "mof_build_texture_map: bad arguments");
+    StreamScope scope(ctx);
+    size_t n = (size_t)W * H;
+    ctx->haveTexture = false;
+    ctx->texW = W, ctx->texH = H;
+    MOF_CUDA(ctx->triUV.alloc(6ull * ctx->T));
+    MOF_CUDA(ctx->tex[0].alloc(3 * n));
+    MOF_CUDA(ctx->tex[1].alloc(3 * n));
+    MOF_CUDA(cudaMemcpyAsync(ctx->triUV.p, triUV, sizeof(double) * 6 * ctx->T, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(ctx->tex[0].p, texA, 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(ctx->tex[1].p, texB, 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    int missed = 0;
+    MOF_TRY(build_texture_map(ctx, W, H, padRadius, &missed));
+    if (misses) *misses = missed;
+    if (missed) {  // the reference exits at the first one (FEM.inl:889)
+        char msg[160];
+        snprintf(msg, sizeof(msg), "[ERROR] FEM::Mesh::exp:\n        Ray does not intersect triangle (%d texels)", missed);
+        return fail(ctx, MOF_E_MESH, msg);
+    }
+    ctx->haveTexture = true;
+    return MOF_OK;
+}
+
+int mof_get_texture_map(mof_ctx* ctx, int* srcT, double* srcP) {
+    if (!ctx) return MOF_E_INVALID;
+    if (!ctx->haveTexture) return fail(ctx, MOF_E_INVALID, "call mof_set_texture_map or mof_build_texture_map first");
+    if (!srcT || !srcP) return fail(ctx, MOF_E_INVALID, "mof_get_texture_map: bad arguments");
+    StreamScope scope(ctx);
+    size_t n = (size_t)ctx->texW * ctx->texH;
+    MOF_CUDA(cudaMemcpyAsync(srcT, ctx->srcT.p, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(srcP, ctx->srcP.p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+
+int mof_sample_textures_to_vertices(mof_ctx* ctx, int bilinear, double* outA, double* outB) {
+    if (!ctx) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    if (!ctx->haveTexture) return fail(ctx, MOF_E_INVALID, "call mof_set_texture_map or mof_build_texture_map first");
+    if (!outA || !outB) return fail(ctx, MOF_E_INVALID, "mof_sample_textures_to_vertices: bad arguments");
+    StreamScope scope(ctx);
+    const int V = ctx->V;
+    MOF_CUDA(ctx->dtmp0.reserve(6ull * V));
+    MOF_CUDA(ctx->dtmp2.reserve(6ull * V));
+    MOF_TRY(sample_textures_to_vertices(ctx, bilinear, ctx->dtmp0.p));
+    MOF_LAUNCH(k_deinterleave, blocks_for(3ll * V, 256), 256, 0, ctx->dtmp0.p, V, ctx->dtmp2.p, ctx->dtmp2.p + 3ull * V);
+    MOF_CUDA(cudaMemcpyAsync(outA, ctx->dtmp2.p, sizeof(double) * 3 * V, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(outB, ctx->dtmp2.p + 3ull * V, sizeof(double) * 3 * V, cudaMemcpyDeviceToHost, ctx->stream));
     MOF_CUDA(cudaStreamSynchronize(ctx->stream));
     return MOF_OK;
 }

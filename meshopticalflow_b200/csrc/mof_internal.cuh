@@ -132,6 +132,11 @@ struct mof_ctx {
     mof::DBuf<int> srcT;
     mof::DBuf<double> srcP, triUV, texOut;
     mof::DBuf<unsigned char> tex[2];
+    // texture-configuration preparation on the device (texprep_kernels.cu): the mesh being subdivided
+    int subV = 0, subT = 0;
+    mof::DBuf<float> subXyz;
+    mof::DBuf<int> subTri;
+    mof::DBuf<double> subUv;
 };
 
 namespace mof {
@@ -268,5 +273,10 @@ void smooth_ahead_destroy(mof_ctx* ctx);
 int update_flow(mof_ctx* ctx, double sWeight, double vfWeight);
 int advect_vertices(mof_ctx* ctx, const double* in6, double lenA, double lenB, double* out6);
 int advect_texels(mof_ctx* ctx, double alpha, int bilinear);
+
+// texprep_kernels.cu — the texture configuration's one-time preparation (MeshFlow.inl:158-467)
+int subdivide_mesh(mof_ctx* ctx, double edgeLength, int* addedOut);                 // ctx->subXyz / subTri / subUv in place
+int build_texture_map(mof_ctx* ctx, int W, int H, int padRadius, int* missesOut);  // ctx->triUV + edge transforms -> ctx->srcT / srcP
+int sample_textures_to_vertices(mof_ctx* ctx, int bilinear, double* d_out6);        // ctx->tex[0|1] -> V x 6 (A rgb, B rgb)
 
 }  // namespace mof
