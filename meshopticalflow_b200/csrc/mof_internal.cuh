@@ -4,6 +4,8 @@
 // MOF_HOST_EMULATION (tests/host_emulation, CPU test tier only): the CUDA runtime calls and the launch syntax are
 // replaced by host stand-ins so that whole .cu files can be compiled by g++ and run one "thread" at a time.
 #ifdef MOF_HOST_EMULATION
+#include <tuple>
+
 #include "emul_cuda_runtime.h"
 #else
 #include <cuda_runtime.h>
@@ -192,10 +194,11 @@ struct PhaseTimer {
 
 // Counts a kernel launch of ours (mof_stats.kernelLaunches) and checks the launch.
 #ifdef MOF_HOST_EMULATION
-#define MOF_LAUNCH(kernel, grid, block, smem, ...)                                  \
-    do {                                                                            \
-        mof_emul::launch((grid), (block), [&] { kernel(__VA_ARGS__); });            \
-        ctx->stats.kernelLaunches++;                                                \
+#define MOF_LAUNCH(kernel, grid, block, smem, ...)                                                                                  \
+    do {                                                                                                                            \
+        auto args__ = std::make_tuple(__VA_ARGS__); /* by value, like a launch: a captured launch runs after this scope is gone */  \
+        mof_emul::submit((grid), (block), [args__] { std::apply([](auto... a) { kernel(a...); }, args__); });                       \
+        ctx->stats.kernelLaunches++;                                                                                                \
     } while (0)
 #else
 #define MOF_LAUNCH(kernel, grid, block, smem, ...)                                  \

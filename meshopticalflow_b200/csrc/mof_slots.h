@@ -3,7 +3,11 @@
 
 namespace mof {
 
+#ifdef MOF_HOST_EMULATION
+constexpr int kSMs = 1;    // CPU test tier (tests/host_emulation): every "CTA" is run thread by thread
+#else
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+#endif
 
 // Device-side scalar slots (one small buffer, fp64).
 enum ScalarSlot {

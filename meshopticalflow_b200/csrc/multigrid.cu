@@ -1009,9 +1009,8 @@ int build_octree(mof_ctx* ctx, Multigrid& mg, const double* pts, int n, double m
     rc = exclusive_scan_int(ctx, cnt.p, mg.aggPtr.p, l1.N + 1, nullptr);
     if (rc == MOF_OK) {
         cudaMemcpyAsync(cursor.p, mg.aggPtr.p, sizeof(int) * (l1.N + 1), cudaMemcpyDeviceToDevice, ctx->stream);
-        k_aggregate_fill<<<blocks_for(n, B), B, 0, ctx->stream>>>(mg.agg.p, n, cursor.p, unsorted.p);
-        k_aggregate_sort<<<blocks_for(32ll * l1.N, B), B, 0, ctx->stream>>>(mg.aggPtr.p, l1.N, unsorted.p, mg.aggList.p);
-        ctx->stats.kernelLaunches += 2;
+        MOF_LAUNCH(k_aggregate_fill, blocks_for(n, B), B, 0, mg.agg.p, n, cursor.p, unsorted.p);
+        MOF_LAUNCH(k_aggregate_sort, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, l1.N, unsorted.p, mg.aggList.p);
         cudaStreamSynchronize(ctx->stream);
     }
     cnt.release(), cursor.release(), unsorted.release();
@@ -1177,15 +1176,12 @@ int fine_residual(mof_ctx* ctx, Multigrid& mg, const double* b, const double* in
 // `zc` (with the level's parent table) = a coarse correction still to be added to lv.z, see k_coarse_apply.
 template <int K, int D>
 int coarse_apply(mof_ctx* ctx, MgLevel& lv, double omega, int mode, creal* out, const creal* zc) {
+    const int* parent = zc ? lv.parent.p : nullptr;
     if (lv.N >= 16384)
-        k_coarse_apply<K, D, 3><<<blocks_for(lv.N, 32), 9 * 32, 0, ctx->stream>>>(lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out,
-                                                                              zc ? lv.parent.p : nullptr, zc);
+        MOF_LAUNCH((k_coarse_apply<K, D, 3>), blocks_for(lv.N, 32), 9 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out, parent, zc);
     else
-        k_coarse_apply<K, D, 1><<<blocks_for(lv.N, 32), 27 * 32, 0, ctx->stream>>>(lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out,
-                                                                               zc ? lv.parent.p : nullptr, zc);
-    ctx->stats.kernelLaunches++;
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? MOF_OK : cuda_fail(ctx, e, "k_coarse_apply");
+        MOF_LAUNCH((k_coarse_apply<K, D, 1>), blocks_for(lv.N, 32), 27 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out, parent, zc);
+    return MOF_OK;
 }
 int coarse_apply(mof_ctx* ctx, Multigrid& mg, MgLevel& lv, double omega, int mode, creal* out, const creal* zc = nullptr) {
     return mg.kind == MG_FLOW ? coarse_apply<9, 3>(ctx, lv, omega, mode, out, zc) : coarse_apply<1, 6>(ctx, lv, omega, mode, out, zc);

@@ -1,9 +1,10 @@
 // TEST INFRASTRUCTURE (CPU tier): host stand-ins for the few CUDA runtime calls and for the kernel-launch syntax that
 // meshopticalflow_b200/csrc uses, so that a .cu file can be compiled by g++ with -DMOF_HOST_EMULATION and its REAL
 // source — kernels and host driver alike — run on the CPU. "Device" memory is malloc'd host memory, streams and events
-// are no-ops (everything is synchronous), and a launch runs the kernel body once per (block, thread) on fibers
-// (ucontext) of one OS thread, __syncthreads() yielding to the next fiber of the block: barrier semantics hold,
-// __shared__ variables (made `static`) are per block because blocks run one after the other.
+// are no-ops (everything is synchronous; a stream capture records launches and copies, a graph launch replays them), and
+// a launch runs the kernel body once per (block, thread) on fibers of one OS thread (emul_runtime.cpp), a thread that
+// reaches __syncthreads() or a warp shuffle giving way to the others: barrier semantics hold, __shared__ variables (made
+// `static`) are per block because blocks run one after the other. A cooperative kernel is run as ONE CTA.
 #pragma once
 
 #include <ucontext.h>
@@ -24,6 +25,7 @@ using std::min;
 #define __forceinline__ inline
 #define __restrict__
 #define __shared__ static
+#define __launch_bounds__(...)
 
 typedef int cudaError_t;
 typedef void* cudaStream_t;
@@ -35,8 +37,22 @@ inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : 2; }
 inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
-inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
-inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(d, s, bytes); return cudaSuccess; }
+namespace mof_emul {
+// Stream capture: while a capture is open, launches and stream-ordered copies are RECORDED (with their arguments, by
+// value) instead of run, like on the device; cudaGraphLaunch runs the recorded list.
+bool capturing();
+void record(std::function<void()> op);
+}  // namespace mof_emul
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) {
+    if (mof_emul::capturing()) mof_emul::record([=] { memset(p, v, bytes); });
+    else memset(p, v, bytes);
+    return cudaSuccess;
+}
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t bytes, cudaMemcpyKind, cudaStream_t) {
+    if (mof_emul::capturing()) mof_emul::record([=] { memmove(d, s, bytes); });
+    else memmove(d, s, bytes);
+    return cudaSuccess;
+}
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
@@ -49,6 +65,45 @@ inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSu
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* least, int* greatest) { *least = *greatest = 0; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = nullptr; return cudaSuccess; }
+typedef void* cudaMemPool_t;
+enum { cudaMemPoolAttrReleaseThreshold = 0 };
+inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
+inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void*) { return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+// cooperative launches are emulated with ONE CTA (a `static` stands in for __shared__, so CTAs cannot be alive together)
+template <class K> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 1; return cudaSuccess; }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 1; return cudaSuccess; }
+enum { cudaHostAllocDefault = 0 };
+inline cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+
+// CUDA graphs by stream capture
+struct EmulGraph { std::vector<std::function<void()>> ops; };
+typedef EmulGraph* cudaGraph_t;
+typedef EmulGraph* cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal, cudaStreamCaptureModeThreadLocal, cudaStreamCaptureModeRelaxed };
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode);
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* graph);
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* exec, cudaGraph_t graph, unsigned long long) { *exec = new EmulGraph(*graph); return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t) { for (auto& op : exec->ops) op(); return cudaSuccess; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { delete g; return cudaSuccess; }
+
+// vector types and cache-hinted loads
+struct float2 { float x, y; };
+struct double2 { double x, y; };
+struct float4 { float x, y, z, w; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
 
 struct EmulDim { unsigned x = 1, y = 1, z = 1; };
 extern EmulDim blockIdx, blockDim, threadIdx, gridDim;
@@ -56,6 +111,8 @@ void __syncthreads();
 
 namespace mof_emul {
 void launch(long long grid, int block, const std::function<void()>& body);
+// A kernel launch as the stream sees it: run now, or recorded into the capture in progress. `body` owns its arguments.
+void submit(long long grid, int block, std::function<void()> body);
 unsigned long long shuffle(unsigned long long bits, int srcLane);  // warp-synchronous exchange of 8 bytes
 int lane();
 template <class T>

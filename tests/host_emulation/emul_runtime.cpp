@@ -1,19 +1,54 @@
-// TEST INFRASTRUCTURE: the fiber scheduler behind emul_cuda_runtime.h. One OS thread; every thread of the block being
-// "executed" is a ucontext fiber; fibers run round-robin and give the processor back at synchronisation points:
+// TEST INFRASTRUCTURE: the fiber scheduler behind emul_cuda_runtime.h. One OS thread; the threads of the block being
+// "executed" run on ucontext fibers; a thread that has to wait gives the processor back at synchronisation points:
 //   __syncthreads()   a counted barrier over the block's live threads (a thread that left the kernel stops counting)
 //   __shfl_*_sync()   publish the value, barrier over the live lanes of the WARP, read the source lane, barrier again
 // Blocks run one after the other (so `static` stands in for __shared__), atomics are plain read-modify-writes.
 #include "emul_cuda_runtime.h"
 
+#include <cstdint>
+
 EmulDim blockIdx, blockDim, threadIdx, gridDim;
+
+// Context switch. x86-64: a dozen instructions (callee-saved registers and the stack pointer; every fiber shares the
+// floating-point control state) — glibc's swapcontext makes a system call per switch (the signal mask), and a kernel
+// with barriers switches some twenty times per thread. Elsewhere, or with -DMOF_EMUL_UCONTEXT: ucontext.
+#if defined(__x86_64__) && !defined(MOF_EMUL_UCONTEXT)
+#define MOF_EMUL_ASM_SWITCH 1
+asm(R"(
+.text
+.globl mof_emul_switch
+.type mof_emul_switch,@function
+mof_emul_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size mof_emul_switch,.-mof_emul_switch
+)");
+extern "C" void mof_emul_switch(void** saveSp, void* loadSp);
+#endif
 
 namespace {
 constexpr int kMaxThreads = 1024;
 constexpr size_t kStack = 128 * 1024;
-ucontext_t mainCtx, fiberCtx[kMaxThreads];
+// A fiber runs thread after thread of the block (the next one that has not started yet) for as long as they run to
+// completion; the first of its threads that has to wait at a synchronisation point parks on it. A kernel without
+// barriers or shuffles therefore runs on ONE fiber with no context switch at all.
 char* stacks[kMaxThreads];
 bool finished[kMaxThreads];
-int current = -1, blockThreads = 0;
+int fiberOf[kMaxThreads];
+int current = -1, blockThreads = 0, nextToStart = 0;
 const std::function<void()>* body = nullptr;
 
 int live = 0, arrived = 0;
@@ -22,17 +57,49 @@ int warpLive[kMaxThreads / 32], warpArrived[kMaxThreads / 32];
 unsigned long long warpGeneration[kMaxThreads / 32];
 unsigned long long slots[kMaxThreads];  // shuffle exchange, 8 bytes per thread
 
-void yield() { swapcontext(&fiberCtx[current], &mainCtx); }
+int runningFiber = -1;
+void fiber_entry();
+#ifdef MOF_EMUL_ASM_SWITCH
+void* mainSp = nullptr;
+void* fiberSp[kMaxThreads];
+void fiber_init(int f) {
+    // the frame mof_emul_switch unwinds on the first switch: six registers, then `ret` into fiber_entry with the stack
+    // pointer where a call would have left it (8 below a 16-byte boundary)
+    uintptr_t top = ((uintptr_t)stacks[f] + kStack) & ~(uintptr_t)15;
+    void** sp = (void**)top;
+    *--sp = nullptr;               // where fiber_entry's caller's return address would be
+    *--sp = (void*)&fiber_entry;
+    for (int i = 0; i < 6; i++) *--sp = nullptr;
+    fiberSp[f] = (void*)sp;
+}
+void to_fiber(int f) { mof_emul_switch(&mainSp, fiberSp[f]); }
+void to_main(int f) { mof_emul_switch(&fiberSp[f], mainSp); }
+#else
+ucontext_t mainCtx, fiberCtx[kMaxThreads];
+void fiber_init(int f) {
+    getcontext(&fiberCtx[f]);
+    fiberCtx[f].uc_stack.ss_sp = stacks[f], fiberCtx[f].uc_stack.ss_size = kStack, fiberCtx[f].uc_link = &mainCtx;
+    makecontext(&fiberCtx[f], fiber_entry, 0);
+}
+void to_fiber(int f) { swapcontext(&mainCtx, &fiberCtx[f]); }
+void to_main(int f) { swapcontext(&fiberCtx[f], &mainCtx); }
+#endif
+
+void yield() { to_main(fiberOf[current]); }
 
 void fiber_entry() {
-    (*body)();
-    const int me = current;
-    finished[me] = true;
-    // a thread that has left no longer takes part in barriers: release whoever is waiting for it
-    live--, warpLive[me >> 5]--;
-    if (live > 0 && arrived == live) arrived = 0, generation++;
-    if (warpLive[me >> 5] > 0 && warpArrived[me >> 5] == warpLive[me >> 5]) warpArrived[me >> 5] = 0, warpGeneration[me >> 5]++;
-    swapcontext(&fiberCtx[me], &mainCtx);
+    const int f = runningFiber;
+    while (nextToStart < blockThreads) {
+        const int me = nextToStart++;
+        current = me, threadIdx.x = (unsigned)me, fiberOf[me] = f;
+        (*body)();
+        finished[me] = true;
+        // a thread that has left no longer takes part in barriers: release whoever is waiting for it
+        live--, warpLive[me >> 5]--;
+        if (live > 0 && arrived == live) arrived = 0, generation++;
+        if (warpLive[me >> 5] > 0 && warpArrived[me >> 5] == warpLive[me >> 5]) warpArrived[me >> 5] = 0, warpGeneration[me >> 5]++;
+    }
+    for (;;) to_main(f);  // never resumed: the next block re-initialises the fiber
 }
 
 void warp_barrier() {
@@ -49,7 +116,28 @@ void __syncthreads() {
     while (generation == mine) yield();
 }
 
+namespace {
+EmulGraph* capture = nullptr;
+}
+cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
+    delete capture;
+    capture = new EmulGraph();
+    return cudaSuccess;
+}
+cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* graph) {
+    *graph = capture;
+    capture = nullptr;
+    return *graph ? cudaSuccess : 1;
+}
+
 namespace mof_emul {
+
+bool capturing() { return capture != nullptr; }
+void record(std::function<void()> op) { capture->ops.push_back(std::move(op)); }
+void submit(long long grid, int block, std::function<void()> b) {
+    if (capture) capture->ops.push_back([grid, block, b] { launch(grid, block, b); });
+    else launch(grid, block, b);
+}
 
 unsigned long long shuffle(unsigned long long bits, int srcLane) {
     const int me = current, w = me >> 5;
@@ -66,24 +154,25 @@ void launch(long long grid, int block, const std::function<void()>& b) {
     body = &b;
     blockThreads = block;
     blockDim.x = (unsigned)block, gridDim.x = (unsigned)grid;
-    for (int t = 0; t < block; t++)
-        if (!stacks[t]) stacks[t] = (char*)malloc(kStack);
     for (long long bi = 0; bi < grid; bi++) {
         blockIdx.x = (unsigned)bi;
-        live = block, arrived = 0;
+        live = block, arrived = 0, nextToStart = 0;
         for (int w = 0; w < (block + 31) / 32; w++) warpLive[w] = std::min(32, block - 32 * w), warpArrived[w] = 0;
-        for (int t = 0; t < block; t++) {
-            getcontext(&fiberCtx[t]);
-            fiberCtx[t].uc_stack.ss_sp = stacks[t], fiberCtx[t].uc_stack.ss_size = kStack, fiberCtx[t].uc_link = &mainCtx;
-            makecontext(&fiberCtx[t], fiber_entry, 0);
-            finished[t] = false;
+        for (int t = 0; t < block; t++) finished[t] = false, fiberOf[t] = -1;
+        // start every thread: each fiber takes threads until one of them has to wait
+        for (int f = 0; nextToStart < block; f++) {
+            if (!stacks[f]) stacks[f] = (char*)malloc(kStack);
+            fiber_init(f);
+            runningFiber = f;
+            to_fiber(f);
         }
+        // then round-robin over the waiting ones
         for (bool any = true; any;) {
             any = false;
             for (int t = 0; t < block; t++) {
                 if (finished[t]) continue;
                 current = t, threadIdx.x = (unsigned)t;
-                swapcontext(&mainCtx, &fiberCtx[t]);
+                to_fiber(fiberOf[t]);
                 any = any || !finished[t];
             }
         }

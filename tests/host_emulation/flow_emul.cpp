@@ -2,8 +2,8 @@
 // loop: DoG, smoothing right-hand sides, triangle walks, data term, Whitney system assembly, step and update, texel
 // advection; kernels AND host driver, the very source the GPU build compiles — built for the host through
 // emul_cuda_runtime.h and linked with vector_fields.cu (vf_emul.cpp, -DEMUL_WITH_FLOW). The linear SOLVERS live in
-// other translation units (pcg_kernels.cu, multigrid.cu: warp shuffles, cooperative launches — not emulated); plain
-// host conjugate-gradient loops stand in for them here, so this tier checks everything around the solves.
+// other translation units (pcg_kernels.cu, multigrid.cu); plain host conjugate-gradient loops stand in for them HERE, so
+// this harness checks everything around the solves tap by tap. library_emul.cpp builds the whole library, solvers included.
 #include "emul_cuda_runtime.h"
 
 #include <vector>

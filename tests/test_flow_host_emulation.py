@@ -3,7 +3,8 @@ data term, Whitney system assembly on the sliced layout, step length and coeffic
 with vector_fields.cu — the real CUDA sources, compiled for the HOST by tests/host_emulation (CUDA runtime calls and the
 launch macro replaced by stand-ins, thread blocks on fibers) — run a whole alignment and are checked against the numpy
 checker and the reference's golden fixtures. The linear solvers (pcg_kernels.cu, multigrid.cu) are NOT part of this:
-host conjugate-gradient loops stand in for them; the GPU tier covers those."""
+host conjugate-gradient loops stand in for them here; tests/test_library_host_emulation.py runs them too (the whole
+library, through the C ABI), and the GPU tier runs everything on a B200."""
 import ctypes
 import os
 import subprocess

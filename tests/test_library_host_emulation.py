@@ -1,0 +1,215 @@
+"""CPU tier: the WHOLE library behind include/mof_b200.h — every .cu file of meshopticalflow_b200/csrc except dist.cu (NCCL),
+kernels, host drivers and the C ABI itself — compiled for the HOST by tests/host_emulation (thread blocks on fibers, counted
+barriers, warp shuffles, atomics, stream capture and graph replay; the cooperative Jacobi-PCG kernel as one CTA) and driven
+through the same ctypes binding the GPU tier uses. What the GPU tier asserts on a B200 is asserted here on the CPU, at sizes
+the emulation finishes in seconds: the reference's golden fixtures, the numpy checker stage by stage, multigrid-PCG against
+Jacobi-PCG, the three bases, the 6-channel blend, the texture configuration end to end.
+
+This is a build of the PRODUCT'S sources for testing, not a CPU path of the product: nothing under meshopticalflow_b200/
+can load it (api.LIB_PATH is patched by the fixture below), and mof_create of the real library still fails without a GPU."""
+import ctypes
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import ROOT, VF_MODES, colour_outliers, csr_from_golden, rel
+from meshopticalflow_b200 import api, synthetic
+from oracle import mof_oracle as O
+
+EMU_DIR = os.path.join(ROOT, "tests", "host_emulation")
+UNITS = 7  # library_emul.cpp: one translation unit per .cu file
+
+
+@pytest.fixture(scope="module")
+def emulated(tmp_path_factory):
+    """api, bound to the emulated build for the duration of this module."""
+    out = tmp_path_factory.mktemp("library_emul")
+    base = ["g++", "-O2", "-std=c++17", "-fPIC", "-c", "-x", "c++", "-DMOF_HOST_EMULATION", "-I.", "-w"]
+    jobs = [base + ["-DEMUL_UNIT=%d" % u, "-o", str(out / ("unit%d.o" % u)), "library_emul.cpp"] for u in range(UNITS)]
+    jobs += [base + ["-o", str(out / "dist_stub.o"), "dist_stub.cpp"], base + ["-o", str(out / "runtime.o"), "emul_runtime.cpp"]]
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        list(pool.map(lambda cmd: subprocess.check_call(cmd, cwd=EMU_DIR), jobs))
+    lib = str(out / "libmof_emul.so")
+    subprocess.check_call(["g++", "-shared", "-o", lib] + [j[j.index("-o") + 1] for j in jobs] + ["-lpthread"])
+    saved = (api.LIB_PATH, api._lib, os.environ.get("MOF_SMOOTH_AHEAD"))
+    api.LIB_PATH, api._lib = lib, None
+    os.environ["MOF_SMOOTH_AHEAD"] = "0"  # the second stream's worker thread would share the emulator's thread/block registers
+    try:
+        yield api
+    finally:
+        api.LIB_PATH, api._lib = saved[0], saved[1]
+        if saved[2] is None:
+            os.environ.pop("MOF_SMOOTH_AHEAD", None)
+        else:
+            os.environ["MOF_SMOOTH_AHEAD"] = saved[2]
+
+
+@pytest.fixture()
+def aligner(emulated):
+    al = emulated.Aligner(0)
+    yield al
+    al.close()
+
+
+def test_the_emulated_build_is_the_whole_c_abi(emulated):
+    lib = emulated.load_library()
+    assert lib._name.endswith("libmof_emul.so")
+    for name in emulated.EXPORTED_SYMBOLS:
+        assert hasattr(lib, name), name
+
+
+def test_vertex_alignment_matches_the_reference_golden(aligner, golden_sphere):
+    """258 vertices: too small for a hierarchy, so every solve is the persistent Jacobi-PCG kernel (pcg_kernels.cu)."""
+    g = golden_sphere
+    v, t = g["input_vertices_f32"].astype(np.float64), g["triangles"]
+    al = aligner
+    al.set_mesh(v, t)
+    assert np.array_equal(al.array(api.ARR_OPPOSITE), g["oppositeEdge"]) and np.array_equal(al.array(api.ARR_REDUCED_EDGE), g["reducedEdgeIndex"])
+    E = al.num_edges
+    S, ref = al.csr(api.CSR_WHITNEY_SMOOTH), csr_from_golden(g, "smoothOperator", (E, E))
+    assert np.array_equal(S.indptr, ref.indptr) and np.array_equal(S.indices, ref.indices) and rel(S.data, ref.data) < 1e-11
+    al.set_signals(g["input_a"].astype(np.float64), g["input_b"].astype(np.float64))
+    for i in range(10):
+        al.iterate(1)
+        assert rel(al.flow(), g["it%02d.tFlowField" % i]) < 1e-6, i  # north_star gate: 1e-3
+    ca, cb = al.advect_vertices(0.5)
+    assert np.abs(ca - g["advected0"]).max() < 1e-4 and np.abs(cb - g["advected1"]).max() < 1e-4
+    out = O.to_uchar_ply((ca + cb) / 2.0)
+    assert np.abs(out.astype(int) - g["output_rgb"].astype(int)).max() <= 1
+    s = al.stats()
+    assert s["flowSolves"] == 10 and s["lastFlowResidual"] <= 1.01e-8 and s["kernelLaunches"] > 0
+
+
+def test_multigrid_and_jacobi_solves_agree_with_the_checker(emulated):
+    """4 098 vertices: three-level hierarchies for the flow and the smoothing systems (sliced fine sweeps, 27-point stencil level,
+    dense coarsest solve, two iterations per replayed graph); then the same alignment with the Jacobi-PCG kernel."""
+    v, t = synthetic.octahedron_sphere(5)
+    a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(v, 1))
+    st, _ = O.align_vertices(v, t, a, b, O.Params(iterations=2))
+    flows, iters = {}, {}
+    saved = {k: os.environ.get(k) for k in ("MOF_FLOW_MG", "MOF_SCALAR_MG")}
+    try:
+        for mode in ("1", "0"):
+            os.environ["MOF_FLOW_MG"] = os.environ["MOF_SCALAR_MG"] = mode  # read when the mesh is set
+            al = emulated.Aligner(0)
+            try:
+                al.set_mesh(v, t)
+                al.set_signals(a, b)
+                al.iterate(2)
+                s = al.stats()
+                assert s["lastFlowResidual"] <= 1.01e-8 and s["lastSmoothResidual"] <= 1.01e-10
+                flows[mode], iters[mode] = al.flow(), (s["flowCgIterations"], s["smoothCgIterations"])
+                if mode == "1":  # the assembled flow system of the last iteration: symmetric, on the pattern of the smoothness operator
+                    A, S = al.csr(api.CSR_FLOW_SYSTEM), al.csr(api.CSR_WHITNEY_SMOOTH)
+                    assert np.array_equal(A.indptr, S.indptr) and np.array_equal(A.indices, S.indices) and abs(A - A.T).max() < 1e-12 * abs(A).max()
+            finally:
+                al.close()
+    finally:
+        for k, val in saved.items():
+            if val is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = val
+    assert rel(flows["1"], st.tfield) < 1e-6 and rel(flows["0"], st.tfield) < 1e-6
+    assert rel(flows["1"], flows["0"]) < 1e-6
+    assert iters["1"][0] < iters["0"][0] / 3 and iters["1"][1] < iters["0"][1]  # the hierarchies are in use
+
+
+@pytest.mark.parametrize("name", sorted(VF_MODES))
+def test_conformal_and_connection_bases_match_the_reference_golden(aligner, golden_modes, name):
+    g = golden_modes
+    vf_mode, c_mode = VF_MODES[name]
+    v, t = g["input_vertices_f32"].astype(np.float64), g["triangles"]
+    p = api.default_params()
+    p.vfMode, p.cMode, p.vfSmooth, p.iterations = vf_mode, c_mode, (3e-6, 5e-7, 1e4)[vf_mode], 4
+    al = aligner
+    al.set_params(p)
+    al.set_mesh(v, t)
+    al.set_signals(g["input_a"].astype(np.float64), g["input_b"].astype(np.float64))
+    for i in range(4):
+        al.iterate(1)
+        assert rel(al.flow(), g["%s.it%02d.tFlowField" % (name, i)]) < 1e-5, (name, i)
+
+
+def test_conformal_basis_with_the_two_cycle_preconditioner(aligner):
+    """1 026 vertices: the scalar hierarchy exists, so the Conformal solve is preconditioned by two of its cycles."""
+    v, t = synthetic.octahedron_sphere(4)
+    a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(v, 2))
+    p = api.default_params()
+    p.vfMode, p.vfSmooth, p.iterations = 1, 5e-7, 2
+    st, ref = O.align_vertices(v, t, a, b, O.Params(iterations=2, vfMode=1))
+    al = aligner
+    al.set_params(p)
+    al.set_mesh(v, t)
+    al.set_signals(a, b)
+    al.iterate(2)
+    assert rel(al.flow(), st.tfield) < 1e-4
+    ca, cb = al.advect_vertices(0.5)
+    assert np.abs((ca + cb) / 2.0 - ref).max() < 1e-2
+
+
+def test_six_channel_blend(aligner):
+    v, t = synthetic.octahedron_sphere(4)
+    a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(v, 3))
+    p = api.default_params()
+    p.dogWeight, p.iterations = 0.5, 2
+    st, ref = O.align_vertices(v, t, a, b, O.Params(iterations=2, dogWeight=0.5))
+    al = aligner
+    al.set_params(p)
+    al.set_mesh(v, t)
+    al.set_signals(a, b)
+    al.iterate(2)
+    assert rel(al.flow(), st.tfield) < 1e-6
+    ca, cb = al.advect_vertices(0.5)
+    assert np.abs((ca + cb) / 2.0 - ref).max() < 1e-4
+
+
+def test_texture_configuration_end_to_end(aligner, golden_torus):
+    """--mesh m.ply --in A.png B.png as the command line drives it with MOF_GPU_TEXPREP=1: subdivision, mesh, texel map and vertex
+    colours on the "device", ten iterations, texel advection — against the reference's golden fixture."""
+    g = golden_torus
+    ta, tb = g["input_tex_a"], g["input_tex_b"]
+    v0 = g["input_vertices_f32"]
+    lo, hi = v0.astype(np.float64).min(0), v0.astype(np.float64).max(0)
+    e_len = float(np.float32(np.float32(0.08) * float(np.sqrt(((hi - lo) ** 2).sum()))))
+    al = aligner
+    v, t, uv = al.subdivide(v0, g["input_triangles"], g["input_uv"].astype(np.float64), e_len)
+    assert np.array_equal(v.astype(np.float64), g["vertices"]) and np.array_equal(t, g["triangles"])
+    al.set_mesh(v.astype(np.float64), t)
+    srcT, srcP = al.build_texture_map(48, 48, 2, uv, ta, tb)
+    assert np.array_equal(srcT, g["textureSource_tIdx"])
+    ca, cb = al.sample_textures_to_vertices()
+    al.set_signals(ca, cb)
+    s6 = al.array(api.ARR_SIGNALS)
+    assert rel(s6[:, :3], g["signals0"]) < 1e-7 and rel(s6[:, 3:], g["signals1"]) < 1e-7
+    for i in range(10):
+        al.iterate(1)
+        assert rel(al.flow(), g["it%02d.tFlowField" % i]) < 1e-5, i
+    oa, ob = al.advect_texels(0.5)
+    assert colour_outliers(oa, g["advected0"], 1.0) < 2e-3 and colour_outliers(ob, g["advected1"], 1.0) < 2e-3
+    pixels = O.to_uchar_png((oa + ob) / 2.0).reshape(48, 48, 3)[::-1]
+    assert colour_outliers(pixels, g["output_pixels"], 1.0) < 2e-3
+
+
+def test_stand_alone_solver_and_error_paths(aligner):
+    import scipy.sparse.linalg as spla
+    rng = np.random.default_rng(5)
+    n = 1203  # not a multiple of the slice height
+    rows, cols, w = rng.integers(0, n, 6 * n), rng.integers(0, n, 6 * n), rng.uniform(0.1, 1.0, 6 * n)
+    W = sp.coo_matrix((w, (rows, cols)), shape=(n, n)).tocsr()
+    W = W + W.T
+    A = (sp.diags(np.asarray(W.sum(1)).ravel() + rng.uniform(0.01, 0.1, n)) - W).tocsr()
+    b = rng.standard_normal(n)
+    x, iters, relres = aligner.pcg_solve_csr(A, b, 1e-10)
+    assert relres <= 1.01e-10 and iters > 0 and rel(x, spla.spsolve(A.tocsc(), b)) < 1e-7
+    al = aligner
+    with pytest.raises(api.MofError) as e:  # half-edge 0->1 used twice (FEM.inl:599)
+        al.set_mesh(np.eye(4, 3), np.array([[0, 1, 2], [0, 1, 3]], dtype=np.int32))
+    assert e.value.code == api.MOF_E_MESH and "Edge is occupied" in e.value.message
+    with pytest.raises(api.MofError) as e:
+        al.iterate(1)
+    assert e.value.code == api.MOF_E_INVALID
