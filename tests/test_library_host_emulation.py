@@ -28,13 +28,16 @@ UNITS = 7  # library_emul.cpp: one translation unit per .cu file
 def emulated(tmp_path_factory):
     """api, bound to the emulated build for the duration of this module."""
     out = tmp_path_factory.mktemp("library_emul")
-    base = ["g++", "-O2", "-std=c++17", "-fPIC", "-c", "-x", "c++", "-DMOF_HOST_EMULATION", "-I.", "-w"]
+    # MOF_EMUL_CXXFLAGS="-O1 -g -fsanitize=address" (with LD_PRELOAD=libasan.so, ASAN_OPTIONS=detect_leaks=0) turns every "device"
+    # buffer overrun of every kernel into a test failure: "device" memory is malloc'd
+    extra = os.environ.get("MOF_EMUL_CXXFLAGS", "-O2").split()
+    base = ["g++"] + extra + ["-std=c++17", "-fPIC", "-c", "-x", "c++", "-DMOF_HOST_EMULATION", "-I.", "-w"]
     jobs = [base + ["-DEMUL_UNIT=%d" % u, "-o", str(out / ("unit%d.o" % u)), "library_emul.cpp"] for u in range(UNITS)]
     jobs += [base + ["-o", str(out / "dist_stub.o"), "dist_stub.cpp"], base + ["-o", str(out / "runtime.o"), "emul_runtime.cpp"]]
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         list(pool.map(lambda cmd: subprocess.check_call(cmd, cwd=EMU_DIR), jobs))
     lib = str(out / "libmof_emul.so")
-    subprocess.check_call(["g++", "-shared", "-o", lib] + [j[j.index("-o") + 1] for j in jobs] + ["-lpthread"])
+    subprocess.check_call(["g++", "-shared"] + [f for f in extra if f.startswith("-fsanitize")] + ["-o", lib] + [j[j.index("-o") + 1] for j in jobs] + ["-lpthread"])
     saved = (api.LIB_PATH, api._lib, os.environ.get("MOF_SMOOTH_AHEAD"))
     api.LIB_PATH, api._lib = lib, None
     os.environ["MOF_SMOOTH_AHEAD"] = "0"  # the second stream's worker thread would share the emulator's thread/block registers

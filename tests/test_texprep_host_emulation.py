@@ -25,7 +25,8 @@ def _p(a, t):
 @pytest.fixture(scope="module")
 def emul(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("texprep_emul") / "libtexprep_emul.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DMOF_HOST_EMULATION", "-I.", "-w", "-o", out, "texprep_emul.cpp",
+    extra = os.environ.get("MOF_EMUL_CXXFLAGS", "-O2").split()  # e.g. "-O1 -g -fsanitize=address", see test_library_host_emulation.py
+    subprocess.check_call(["g++"] + extra + ["-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DMOF_HOST_EMULATION", "-I.", "-w", "-o", out, "texprep_emul.cpp",
                            "emul_runtime.cpp"], cwd=EMU_DIR)
     return ctypes.CDLL(out)
 
