@@ -95,9 +95,9 @@ inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSucces
 inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { delete g; return cudaSuccess; }
 
 // vector types and cache-hinted loads
-struct float2 { float x, y; };
-struct double2 { double x, y; };
-struct float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };     // the device's alignment requirements: -fsanitize=alignment then reports a vector
+struct alignas(16) double2 { double x, y; };  // load that would be a "misaligned address" fault on the GPU
+struct alignas(16) float4 { float x, y, z, w; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
