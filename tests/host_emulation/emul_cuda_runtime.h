@@ -5,6 +5,10 @@
 // a launch runs the kernel body once per (block, thread) on fibers of one OS thread (emul_runtime.cpp), a thread that
 // reaches __syncthreads() or a warp shuffle giving way to the others: barrier semantics hold, __shared__ variables (made
 // `static`) are per block because blocks run one after the other. A cooperative kernel is run as ONE CTA.
+//
+// Build with -fno-gnu-unique: several emulated libraries live in one pytest process, and a `static` inside an inline or
+// template kernel (every __shared__ variable of one) is otherwise a STB_GNU_UNIQUE symbol that the dynamic linker shares
+// between ALL of them — including between the per-thread (MOF_EMUL_THREADS) and the plain variant of the same variable.
 #pragma once
 
 #include <ucontext.h>
@@ -24,7 +28,14 @@ using std::min;
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
-#define __shared__ static
+// -DMOF_EMUL_THREADS: several "GPUs" in one process, one OS thread each (the partitioned-mesh path, nccl.h here): the
+// emulator's state and the kernels' __shared__ variables are then per thread.
+#ifdef MOF_EMUL_THREADS
+#define MOF_EMUL_TLS thread_local
+#else
+#define MOF_EMUL_TLS
+#endif
+#define __shared__ static MOF_EMUL_TLS
 #define __launch_bounds__(...)
 
 typedef int cudaError_t;
@@ -106,7 +117,7 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T __ldcs(const T* p) { return *p; }
 
 struct EmulDim { unsigned x = 1, y = 1, z = 1; };
-extern EmulDim blockIdx, blockDim, threadIdx, gridDim;
+extern MOF_EMUL_TLS EmulDim blockIdx, blockDim, threadIdx, gridDim;
 void __syncthreads();
 
 namespace mof_emul {

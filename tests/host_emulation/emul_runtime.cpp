@@ -7,7 +7,7 @@
 
 #include <cstdint>
 
-EmulDim blockIdx, blockDim, threadIdx, gridDim;
+MOF_EMUL_TLS EmulDim blockIdx, blockDim, threadIdx, gridDim;
 
 // Context switch. x86-64: a dozen instructions (callee-saved registers and the stack pointer; every fiber shares the
 // floating-point control state) — glibc's swapcontext makes a system call per switch (the signal mask), and a kernel
@@ -45,23 +45,23 @@ constexpr size_t kStack = 128 * 1024;
 // A fiber runs thread after thread of the block (the next one that has not started yet) for as long as they run to
 // completion; the first of its threads that has to wait at a synchronisation point parks on it. A kernel without
 // barriers or shuffles therefore runs on ONE fiber with no context switch at all.
-char* stacks[kMaxThreads];
-bool finished[kMaxThreads];
-int fiberOf[kMaxThreads];
-int current = -1, blockThreads = 0, nextToStart = 0;
-const std::function<void()>* body = nullptr;
+MOF_EMUL_TLS char* stacks[kMaxThreads];
+MOF_EMUL_TLS bool finished[kMaxThreads];
+MOF_EMUL_TLS int fiberOf[kMaxThreads];
+MOF_EMUL_TLS int current = -1, blockThreads = 0, nextToStart = 0;
+MOF_EMUL_TLS const std::function<void()>* body = nullptr;
 
-int live = 0, arrived = 0;
-unsigned long long generation = 0;
-int warpLive[kMaxThreads / 32], warpArrived[kMaxThreads / 32];
-unsigned long long warpGeneration[kMaxThreads / 32];
-unsigned long long slots[kMaxThreads];  // shuffle exchange, 8 bytes per thread
+MOF_EMUL_TLS int live = 0, arrived = 0;
+MOF_EMUL_TLS unsigned long long generation = 0;
+MOF_EMUL_TLS int warpLive[kMaxThreads / 32], warpArrived[kMaxThreads / 32];
+MOF_EMUL_TLS unsigned long long warpGeneration[kMaxThreads / 32];
+MOF_EMUL_TLS unsigned long long slots[kMaxThreads];  // shuffle exchange, 8 bytes per thread
 
-int runningFiber = -1;
+MOF_EMUL_TLS int runningFiber = -1;
 void fiber_entry();
 #ifdef MOF_EMUL_ASM_SWITCH
-void* mainSp = nullptr;
-void* fiberSp[kMaxThreads];
+MOF_EMUL_TLS void* mainSp = nullptr;
+MOF_EMUL_TLS void* fiberSp[kMaxThreads];
 void fiber_init(int f) {
     // the frame mof_emul_switch unwinds on the first switch: six registers, then `ret` into fiber_entry with the stack
     // pointer where a call would have left it (8 below a 16-byte boundary)
@@ -75,7 +75,7 @@ void fiber_init(int f) {
 void to_fiber(int f) { mof_emul_switch(&mainSp, fiberSp[f]); }
 void to_main(int f) { mof_emul_switch(&fiberSp[f], mainSp); }
 #else
-ucontext_t mainCtx, fiberCtx[kMaxThreads];
+MOF_EMUL_TLS ucontext_t mainCtx, fiberCtx[kMaxThreads];
 void fiber_init(int f) {
     getcontext(&fiberCtx[f]);
     fiberCtx[f].uc_stack.ss_sp = stacks[f], fiberCtx[f].uc_stack.ss_size = kStack, fiberCtx[f].uc_link = &mainCtx;
@@ -117,7 +117,7 @@ void __syncthreads() {
 }
 
 namespace {
-EmulGraph* capture = nullptr;
+MOF_EMUL_TLS EmulGraph* capture = nullptr;
 }
 cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
     delete capture;

@@ -23,7 +23,7 @@ _D, _I = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
 @pytest.fixture(scope="module")
 def emul(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("flow_emul") / "libflow_emul.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DMOF_HOST_EMULATION", "-DEMUL_WITH_FLOW", "-I.", "-w", "-o", out,
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DMOF_HOST_EMULATION", "-fno-gnu-unique", "-DEMUL_WITH_FLOW", "-I.", "-w", "-o", out,
                            "flow_emul.cpp", "vf_emul.cpp", "emul_runtime.cpp", "-lpthread"], cwd=EMU_DIR)
     return ctypes.CDLL(out)
 

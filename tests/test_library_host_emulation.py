@@ -31,7 +31,7 @@ def emulated(tmp_path_factory):
     # MOF_EMUL_CXXFLAGS="-O1 -g -fsanitize=address" (with LD_PRELOAD=libasan.so, ASAN_OPTIONS=detect_leaks=0) turns every "device"
     # buffer overrun of every kernel into a test failure: "device" memory is malloc'd
     extra = os.environ.get("MOF_EMUL_CXXFLAGS", "-O2").split()
-    base = ["g++"] + extra + ["-std=c++17", "-fPIC", "-c", "-x", "c++", "-DMOF_HOST_EMULATION", "-I.", "-w"]
+    base = ["g++"] + extra + ["-std=c++17", "-fPIC", "-c", "-x", "c++", "-DMOF_HOST_EMULATION", "-fno-gnu-unique", "-I.", "-w"]
     jobs = [base + ["-DEMUL_UNIT=%d" % u, "-o", str(out / ("unit%d.o" % u)), "library_emul.cpp"] for u in range(UNITS)]
     jobs += [base + ["-o", str(out / "dist_stub.o"), "dist_stub.cpp"], base + ["-o", str(out / "runtime.o"), "emul_runtime.cpp"]]
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:

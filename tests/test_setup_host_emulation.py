@@ -21,7 +21,7 @@ EMU_DIR = os.path.join(ROOT, "tests", "host_emulation")
 @pytest.fixture(scope="module")
 def emul(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("setup_emul") / "libsetup_emul.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DMOF_HOST_EMULATION", "-I.", "-w", "-o", out, "setup_emul.cpp",
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DMOF_HOST_EMULATION", "-fno-gnu-unique", "-I.", "-w", "-o", out, "setup_emul.cpp",
                            "emul_runtime.cpp"], cwd=EMU_DIR)
     return ctypes.CDLL(out)
 

@@ -26,7 +26,7 @@ def _p(a, t):
 def emul(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("texprep_emul") / "libtexprep_emul.so")
     extra = os.environ.get("MOF_EMUL_CXXFLAGS", "-O2").split()  # e.g. "-O1 -g -fsanitize=address", see test_library_host_emulation.py
-    subprocess.check_call(["g++"] + extra + ["-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DMOF_HOST_EMULATION", "-I.", "-w", "-o", out, "texprep_emul.cpp",
+    subprocess.check_call(["g++"] + extra + ["-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DMOF_HOST_EMULATION", "-fno-gnu-unique", "-I.", "-w", "-o", out, "texprep_emul.cpp",
                            "emul_runtime.cpp"], cwd=EMU_DIR)
     return ctypes.CDLL(out)
 

@@ -20,7 +20,7 @@ _D, _I = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
 @pytest.fixture(scope="module")
 def emul(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("vf_emul") / "libvf_emul.so")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DMOF_HOST_EMULATION", "-I.", "-w", "-o", out, "vf_emul.cpp",
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-DMOF_HOST_EMULATION", "-fno-gnu-unique", "-I.", "-w", "-o", out, "vf_emul.cpp",
                            "emul_runtime.cpp"], cwd=EMU_DIR)
     return ctypes.CDLL(out)
 
