@@ -1490,7 +1490,7 @@ inline int dist_allreduce(mof_ctx* c, float* v, int n) { return dist_allreduce_f
 inline int dist_allreduce(mof_ctx* c, double* v, int n) { return dist_allreduce_f64(c, v, n); }
 
 // Raw slots of mg.scal for this rank's partial sums (all-reduced in place), and the scalar each one feeds.
-enum { R_PQ = 8, R_RR = 9, R_RZ = 10, R_RZNEW = 11, R_BB = 12 };
+enum { R_PQ = 8, R_RR = 9, R_RZNEW = 10, R_RZ = 11, R_BB = 12 };  // R_RR and R_RZNEW adjacent: one all-reduce carries both
 __global__ void k_derive(int raw, double* __restrict__ scal) {
     const double v = scal[raw];
     if (raw == R_PQ) scal[S_PQ] = v, scal[S_ALPHA] = v != 0 ? scal[S_RZ] / v : 0.;
@@ -1503,8 +1503,9 @@ __global__ void k_derive(int raw, double* __restrict__ scal) {
 // The multigrid-PCG of either hierarchy with the fine level row-partitioned over the ranks. Every rank runs this with
 // the same b (and the same initial x unless zeroGuess); vectors are full length, a rank computes the rows [r0, r1) of
 // each (FLOW: = slices [s0, s1); SCALAR: six values per row). Per iteration: three halo exchanges (p in fp64, the
-// cycle's iterate twice in fp32), four all-reduces (p.q, r.r, the level-1 restriction, r.z); the coarse levels are
-// replicated. x is complete on every rank at the end.
+// cycle's iterate twice in fp32), three all-reduces (p.q; the level-1 restriction; r.r together with r.z — the residual
+// norm only feeds the stopping test, so it waits for the cycle's own reduction); the coarse levels are replicated. x is
+// complete on every rank at the end.
 int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGuess, double tol, int maxIters, int* itersOut, double* relresOut) {
     const bool flow = mg.kind == MG_FLOW;
     const int kind = flow ? 0 : 1, W = mg.nrhs;
@@ -1535,8 +1536,9 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
         return MOF_OK;
     };
     const int D = mg.dofs();
-    // z = cycle(r) on my rows (mg.fz), r.z into scal via `rawSlot`
-    auto cycle = [&](bool presmoothed, int rawSlot) -> int {
+    // z = cycle(r) on my rows (mg.fz), r.z into scal via `rawSlot`. With `withRR` this rank's part of r.r is waiting in
+    // scal[R_RR] (folded by the caller): it joins the all-reduce of r.z (rawSlot = R_RZNEW, the slot next to it).
+    auto cycle = [&](bool presmoothed, int rawSlot, bool withRR = false) -> int {
         if (!presmoothed && len) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r + e0, mg.fdinv.p + r0, mg.omega0, len, W, mg.fz.p + e0);
         MOF_TRY(dist_halo(ctx, kind, mg.fz.p));
         MOF_TRY(spmv((const creal*)mg.fval.p, r, mg.omega0, (const creal*)mg.fz.p, mg.ft.p, 1, NO_FOLD));
@@ -1558,7 +1560,13 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
         }
         MOF_TRY(dist_halo(ctx, kind, mg.fz.p));
         MOF_TRY(spmv((const creal*)mg.fval.p, r, mg.omega0, (const creal*)mg.fz.p, mg.fz2.p, 2, partials));
-        MOF_TRY(reduce(FINE_GRID, rawSlot));
+        if (withRR) {
+            MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, FINE_GRID, R_RZNEW, mg.scal.p);
+            MOF_TRY(dist_allreduce(ctx, mg.scal.p + R_RR, 2));
+            MOF_LAUNCH(k_derive, 1, 1, 0, R_RR, mg.scal.p);
+            MOF_LAUNCH(k_derive, 1, 1, 0, R_RZNEW, mg.scal.p);
+        } else
+            MOF_TRY(reduce(FINE_GRID, rawSlot));
         std::swap(mg.fz.p, mg.fz2.p);
         return MOF_OK;
     };
@@ -1591,9 +1599,9 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
             MOF_TRY(spmv(sysVal, (const double*)nullptr, 0., (const double*)p, q, 0, partials));
             MOF_TRY(reduce(FINE_GRID, R_PQ));
             MOF_LAUNCH(k_update_xr, NBLK, B, 0, p + e0, q + e0, len, x + e0, r + e0, mg.fdinv.p + r0, mg.omega0, W, mg.fz.p + e0, partials);
-            MOF_TRY(reduce(NBLK, R_RR));
+            MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, R_RR, mg.scal.p);  // this rank's part; all-reduced with r.z at the end of the cycle
+            MOF_TRY(cycle(true, R_RZNEW, true));
             MOF_CUDA(cudaMemcpyAsync(mg.hostRR + half, mg.scal.p + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            MOF_TRY(cycle(true, R_RZNEW));
             if (len) MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p + e0, mg.scal.p, len, 0, p + e0);
             return MOF_OK;
         };
