@@ -31,6 +31,14 @@ __global__ void k_deinterleave(const double* __restrict__ in6, int V, double* __
     a[i] = in6[6 * v + c], b[i] = in6[6 * v + 3 + c];
 }
 
+// Indices are 32-bit like the reference's (SparseMatrix<T, int>): the Whitney pattern holds ~33 entries per vertex, the
+// half-edge table 8 slots per triangle. Beyond these sizes an index would wrap (and one B200 could not hold the operators).
+int check_mesh_size(mof_ctx* ctx, int V, int T, const char* who) {
+    if (V < 3 || T < 1) return fail(ctx, MOF_E_INVALID, std::string(who) + ": empty mesh");
+    if (V > 60000000 || T > 120000000) return fail(ctx, MOF_E_INVALID, std::string(who) + ": more than 60M vertices / 120M triangles do not fit 32-bit matrix indices");
+    return MOF_OK;
+}
+
 int require_mesh(mof_ctx* ctx) { return ctx->haveMesh ? MOF_OK : fail(ctx, MOF_E_INVALID, "call mof_set_mesh first"); }
 int require_signals(mof_ctx* ctx) { return ctx->haveSignals ? MOF_OK : fail(ctx, MOF_E_INVALID, "call mof_set_signals first"); }
 
@@ -202,7 +210,8 @@ int mof_dist_init(mof_ctx* ctx, int world, int rank, const unsigned char id128[1
 
 int mof_set_mesh(mof_ctx* ctx, const double* xyz, int V, const int* tri, int T) {
     if (!ctx) return MOF_E_INVALID;
-    if (!xyz || !tri || V < 3 || T < 1) return fail(ctx, MOF_E_INVALID, "mof_set_mesh: empty mesh");
+    if (!xyz || !tri) return fail(ctx, MOF_E_INVALID, "mof_set_mesh: empty mesh");
+    MOF_TRY(check_mesh_size(ctx, V, T, "mof_set_mesh"));
     StreamScope scope(ctx);
     ctx->V = V, ctx->T = T;
     MOF_CUDA(ctx->pos.alloc(3ull * V));
@@ -214,7 +223,8 @@ int mof_set_mesh(mof_ctx* ctx, const double* xyz, int V, const int* tri, int T) 
 
 int mof_set_mesh_device(mof_ctx* ctx, const double* d_xyz, int V, const int* d_tri, int T) {
     if (!ctx) return MOF_E_INVALID;
-    if (!d_xyz || !d_tri || V < 3 || T < 1) return fail(ctx, MOF_E_INVALID, "mof_set_mesh_device: empty mesh");
+    if (!d_xyz || !d_tri) return fail(ctx, MOF_E_INVALID, "mof_set_mesh_device: empty mesh");
+    MOF_TRY(check_mesh_size(ctx, V, T, "mof_set_mesh_device"));
     StreamScope scope(ctx);
     ctx->V = V, ctx->T = T;
     MOF_CUDA(ctx->pos.alloc(3ull * V));

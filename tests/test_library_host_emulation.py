@@ -216,3 +216,8 @@ def test_stand_alone_solver_and_error_paths(aligner):
     with pytest.raises(api.MofError) as e:
         al.iterate(1)
     assert e.value.code == api.MOF_E_INVALID
+    # sizes are checked before anything is read: an empty mesh, and one whose matrix indices would not fit 32 bits
+    lib, one, tri = al._lib, np.zeros(9), np.zeros(3, dtype=np.int32)
+    ptr_d, ptr_i = one.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), tri.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    assert lib.mof_set_mesh(al._ctx, ptr_d, 0, ptr_i, 0) == api.MOF_E_INVALID and b"empty mesh" in lib.mof_last_error(al._ctx)
+    assert lib.mof_set_mesh(al._ctx, ptr_d, 70000000, ptr_i, 140000000) == api.MOF_E_INVALID and b"32-bit" in lib.mof_last_error(al._ctx)
