@@ -221,3 +221,38 @@ def test_stand_alone_solver_and_error_paths(aligner):
     ptr_d, ptr_i = one.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), tri.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
     assert lib.mof_set_mesh(al._ctx, ptr_d, 0, ptr_i, 0) == api.MOF_E_INVALID and b"empty mesh" in lib.mof_last_error(al._ctx)
     assert lib.mof_set_mesh(al._ctx, ptr_d, 70000000, ptr_i, 140000000) == api.MOF_E_INVALID and b"32-bit" in lib.mof_last_error(al._ctx)
+
+
+# ------------------------------------------------------------------ the GPU tier's own assertions, on the emulated build
+#
+# The functions below are the GPU tier's tests, imported and called with THIS module's aligner (the `gpu` marker of their
+# modules applies to collection there, not to a call from here): what will be asserted on a B200 is asserted here first.
+
+def test_gpu_tier_every_stage_matches_the_oracle(aligner):
+    import test_gpu_parity
+    test_gpu_parity.test_every_stage_matches_the_oracle(aligner)
+
+
+def test_gpu_tier_error_paths_and_symmetries(aligner):
+    import test_gpu_parity
+    test_gpu_parity.test_error_paths(aligner)
+    test_gpu_parity.test_identical_signals_give_zero_flow_and_swapping_flips_it(aligner)
+
+
+def test_gpu_tier_switching_bases_on_one_context(aligner):
+    import test_gpu_modes
+    test_gpu_modes.test_switching_bases_on_one_context(aligner)
+
+
+@pytest.mark.parametrize("case", ["seams_pad3_bilinear", "large_triangles_nearest", "no_padding", "vertices_on_texels"])
+def test_gpu_tier_texel_map_matches_the_checker(aligner, case):
+    import test_gpu_texprep
+    test_gpu_texprep.test_texel_map_matches_the_checker(aligner, case)
+
+
+def test_gpu_tier_texture_preparation(aligner, golden_torus):
+    import test_gpu_texprep
+    test_gpu_texprep.test_subdivision_matches_the_reference_golden(aligner, golden_torus)
+    test_gpu_texprep.test_subdivision_matches_the_checker(aligner, 9, 5, 0.05)
+    test_gpu_texprep.test_error_paths(aligner)
+    test_gpu_texprep.test_texel_map_and_vertex_colours_match_the_reference_golden(aligner, golden_torus)
