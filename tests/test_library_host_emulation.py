@@ -256,3 +256,27 @@ def test_gpu_tier_texture_preparation(aligner, golden_torus):
     test_gpu_texprep.test_subdivision_matches_the_checker(aligner, 9, 5, 0.05)
     test_gpu_texprep.test_error_paths(aligner)
     test_gpu_texprep.test_texel_map_and_vertex_colours_match_the_reference_golden(aligner, golden_torus)
+
+
+def test_command_line_on_the_emulated_build(emulated, tmp_path, golden_torus):
+    """The drop-in command line (csrc/host/*.cpp) linked against the emulated library instead of libmof_b200.so: the texture
+    configuration from files to file, with the preparation on the host (default) and on the "device" (MOF_GPU_TEXPREP=1)."""
+    from PIL import Image
+    host = os.path.join(ROOT, "meshopticalflow_b200", "csrc", "host")
+    lib = emulated.load_library()._name
+    exe = str(tmp_path / "OpticalFlow_emul")
+    sources = [os.path.join(host, f) for f in ("optical_flow_main.cpp", "ply_io.cpp", "png_codec.cpp", "texture_prep.cpp", "cmdline.cpp")]
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", exe] + sources + [lib, "-lz", "-Wl,-rpath," + os.path.dirname(lib)])
+    g = golden_torus
+    synthetic.write_ply_textured(str(tmp_path / "m.ply"), g["input_vertices_f32"], g["input_triangles"], g["input_uv"])
+    open(tmp_path / "A.png", "wb").write(g["png_a"].tobytes())
+    open(tmp_path / "B.png", "wb").write(g["png_b"].tobytes())
+    pictures = []
+    for mode in ("0", "1"):
+        r = subprocess.run([exe, "--mesh", "m.ply", "--in", "A.png", "B.png", "--out", "r%s.png" % mode, "--eLength", "0.08"], cwd=tmp_path, capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, MOF_GPU_TEXPREP=mode, MOF_SMOOTH_AHEAD="0"))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "Num vertices %d" % g["vertices"].shape[0] in r.stdout  # OpticalFlow.cpp:716
+        pictures.append(np.asarray(Image.open(tmp_path / ("r%s.png" % mode))).astype(int))
+    assert pictures[0].shape == (48, 48, 3) and np.array_equal(pictures[0], pictures[1])  # same preparation, bit for bit => same file
+    assert colour_outliers(pictures[1], g["output_pixels"], 1.0) < 2e-3
