@@ -348,10 +348,10 @@ static int launch_pcg(mof_ctx* ctx, PcgArgs<N>& args, int* iters, double* relres
     MOF_CUDA(w.result.reserve(8));
     args.partial = w.partial.p, args.result = w.result.p;
     void* params[] = {&args};
-#ifdef MOF_HOST_EMULATION  // CPU test tier: one CTA (grid.sync() is then the CTA barrier), see tests/host_emulation
+#ifdef MOF_HOST_EMULATION  // CPU test tier, see tests/host_emulation: one CTA, or one OS thread per CTA
     (void)params;
     const PcgArgs<N> byValue = args;
-    mof_emul::submit(grid, PCG_T, [byValue] { k_pcg<N>(byValue); });
+    mof_emul::launch_cooperative(grid, PCG_T, [byValue] { k_pcg<N>(byValue); });
     cudaError_t e = cudaSuccess;
 #else
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_pcg<N>, dim3(grid), dim3(PCG_T), params, 0, ctx->stream);

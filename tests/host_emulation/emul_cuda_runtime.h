@@ -85,10 +85,15 @@ inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool
 inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void*) { return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-// cooperative launches are emulated with ONE CTA (a `static` stands in for __shared__, so CTAs cannot be alive together)
+// cooperative launches: ONE CTA (a `static` stands in for __shared__, so CTAs cannot be alive together on one OS thread), or with
+// -DMOF_EMUL_THREADS three CTAs on three OS threads (emul_runtime.cpp: launch_cooperative)
 template <class K> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 1; return cudaSuccess; }
 enum { cudaDevAttrMultiProcessorCount = 16 };
+#ifdef MOF_EMUL_THREADS
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 3; return cudaSuccess; }  // three "multiprocessors": three CTAs, three OS threads
+#else
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 1; return cudaSuccess; }
+#endif
 enum { cudaHostAllocDefault = 0 };
 inline cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : 2; }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
@@ -124,6 +129,9 @@ namespace mof_emul {
 void launch(long long grid, int block, const std::function<void()>& body);
 // A kernel launch as the stream sees it: run now, or recorded into the capture in progress. `body` owns its arguments.
 void submit(long long grid, int block, std::function<void()> body);
+// Cooperative kernels: all CTAs alive together, one OS thread each (MOF_EMUL_THREADS), meeting in grid_sync(); else one CTA.
+void launch_cooperative(long long grid, int block, const std::function<void()>& body);
+void grid_sync();
 unsigned long long shuffle(unsigned long long bits, int srcLane);  // warp-synchronous exchange of 8 bytes
 int lane();
 template <class T>

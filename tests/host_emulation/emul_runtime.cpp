@@ -5,7 +5,10 @@
 // Blocks run one after the other (so `static` stands in for __shared__), atomics are plain read-modify-writes.
 #include "emul_cuda_runtime.h"
 
+#include <condition_variable>
 #include <cstdint>
+#include <mutex>
+#include <thread>
 
 MOF_EMUL_TLS EmulDim blockIdx, blockDim, threadIdx, gridDim;
 
@@ -150,32 +153,83 @@ unsigned long long shuffle(unsigned long long bits, int srcLane) {
 }
 int lane() { return current & 31; }
 
-void launch(long long grid, int block, const std::function<void()>& b) {
+// One thread block of a grid, thread by thread, on the calling OS thread.
+static void run_block(long long bi, long long grid, int block, const std::function<void()>& b) {
     body = &b;
     blockThreads = block;
     blockDim.x = (unsigned)block, gridDim.x = (unsigned)grid;
-    for (long long bi = 0; bi < grid; bi++) {
-        blockIdx.x = (unsigned)bi;
-        live = block, arrived = 0, nextToStart = 0;
-        for (int w = 0; w < (block + 31) / 32; w++) warpLive[w] = std::min(32, block - 32 * w), warpArrived[w] = 0;
-        for (int t = 0; t < block; t++) finished[t] = false, fiberOf[t] = -1;
-        // start every thread: each fiber takes threads until one of them has to wait
-        for (int f = 0; nextToStart < block; f++) {
-            if (!stacks[f]) stacks[f] = (char*)malloc(kStack);
-            fiber_init(f);
-            runningFiber = f;
-            to_fiber(f);
-        }
-        // then round-robin over the waiting ones
-        for (bool any = true; any;) {
-            any = false;
-            for (int t = 0; t < block; t++) {
-                if (finished[t]) continue;
-                current = t, threadIdx.x = (unsigned)t;
-                to_fiber(fiberOf[t]);
-                any = any || !finished[t];
-            }
+    blockIdx.x = (unsigned)bi;
+    live = block, arrived = 0, nextToStart = 0;
+    for (int w = 0; w < (block + 31) / 32; w++) warpLive[w] = std::min(32, block - 32 * w), warpArrived[w] = 0;
+    for (int t = 0; t < block; t++) finished[t] = false, fiberOf[t] = -1;
+    // start every thread: each fiber takes threads until one of them has to wait
+    for (int f = 0; nextToStart < block; f++) {
+        if (!stacks[f]) stacks[f] = (char*)malloc(kStack);
+        fiber_init(f);
+        runningFiber = f;
+        to_fiber(f);
+    }
+    // then round-robin over the waiting ones
+    for (bool any = true; any;) {
+        any = false;
+        for (int t = 0; t < block; t++) {
+            if (finished[t]) continue;
+            current = t, threadIdx.x = (unsigned)t;
+            to_fiber(fiberOf[t]);
+            any = any || !finished[t];
         }
     }
+}
+
+void launch(long long grid, int block, const std::function<void()>& b) {
+    for (long long bi = 0; bi < grid; bi++) run_block(bi, grid, block, b);
+}
+
+// A cooperative launch: the CTAs have to be alive together (they meet in grid_sync), and a `static` stands in for
+// __shared__ — so they can only be alive together on different OS threads with per-thread statics (-DMOF_EMUL_THREADS).
+// Without it a cooperative kernel is run as ONE CTA (cudaDeviceGetAttribute reports one multiprocessor).
+namespace {
+struct GridBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int size = 0, waiting = 0;
+    unsigned long long generation = 0;
+    void wait() {
+        std::unique_lock<std::mutex> lock(m);
+        const unsigned long long mine = generation;
+        if (++waiting == size) waiting = 0, generation++, cv.notify_all();
+        else cv.wait(lock, [&] { return generation != mine; });
+    }
+};
+MOF_EMUL_TLS GridBarrier* gridBarrier = nullptr;
+}  // namespace
+
+void grid_sync() {
+    __syncthreads();
+    if (gridBarrier && threadIdx.x == 0) gridBarrier->wait();
+    __syncthreads();
+}
+
+void launch_cooperative(long long grid, int block, const std::function<void()>& b) {
+#ifdef MOF_EMUL_THREADS
+    if (grid > 1) {
+        GridBarrier barrier;
+        barrier.size = (int)grid;
+        std::vector<std::thread> ctas;
+        auto cta = [&](long long bi, bool worker) {
+            gridBarrier = &barrier;
+            run_block(bi, grid, block, b);
+            gridBarrier = nullptr;
+            if (worker)  // the worker's fiber stacks die with it
+                for (int f = 0; f < kMaxThreads; f++) free(stacks[f]), stacks[f] = nullptr;
+        };
+        for (long long bi = 1; bi < grid; bi++) ctas.emplace_back(cta, bi, true);
+        cta(0, false);
+        for (std::thread& t : ctas) t.join();
+        return;
+    }
+#endif
+    if (grid != 1) abort();  // see above
+    run_block(0, 1, block, b);
 }
 }  // namespace mof_emul

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import pytest
 
-from conftest import ROOT, rel
+from conftest import ROOT, rel  # noqa: F401 (golden_sphere comes from conftest)
 from meshopticalflow_b200 import api, synthetic
 
 EMU_DIR = os.path.join(ROOT, "tests", "host_emulation")
@@ -136,3 +136,21 @@ def test_repeatable_and_basis_restriction(emulated, workload):
     for th in threads:
         th.join(timeout=300)
     assert all(e is not None and e.code == api.MOF_E_UNSUPPORTED for e in errors)
+
+
+def test_cooperative_jacobi_pcg_on_three_ctas(emulated, golden_sphere):
+    """This build runs a cooperative kernel with one OS thread per CTA (three of them, meeting in grid.sync()): the persistent
+    Jacobi-PCG kernel of pcg_kernels.cu — every solve of a mesh too small for a hierarchy — with its per-CTA partial sums in
+    three rotating banks, against the reference's golden flow."""
+    g = golden_sphere
+    al = emulated.Aligner(0)
+    try:
+        al.set_mesh(g["input_vertices_f32"].astype(np.float64), g["triangles"])
+        al.set_signals(g["input_a"].astype(np.float64), g["input_b"].astype(np.float64))
+        for i in range(4):
+            al.iterate(1)
+            assert rel(al.flow(), g["it%02d.tFlowField" % i]) < 1e-6, i
+        s = al.stats()
+        assert s["lastFlowResidual"] <= 1.01e-8 and s["lastSmoothResidual"] <= 1.01e-10
+    finally:
+        al.close()
