@@ -129,7 +129,7 @@ int mof_create(int device, void* stream, mof_ctx** out) {
         ctx->ownStream = true;
     }
     if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return MOF_E_CUDA; }
-    if (cudaHostAlloc((void**)&ctx->pinned, 64 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return MOF_E_CUDA; }
+    if (cudaHostAlloc((void**)&ctx->pinned, 256 * sizeof(double), cudaHostAllocDefault) != cudaSuccess) { delete ctx; return MOF_E_CUDA; }
     // keep freed blocks in the stream-ordered pool instead of handing them back to the driver at every synchronisation
     cudaMemPool_t pool = nullptr;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {

@@ -68,6 +68,18 @@ struct MgLevel {
 }  // namespace
 
 enum MgKind { MG_FLOW = 0, MG_SCALAR = 1 };
+// One instantiated CUDA graph of a whole PCG solve (first cycle, a WHILE node around two iterations whose condition a kernel
+// of the loop sets on the device, true residual, read-back): launched once per solve, no host in the loop. Nothing the
+// next system changes is in its kernel parameters (damping factors, tolerances and counters are read from device memory),
+// so it is captured once per mesh and pair of buffers.
+struct PcgGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const double* b = nullptr;
+    double* x = nullptr;
+    long long launchesOnce = 0, launchesPerPass = 0;  // kernels of ours outside the loop / per pass of its body (two iterations)
+};
+enum { OM_MINUS_ONE = 14, OM_ZERO = 15, OM_COUNT = 16 };  // slots of Multigrid::domega holding -1 (power iteration: z + Minv A z) and 0
 
 struct Multigrid {
     MgKind kind = MG_FLOW;
@@ -87,6 +99,11 @@ struct Multigrid {
     DBuf<double> partial, scal;
     DBuf<unsigned> counter;         // arrival counter of the last-CTA folds (self-resetting)
     double omega0 = 0.6;
+    // Damping factors as the kernels read them (device): [0] fine level, [1 + l] coarse level l, two constants. By pointer
+    // rather than by value so that a captured PCG graph stays valid when the next system changes them.
+    DBuf<double> domega;
+    const double* om(int slot) const { return domega.p + slot; }
+    double hostOmega[16];
     // Cycle shape: `gamma` coarse corrections per visit on the first `gammaLevels` coarse levels, one below. Default
     // (gammaLevels < 0): W (gamma 2) on all but the four (FLOW) / five (SCALAR) coarsest levels — the large levels,
     // where a second visit halves what PCG has left to do (flow solve at 1M vertices: 68 iterations instead of 108,
@@ -95,7 +112,16 @@ struct Multigrid {
     // count; the smoothing systems are better conditioned (most of their solves take ~15 iterations) and want one
     // W level less.
     int gamma = 2, gammaLevels = -1;
-    double* hostRR = nullptr;       // pinned (a slice of ctx->pinned): residual norms of the two iterations of one graph replay
+    int fineSweeps = 1;             // damped-Jacobi sweeps on the fine level before and after the coarse correction (MOF_MG_FINE_SWEEPS[_SCALAR])
+    double* hostRR = nullptr;       // pinned (a slice of ctx->pinned): what a solve reports back (PCG scalars)
+    // The small levels as one kernel on one cluster (k_coarse_tail): first level handled there (-1: none), CTAs of the cluster.
+    int tailStart = -1, tailGrid = 0;
+    bool noWhile = false;           // the driver refused the conditional graph node once: host-driven replays from then on
+    DBuf<unsigned long long> tailTrace;
+    unsigned char traceOps[256];    // the program of the last launch (what the trace's intervals are)
+    int traceN = 0;
+    // PCG loops captured once per (right-hand side, solution) pair of buffers and kept: see PcgGraph.
+    std::vector<struct PcgGraph> graphs;
     std::vector<double> hostBlocks, hostDense;
     std::vector<int> hostNbr;
     int comps() const { return kind == MG_FLOW ? 9 : 1; }     // K
@@ -288,7 +314,7 @@ __global__ void k_entry_slots_scalar(const int* __restrict__ rowptr, const int* 
 // A_ef * v_e v_f^T. One thread per (I, slot); the 27 threads of a cell walk the same entries (broadcast).
 __global__ void k_level1_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const int* __restrict__ wRowptr, const int* __restrict__ sliceBase,
                               const int* __restrict__ wCol, const double* __restrict__ wA, const signed char* __restrict__ slotOf, const double* __restrict__ evec,
-                              const int* __restrict__ nbr, int N, double* __restrict__ blocks) {
+                              const int* __restrict__ nbr, int N, double scale, double* __restrict__ blocks) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * 27) return;
     int I = i / 27, s = i - 27 * I;
@@ -308,11 +334,11 @@ __global__ void k_level1_flow(const int* __restrict__ aggPtr, const int* __restr
             for (int r = 0; r < 3; r++)
                 for (int c = 0; c < 3; c++) acc[3 * r + c] += ve[r] * w[c];
         }
-    for (int k = 0; k < 9; k++) blocks[blk<9>(N, I, s, k)] = acc[k];
+    for (int k = 0; k < 9; k++) blocks[blk<9>(N, I, s, k)] = scale * acc[k];
 }
 // SCALAR level-1 weight (I, slot) = sum over vertices v of I of the entries of row v that fall in that cell.
 __global__ void k_level1_scalar(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const int* __restrict__ rowptr, const double* __restrict__ val,
-                                const signed char* __restrict__ slotOf, const int* __restrict__ nbr, int N, double* __restrict__ blocks) {
+                                const signed char* __restrict__ slotOf, const int* __restrict__ nbr, int N, double scale, double* __restrict__ blocks) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * 27) return;
     int I = i / 27, s = i - 27 * I;
@@ -323,13 +349,13 @@ __global__ void k_level1_scalar(const int* __restrict__ aggPtr, const int* __res
             for (int k = rowptr[v]; k < rowptr[v + 1]; k++)
                 if (slotOf[k] == s) acc += val[k];
         }
-    blocks[blk<1>(N, I, s, 0)] = acc;
+    blocks[blk<1>(N, I, s, 0)] = scale * acc;
 }
 
 // Coarser coefficient (I', slot') = sum of the finer ones (I, s) with parent(I) = I' and parent(nbr(I, s)) = nbr'(I', slot').
 template <int K>
 __global__ void k_coarsen_blocks(const int* __restrict__ firstChild, const int* __restrict__ nbrFine, const int* __restrict__ parentFine, const double* __restrict__ blocksFine,
-                                 int Nfine, const int* __restrict__ nbrCoarse, int Ncoarse, double* __restrict__ blocksCoarse) {
+                                 int Nfine, const int* __restrict__ nbrCoarse, int Ncoarse, double scale, double* __restrict__ blocksCoarse) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ncoarse * 27) return;
     int Ip = i / 27, sp = i - 27 * Ip;
@@ -343,7 +369,7 @@ __global__ void k_coarsen_blocks(const int* __restrict__ firstChild, const int* 
                 if (J < 0 || parentFine[J] != Jp) continue;
                 for (int k = 0; k < K; k++) acc[k] += blocksFine[blk<K>(Nfine, I, s, k)];
             }
-    for (int k = 0; k < K; k++) blocksCoarse[blk<K>(Ncoarse, Ip, sp, k)] = acc[k];
+    for (int k = 0; k < K; k++) blocksCoarse[blk<K>(Ncoarse, Ip, sp, k)] = scale * acc[k];
 }
 
 // FLOW: pseudo-inverse of the diagonal 3x3 block through its eigen-decomposition (cyclic Jacobi rotations, accurate
@@ -407,13 +433,21 @@ __global__ void k_to_creal(const double* __restrict__ src, long long n, creal* _
 
 // z = omega * dinv[row] * r, flat over nrhs interleaved right-hand sides
 template <class TZ>
-__global__ void k_fine_presmooth(const double* __restrict__ r, const creal* __restrict__ dinv, double omega, long long len, int nrhs, TZ* __restrict__ z) {
+__global__ void k_fine_presmooth(const double* __restrict__ r, const creal* __restrict__ dinv, const double* __restrict__ omegaP, long long len, int nrhs,
+                                 TZ* __restrict__ z) {
+    const double omega = *omegaP;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < len) z[i] = (TZ)(omega * (double)dinv[i / nrhs] * r[i]);
 }
 
 // Slots of the PCG scalars (mg.scal).
-enum { S_RZ = 0, S_PQ = 1, S_ALPHA = 2, S_BETA = 3, S_RR = 4, S_BB = 5, S_RZNEW = 6 };
+enum { S_RZ = 0, S_PQ = 1, S_ALPHA = 2, S_BETA = 3, S_RR = 4, S_BB = 5, S_RZNEW = 6,
+       // the device-side loop control of a captured solve (slots 16..39 belong to the power iterations of the set-up)
+       S_THR = 40,    // tol^2 * b.b: the recurrence residual r.r stops the loop at or below it
+       S_IT = 41,     // iterations done
+       S_MAXIT = 42,  // ... and their limit
+       S_RR0 = 43,    // r.r after the first of the two iterations of a pass
+       S_REPORT = 48 };  // scal[0 .. S_REPORT) is what a solve copies back to the host
 
 // One CTA (all B threads): adds `np` per-CTA partials in index order into scal[slot] and derives the PCG scalar that
 // depends on it.
@@ -481,8 +515,9 @@ struct Fold {
 constexpr int BATCH = 6;
 template <class TV, class TX, bool PART = false>
 __global__ void __launch_bounds__(B, 8) k_fine_apply_flow(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const TV* __restrict__ val,
-                                                      const double* __restrict__ b, const creal* __restrict__ dinv, double omega, const TX* __restrict__ in,
-                                                      TX* __restrict__ out, int mode, Fold f, int s0 = 0, int s1 = 0) {
+                                                      const double* __restrict__ b, const creal* __restrict__ dinv, const double* __restrict__ omegaP,
+                                                      const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f, int s0 = 0, int s1 = 0) {
+    const double omega = *omegaP;
     const int lane = threadIdx.x & 31;
     const int slices = PART ? s1 : (n + 31) >> 5;
     const int warps = gridDim.x * (B / 32);
@@ -536,8 +571,9 @@ template <> struct Pair<float> { using type = float2; };
 template <> struct Pair<double> { using type = double2; };
 template <class TV, class TX>
 __global__ void __launch_bounds__(B) k_fine_apply_scalar_row(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const TV* __restrict__ val,
-                                                            const double* __restrict__ b, const creal* __restrict__ dinv, double omega, const TX* __restrict__ in,
-                                                            TX* __restrict__ out, int mode, Fold f) {
+                                                            const double* __restrict__ b, const creal* __restrict__ dinv, const double* __restrict__ omegaP,
+                                                            const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f) {
+    const double omega = *omegaP;
     using P2 = typename Pair<TX>::type;
     double dot = 0;
     for (int row = blockIdx.x * B + threadIdx.x; row < n; row += gridDim.x * B) {
@@ -586,8 +622,9 @@ __global__ void __launch_bounds__(B) k_fine_apply_scalar_row(int n, const int* _
 // PART (one mesh over several GPUs): only the rows [r0, r1) of this rank.
 template <class TV, class TX, bool PART = false>
 __global__ void __launch_bounds__(B, 8) k_fine_apply_scalar(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const TV* __restrict__ val,
-                                                        const double* __restrict__ b, const creal* __restrict__ dinv, double omega, const TX* __restrict__ in,
-                                                        TX* __restrict__ out, int mode, Fold f, int r0 = 0, int r1 = 0) {
+                                                        const double* __restrict__ b, const creal* __restrict__ dinv, const double* __restrict__ omegaP,
+                                                        const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f, int r0 = 0, int r1 = 0) {
+    const double omega = *omegaP;
     const long long len = PART ? 6ll * r1 : 6ll * n;
     double dot = 0;
     for (long long i = (PART ? 6ll * r0 : 0ll) + (long long)blockIdx.x * B + threadIdx.x; i < len; i += (long long)gridDim.x * B) {
@@ -631,9 +668,10 @@ __device__ __forceinline__ void apply_binv(const creal* __restrict__ binv, int N
 // zc = omega * Binv * rc.
 // FLOW restriction: rc[I] = sum over the edges of aggregate I of v_e * r_e (P1^T r). One warp per aggregate.
 __global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ evec, const creal* __restrict__ r, int N,
-                                const creal* __restrict__ binv, creal omega, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1) {
+                                const creal* __restrict__ binv, const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1) {
     int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (I >= N) return;
+    const creal omega = (creal)*omegaP;
     const creal bk = lane < 9 ? binv[(size_t)lane * N + I] : (creal)0;  // the cell's block inverse, fetched alongside the sums
     creal a0 = 0, a1 = 0, a2 = 0;
     for (int q = aggPtr[I] + lane; q < aggPtr[I + 1]; q += 32) {
@@ -663,9 +701,10 @@ __global__ void k_prolong_flow(const int* __restrict__ agg, const creal* __restr
 }
 // SCALAR restriction / prolongation: sums and copies per channel. One thread per (cell, channel) / (vertex, channel).
 __global__ void k_restrict_scalar(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ r, int N, const creal* __restrict__ binv,
-                                  creal omega, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1) {
+                                  const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 6 * N) return;
+    const creal omega = (creal)*omegaP;
     int I = i / 6, c = i - 6 * I;
     creal a = 0;
     for (int q = aggPtr[I]; q < aggPtr[I + 1]; q++) {
@@ -691,9 +730,10 @@ __global__ void k_prolong_scalar(const int* __restrict__ agg, const creal* __res
 // partial sums per (cell, component) are then added in warp order by 32*D threads, which also apply the block inverse.
 template <int K, int D, int SLOTS>
 __global__ void __launch_bounds__(27 / SLOTS * 32) k_coarse_apply(const creal* __restrict__ blocks, const int* __restrict__ nbr, const creal* __restrict__ binv,
-                                                                 const creal* __restrict__ r, const creal* __restrict__ z, creal omega, int N, int mode,
-                                                                 creal* __restrict__ out, const int* __restrict__ parent, const creal* __restrict__ zc) {
+                                                                 const creal* __restrict__ r, const creal* __restrict__ z, const double* __restrict__ omegaP, int N,
+                                                                 int mode, creal* __restrict__ out, const int* __restrict__ parent, const creal* __restrict__ zc) {
     constexpr int WARPS = 27 / SLOTS;
+    const creal omega = (creal)*omegaP;
     __shared__ creal part[WARPS][32 * D];
     __shared__ creal resS[32 * D];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -780,10 +820,11 @@ __global__ void __launch_bounds__(27 / SLOTS * 32) k_coarse_apply(const creal* _
 // Restriction between coarse levels (children of a cell are contiguous) with the first sweep of the coarser level.
 // One thread per coarse cell.
 template <int K, int D>
-__global__ void k_restrict_coarse(const int* __restrict__ firstChild, const creal* __restrict__ rFine, int Ncoarse, const creal* __restrict__ binv, creal omega,
-                                  creal* __restrict__ rc, creal* __restrict__ zc) {
+__global__ void k_restrict_coarse(const int* __restrict__ firstChild, const creal* __restrict__ rFine, int Ncoarse, const creal* __restrict__ binv,
+                                  const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc) {
     int Ip = blockIdx.x * blockDim.x + threadIdx.x;
     if (Ip >= Ncoarse) return;
+    const creal omega = (creal)*omegaP;
     creal a[D], o[D];
 #pragma unroll
     for (int c = 0; c < D; c++) a[c] = 0;
@@ -796,9 +837,10 @@ __global__ void k_restrict_coarse(const int* __restrict__ firstChild, const crea
 }
 // z = omega * Binv * r on a level (partitioned mesh: the first sweep of level 1, after the restriction was all-reduced)
 template <int K, int D>
-__global__ void k_level_presmooth(const creal* __restrict__ binv, const creal* __restrict__ r, creal omega, int N, creal* __restrict__ z) {
+__global__ void k_level_presmooth(const creal* __restrict__ binv, const creal* __restrict__ r, const double* __restrict__ omegaP, int N, creal* __restrict__ z) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= N) return;
+    const creal omega = (creal)*omegaP;
     creal v[D], o[D];
 #pragma unroll
     for (int c = 0; c < D; c++) v[c] = r[(size_t)D * I + c];
@@ -850,6 +892,339 @@ __global__ void __launch_bounds__(B) k_dense_restrict_apply(const int* __restric
     }
 }
 
+// ----------------------------------------------------------- the small levels as ONE kernel on ONE cluster
+//
+// Below a few thousand cells a level is latency-bound: each of its kernels runs 4-9 us whatever it computes (launch ramp, then
+// two or three DEPENDENT trips to global memory at ~1 000 cycles each: neighbour table -> neighbour's value -> ...), and a
+// cycle visits the small levels of a hierarchy 30-50 times (W shape on the large levels). k_coarse_tail runs a whole visit of
+// such a level — restriction from the level above, residual, the recursive visit of everything below down to the dense
+// coarsest solve, W passes, post-smoothing — as one launch of ONE thread-block cluster (16 CTAs of 27 warps, one GPC):
+//  * every level's cells are dealt to the CTAs in contiguous ranges; its vectors (r, iterate, scratch), neighbour table,
+//    block inverses, parent / child links live in the owning CTA's SHARED memory for the whole launch, and so do the stencil
+//    coefficients of the levels of <= 1 536 cells ("resident"; a larger level streams its coefficients from global memory
+//    in every application — loads that depend on nothing and are issued ahead of everything else);
+//  * a neighbour's value is read from the owner's shared memory (distributed shared memory, ~200 cycles), and the operations
+//    of the visit are separated by the cluster's hardware barrier instead of a kernel boundary: no operation has a trip to
+//    global memory on its critical path.
+// Measured on the way here (profiles/r2c_tail_trace.txt): the same interpreter as a cooperative grid over all 148 SMs with a
+// barrier through global memory costs 3.3-5 us per operation, and as one cluster with the vectors left in global memory
+// 2.3-5 us — no better than a launch; the dependent global loads (and the fences that publish global stores) are the cost, not
+// the launch.
+// The host walks the same recursion as coarse_cycle() and writes the operations into the kernel's parameters (TailArgs::op);
+// the kernel is an interpreter over them. The arithmetic of every operation, and the order of every sum, are those of the
+// stand-alone kernels above (k_coarse_apply<K, D, 1>, k_restrict_coarse, k_prolong_coarse, k_dense_restrict_apply), so both
+// paths give the same bits.
+constexpr int TAIL_T = 27 * 32;
+constexpr int TAIL_MAX_OPS = 200;
+constexpr int TAIL_BATCH = 96;         // cells of a CTA's range per pass of an operator application
+constexpr int TAIL_MAX_CTAS = 16;
+enum : unsigned char { T_RESIDUAL = 0, T_RESTRICT = 1, T_DENSE = 2, T_PROLONG = 3, T_SMOOTH = 4, T_LOAD = 5 };
+struct TailLevel {
+    // global memory
+    const creal* blocks;
+    const int* nbr;
+    const creal* binv;
+    const int* parent;      // of this level's cells, on the next coarser level
+    const int* firstChild;  // of this level's cells, on the next finer level
+    creal* r;               // level vectors: read / written only for the level above the tail (its residual) and the tail's
+    creal* z;               // first level (what comes in when there is no level above; the result)
+    creal* t;
+    int N, cpc;             // cells; cells per CTA (CTA k owns cells [k * cpc, (k + 1) * cpc))
+    int resident;           // stencil coefficients staged in shared memory
+    // word offsets of this level's pieces in every CTA's dynamic shared memory
+    int oBlocks, oNbr, oBinv, oParent, oChild, oR, oBuf[2];
+};
+struct TailArgs {
+    TailLevel lev[MAXL + 1];
+    const creal* cinv;      // dense inverse of the coarsest level, nDense x nDense
+    const double* omega;    // Multigrid::domega
+    unsigned long long* trace;  // MOF_MG_TAIL_TRACE=1: %globaltimer of CTA 0 at the start of every operation and at the end
+    int first, last;        // stencil levels first .. last - 1 and the dense level `last` are held in shared memory
+    int oCinv, oPart, oRes, oDense;  // more word offsets: this CTA's rows of cinv, the slot products, residuals, the dense right-hand side
+    int smemBytes;
+    int nOps, nDense;
+    unsigned char op[TAIL_MAX_OPS], lvl[TAIL_MAX_OPS], flip[TAIL_MAX_OPS];  // flip: bit 0 = where level lvl's iterate is, bit 1 = level lvl+1's
+};
+
+// Barrier over the whole cluster (= the whole grid) with release / acquire semantics: what a CTA wrote (to its shared memory,
+// to global memory) before it is visible to every CTA after it.
+__device__ __forceinline__ void tail_barrier() {
+#ifdef MOF_HOST_EMULATION
+    mof_emul::grid_sync();
+#else
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
+}
+// The dynamic shared memory of CTA `rank` of the cluster, as a generic pointer.
+__device__ __forceinline__ creal* tail_peer(creal* mine, int rank) {
+#ifdef MOF_HOST_EMULATION
+    return (creal*)mof_emul::peer_smem(mine, rank);
+#else
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)mine), "r"(rank));
+    return (creal*)out;
+#endif
+}
+// (owner CTA, index in its range) of cell I of a level dealt in ranges of cpc cells, packed.
+__device__ __forceinline__ int tail_pack(int I, int cpc) {
+    const int owner = I / cpc;
+    return (owner << 16) | (I - owner * cpc);
+}
+
+template <int K, int D>
+__global__ void __launch_bounds__(TAIL_T, 1) k_coarse_tail(const TailArgs a) {
+    constexpr int C = D == 3 ? 1 : 6;
+    constexpr int PROW = TAIL_BATCH * D;  // part[slot][cell of the batch][component]
+#ifdef MOF_HOST_EMULATION
+    creal* smem = (creal*)mof_emul::dynamic_smem((size_t)a.smemBytes);
+#else
+    extern __shared__ creal smem[];
+#endif
+    __shared__ creal* peers[TAIL_MAX_CTAS];
+    const int rank = blockIdx.x, tid = threadIdx.x;
+#ifdef MOF_HOST_EMULATION
+    mof_emul::grid_sync();  // (every emulated CTA has registered its buffer)
+#else
+    if (a.trace && rank == 0 && tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        a.trace[255] = now;
+    }
+#endif
+    if (tid < (int)gridDim.x) peers[tid] = tail_peer(smem, tid);
+    creal* part = smem + a.oPart;
+    creal* resS = smem + a.oRes;
+    creal* dr = smem + a.oDense;
+    int* ismem = reinterpret_cast<int*>(smem);
+
+    // ---- staging: everything static of my cell ranges, once per launch. Eight independent loads per thread in flight at a time.
+#define MOF_STAGE(total, SRC, DSTSTMT)                                   \
+    for (int k0 = tid; k0 < (total); k0 += 8 * TAIL_T) {                 \
+        creal v8[8];                                                     \
+        _Pragma("unroll") for (int u8 = 0; u8 < 8; u8++) {               \
+            const int k = k0 + u8 * TAIL_T;                              \
+            if (k < (total)) v8[u8] = (SRC);                             \
+        }                                                                \
+        _Pragma("unroll") for (int u8 = 0; u8 < 8; u8++) {               \
+            const int k = k0 + u8 * TAIL_T;                              \
+            const creal v = v8[u8];                                      \
+            if (k < (total)) { DSTSTMT; }                                \
+        }                                                                \
+    }
+    for (int l = a.first; l <= a.last; l++) {
+        const TailLevel& L = a.lev[l];
+        const int c0 = rank * L.cpc, n = max(0, min(L.N, c0 + L.cpc) - c0);
+        if (l == a.last) {  // the dense level: the child links of ALL its cells (every CTA restricts the whole right-hand side), my rows of the inverse
+            for (int i = tid; i <= L.N; i += TAIL_T) ismem[L.oChild + i] = L.firstChild[i];
+            const int bs = D == 3 ? 3 : 1, rows = bs * n, nd = a.nDense;
+            MOF_STAGE(rows * nd, a.cinv[(size_t)bs * c0 * nd + k], smem[a.oCinv + k] = v)
+            continue;
+        }
+        if (n <= 0) continue;
+        if (L.firstChild)
+            for (int i = tid; i <= n; i += TAIL_T) ismem[L.oChild + i] = L.firstChild[c0 + i];
+        const int cpcUp = a.lev[l + 1].cpc;
+        for (int k = tid; k < 27 * n; k += TAIL_T) {
+            const int i = k / 27, s = k - 27 * i;
+            int J = L.nbr[(size_t)c0 * 27 + k];
+            ismem[L.oNbr + s * L.cpc + i] = tail_pack(J < 0 ? c0 + i : J, L.cpc);
+        }
+        MOF_STAGE(K * n, L.binv[(size_t)(k / n) * L.N + c0 + k % n], smem[L.oBinv + (k / n) * L.cpc + k % n] = v)
+        for (int i = tid; i < n; i += TAIL_T) ismem[L.oParent + i] = tail_pack(L.parent[c0 + i], cpcUp);
+        if (L.resident) MOF_STAGE(27 * K * n, L.blocks[(size_t)(k / n) * L.N + c0 + k % n], smem[L.oBlocks + (k / n) * L.cpc + k % n] = v)
+    }
+#undef MOF_STAGE
+    __syncthreads();
+
+    const int w = tid >> 5, lane = tid & 31;
+    for (int op = 0; op <= a.nOps; op++) {
+        if (op) tail_barrier();
+#ifndef MOF_HOST_EMULATION
+        if (a.trace && rank == 0 && tid == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            a.trace[op] = now;
+        }
+#endif
+        if (op == a.nOps) break;
+        const int l = a.lvl[op], fl = a.flip[op] & 1, fu = (a.flip[op] >> 1) & 1;
+        const TailLevel& L = a.lev[l];
+        const TailLevel& U = a.lev[l + 1];
+        const int what = a.op[op];
+        if (what == T_RESIDUAL || what == T_SMOOTH) {
+            // mode 1: scratch = r - A z ; mode 2: scratch = z + omega Binv (r - A z). Warp = stencil slot, lane = cell; the 27 products of
+            // a cell meet in shared memory and are added in slot order.
+            const int c0 = rank * L.cpc, n = max(0, min(L.N, c0 + L.cpc) - c0);
+            const creal omega = (creal)a.omega[1 + l];
+            const int oZ = L.oBuf[fl];
+            creal* out = smem + L.oBuf[1 - fl];
+            const bool corr = what == T_SMOOTH;  // post-smoothing adds the coarse correction on the fly: z stands for z + P zc
+            const int oZc = U.oBuf[fu];
+            for (int b0 = 0; b0 < n; b0 += TAIL_BATCH) {
+                const int nb = min(TAIL_BATCH, n - b0);
+                for (int i = lane; i < nb; i += 32) {
+                    creal m[K], zj[D];
+                    if (L.resident) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) m[k] = smem[L.oBlocks + (w * K + k) * L.cpc + b0 + i];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; k++) m[k] = L.blocks[(size_t)(w * K + k) * L.N + c0 + b0 + i];
+                    }
+                    const int pj = ismem[L.oNbr + w * L.cpc + b0 + i];
+                    const creal* base = peers[pj >> 16];
+                    const creal* zsrc = base + oZ + (pj & 0xffff) * D;
+#pragma unroll
+                    for (int c = 0; c < D; c++) zj[c] = zsrc[c];
+                    if (corr) {
+                        const int pp = reinterpret_cast<const int*>(base)[L.oParent + (pj & 0xffff)];
+                        const creal* csrc = peers[pp >> 16] + oZc + (pp & 0xffff) * D;
+#pragma unroll
+                        for (int c = 0; c < D; c++) zj[c] += csrc[c];
+                    }
+                    creal* dst = part + w * PROW + i * D;
+                    if (K == 9) {
+                        creal t3[3];
+                        mat3_vec(m, zj, t3);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) dst[c] = t3[c];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < D; c++) dst[c] = m[0] * zj[c];
+                    }
+                }
+                __syncthreads();
+                creal sres = 0;
+                const bool live = tid < nb * D;
+                const int i = tid / D, c = tid - D * i;
+                if (live) {
+#pragma unroll
+                    for (int q = 0; q < 27; q++) sres += part[q * PROW + tid];
+                    sres = smem[L.oR + (b0 + i) * D + c] - sres;
+                    if (what == T_RESIDUAL) out[(b0 + i) * D + c] = sres;
+                    else if (K == 9) resS[tid] = sres;
+                }
+                if (what == T_SMOOTH) {
+                    if (K == 9) __syncthreads();
+                    if (live) {
+                        creal u;
+                        if (K == 9) {
+                            u = 0;
+#pragma unroll
+                            for (int k = 0; k < 3; k++) u += smem[L.oBinv + (3 * c + k) * L.cpc + b0 + i] * resS[i * D + k];
+                        } else
+                            u = smem[L.oBinv + b0 + i] * sres;
+                        const int pp = ismem[L.oParent + b0 + i];
+                        const creal zi = smem[oZ + (b0 + i) * D + c] + peers[pp >> 16][oZc + (pp & 0xffff) * D + c];
+                        out[(b0 + i) * D + c] = zi + omega * u;
+                    }
+                }
+                __syncthreads();  // part / resS are written again by the next batch
+            }
+        } else if (what == T_RESTRICT) {
+            // the level below's residual (sum over the children, which are consecutive cells) and first sweep; the children's
+            // residuals come from the level above the tail in global memory (l < first) or from the owners' shared memory
+            const int c0 = rank * U.cpc, n = max(0, min(U.N, c0 + U.cpc) - c0);
+            const creal omega = (creal)a.omega[2 + l];
+            const bool fromGlobal = l < a.first;
+            const int oT = fromGlobal ? 0 : L.oBuf[1 - fl];
+            for (int i = tid; i < n; i += TAIL_T) {
+                creal sum[D], o[D];
+#pragma unroll
+                for (int c = 0; c < D; c++) sum[c] = 0;
+                const int f0 = ismem[U.oChild + i], f1 = ismem[U.oChild + i + 1];
+                if (fromGlobal) {
+                    for (int I = f0; I < f1; I++)
+#pragma unroll
+                        for (int c = 0; c < D; c++) sum[c] += __ldcg(L.t + (size_t)D * I + c);
+                } else {
+                    int owner = f0 / L.cpc, local = f0 - owner * L.cpc;
+                    for (int I = f0; I < f1; I++) {
+                        const creal* src = peers[owner] + oT + local * D;
+#pragma unroll
+                        for (int c = 0; c < D; c++) sum[c] += src[c];
+                        if (++local == L.cpc) local = 0, owner++;
+                    }
+                }
+                if (K == 9) {
+                    creal m[9];
+#pragma unroll
+                    for (int k = 0; k < 9; k++) m[k] = smem[U.oBinv + k * U.cpc + i];
+                    mat3_vec(m, sum, o);
+                } else {
+                    const creal wv = smem[U.oBinv + i];
+#pragma unroll
+                    for (int c = 0; c < D; c++) o[c] = wv * sum[c];
+                }
+#pragma unroll
+                for (int c = 0; c < D; c++) smem[U.oR + i * D + c] = sum[c], smem[U.oBuf[fu] + i * D + c] = omega * o[c];
+            }
+        } else if (what == T_DENSE) {
+            // coarsest level: every CTA restricts the whole right-hand side into its shared memory (it is tiny), then applies its rows of
+            // the dense inverse: one warp per row, lanes across the columns
+            const int nd = a.nDense, total = nd * C;
+            const int c0 = rank * U.cpc, n = max(0, min(U.N, c0 + U.cpc) - c0);
+            const int bs = D == 3 ? 3 : 1;
+            const bool fromGlobal = l < a.first;
+            const int oT = fromGlobal ? 0 : L.oBuf[1 - fl];
+            if (n > 0) {
+                for (int k = tid; k < total; k += TAIL_T) {
+                    const int Ip = k / D, c = k - D * Ip;
+                    const int f0 = ismem[U.oChild + Ip], f1 = ismem[U.oChild + Ip + 1];
+                    creal sum = 0;
+                    if (fromGlobal) {
+                        for (int I = f0; I < f1; I++) sum += __ldcg(L.t + (size_t)D * I + c);
+                    } else {
+                        int owner = f0 / L.cpc, local = f0 - owner * L.cpc;
+                        for (int I = f0; I < f1; I++) {
+                            sum += peers[owner][oT + local * D + c];
+                            if (++local == L.cpc) local = 0, owner++;
+                        }
+                    }
+                    dr[k] = sum;
+                }
+                __syncthreads();
+                for (int row = w; row < bs * n; row += TAIL_T / 32) {
+                    creal acc[C];
+#pragma unroll
+                    for (int c = 0; c < C; c++) acc[c] = 0;
+                    for (int k = lane; k < nd; k += 32) {
+                        const creal mv = smem[a.oCinv + row * nd + k];
+#pragma unroll
+                        for (int c = 0; c < C; c++) acc[c] += mv * dr[k * C + c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; c++)
+                        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                    if (lane == 0)
+#pragma unroll
+                        for (int c = 0; c < C; c++) smem[U.oBuf[fu] + row * C + c] = acc[c];
+                }
+            }
+        } else if (what == T_PROLONG) {  // z += P zc (before post-smoothing, and between the passes of a W visit)
+            const int c0 = rank * L.cpc, n = max(0, min(L.N, c0 + L.cpc) - c0);
+            for (int k = tid; k < n * D; k += TAIL_T) {
+                const int i = k / D, c = k - D * i;
+                const int pp = ismem[L.oParent + i];
+                smem[L.oBuf[fl] + k] += peers[pp >> 16][U.oBuf[fu] + (pp & 0xffff) * D + c];
+            }
+        } else {  // T_LOAD: the tail starts at the hierarchy's first level — its residual and first sweep are in global memory
+            const int c0 = rank * L.cpc, n = max(0, min(L.N, c0 + L.cpc) - c0);
+            for (int k = tid; k < n * D; k += TAIL_T) {
+                smem[L.oR + k] = __ldcg(L.r + (size_t)D * c0 + k);
+                smem[L.oBuf[fl] + k] = __ldcg(L.z + (size_t)D * c0 + k);
+            }
+        }
+    }
+    // the result: the first level's iterate, for the level above (or the fine level's prolongation)
+    {
+        const TailLevel& L = a.lev[a.first];
+        const int fin = a.flip[a.nOps] & 1;
+        const int c0 = rank * L.cpc, n = max(0, min(L.N, c0 + L.cpc) - c0);
+        for (int k = tid; k < n * D; k += TAIL_T) L.z[(size_t)D * c0 + k] = smem[L.oBuf[fin] + k];
+    }
+}
+
 // ------------------------------------------------------------------------------------- PCG kernels
 
 template <class TA, class TB>
@@ -870,8 +1245,8 @@ __global__ void k_fold(const double* __restrict__ partial, int np, int slot, dou
 // x += alpha p ; r -= alpha q ; partial(r.r) ; and the cycle's pre-smoothing of the new residual, z = omega * dinv * r
 // (the last CTA folds r.r into scal[S_RR])
 __global__ void k_update_xr(const double* __restrict__ p, const double* __restrict__ q, long long n, double* __restrict__ x, double* __restrict__ r,
-                            const creal* __restrict__ dinv, double omega, int nrhs, creal* __restrict__ z, Fold f) {
-    const double alpha = f.scal[S_ALPHA];
+                            const creal* __restrict__ dinv, const double* __restrict__ omegaP, int nrhs, creal* __restrict__ z, Fold f) {
+    const double alpha = f.scal[S_ALPHA], omega = *omegaP;
     double s = 0;
     for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < n; i += (long long)gridDim.x * B) {
         double rv = r[i] - alpha * q[i];
@@ -885,6 +1260,23 @@ __global__ void k_update_xr(const double* __restrict__ p, const double* __restri
 __global__ void k_direction(const creal* __restrict__ z, const double* __restrict__ scal, long long n, int first, double* __restrict__ p) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = first ? (double)z[i] : (double)z[i] + scal[S_BETA] * p[i];
+}
+// Loop control of a captured solve, one thread each.
+// Before a solve: the threshold from b.b (already in scal), the counters.
+__global__ void k_pcg_begin(double* __restrict__ scal, double tol2, int maxIters) {
+    scal[S_THR] = tol2 * scal[S_BB], scal[S_IT] = 0, scal[S_MAXIT] = maxIters, scal[S_RR0] = 0;
+}
+// In front of the loop (enter = 1): run it at all? At the end of a pass of two iterations (enter = 0): another one? The
+// same test the host made between graph replays: both residual norms of the pass above the threshold, finite, iterations left.
+__global__ void k_pcg_continue(cudaGraphConditionalHandle loop, double* __restrict__ scal, int enter) {
+    const double thr = scal[S_THR], rr = scal[S_RR];
+    bool go = scal[S_BB] > 0 && rr > thr && rr < 1e300;  // (also false for NaN)
+    if (!enter) {
+        scal[S_IT] += 2;
+        go = go && scal[S_RR0] > thr;
+    }
+    go = go && scal[S_IT] < scal[S_MAXIT];
+    cudaGraphSetConditional(loop, go ? 1u : 0u);
 }
 // Power iteration support (spectral radius of Minv A per level, for the Jacobi damping).
 __global__ void k_pseudo_random(long long n, creal* __restrict__ v) {
@@ -901,15 +1293,25 @@ __global__ void k_normalise(const creal* __restrict__ t, const double* __restric
     v[i] = (creal)(s > 0 ? (double)t[i] / sqrt(s) : 0.);
 }
 
+void drop_graphs(Multigrid& mg) {
+    for (PcgGraph& g : mg.graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
+    mg.graphs.clear();
+}
+
 void release_mg(Multigrid* mg) {
     if (!mg) return;
+    drop_graphs(*mg);
+    mg->tailTrace.release();
     for (MgLevel& l : mg->lev) {
         l.code.release(), l.nbr.release(), l.parent.release(), l.firstChild.release(), l.blocks.release(), l.cblocks.release(), l.binv.release(), l.r.release(),
             l.z.release(), l.t.release();
     }
     mg->evec.release(), mg->cevec.release(), mg->agg.release(), mg->aggPtr.release(), mg->aggList.release(), mg->slotOf.release(), mg->cinv.release();
     mg->fval.release(), mg->fdinv.release();
-    mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release(), mg->counter.release();
+    mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release(), mg->counter.release(), mg->domega.release();
     delete mg;
 }
 
@@ -1020,6 +1422,20 @@ int build_octree(mof_ctx* ctx, Multigrid& mg, const double* pts, int n, double m
     return MOF_OK;
 }
 
+int plan_tail(mof_ctx* ctx, Multigrid& mg);  // below, with the cycle
+
+// Over-correction: piecewise-constant aggregation makes the Galerkin operator of a Laplacian-like system too stiff (the energy
+// of a step function over-estimates that of the smooth function it stands for), so its coarse corrections come out too small.
+// Dividing every coarse operator by a factor (relative to the Galerkin product of the level above) enlarges them; the cycle
+// stays symmetric positive definite. MOF_MG_OVERCORRECT / MOF_MG_OVERCORRECT_SCALAR (default 1: plain Galerkin).
+double coarse_scale(const Multigrid& mg, int level) {
+    (void)level;
+    static const double flow = [] { const char* e = getenv("MOF_MG_OVERCORRECT"); return e && *e ? atof(e) : 1.0; }();
+    static const double scalar = [] { const char* e = getenv("MOF_MG_OVERCORRECT_SCALAR"); return e && *e ? atof(e) : 1.0; }();
+    const double a = mg.kind == MG_FLOW ? flow : scalar;
+    return a > 0 ? 1. / a : 1.;
+}
+
 int alloc_common(mof_ctx* ctx, Multigrid& mg) {
     const size_t len = mg.fineLen();
     MOF_CUDA(mg.fz.alloc(len));
@@ -1039,18 +1455,34 @@ int alloc_common(mof_ctx* ctx, Multigrid& mg) {
     return MOF_OK;
 }
 
+int upload_omegas(mof_ctx* ctx, Multigrid& mg) {
+    double* h = mg.hostOmega;
+    for (int i = 0; i < OM_COUNT; i++) h[i] = 0.6;
+    h[0] = mg.omega0;
+    for (int l = 0; l < mg.K && 1 + l < OM_MINUS_ONE; l++) h[1 + l] = mg.lev[l].omega;
+    h[OM_MINUS_ONE] = -1., h[OM_ZERO] = 0.;
+    MOF_CUDA(cudaMemcpyAsync(mg.domega.p, h, sizeof(double) * OM_COUNT, cudaMemcpyHostToDevice, ctx->stream));
+    return MOF_OK;
+}
+
 // A hierarchy object is kept from mesh to mesh: its buffers are re-sized in place (DBuf keeps memory that still fits).
 Multigrid* new_mg(mof_ctx* ctx, Multigrid* old, MgKind kind, int nFine, int* rcOut) {
     Multigrid* mg = old ? old : new Multigrid();
     mg->usable = false, mg->K = 0;
+    drop_graphs(*mg);  // captured for the previous mesh's buffers
+    mg->tailStart = -1;
     mg->kind = kind, mg->nFine = nFine, mg->nrhs = kind == MG_FLOW ? 1 : 6;
     mg->gamma = std::max(1, std::min(2, env_int("MOF_MG_GAMMA", 2)));
+    mg->fineSweeps = std::max(1, std::min(4, env_int(kind == MG_FLOW ? "MOF_MG_FINE_SWEEPS" : "MOF_MG_FINE_SWEEPS_SCALAR", 1)));
     mg->gammaLevels = env_int(kind == MG_FLOW ? "MOF_MG_GAMMA_LEVELS" : "MOF_MG_GAMMA_LEVELS_SCALAR", -1);  // < 0: by depth, see coarse_cycle
     cudaError_t e = mg->partial.alloc(8192);  // per-CTA partials: NBLK of ours, or the persistent-grid size of k_spmv_dot
     if (e == cudaSuccess) e = mg->scal.alloc(64);
     if (e == cudaSuccess) e = mg->counter.alloc(4);
+    if (e == cudaSuccess) e = mg->domega.alloc(OM_COUNT);
+    if (e == cudaSuccess && upload_omegas(ctx, *mg) != MOF_OK) e = cudaErrorInvalidValue;
     if (e == cudaSuccess) e = cudaMemsetAsync(mg->counter.p, 0, 4 * sizeof(unsigned), ctx->stream);
-    mg->hostRR = ctx->pinned + (kind == MG_FLOW ? 0 : 8);
+    if (e == cudaSuccess && env_int("MOF_MG_TAIL_TRACE", 0)) e = mg->tailTrace.alloc(256);
+    mg->hostRR = ctx->pinned + (kind == MG_FLOW ? 0 : 64);
     *rcOut = e == cudaSuccess ? MOF_OK : cuda_fail(ctx, e, "multigrid workspace");
     return mg;
 }
@@ -1097,6 +1529,7 @@ int mg_setup_mesh(mof_ctx* ctx) {
             MOF_CUDA(cudaStreamSynchronize(ctx->stream));
             if (!hflag) {
                 rc = alloc_common(ctx, mf);
+                if (rc == MOF_OK) rc = plan_tail(ctx, mf);
                 mf.usable = rc == MOF_OK;
             }
         }
@@ -1115,6 +1548,7 @@ int mg_setup_mesh(mof_ctx* ctx) {
             MOF_CUDA(cudaStreamSynchronize(ctx->stream));
             if (!hflag) {
                 rc = alloc_common(ctx, ms);
+                if (rc == MOF_OK) rc = plan_tail(ctx, ms);
                 ms.usable = rc == MOF_OK;
             }
         }
@@ -1150,7 +1584,7 @@ bool scalar_row_kernel() {
     return on;
 }
 
-int fine_apply(mof_ctx* ctx, Multigrid& mg, const double* b, double omega, const creal* in, creal* out, int mode, int dotSlot = -1) {
+int fine_apply(mof_ctx* ctx, Multigrid& mg, const double* b, const double* omega, const creal* in, creal* out, int mode, int dotSlot = -1) {
     const Fold f = dotSlot >= 0 ? fold_into(mg, dotSlot) : NO_FOLD;
     if (mg.kind != MG_FLOW && scalar_row_kernel()) {
         MOF_LAUNCH((k_fine_apply_scalar_row<creal, creal>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, f);
@@ -1165,25 +1599,25 @@ int fine_apply(mof_ctx* ctx, Multigrid& mg, const double* b, double omega, const
 // out = b - A in with the fp64 matrix (initial and true residuals of PCG)
 int fine_residual(mof_ctx* ctx, Multigrid& mg, const double* b, const double* in, double* out) {
     if (mg.kind == MG_FLOW)
-        MOF_LAUNCH((k_fine_apply_flow<double, double>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, b, (const creal*)nullptr, 0., in, out, 1,
+        MOF_LAUNCH((k_fine_apply_flow<double, double>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, b, (const creal*)nullptr, mg.om(OM_ZERO), in, out, 1,
                    NO_FOLD);
     else
-        MOF_LAUNCH((k_fine_apply_scalar<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, b, (const creal*)nullptr, 0., in, out, 1,
+        MOF_LAUNCH((k_fine_apply_scalar<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, b, (const creal*)nullptr, mg.om(OM_ZERO), in, out, 1,
                    NO_FOLD);
     return MOF_OK;
 }
 
 // `zc` (with the level's parent table) = a coarse correction still to be added to lv.z, see k_coarse_apply.
 template <int K, int D>
-int coarse_apply(mof_ctx* ctx, MgLevel& lv, double omega, int mode, creal* out, const creal* zc) {
+int coarse_apply(mof_ctx* ctx, MgLevel& lv, const double* omega, int mode, creal* out, const creal* zc) {
     const int* parent = zc ? lv.parent.p : nullptr;
     if (lv.N >= 16384)
-        MOF_LAUNCH((k_coarse_apply<K, D, 3>), blocks_for(lv.N, 32), 9 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out, parent, zc);
+        MOF_LAUNCH((k_coarse_apply<K, D, 3>), blocks_for(lv.N, 32), 9 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, omega, lv.N, mode, out, parent, zc);
     else
-        MOF_LAUNCH((k_coarse_apply<K, D, 1>), blocks_for(lv.N, 32), 27 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, (creal)omega, lv.N, mode, out, parent, zc);
+        MOF_LAUNCH((k_coarse_apply<K, D, 1>), blocks_for(lv.N, 32), 27 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, omega, lv.N, mode, out, parent, zc);
     return MOF_OK;
 }
-int coarse_apply(mof_ctx* ctx, Multigrid& mg, MgLevel& lv, double omega, int mode, creal* out, const creal* zc = nullptr) {
+int coarse_apply(mof_ctx* ctx, Multigrid& mg, MgLevel& lv, const double* omega, int mode, creal* out, const creal* zc = nullptr) {
     return mg.kind == MG_FLOW ? coarse_apply<9, 3>(ctx, lv, omega, mode, out, zc) : coarse_apply<1, 6>(ctx, lv, omega, mode, out, zc);
 }
 
@@ -1196,9 +1630,9 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
         MgLevel& lv = mg.lev[l];
         MgLevel& up = mg.lev[l + 1];
         if (mg.kind == MG_FLOW)
-            MOF_LAUNCH(k_coarsen_blocks<9>, blocks_for(27ll * up.N, B), B, 0, up.firstChild.p, lv.nbr.p, lv.parent.p, lv.blocks.p, lv.N, up.nbr.p, up.N, up.blocks.p);
+            MOF_LAUNCH(k_coarsen_blocks<9>, blocks_for(27ll * up.N, B), B, 0, up.firstChild.p, lv.nbr.p, lv.parent.p, lv.blocks.p, lv.N, up.nbr.p, up.N, coarse_scale(mg, l + 1), up.blocks.p);
         else
-            MOF_LAUNCH(k_coarsen_blocks<1>, blocks_for(27ll * up.N, B), B, 0, up.firstChild.p, lv.nbr.p, lv.parent.p, lv.blocks.p, lv.N, up.nbr.p, up.N, up.blocks.p);
+            MOF_LAUNCH(k_coarsen_blocks<1>, blocks_for(27ll * up.N, B), B, 0, up.firstChild.p, lv.nbr.p, lv.parent.p, lv.blocks.p, lv.N, up.nbr.p, up.N, coarse_scale(mg, l + 1), up.blocks.p);
     }
     // Damping of the Jacobi smoothers: omega_l = 1.4 / rho_l with rho_l the spectral radius of Minv A on that level,
     // estimated by power iteration on I + Minv A (all eigenvalues of Minv A are positive). omega * rho < 2 keeps the
@@ -1214,7 +1648,7 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
             MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, 16, mg.scal.p);
             if (it == powerIts) break;
             MOF_LAUNCH(k_normalise, blocks_for((long long)len, B), B, 0, mg.fz.p, mg.scal.p, 16, (long long)len, mg.fz.p);
-            MOF_TRY(fine_apply(ctx, mg, mg.fq.p, -1., mg.fz.p, mg.fz2.p, 2));
+            MOF_TRY(fine_apply(ctx, mg, mg.fq.p, mg.om(OM_MINUS_ONE), mg.fz.p, mg.fz2.p, 2));
             std::swap(mg.fz.p, mg.fz2.p);
         }
     }
@@ -1232,7 +1666,7 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
             MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, 17 + l, mg.scal.p);
             if (it == powerIts) break;
             MOF_LAUNCH(k_normalise, blocks_for(nd, B), B, 0, lv.z.p, mg.scal.p, 17 + l, nd, lv.z.p);
-            MOF_TRY(coarse_apply(ctx, mg, lv, -1., 2, lv.t.p));
+            MOF_TRY(coarse_apply(ctx, mg, lv, mg.om(OM_MINUS_ONE), 2, lv.t.p));
             std::swap(lv.z.p, lv.t.p);
         }
     }
@@ -1255,6 +1689,7 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
     };
     mg.omega0 = damping(hs[16]);
     for (int l = 0; l + 1 < mg.K; l++) mg.lev[l].omega = damping(hs[17 + l]);
+    MOF_TRY(upload_omegas(ctx, mg));
     if (env_int("MOF_MG_VERBOSE", 0)) {
         fprintf(stderr, "[mg %s] fine: n=%d rho %.3f omega %.3f\n", mg.kind == MG_FLOW ? "flow" : "scalar", mg.nFine, std::sqrt(hs[16]) - 1., mg.omega0);
         for (int l = 0; l < mg.K; l++)
@@ -1314,34 +1749,206 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
     return MOF_OK;
 }
 
+int cycle_passes(const Multigrid& mg, int l) {
+    const int wLevels = mg.gammaLevels >= 0 ? mg.gammaLevels : mg.K - (mg.kind == MG_FLOW ? 4 : 5);
+    return l < wLevels ? mg.gamma : 1;
+}
+
+// The operations of a visit of level l (see coarse_cycle), appended to a k_coarse_tail program. `flip` follows which of a
+// level's two buffers holds its iterate.
+struct TailProgram {
+    TailArgs a;
+    int flip[MAXL + 2];
+    bool overflow = false;
+    void emit(unsigned char op, int l) {
+        if (a.nOps >= TAIL_MAX_OPS - 1) { overflow = true; return; }
+        a.op[a.nOps] = op, a.lvl[a.nOps] = (unsigned char)l, a.flip[a.nOps] = (unsigned char)(flip[l] | (flip[l + 1] << 1));
+        a.nOps++;
+    }
+    void restrict_from(const Multigrid& mg, int l) { emit(l + 1 == mg.K - 1 ? T_DENSE : T_RESTRICT, l); }
+    void visit(const Multigrid& mg, int l) {
+        if (l == mg.K - 1) return;
+        const int passes = cycle_passes(mg, l);
+        for (int g = 0; g < passes; g++) {
+            emit(T_RESIDUAL, l);
+            restrict_from(mg, l);
+            visit(mg, l + 1);
+            if (g + 1 < passes) emit(T_PROLONG, l);  // W: the correction has to be in the iterate before the next residual
+        }
+        emit(T_SMOOTH, l);
+        flip[l] ^= 1;
+    }
+};
+
+// Shared-memory layout of a launch that holds levels first .. K-1 on a cluster of `ctas` CTAs; fills the level table of `a`
+// and returns the bytes of dynamic shared memory per CTA.
+size_t tail_layout(const Multigrid& mg, int first, int ctas, int residentCells, TailArgs& a) {
+    const int K = mg.comps(), D = mg.dofs(), bs = mg.kind == MG_FLOW ? 3 : 1;
+    int words = 0;
+    auto take = [&](int n) { int o = words; words += (n + 3) & ~3; return o; };
+    a.first = first, a.last = mg.K - 1;
+    a.nDense = bs * mg.lev.back().N;
+    for (int l = 0; l < mg.K; l++) {
+        const MgLevel& lv = mg.lev[l];
+        TailLevel& t = a.lev[l];
+        t.blocks = lv.cblocks.p, t.nbr = lv.nbr.p, t.binv = lv.binv.p, t.parent = lv.parent.p, t.firstChild = lv.firstChild.p;
+        t.r = lv.r.p, t.z = lv.z.p, t.t = lv.t.p, t.N = lv.N;
+        t.cpc = (lv.N + ctas - 1) / ctas;
+        t.resident = lv.N <= residentCells;
+        if (l < first) continue;
+        const int n = t.cpc;
+        if (l == mg.K - 1) {
+            t.oChild = take(lv.N + 1);
+            t.oBuf[0] = t.oBuf[1] = take(D * n);
+            a.oCinv = take(bs * n * a.nDense);
+            continue;
+        }
+        t.oNbr = take(27 * n), t.oBinv = take(K * n), t.oParent = take(n), t.oChild = take(n + 1);
+        t.oR = take(D * n), t.oBuf[0] = take(D * n), t.oBuf[1] = take(D * n);
+        t.oBlocks = t.resident ? take(27 * K * n) : 0;
+    }
+    a.oPart = take(27 * TAIL_BATCH * D), a.oRes = take(TAIL_BATCH * D), a.oDense = take(DENSE_MAX);
+    a.smemBytes = words * (int)sizeof(creal);
+    return (size_t)a.smemBytes;
+}
+
+int tail_resident_cells() { return env_int("MOF_MG_TAIL_RESIDENT", 1536); }
+
+// Everything from level `first` down in one launch: with fromAbove, the restriction of lev[first - 1].t comes first; without,
+// lev[first].r and the pre-smoothed lev[first].z are read from global memory. The result is written to lev[first].z.
+int launch_tail(mof_ctx* ctx, Multigrid& mg, int first, bool fromAbove) {
+    TailProgram prog;
+    TailArgs& a = prog.a;
+    memset(&a, 0, sizeof(a));
+    for (int l = 0; l <= MAXL + 1; l++) prog.flip[l] = 0;
+    const size_t smem = tail_layout(mg, first, mg.tailGrid, tail_resident_cells(), a);
+    a.cinv = mg.cinv.p, a.omega = mg.domega.p;
+    a.trace = mg.tailTrace.p;  // nullptr unless MOF_MG_TAIL_TRACE
+    if (fromAbove) prog.restrict_from(mg, first - 1);
+    else prog.emit(T_LOAD, first);
+    prog.visit(mg, first);
+    if (prog.overflow) return fail(ctx, MOF_E_INVALID, "multigrid: the program of the small levels does not fit");
+    a.flip[a.nOps] = (unsigned char)prog.flip[first];
+#ifdef MOF_HOST_EMULATION
+    (void)smem;
+    if (mg.kind == MG_FLOW) mof_emul::submit_cooperative(mg.tailGrid, TAIL_T, [a] { k_coarse_tail<9, 3>(a); });
+    else mof_emul::submit_cooperative(mg.tailGrid, TAIL_T, [a] { k_coarse_tail<1, 6>(a); });
+    cudaError_t e = cudaSuccess;
+#else
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(mg.tailGrid), cfg.blockDim = dim3(TAIL_T), cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = mg.tailGrid, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = mg.kind == MG_FLOW ? cudaLaunchKernelEx(&cfg, k_coarse_tail<9, 3>, a) : cudaLaunchKernelEx(&cfg, k_coarse_tail<1, 6>, a);
+#endif
+    ctx->stats.kernelLaunches++;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaLaunchKernelEx(k_coarse_tail)");
+    mg.traceN = a.nOps;
+    for (int i = 0; i < a.nOps; i++) mg.traceOps[i] = (unsigned char)(a.op[i] * 16 + a.lvl[i]);
+    return MOF_OK;
+}
+
+// The cluster: the largest the device co-schedules with this much shared memory — 16 CTAs (sm_100a, opt-in size), else 8, ...
+template <int K, int D>
+int tail_cluster_size(mof_ctx* ctx, size_t* smemLimit, int* ctas) {
+    *ctas = 0;
+#ifdef MOF_HOST_EMULATION
+    *smemLimit = (size_t)64 << 20;  // (one emulated CTA holds what sixteen would share)
+    MOF_CUDA(cudaDeviceGetAttribute(ctas, cudaDevAttrMultiProcessorCount, ctx->device));  // one emulated CTA; three (OS threads) in the threads build
+#else
+    int optin = 0;
+    MOF_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    cudaFuncAttributes fa;
+    MOF_CUDA(cudaFuncGetAttributes(&fa, k_coarse_tail<K, D>));
+    const size_t smem = (size_t)optin - fa.sharedSizeBytes - 256;  // what is left beside the kernel's static shared memory
+    *smemLimit = smem;
+    MOF_CUDA(cudaFuncSetAttribute(k_coarse_tail<K, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool wide = cudaFuncSetAttribute(k_coarse_tail<K, D>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    cudaGetLastError();
+    const int want = std::max(2, std::min(TAIL_MAX_CTAS, env_int("MOF_MG_TAIL_CTAS", 16)));
+    for (int c = wide ? want : std::min(want, 8); c >= 2 && !*ctas; c /= 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(c), cfg.blockDim = dim3(TAIL_T), cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = c, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, k_coarse_tail<K, D>, &cfg) == cudaSuccess && clusters >= 1) *ctas = c;
+        cudaGetLastError();
+    }
+#endif
+    return MOF_OK;
+}
+
+// OFF by default (MOF_MG_TAIL_CELLS=0): on a B200 the launch is no faster than the 7-13 stand-alone kernels it replaces
+// (1M vertices: 626 us per flow PCG iteration without it, 651 us with levels 3-5 on the cluster, 740 us with level 2 streamed as
+// well) — staging the tables costs 10-18 us per launch and an operation still takes 1.4-3 us (cluster barrier with release /
+// acquire ~0.7 us, distributed-shared-memory gathers at ~20 B/cycle/SM); profiles/r2f_tail_dsmem_trace.txt. Kept as an
+// experiment that is bit-identical to the stand-alone path and covered by the CPU tier (MOF_MG_TAIL_CELLS=6144 there).
+// Which levels go into k_coarse_tail: from the first one with at most MOF_MG_TAIL_CELLS cells (0: none) whose
+// layout — coefficients resident up to MOF_MG_TAIL_RESIDENT cells (default 1536), streamed above — fits the shared memory of
+// the cluster, down to the dense coarsest level. The dense level alone is not worth it (it already is one kernel).
+int plan_tail(mof_ctx* ctx, Multigrid& mg) {
+    mg.tailStart = -1;
+    const int cells = env_int("MOF_MG_TAIL_CELLS", 0);
+    if (cells <= 0 || mg.K < 2) return MOF_OK;
+    size_t limit = 0;
+    if (mg.kind == MG_FLOW) MOF_TRY((tail_cluster_size<9, 3>(ctx, &limit, &mg.tailGrid)));
+    else MOF_TRY((tail_cluster_size<1, 6>(ctx, &limit, &mg.tailGrid)));
+    if (mg.tailGrid < 1) return MOF_OK;
+    size_t bytes = 0;
+    for (int l = 0; l + 1 < mg.K && mg.tailStart < 0; l++) {
+        if (mg.lev[l].N > cells || mg.lev[l].N > 60000 * mg.tailGrid) continue;  // (a packed cell index has 16 bits for the index in the owner's range)
+        TailProgram prog;
+        memset(&prog.a, 0, sizeof(prog.a));
+        for (int q = 0; q <= MAXL + 1; q++) prog.flip[q] = 0;
+        bytes = tail_layout(mg, l, mg.tailGrid, tail_resident_cells(), prog.a);
+        if (bytes > limit) continue;
+        prog.emit(T_RESTRICT, 0);
+        prog.visit(mg, l);
+        if (!prog.overflow) mg.tailStart = l;
+    }
+    if (env_int("MOF_MG_VERBOSE", 0))
+        fprintf(stderr, "[mg %s] small levels: from level %d down on one cluster of %d CTAs, %zu bytes of shared memory each\n", mg.kind == MG_FLOW ? "flow" : "scalar",
+                mg.tailStart + 1, mg.tailGrid, bytes);
+    return MOF_OK;
+}
+
 // One cycle on the coarse hierarchy below level l: lev[l].r and the pre-smoothed lev[l].z in (the restriction kernels
 // leave both), lev[l].z out. Launches per level: residual, restriction (+ first sweep of the next level, or the dense
-// solve on the coarsest), post-smoothing (which adds the coarse correction while gathering).
+// solve on the coarsest), post-smoothing (which adds the coarse correction while gathering). From level mg.tailStart down
+// it is one launch per visit (k_coarse_tail), which starts with the restriction from the level above.
 int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
     MgLevel& lv = mg.lev[l];
     const bool flow = mg.kind == MG_FLOW;
     if (l == mg.K - 1) return MOF_OK;  // solved by the restriction that filled it
+    if (mg.tailStart >= 0 && l >= mg.tailStart) return launch_tail(ctx, mg, l, false);
     MgLevel& up = mg.lev[l + 1];
     const bool upDense = l + 1 == mg.K - 1;
-    const int wLevels = mg.gammaLevels >= 0 ? mg.gammaLevels : mg.K - (flow ? 4 : 5);
-    const int passes = l < wLevels ? mg.gamma : 1;
+    const int passes = cycle_passes(mg, l);
     for (int g = 0; g < passes; g++) {
-        MOF_TRY(coarse_apply(ctx, mg, lv, lv.omega, 1, lv.t.p));
-        if (upDense) {
-            const int n = (flow ? 3 : 1) * up.N;
-            if (flow) MOF_LAUNCH(k_dense_restrict_apply<3>, DENSE_CTAS, B, 0, up.firstChild.p, lv.t.p, mg.cinv.p, n, up.z.p);
-            else MOF_LAUNCH(k_dense_restrict_apply<6>, DENSE_CTAS, B, 0, up.firstChild.p, lv.t.p, mg.cinv.p, n, up.z.p);
-        } else if (flow)
-            MOF_LAUNCH((k_restrict_coarse<9, 3>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, (creal)up.omega, up.r.p, up.z.p);
-        else
-            MOF_LAUNCH((k_restrict_coarse<1, 6>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, (creal)up.omega, up.r.p, up.z.p);
-        MOF_TRY(coarse_cycle(ctx, mg, l + 1));
+        MOF_TRY(coarse_apply(ctx, mg, lv, mg.om(1 + l), 1, lv.t.p));
+        if (mg.tailStart == l + 1) MOF_TRY(launch_tail(ctx, mg, l + 1, true));
+        else {
+            if (upDense) {
+                const int n = (flow ? 3 : 1) * up.N;
+                if (flow) MOF_LAUNCH(k_dense_restrict_apply<3>, DENSE_CTAS, B, 0, up.firstChild.p, lv.t.p, mg.cinv.p, n, up.z.p);
+                else MOF_LAUNCH(k_dense_restrict_apply<6>, DENSE_CTAS, B, 0, up.firstChild.p, lv.t.p, mg.cinv.p, n, up.z.p);
+            } else if (flow)
+                MOF_LAUNCH((k_restrict_coarse<9, 3>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, mg.om(2 + l), up.r.p, up.z.p);
+            else
+                MOF_LAUNCH((k_restrict_coarse<1, 6>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, mg.om(2 + l), up.r.p, up.z.p);
+            MOF_TRY(coarse_cycle(ctx, mg, l + 1));
+        }
         if (g + 1 < passes) {  // W-cycle: the correction has to be in z before the next residual
             if (flow) MOF_LAUNCH(k_prolong_coarse<3>, blocks_for(3ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p);
             else MOF_LAUNCH(k_prolong_coarse<6>, blocks_for(6ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p);
         }
     }
-    MOF_TRY(coarse_apply(ctx, mg, lv, lv.omega, 2, lv.t.p, up.z.p));
+    MOF_TRY(coarse_apply(ctx, mg, lv, mg.om(1 + l), 2, lv.t.p, up.z.p));
     std::swap(lv.z.p, lv.t.p);
     return MOF_OK;
 }
@@ -1351,12 +1958,16 @@ int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
 int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed, int rzSlot) {
     const long long len = (long long)mg.fineLen();
     MgLevel& l1 = mg.lev[0];
-    if (!presmoothed) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r, mg.fdinv.p, mg.omega0, len, mg.nrhs, mg.fz.p);
-    MOF_TRY(fine_apply(ctx, mg, r, mg.omega0, mg.fz.p, mg.ft.p, 1));
+    if (!presmoothed) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r, mg.fdinv.p, mg.om(0), len, mg.nrhs, mg.fz.p);
+    for (int sweep = 1; sweep < mg.fineSweeps; sweep++) {  // further pre-smoothing sweeps (the first one is the scaling of r above)
+        MOF_TRY(fine_apply(ctx, mg, r, mg.om(0), mg.fz.p, mg.fz2.p, 2));
+        std::swap(mg.fz.p, mg.fz2.p);
+    }
+    MOF_TRY(fine_apply(ctx, mg, r, mg.om(0), mg.fz.p, mg.ft.p, 1));
     if (mg.kind == MG_FLOW)
-        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, 0, mg.nFine);
+        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine);
     else
-        MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, 0, mg.nFine);
+        MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine);
     if (mg.K == 1) {  // the aggregates are already the coarsest level
         const bool flow = mg.kind == MG_FLOW;
         const int n = (flow ? 3 : 1) * l1.N;
@@ -1366,7 +1977,11 @@ int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed, i
     MOF_TRY(coarse_cycle(ctx, mg, 0));
     if (mg.kind == MG_FLOW) MOF_LAUNCH(k_prolong_flow, blocks_for(mg.nFine, B), B, 0, mg.agg.p, mg.cevec.p, l1.z.p, mg.nFine, mg.fz.p);
     else MOF_LAUNCH(k_prolong_scalar, blocks_for(len, B), B, 0, mg.agg.p, l1.z.p, mg.nFine, mg.fz.p);
-    MOF_TRY(fine_apply(ctx, mg, r, mg.omega0, mg.fz.p, mg.fz2.p, 2, rzSlot));
+    for (int sweep = 1; sweep < mg.fineSweeps; sweep++) {  // post-smoothing: as many sweeps as before the coarse correction (symmetry)
+        MOF_TRY(fine_apply(ctx, mg, r, mg.om(0), mg.fz.p, mg.fz2.p, 2));
+        std::swap(mg.fz.p, mg.fz2.p);
+    }
+    MOF_TRY(fine_apply(ctx, mg, r, mg.om(0), mg.fz.p, mg.fz2.p, 2, rzSlot));
     MOF_TRY(fold_after(ctx, mg, FINE_GRID, rzSlot));
     std::swap(mg.fz.p, mg.fz2.p);
     return MOF_OK;
@@ -1383,17 +1998,17 @@ int apply_dot(mof_ctx* ctx, Multigrid& mg, const double* p, double* q) {
     }
     if (scalar_row_kernel())
         MOF_LAUNCH((k_fine_apply_scalar_row<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, (const double*)nullptr,
-                   (const creal*)nullptr, 0., p, q, 0, fold_into(mg, S_PQ));
+                   (const creal*)nullptr, mg.om(OM_ZERO), p, q, 0, fold_into(mg, S_PQ));
     else
         MOF_LAUNCH((k_fine_apply_scalar<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, (const double*)nullptr,
-                   (const creal*)nullptr, 0., p, q, 0, fold_into(mg, S_PQ));
+                   (const creal*)nullptr, mg.om(OM_ZERO), p, q, 0, fold_into(mg, S_PQ));
     return fold_after(ctx, mg, FINE_GRID, S_PQ);
 }
 
 // PCG with the cycle as preconditioner on the hierarchy's fine system: A x = b. With zeroGuess x starts at 0, otherwise
 // from its content. SCALAR treats the six channels as one block-diagonal system (one alpha/beta for all), which keeps
 // every vector operation flat; the stopping test is on the stacked residual.
-int mg_pcg(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGuess, double tol, int maxIters, int* itersOut, double* relresOut) {
+int mg_pcg_replay(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGuess, double tol, int maxIters, int* itersOut, double* relresOut) {
     const long long len = (long long)mg.fineLen();
     double* r = mg.fr.p;
     double* p = mg.fp.p;
@@ -1427,13 +2042,14 @@ int mg_pcg(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGue
         // even number of cycles). The residual norms of both iterations land in pinned host memory.
         auto iteration = [&](int slot) -> int {
             MOF_TRY(apply_dot(ctx, mg, p, q));
-            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p, q, len, x, r, mg.fdinv.p, mg.omega0, mg.nrhs, mg.fz.p, fold_into(mg, S_RR));
+            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p, q, len, x, r, mg.fdinv.p, mg.om(0), mg.nrhs, mg.fz.p, fold_into(mg, S_RR));
             MOF_TRY(fold_after(ctx, mg, NBLK, S_RR));
             MOF_CUDA(cudaMemcpyAsync(mg.hostRR + slot, mg.scal.p + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             MOF_TRY(fine_cycle(ctx, mg, r, true, S_RZNEW));
             MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 0, p);
             return MOF_OK;
         };
+        // (the path of MOF_MG_WHILE=0: a graph of two iterations per attempt, replayed from the host; mg_pcg below keeps the host out)
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         const long long launchesBefore = ctx->stats.kernelLaunches;
@@ -1471,6 +2087,154 @@ int mg_pcg(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGue
         MOF_CUDA(cudaMemcpyAsync(&rr, mg.scal.p + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         MOF_CUDA(cudaStreamSynchronize(ctx->stream));
         if (it >= maxIters || !std::isfinite(rr)) break;
+    }
+    *itersOut = it;
+    *relresOut = std::sqrt(rr / bb);
+    if (!std::isfinite(rr) || (!(*relresOut <= tol * 1.0001) && (it >= maxIters || !(*relresOut <= 1e-4)))) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "[ERROR] multigrid PCG did not reach %g in %d iterations (relative residual %g)", tol, it, *relresOut);
+        return fail(ctx, MOF_E_NOCONVERGE, msg);
+    }
+    return MOF_OK;
+}
+
+// The solve's graph for this pair of buffers: captured on first use, kept until the mesh changes.
+//   [first cycle: z = M r, p = z, r.z] -> [continue?] -> WHILE { two PCG iterations ; continue? } -> [r = b - A x in fp64, r.r] -> [scalars to the host]
+// The loop's condition is set on the device (k_pcg_continue), so a solve is one graph launch and one synchronisation, and the
+// ping-pong buffers of the cycle are back in place after the two cycles of a pass.
+int pcg_graph(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, PcgGraph** out) {
+    for (PcgGraph& g : mg.graphs)
+        if (g.b == b && g.x == x) { *out = &g; return MOF_OK; }
+    if (mg.graphs.size() >= 6) drop_graphs(mg);
+    const long long len = (long long)mg.fineLen();
+    double* r = mg.fr.p;
+    double* p = mg.fp.p;
+    double* q = mg.fq.p;
+    PcgGraph g;
+    g.b = b, g.x = x;
+    const long long launchesBefore = ctx->stats.kernelLaunches;
+    cudaGraph_t body = nullptr;
+    cudaGraphConditionalHandle loop{};
+    int crc = MOF_OK;
+    cudaError_t ce = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed);
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "cudaStreamBeginCapture(pcg)");
+    auto captured = [&]() -> int {
+        MOF_TRY(fine_cycle(ctx, mg, r, false, S_RZ));
+        MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 1, p);
+        // the WHILE node goes where the capture stands
+        cudaStreamCaptureStatus status;
+        cudaGraph_t capturing = nullptr;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t ndeps = 0;
+        MOF_CUDA(cudaStreamGetCaptureInfo(ctx->stream, &status, nullptr, &capturing, &deps, &ndeps));
+        MOF_CUDA(cudaGraphConditionalHandleCreate(&loop, capturing, 0, cudaGraphCondAssignDefault));
+        MOF_LAUNCH(k_pcg_continue, 1, 1, 0, loop, mg.scal.p, 1);
+        MOF_CUDA(cudaStreamGetCaptureInfo(ctx->stream, &status, nullptr, &capturing, &deps, &ndeps));
+        cudaGraphNodeParams params = {cudaGraphNodeTypeConditional};
+        params.type = cudaGraphNodeTypeConditional;
+        params.conditional.handle = loop;
+        params.conditional.type = cudaGraphCondTypeWhile;
+        params.conditional.size = 1;
+        cudaGraphNode_t node = nullptr;
+        MOF_CUDA(cudaGraphAddNode(&node, capturing, deps, ndeps, &params));
+        body = params.conditional.phGraph_out[0];
+        MOF_CUDA(cudaStreamUpdateCaptureDependencies(ctx->stream, &node, 1, cudaStreamSetCaptureDependencies));
+        // after the loop: the true residual of x and what the host wants to know
+        MOF_TRY(fine_residual(ctx, mg, b, x, r));
+        MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, r, r, len, mg.partial.p);
+        MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, S_RR, mg.scal.p);
+        MOF_CUDA(cudaMemcpyAsync(mg.hostRR, mg.scal.p, sizeof(double) * S_REPORT, cudaMemcpyDeviceToHost, ctx->stream));
+        return MOF_OK;
+    };
+    crc = captured();
+    ce = cudaStreamEndCapture(ctx->stream, &g.graph);
+    g.launchesOnce = ctx->stats.kernelLaunches - launchesBefore;
+    if (crc == MOF_OK && ce == cudaSuccess && g.graph && body) {
+        const long long before = ctx->stats.kernelLaunches;
+        ce = cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed);
+        if (ce == cudaSuccess) {
+            auto iteration = [&](int rrSlot) -> int {
+                MOF_TRY(apply_dot(ctx, mg, p, q));
+                MOF_LAUNCH(k_update_xr, NBLK, B, 0, p, q, len, x, r, mg.fdinv.p, mg.om(0), mg.nrhs, mg.fz.p, fold_into(mg, rrSlot));
+                MOF_TRY(fold_after(ctx, mg, NBLK, rrSlot));
+                MOF_TRY(fine_cycle(ctx, mg, r, true, S_RZNEW));
+                MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 0, p);
+                return MOF_OK;
+            };
+            auto pass = [&]() -> int {
+                MOF_TRY(iteration(S_RR0));
+                MOF_TRY(iteration(S_RR));
+                MOF_LAUNCH(k_pcg_continue, 1, 1, 0, loop, mg.scal.p, 0);
+                return MOF_OK;
+            };
+            crc = pass();
+            cudaGraph_t same = nullptr;
+            ce = cudaStreamEndCapture(ctx->stream, &same);
+        }
+        g.launchesPerPass = ctx->stats.kernelLaunches - before;
+    }
+    ctx->stats.kernelLaunches = launchesBefore;
+    if (crc == MOF_OK && ce == cudaSuccess && g.graph) ce = cudaGraphInstantiate(&g.exec, g.graph, 0);
+    if (crc != MOF_OK || ce != cudaSuccess || !g.exec) {
+        if (g.graph) cudaGraphDestroy(g.graph);
+        cudaGetLastError();
+        return crc != MOF_OK ? crc : cuda_fail(ctx, ce, "capture of the PCG loop (conditional graph node)");
+    }
+    mg.graphs.push_back(g);
+    *out = &mg.graphs.back();
+    return MOF_OK;
+}
+
+bool pcg_while_enabled() { return env_int("MOF_MG_WHILE", 1) != 0; }  // (read per solve: tests flip it inside one process)
+
+// PCG with the cycle as preconditioner on the hierarchy's fine system: A x = b. With zeroGuess x starts at 0, otherwise
+// from its content. SCALAR treats the six channels as one block-diagonal system (one alpha/beta for all), which keeps
+// every vector operation flat; the stopping test is on the stacked residual. One graph launch per attempt (pcg_graph); an
+// attempt whose true residual misses the tolerance (drift of the recurrence) is followed by another from the x reached.
+int mg_pcg(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool zeroGuess, double tol, int maxIters, int* itersOut, double* relresOut) {
+    if (!pcg_while_enabled() || mg.noWhile) return mg_pcg_replay(ctx, mg, b, x, zeroGuess, tol, maxIters, itersOut, relresOut);
+    PcgGraph* g = nullptr;
+    if (pcg_graph(ctx, mg, b, x, &g) != MOF_OK) {  // no conditional nodes on this driver: the replay loop does the same job
+        mg.noWhile = true;
+        return mg_pcg_replay(ctx, mg, b, x, zeroGuess, tol, maxIters, itersOut, relresOut);
+    }
+    const long long len = (long long)mg.fineLen();
+    double* r = mg.fr.p;
+    if (zeroGuess) {
+        MOF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * len, ctx->stream));
+        MOF_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * len, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else
+        MOF_TRY(fine_residual(ctx, mg, b, x, r));
+    MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, b, b, len, mg.partial.p);
+    MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, S_BB, mg.scal.p);
+    MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, r, r, len, mg.partial.p);
+    MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, S_RR, mg.scal.p);
+    MOF_LAUNCH(k_pcg_begin, 1, 1, 0, mg.scal.p, tol * tol, maxIters);
+    *itersOut = 0, *relresOut = 0;
+    double rr = 0, bb = 0;
+    int it = 0;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        cudaError_t ce = cudaGraphLaunch(g->exec, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) return cuda_fail(ctx, ce, "cudaGraphLaunch(pcg)");
+        const double* h = mg.hostRR;
+        const int itNow = (int)h[S_IT];
+        ctx->stats.kernelLaunches += g->launchesOnce + g->launchesPerPass * ((itNow - it) / 2);
+        it = itNow, rr = h[S_RR], bb = h[S_BB];
+        if (!(bb > 0)) {
+            if (!zeroGuess) MOF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * len, ctx->stream));
+            return MOF_OK;
+        }
+        if (!(rr > tol * tol * bb) || it >= maxIters || !std::isfinite(rr)) break;
+    }
+    if (mg.tailTrace.p && mg.traceN > 0) {  // diagnostic: where the time of the last k_coarse_tail launch went
+        std::vector<unsigned long long> h(256);
+        MOF_CUDA(read_back(ctx, h.data(), mg.tailTrace.p, h.size()));
+        static const char* names[] = {"residual", "restrict", "dense", "prolong", "smooth", "load"};
+        fprintf(stderr, "[mg tail %s] staging %.2f us, %d operations, %.2f us:", mg.kind == MG_FLOW ? "flow" : "scalar", (h[0] - h[255]) * 1e-3, mg.traceN,
+                (h[mg.traceN] - h[0]) * 1e-3);
+        for (int i = 0; i < mg.traceN; i++) fprintf(stderr, " %s%d=%.2f", names[mg.traceOps[i] / 16], mg.traceOps[i] % 16, (h[i + 1] - h[i]) * 1e-3);
+        fprintf(stderr, "\n");
     }
     *itersOut = it;
     *relresOut = std::sqrt(rr / bb);
@@ -1529,7 +2293,7 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
     };
     // my rows of the fine operator, on the cycle's fp32 copy (mg.fval) or on the fp64 system matrix
     const double* sysVal = flow ? ctx->wA.p : ctx->sSys.p;
-    auto spmv = [&](const auto* val, const double* rhs, double omega, const auto* in, auto* out, int mode, Fold f) -> int {
+    auto spmv = [&](const auto* val, const double* rhs, const double* omega, const auto* in, auto* out, int mode, Fold f) -> int {
         using TV = std::remove_cv_t<std::remove_pointer_t<decltype(val)>>;
         if (flow) MOF_LAUNCH((k_fine_apply_flow<TV, TV, true>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, val, rhs, mg.fdinv.p, omega, in, out, mode, f, s0, s1);
         else MOF_LAUNCH((k_fine_apply_scalar<TV, TV, true>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, val, rhs, mg.fdinv.p, omega, in, out, mode, f, r0, r1);
@@ -1539,16 +2303,16 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
     // z = cycle(r) on my rows (mg.fz), r.z into scal via `rawSlot`. With `withRR` this rank's part of r.r is waiting in
     // scal[R_RR] (folded by the caller): it joins the all-reduce of r.z (rawSlot = R_RZNEW, the slot next to it).
     auto cycle = [&](bool presmoothed, int rawSlot, bool withRR = false) -> int {
-        if (!presmoothed && len) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r + e0, mg.fdinv.p + r0, mg.omega0, len, W, mg.fz.p + e0);
+        if (!presmoothed && len) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r + e0, mg.fdinv.p + r0, mg.om(0), len, W, mg.fz.p + e0);
         MOF_TRY(dist_halo(ctx, kind, mg.fz.p));
-        MOF_TRY(spmv((const creal*)mg.fval.p, r, mg.omega0, (const creal*)mg.fz.p, mg.ft.p, 1, NO_FOLD));
+        MOF_TRY(spmv((const creal*)mg.fval.p, r, mg.om(0), (const creal*)mg.fz.p, mg.ft.p, 1, NO_FOLD));
         if (flow)
-            MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, r0, r1);
+            MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, r0, r1);
         else
-            MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, (creal)l1.omega, l1.r.p, l1.z.p, r0, r1);
+            MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, r0, r1);
         MOF_TRY(dist_allreduce(ctx, l1.r.p, D * l1.N));
-        if (flow) MOF_LAUNCH((k_level_presmooth<9, 3>), blocks_for(l1.N, B), B, 0, l1.binv.p, l1.r.p, (creal)l1.omega, l1.N, l1.z.p);
-        else MOF_LAUNCH((k_level_presmooth<1, 6>), blocks_for(l1.N, B), B, 0, l1.binv.p, l1.r.p, (creal)l1.omega, l1.N, l1.z.p);
+        if (flow) MOF_LAUNCH((k_level_presmooth<9, 3>), blocks_for(l1.N, B), B, 0, l1.binv.p, l1.r.p, mg.om(1), l1.N, l1.z.p);
+        else MOF_LAUNCH((k_level_presmooth<1, 6>), blocks_for(l1.N, B), B, 0, l1.binv.p, l1.r.p, mg.om(1), l1.N, l1.z.p);
         if (mg.K == 1) {
             if (flow) MOF_LAUNCH(k_dense_restrict_apply<3>, DENSE_CTAS, B, 0, (const int*)nullptr, l1.r.p, mg.cinv.p, 3 * l1.N, l1.z.p);
             else MOF_LAUNCH(k_dense_restrict_apply<6>, DENSE_CTAS, B, 0, (const int*)nullptr, l1.r.p, mg.cinv.p, l1.N, l1.z.p);
@@ -1559,7 +2323,7 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
             else MOF_LAUNCH(k_prolong_scalar, blocks_for(len, B), B, 0, mg.agg.p + r0, l1.z.p, rows, mg.fz.p + e0);
         }
         MOF_TRY(dist_halo(ctx, kind, mg.fz.p));
-        MOF_TRY(spmv((const creal*)mg.fval.p, r, mg.omega0, (const creal*)mg.fz.p, mg.fz2.p, 2, partials));
+        MOF_TRY(spmv((const creal*)mg.fval.p, r, mg.om(0), (const creal*)mg.fz.p, mg.fz2.p, 2, partials));
         if (withRR) {
             MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, FINE_GRID, R_RZNEW, mg.scal.p);
             MOF_TRY(dist_allreduce(ctx, mg.scal.p + R_RR, 2));
@@ -1575,7 +2339,7 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
         MOF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * full, ctx->stream));
         MOF_CUDA(cudaMemcpyAsync(r, b, sizeof(double) * full, cudaMemcpyDeviceToDevice, ctx->stream));
     } else  // x is complete on every rank: no exchange needed for the first residual
-        MOF_TRY(spmv(sysVal, b, 0., (const double*)x, r, 1, NO_FOLD));
+        MOF_TRY(spmv(sysVal, b, mg.om(OM_ZERO), (const double*)x, r, 1, NO_FOLD));
     MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, b + e0, b + e0, len, mg.partial.p);
     MOF_TRY(reduce(NBLK, R_BB));
     MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, r + e0, r + e0, len, mg.partial.p);
@@ -1596,9 +2360,9 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
         if (len) MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p + e0, mg.scal.p, len, 1, p + e0);
         auto iteration = [&](int half) -> int {
             MOF_TRY(dist_halo(ctx, kind, p));
-            MOF_TRY(spmv(sysVal, (const double*)nullptr, 0., (const double*)p, q, 0, partials));
+            MOF_TRY(spmv(sysVal, (const double*)nullptr, mg.om(OM_ZERO), (const double*)p, q, 0, partials));
             MOF_TRY(reduce(FINE_GRID, R_PQ));
-            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p + e0, q + e0, len, x + e0, r + e0, mg.fdinv.p + r0, mg.omega0, W, mg.fz.p + e0, partials);
+            MOF_LAUNCH(k_update_xr, NBLK, B, 0, p + e0, q + e0, len, x + e0, r + e0, mg.fdinv.p + r0, mg.om(0), W, mg.fz.p + e0, partials);
             MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, R_RR, mg.scal.p);  // this rank's part; all-reduced with r.z at the end of the cycle
             MOF_TRY(cycle(true, R_RZNEW, true));
             MOF_CUDA(cudaMemcpyAsync(mg.hostRR + half, mg.scal.p + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1649,7 +2413,7 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
         if (lrc != MOF_OK) return lrc;
         // true residual of x
         MOF_TRY(dist_halo(ctx, kind, x));
-        MOF_TRY(spmv(sysVal, b, 0., (const double*)x, r, 1, NO_FOLD));
+        MOF_TRY(spmv(sysVal, b, mg.om(OM_ZERO), (const double*)x, r, 1, NO_FOLD));
         MOF_LAUNCH((k_dot_partial<double, double>), NBLK, B, 0, r + e0, r + e0, len, mg.partial.p);
         MOF_TRY(reduce(NBLK, R_RR));
         MOF_CUDA(read_back(ctx, &rr, mg.scal.p + S_RR));
@@ -1673,7 +2437,7 @@ int mg_flow_update(mof_ctx* ctx) {
     Multigrid& mg = *ctx->mg;
     MgLevel& l1 = mg.lev[0];
     MOF_LAUNCH(k_level1_flow, blocks_for(27ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, ctx->wRowptr.p, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, mg.slotOf.p, mg.evec.p,
-               l1.nbr.p, l1.N, l1.blocks.p);
+               l1.nbr.p, l1.N, coarse_scale(mg, 0), l1.blocks.p);
     MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->wA.p, ctx->wPadded, mg.fval.p);
     MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->wDinv.p, (long long)ctx->E, mg.fdinv.p);
     return finish_values(ctx, mg);
@@ -1688,7 +2452,7 @@ int mg_flow_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double*
 int mg_scalar_update(mof_ctx* ctx) {
     Multigrid& mg = *ctx->mgs;
     MgLevel& l1 = mg.lev[0];
-    MOF_LAUNCH(k_level1_scalar, blocks_for(27ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, ctx->sRowptr.p, ctx->sSys.p, mg.slotOf.p, l1.nbr.p, l1.N, l1.blocks.p);
+    MOF_LAUNCH(k_level1_scalar, blocks_for(27ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, ctx->sRowptr.p, ctx->sSys.p, mg.slotOf.p, l1.nbr.p, l1.N, coarse_scale(mg, 0), l1.blocks.p);
     MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->sSys.p, ctx->nnzS, mg.fval.p);
     MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->sDinv.p, (long long)ctx->V, mg.fdinv.p);
     return finish_values(ctx, mg);

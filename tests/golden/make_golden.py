@@ -10,7 +10,14 @@ seeded inputs and stores inputs + selected reference outputs as compressed .npz:
   sphere3_modes.npz    the 258-vertex sphere again with 4 iterations of --vfMode 1, --vfMode 2 --cMode 0|1|2 (taps) and of
                        --dogWeight 0.5 (the 6-channel blend: output colours only, the tap build is 3-channel)
 
-    python tests/golden/make_golden.py
+  sphere7_vertex.npz / sphere8_vertex.npz   the 65 538- and 262 146-vertex spheres (BASELINE.json configs[2]'s generator at the two
+                       sizes below the headline one that the reference finishes in minutes), 3 iterations: per-iteration flow on
+                       every 16th / 64th triangle with its global norm, advected colours on every 16th / 64th vertex, all output colours
+  example.npz          the reference's own Example/ (BASELINE.json configs[0] and [1]): mesh.ply, A.png, B.png byte for byte (input
+                       vectors the reference holds), the reference's output picture for --mesh mesh.ply --in A.png B.png and its output
+                       colours for --in A.ply B.ply (A.ply / B.ply = the reference's SampleTextureToVertices_ref --eLength 0.006)
+
+    python tests/golden/make_golden.py [midsize 7|8 | example | modes | tool]
 """
 import os
 import subprocess
@@ -140,11 +147,67 @@ def modes():
     print("sphere3_modes.npz", os.path.getsize(os.path.join(HERE, "sphere3_modes.npz")) // 1024, "KiB")
 
 
+def midsize(level):
+    """Per-vertex alignment of the synthetic sphere of `level` (float32 positions, like any PLY), 3 iterations, taps subsampled."""
+    stride = 16 if level <= 7 else 64
+    v, t = synthetic.octahedron_sphere(level)
+    a, b = synthetic.smooth_rgb_pair(v, 0)
+    with tempfile.TemporaryDirectory() as d:
+        synthetic.write_ply_colored(os.path.join(d, "A.ply"), v, a, t)
+        synthetic.write_ply_colored(os.path.join(d, "B.ply"), v, b, t)
+        subprocess.check_call([REF, "--in", "A.ply", "B.ply", "--out", "r.ply", "--iterations", "3", "--tap", "tap"], cwd=d, stdout=subprocess.DEVNULL)
+        tapdir = os.path.join(d, "tap")
+        data = {"level": np.int32(level), "stride": np.int32(stride), "iterations": np.int32(3)}
+        for i in range(3):
+            f = np.load(os.path.join(tapdir, "it%02d.tFlowField.npy" % i))
+            data["it%02d.tFlowField.sub" % i] = f[::stride].copy()
+            data["it%02d.tFlowField.norm" % i] = np.float64(np.linalg.norm(f))
+            data["it%02d.x.norm" % i] = np.float64(np.linalg.norm(np.load(os.path.join(tapdir, "it%02d.x.npy" % i))))
+        for k in ("advected0", "advected1"):
+            data[k + ".sub"] = np.load(os.path.join(tapdir, k + ".npy"))[::stride].copy()
+        opp = np.load(os.path.join(tapdir, "oppositeEdge.npy"))
+        red = np.load(os.path.join(tapdir, "reducedEdgeIndex.npy"))
+        data["oppositeEdge.sub"], data["reducedEdgeIndex.sub"] = opp[::stride].copy(), red[::stride].copy()
+        data["oppositeEdge.sum"], data["reducedEdgeIndex.sum"] = np.int64(opp.astype(np.int64).sum()), np.int64(red.astype(np.int64).sum())
+        out = synthetic.read_ply(os.path.join(d, "r.ply"))
+    data["output_rgb"] = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.uint8)
+    name = "sphere%d_vertex.npz" % level
+    np.savez_compressed(os.path.join(HERE, name), **data)
+    print(name, os.path.getsize(os.path.join(HERE, name)) // 1024, "KiB")
+
+
+def example():
+    """The reference's Example/ through the reference binary: the texture configuration and the per-vertex configuration."""
+    from PIL import Image
+    ref_tool = os.path.join(ROOT, "oracle", "_ref", "SampleTextureToVertices_ref")
+    src = os.path.join(os.environ.get("MOF_REFERENCE", "/root/reference"), "Example")
+    data = {}
+    for f in ("mesh.ply", "A.png", "B.png"):
+        data["in_" + f] = np.frombuffer(open(os.path.join(src, f), "rb").read(), dtype=np.uint8)
+    with tempfile.TemporaryDirectory() as d:
+        for f in ("mesh.ply", "A.png", "B.png"):
+            open(os.path.join(d, f), "wb").write(data["in_" + f].tobytes())
+        subprocess.check_call([REF, "--mesh", "mesh.ply", "--in", "A.png", "B.png", "--out", "result.png"], cwd=d, stdout=subprocess.DEVNULL)
+        data["texture_output_pixels"] = np.asarray(Image.open(os.path.join(d, "result.png")))
+        for n in ("A", "B"):
+            subprocess.check_call([ref_tool, "--in", "mesh.ply", "--texture", n + ".png", "--out", n + ".ply", "--eLength", "0.006"], cwd=d, stdout=subprocess.DEVNULL)
+        subprocess.check_call([REF, "--in", "A.ply", "B.ply", "--out", "result.ply"], cwd=d, stdout=subprocess.DEVNULL)
+        out = synthetic.read_ply(os.path.join(d, "result.ply"))
+        data["vertex_output_rgb"] = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.uint8)
+        data["vertex_output_xyz"] = np.stack([out["vertex"][k] for k in ("x", "y", "z")], 1).astype(np.float32)
+        data["vertex_output_faces_crc"] = np.int64(np.asarray(out["face"]["vertex_indices"], dtype=np.int64).sum())
+    np.savez_compressed(os.path.join(HERE, "example.npz"), **data)
+    print("example.npz", os.path.getsize(os.path.join(HERE, "example.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/OpticalFlow_ref is missing: run oracle/ref/build_ref.sh (needs /root/reference)")
-    if len(sys.argv) > 1 and sys.argv[1] in ("modes", "tool"):
-        {"modes": modes, "tool": tool}[sys.argv[1]]()
+    if len(sys.argv) > 1 and sys.argv[1] in ("modes", "tool", "example"):
+        {"modes": modes, "tool": tool, "example": example}[sys.argv[1]]()
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[1] == "midsize":
+        midsize(int(sys.argv[2]))
         sys.exit(0)
     sphere()
     torus()

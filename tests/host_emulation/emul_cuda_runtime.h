@@ -41,7 +41,7 @@ using std::min;
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
-enum { cudaSuccess = 0 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
@@ -99,16 +99,76 @@ inline cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { *p = malloc
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 
 // CUDA graphs by stream capture
-struct EmulGraph { std::vector<std::function<void()>> ops; };
+struct EmulGraph {
+    std::vector<std::function<void()>> ops;
+    // conditional nodes: the graph owns the condition words of its handles (with their defaults, assigned at every launch)
+    // and the body graphs of its WHILE nodes
+    std::vector<std::pair<unsigned*, unsigned>> conditions;
+    std::vector<EmulGraph*> bodies;
+    bool isBody = false;
+};
 typedef EmulGraph* cudaGraph_t;
 typedef EmulGraph* cudaGraphExec_t;
 enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal, cudaStreamCaptureModeThreadLocal, cudaStreamCaptureModeRelaxed };
 cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode);
 cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* graph);
+// (an instantiated graph shares the condition words and bodies of the graph it came from: keep that one alive)
 inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* exec, cudaGraph_t graph, unsigned long long) { *exec = new EmulGraph(*graph); return cudaSuccess; }
-inline cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t) { for (auto& op : exec->ops) op(); return cudaSuccess; }
-inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t exec, cudaStream_t) {
+    for (auto& c : exec->conditions) *c.first = c.second;
+    for (auto& op : exec->ops) op();
+    return cudaSuccess;
+}
 inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) {
+    if (g) {
+        for (auto& c : g->conditions) delete c.first;
+        for (EmulGraph* b : g->bodies) cudaGraphDestroy(b);
+    }
+    delete g;
+    return cudaSuccess;
+}
+// Conditional WHILE nodes, as far as multigrid.cu uses them: a handle is a pointer to the graph's condition word, the node an
+// operation that runs its body graph while the word is non-zero, the body filled by a capture "to graph".
+typedef unsigned* cudaGraphConditionalHandle;
+typedef void* cudaGraphNode_t;
+enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone, cudaStreamCaptureStatusActive };
+enum { cudaGraphCondAssignDefault = 1, cudaStreamSetCaptureDependencies = 1 };
+enum cudaGraphNodeType { cudaGraphNodeTypeConditional = 13 };
+enum cudaGraphConditionalNodeType { cudaGraphCondTypeIf = 0, cudaGraphCondTypeWhile = 1 };
+struct cudaConditionalNodeParams {
+    cudaGraphConditionalHandle handle;
+    cudaGraphConditionalNodeType type;
+    unsigned size;
+    cudaGraph_t* phGraph_out;
+};
+struct cudaGraphNodeParams {
+    cudaGraphNodeType type;
+    cudaConditionalNodeParams conditional;
+};
+cudaError_t cudaStreamGetCaptureInfo(cudaStream_t, cudaStreamCaptureStatus* status, unsigned long long* id, cudaGraph_t* graph, const cudaGraphNode_t** deps, size_t* ndeps);
+inline cudaError_t cudaGraphConditionalHandleCreate(cudaGraphConditionalHandle* h, cudaGraph_t graph, unsigned defaultValue, unsigned) {
+    *h = new unsigned(defaultValue);
+    graph->conditions.push_back({*h, defaultValue});
+    return cudaSuccess;
+}
+inline cudaError_t cudaGraphAddNode(cudaGraphNode_t* node, cudaGraph_t graph, const cudaGraphNode_t*, size_t, cudaGraphNodeParams* params) {
+    if (params->type != cudaGraphNodeTypeConditional || params->conditional.type != cudaGraphCondTypeWhile) return 1;
+    EmulGraph* body = new EmulGraph();
+    body->isBody = true;
+    graph->bodies.push_back(body);
+    unsigned* cond = params->conditional.handle;
+    graph->ops.push_back([body, cond] {
+        while (*cond)
+            for (auto& op : body->ops) op();
+    });
+    params->conditional.phGraph_out = &graph->bodies.back();
+    *node = body;
+    return cudaSuccess;
+}
+inline cudaError_t cudaStreamUpdateCaptureDependencies(cudaStream_t, cudaGraphNode_t*, size_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaStreamBeginCaptureToGraph(cudaStream_t, cudaGraph_t graph, const cudaGraphNode_t*, const void*, size_t, cudaStreamCaptureMode);
+inline void cudaGraphSetConditional(cudaGraphConditionalHandle h, unsigned value) { *h = value; }
 
 // vector types and cache-hinted loads
 struct alignas(8) float2 { float x, y; };     // the device's alignment requirements: -fsanitize=alignment then reports a vector
@@ -131,7 +191,10 @@ void launch(long long grid, int block, const std::function<void()>& body);
 void submit(long long grid, int block, std::function<void()> body);
 // Cooperative kernels: all CTAs alive together, one OS thread each (MOF_EMUL_THREADS), meeting in grid_sync(); else one CTA.
 void launch_cooperative(long long grid, int block, const std::function<void()>& body);
+void submit_cooperative(long long grid, int block, std::function<void()> body);  // ... as the stream sees it (run now, or recorded)
 void grid_sync();
+void* dynamic_smem(size_t bytes);  // the running CTA's dynamic shared memory (one buffer per OS thread, grown on demand)
+void* peer_smem(void* mine, int rank);  // ... and that of another CTA of the same cooperative launch (threads build; else `mine`)
 unsigned long long shuffle(unsigned long long bits, int srcLane);  // warp-synchronous exchange of 8 bytes
 int lane();
 template <class T>

@@ -123,14 +123,26 @@ namespace {
 MOF_EMUL_TLS EmulGraph* capture = nullptr;
 }
 cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
-    delete capture;
+    if (capture && !capture->isBody) delete capture;
     capture = new EmulGraph();
     return cudaSuccess;
+}
+cudaError_t cudaStreamBeginCaptureToGraph(cudaStream_t, cudaGraph_t graph, const cudaGraphNode_t*, const void*, size_t, cudaStreamCaptureMode) {
+    capture = graph;  // owned by the graph of its conditional node
+    return graph ? cudaSuccess : 1;
 }
 cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* graph) {
     *graph = capture;
     capture = nullptr;
     return *graph ? cudaSuccess : 1;
+}
+cudaError_t cudaStreamGetCaptureInfo(cudaStream_t, cudaStreamCaptureStatus* status, unsigned long long* id, cudaGraph_t* graph, const cudaGraphNode_t** deps, size_t* ndeps) {
+    if (status) *status = capture ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone;
+    if (id) *id = 0;
+    if (graph) *graph = capture;
+    if (deps) *deps = nullptr;
+    if (ndeps) *ndeps = 0;
+    return cudaSuccess;
 }
 
 namespace mof_emul {
@@ -140,6 +152,26 @@ void record(std::function<void()> op) { capture->ops.push_back(std::move(op)); }
 void submit(long long grid, int block, std::function<void()> b) {
     if (capture) capture->ops.push_back([grid, block, b] { launch(grid, block, b); });
     else launch(grid, block, b);
+}
+namespace {
+MOF_EMUL_TLS std::vector<void*>* clusterSmem = nullptr;  // the dynamic shared memory of every CTA of the running cooperative launch
+}
+void* dynamic_smem(size_t bytes) {
+    static MOF_EMUL_TLS char* buffer = nullptr;
+    static MOF_EMUL_TLS size_t capacity = 0;
+    if (bytes > capacity) {
+        free(buffer);
+        buffer = (char*)malloc(bytes);
+        capacity = bytes;
+    }
+    if (clusterSmem && threadIdx.x == 0) (*clusterSmem)[blockIdx.x] = buffer;
+    return buffer;
+}
+// Distributed shared memory: CTA `rank`'s buffer (valid after a grid_sync() that follows every CTA's dynamic_smem call).
+void* peer_smem(void* mine, int rank) { return clusterSmem ? (*clusterSmem)[rank] : mine; }
+void submit_cooperative(long long grid, int block, std::function<void()> b) {
+    if (capture) capture->ops.push_back([grid, block, b] { launch_cooperative(grid, block, b); });
+    else launch_cooperative(grid, block, b);
 }
 
 unsigned long long shuffle(unsigned long long bits, int srcLane) {
@@ -215,11 +247,14 @@ void launch_cooperative(long long grid, int block, const std::function<void()>& 
     if (grid > 1) {
         GridBarrier barrier;
         barrier.size = (int)grid;
+        std::vector<void*> smemOf((size_t)grid, nullptr);
         std::vector<std::thread> ctas;
         auto cta = [&](long long bi, bool worker) {
             gridBarrier = &barrier;
+            clusterSmem = &smemOf;
             run_block(bi, grid, block, b);
             gridBarrier = nullptr;
+            clusterSmem = nullptr;
             if (worker)  // the worker's fiber stacks die with it
                 for (int f = 0; f < kMaxThreads; f++) free(stacks[f]), stacks[f] = nullptr;
         };

@@ -122,6 +122,34 @@ def test_multigrid_and_jacobi_solves_agree_with_the_checker(emulated):
     assert iters["1"][0] < iters["0"][0] / 3 and iters["1"][1] < iters["0"][1]  # the hierarchies are in use
 
 
+def test_solver_variants_give_the_same_bits(emulated, monkeypatch):
+    """The PCG loop as one graph with a device-side WHILE node (default) against host-driven replays of two iterations
+    (MOF_MG_WHILE=0), and the small multigrid levels as one kernel on one thread-block cluster (MOF_MG_TAIL_CELLS=6144: operation
+    program, staging, slot-ordered sums, fused correction) against the stand-alone kernels: same flow, bit for bit, same counts."""
+    v, t = synthetic.octahedron_sphere(5)
+    a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(v, 4))
+    runs = {}
+    for name, env in (("default", {}), ("replay", {"MOF_MG_WHILE": "0"}), ("cluster", {"MOF_MG_TAIL_CELLS": "6144"}),
+                      ("cluster_streamed", {"MOF_MG_TAIL_CELLS": "6144", "MOF_MG_TAIL_RESIDENT": "100"})):
+        for k in ("MOF_MG_WHILE", "MOF_MG_TAIL_CELLS", "MOF_MG_TAIL_RESIDENT"):
+            monkeypatch.delenv(k, raising=False)
+        for k, val in env.items():
+            monkeypatch.setenv(k, val)
+        al = emulated.Aligner(0)
+        try:
+            al.set_mesh(v, t)
+            al.set_signals(a, b)
+            al.iterate(2)
+            s = al.stats()
+            runs[name] = (al.flow(), al.array(api.ARR_SMOOTHED), s["flowCgIterations"], s["smoothCgIterations"], s["kernelLaunches"])
+        finally:
+            al.close()
+    for name in ("replay", "cluster", "cluster_streamed"):
+        assert np.array_equal(runs[name][0], runs["default"][0]) and np.array_equal(runs[name][1], runs["default"][1]), name
+        assert runs[name][2:4] == runs["default"][2:4], name
+    assert runs["cluster"][4] < runs["default"][4]  # fewer launches: the cluster kernel was in use
+
+
 @pytest.mark.parametrize("name", sorted(VF_MODES))
 def test_conformal_and_connection_bases_match_the_reference_golden(aligner, golden_modes, name):
     g = golden_modes
