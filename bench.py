@@ -16,9 +16,16 @@ final halfway advection — what the reference does between loading its inputs a
           data-path collective; weak scaling; time = max over ranks.
           --partitioned (configs[4]): instead, ONE pair per step for the whole job, its linear solves row-partitioned
           over the ranks (NCCL halo exchange + all-reduce); strong scaling; use with --level 10 / 11.
-  roofline      the PCG's SpMV+dot kernel on the workload's own flow matrix, timed live with CUDA events.
+  roofline      the PCG's SpMV+dot kernel on the workload's own flow matrix, timed live with CUDA events; roofline.kernels = the
+                same for every large kernel of a PCG iteration and the walk (mof_time_kernel: each alone, the solver's own grid),
+                with launches per step and share of the step; roofline.flow_iteration_frac = the streaming kernels' algorithmic
+                bytes of one flow PCG iteration / peak bandwidth / the measured time of an iteration.
   cpu_baseline  the reference's own binary (oracle/_ref, built from the unmodified sources) timed on this box's
-                host cores on a bounded sample, rank 0, N=1 only.
+                host cores on a bounded sample, rank 0, N=1 only; cpu_baseline.like_for_like = the SAME input (65 538-vertex
+                sphere pair, 3 iterations) timed through the reference binary and through this library's host-pointer API in
+                this run; cpu_baseline.growth = the reference's seconds per alignment at the sizes it finishes in seconds.
+  N > 1 also appends `partitioned`: one 4.2M-vertex mesh (3 iterations) with its solves row-partitioned over all ranks, against
+                the same on rank 0 alone (BASELINE.json configs[4]).
   --impl reference   only the reference arm, same metric/unit/config, bounded sample per step.
 """
 from __future__ import annotations
@@ -42,6 +49,8 @@ METRIC = "1M-vertex pair alignments/sec"
 UNIT = "alignments/s"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "OpticalFlow_ref")
 SAMPLE_LEVEL = 6  # 16 386 vertices: about 10 s of reference CPU work per alignment
+LIKE_LEVEL, LIKE_ITERATIONS = 7, 3  # the like-for-like pair: 65 538 vertices, 3 iterations (~45 s of reference CPU work)
+PARTITIONED_LEVEL, PARTITIONED_ITERATIONS = 10, 3  # the `partitioned` sub-record of N > 1: 4 194 306 vertices
 
 
 def measured_peak_gbs():
@@ -97,20 +106,21 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------- reference arm
 
-def reference_sample_inputs(tmp: str):
+def reference_sample_inputs(tmp: str, level: int = SAMPLE_LEVEL):
     from meshopticalflow_b200 import synthetic
-    v, t = synthetic.octahedron_sphere(SAMPLE_LEVEL)
+    v, t = synthetic.octahedron_sphere(level)
     a, b = synthetic.smooth_rgb_pair(v, 0)
     synthetic.write_ply_colored(os.path.join(tmp, "A.ply"), v, a, t)
     synthetic.write_ply_colored(os.path.join(tmp, "B.ply"), v, b, t)
     return v.shape[0]
 
 
-def time_reference_once(tmp: str) -> float:
+def time_reference_once(tmp: str, iterations: int = 10) -> float:
     """One alignment of the bounded sample by the reference's CPU implementation, all host threads."""
     t0 = time.perf_counter()
     if os.path.exists(REF_BIN):
-        subprocess.check_call([REF_BIN, "--in", "A.ply", "B.ply", "--out", "r.ply"], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.check_call([REF_BIN, "--in", "A.ply", "B.ply", "--out", "r.ply", "--iterations", str(iterations)], cwd=tmp, stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
     else:  # the oracle port (only when the reference binary could not be built)
         from meshopticalflow_b200 import synthetic
         from oracle import mof_oracle as O
@@ -119,8 +129,45 @@ def time_reference_once(tmp: str) -> float:
         v = np.stack([p["vertex"][k] for k in "xyz"], 1).astype(np.float64)
         ca = np.stack([p["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.float64)
         cb = np.stack([q["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.float64)
-        O.align_vertices(v, p["face"]["vertex_indices"], ca, cb)
+        O.align_vertices(v, p["face"]["vertex_indices"], ca, cb, O.Params(iterations=iterations))
     return time.perf_counter() - t0
+
+
+def reference_like_for_like():
+    """The reference on the like-for-like input (files on disk -> file on disk, like its command line), and its growth with size."""
+    out = {"growth": []}
+    for level in (5, SAMPLE_LEVEL):
+        with tempfile.TemporaryDirectory() as tmp:
+            nv = reference_sample_inputs(tmp, level)
+            out["growth"].append({"vertices": nv, "iterations": 10, "seconds": time_reference_once(tmp)})
+    with tempfile.TemporaryDirectory() as tmp:
+        nv = reference_sample_inputs(tmp, LIKE_LEVEL)
+        sec = time_reference_once(tmp, LIKE_ITERATIONS)
+    out["growth"].append({"vertices": nv, "iterations": LIKE_ITERATIONS, "seconds": sec})
+    out["like_for_like"] = {"vertices": nv, "iterations": LIKE_ITERATIONS, "ref_s": sec}
+    return out
+
+
+def gpu_like_for_like(al, api):
+    """The same input through this library's host-pointer API (uploads and the read-back inside the clock), best of three."""
+    from meshopticalflow_b200 import synthetic
+    v, t = synthetic.octahedron_sphere(LIKE_LEVEL)
+    a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(v, 0))
+    v = v.astype(np.float32).astype(np.float64)  # what a PLY file holds
+    p = api.default_params()
+    p.iterations = LIKE_ITERATIONS
+    al.set_params(p)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        al.set_mesh(v, t)
+        al.set_signals(a, b)
+        al.iterate(LIKE_ITERATIONS)
+        al.advect_vertices(0.5)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    al.set_params(api.default_params())
+    return best
 
 
 def cpu_baseline_dict(seconds: float, sample_vertices: int, target_vertices: int):
@@ -129,7 +176,7 @@ def cpu_baseline_dict(seconds: float, sample_vertices: int, target_vertices: int
     scale = target_vertices / sample_vertices
     return {
         "value": 1.0 / (seconds * scale), "unit": UNIT, "cores": cores if kind == "reference" else 1, "kind": kind,
-        "sample_seconds": seconds, "sample_vertices": sample_vertices,
+        "sample_seconds": seconds, "sample_vertices": sample_vertices, "extrapolated": True,
         "sample": (f"one full alignment (defaults, 10 iterations) of the level-{SAMPLE_LEVEL} sphere pair ({sample_vertices} vertices) by "
                    f"{'oracle/_ref/OpticalFlow_ref (unmodified reference, Eigen LDLT/LLT, OpenMP, MKL off)' if kind == 'reference' else 'the oracle port (scipy SuperLU)'}"
                    f": {seconds:.2f} s; value = 1/(seconds * {scale:.0f}), a LINEAR-in-vertices extrapolation to {target_vertices} vertices — the reference's sparse"
@@ -151,6 +198,8 @@ def run_reference_arm(args, config):
         sec = (time.perf_counter() - t0) / args.steps
     target = config["vertices"]
     base = cpu_baseline_dict(sec, nv, target)
+    if not args.quick:
+        base.update(reference_like_for_like())  # once, outside the step loop
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -159,6 +208,72 @@ def run_reference_arm(args, config):
 
 
 # --------------------------------------------------------------------------------------- the GPU arm
+
+def partitioned_record(api, sharding, synthetic, torch, dev, stream, rank, local_rank, world):
+    """One PARTITIONED_LEVEL mesh, PARTITIONED_ITERATIONS iterations: all ranks together (row-partitioned solves, NCCL halo
+    exchange + all-reduce) and rank 0 alone; device time of mof_iterate (CUDA events, max over ranks)."""
+    verts, tris = synthetic.octahedron_sphere(PARTITIONED_LEVEL)
+    a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(verts, 0))
+    p = api.default_params()
+    p.iterations = PARTITIONED_ITERATIONS
+    out = {"vertices": int(verts.shape[0]), "iterations": PARTITIONED_ITERATIONS, "n_gpus": world}
+
+    def run(al):
+        al.set_params(p)
+        ms = []
+        for _ in range(2):  # the second run is the steady state (memory pool, NCCL channels warm)
+            al.set_mesh(verts, tris)
+            al.set_signals(a, b)
+            torch.cuda.synchronize(dev)
+            sharding.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            al.iterate(PARTITIONED_ITERATIONS)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms.append(e0.elapsed_time(e1))
+        return ms[-1], al.stats(), al.flow()
+
+    al = api.Aligner(local_rank, stream.cuda_stream)
+    try:
+        uid = sharding.broadcast_bytes(api.dist_unique_id() if rank == 0 else None, 128, 0, dev)
+        al.dist_init(world, rank, uid)
+        ms_local, st, flow = run(al)
+    finally:
+        al.close()
+    ms_all = sharding.max_over_ranks(ms_local, dev)
+    out.update({"ms_all_ranks": ms_all, "flow_iterations": st["flowCgIterations"] / 2, "smooth_iterations": st["smoothCgIterations"] / 2,
+                "flow_solve_ms": st["flowSolveMs"] / 2, "smooth_solve_ms": st["smoothSolveMs"] / 2, "halo_entries_rank0": st["haloEntries"]})
+    ms_one, flow_one = 0.0, None
+    if rank == 0:
+        al = api.Aligner(local_rank, stream.cuda_stream)
+        try:
+            os.environ["MOF_SMOOTH_AHEAD"] = "0"  # one stream on both sides of the comparison
+            ms_one, st1, flow_one = run_single(al, p, verts, tris, a, b, torch, dev, stream)
+        finally:
+            os.environ.pop("MOF_SMOOTH_AHEAD", None)
+            al.close()
+        out.update({"ms_rank0_alone": ms_one, "speedup": ms_one / ms_all, "flow_rel_difference": float(np.linalg.norm(flow - flow_one) / np.linalg.norm(flow_one)),
+                    "flow_iterations_rank0_alone": st1["flowCgIterations"] / 2})
+    sharding.barrier()
+    return out
+
+
+def run_single(al, p, verts, tris, a, b, torch, dev, stream):
+    al.set_params(p)
+    ms = []
+    for _ in range(2):
+        al.set_mesh(verts, tris)
+        al.set_signals(a, b)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        al.iterate(p.iterations)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms.append(e0.elapsed_time(e1))
+    return ms[-1], al.stats(), al.flow()
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -169,11 +284,14 @@ def main():
     ap.add_argument("--level", type=int, default=9, help="octahedron subdivision level of the workload (9 = 1 048 578 vertices)")
     ap.add_argument("--partitioned", action="store_true",
                     help="configs[4]: ONE pair per step for the whole job, its flow solves row-partitioned over the ranks (NCCL halo exchange + all-reduce); strong scaling")
+    ap.add_argument("--quick", action="store_true", help="skip the like-for-like reference timing (about a minute of CPU work) — for the CPU-tier test of the contract line")
     args = ap.parse_args()
 
     V = 4 * 4 ** args.level + 2
-    config = {"workload": f"synthetic subdivided-octahedron sphere, {V} vertices / {2 * V - 4} triangles / {3 * V - 6} Whitney unknowns, smooth random RGB "
+    config = {"workload": f"synthetic subdivided-octahedron sphere, {V} vertices / {2 * V - 4} triangles / {3 * V - 6} Whitney unknowns, vertices and triangles "
+                          "numbered along a Morton curve by the generator (outside the timed region; the library does not reorder), smooth random RGB "
                           "per-vertex signals (B = A rotated 4 deg), reference defaults (10 iterations), one pair per GPU per step",
+              "numbering": "Morton-sorted (synthetic.octahedron_sphere spatial_sort=True)",
               "vertices": V, "pairs_per_step": 1 if args.partitioned else args.gpus,
               "parallelism": (f"one mesh, flow solves row-partitioned x{args.gpus} (NCCL halo exchange + all-reduce), everything else replicated" if args.partitioned
                               else f"independent pairs x{args.gpus} (no communication)"),
@@ -274,12 +392,27 @@ def main():
         sharding.barrier()
         e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
         e2e_stats = al.stats()
+
+        # every large kernel of a PCG iteration and the walk, each alone (rank 0; not on a partitioned mesh)
+        kernel_rows = []
+        if rank == 0 and not args.partitioned:
+            for name, which in api.KERNELS.items():
+                try:
+                    us, nbytes = al.time_kernel(which, 30)
+                    kernel_rows.append((name, us, nbytes))
+                except api.MofError as e:
+                    kernel_rows.append((name, None, str(e)))
+        like_gpu_s = gpu_like_for_like(al, api) if (rank == 0 and world == 1 and not args.partitioned and not args.quick) else None
         al.close()
+
+        # N > 1: BASELINE.json configs[4] next to the sharded pairs — one mesh, its solves row-partitioned over all ranks, against rank 0 alone
+        partitioned = None
+        if world > 1 and not args.partitioned:
+            partitioned = partitioned_record(api, sharding, synthetic, torch, dev, stream, rank, local_rank, world)
     sharding.shutdown()
 
     if rank != 0:
         return 0
-    peak, peak_src = measured_peak_gbs()
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -288,8 +421,33 @@ def main():
             traffic = json.load(open(tpath)).get("k_spmv_dot_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    peak, peak_src = measured_peak_gbs()
     iters = max(stats["flowCgIterations"], 1)
     jobs = 1 if args.partitioned else world  # alignments completed per step by the whole job
+    # per-kernel table: launches per step from the iteration counts (per PCG iteration: one matrix product, two fine sweeps — the
+    # cycle's residual and its post-smoothing —, one update, one restriction, one prolongation, one new direction, three level-1
+    # stencil applications — two residuals of the W visit and the post-smoothing; per UpdateFlow iteration: one walk launch)
+    per_iter = {"flow_spmv": 1, "flow_fine_sweep": 2, "flow_update": 1, "flow_restrict": 1, "flow_prolong": 1, "flow_direction": 1, "flow_level1": 3,
+                "scalar_spmv": 1, "scalar_fine_sweep": 2, "scalar_update": 1, "scalar_level1": 3}
+    flow_it, smooth_it = stats["flowCgIterations"] / args.steps, stats["smoothCgIterations"] / args.steps
+    step_us = ms / args.steps * 1e3
+    kernels, flow_stream_bytes, flow_stream_us = [], 0.0, 0.0
+    for name, us, nbytes in kernel_rows:
+        if us is None:
+            kernels.append({"name": name, "unavailable": nbytes})
+            continue
+        count = (per_iter.get(name, 0) * (flow_it if name.startswith("flow") else smooth_it)) if name != "walk" else float(params.iterations)
+        row = {"name": name, "us": us, "launches_per_step": count, "share_of_step": count * us / step_us}
+        if nbytes > 0:
+            gbs = nbytes / (us * 1e-6) / 1e9
+            row.update({"algorithmic_bytes": nbytes, "achieved_gbs": gbs, "frac": gbs / peak})
+        else:
+            row.update({"algorithmic_bytes": None, "note": "latency / divergence bound: trip counts are data dependent"})
+        kernels.append(row)
+        if name.startswith("flow") and nbytes > 0:
+            flow_stream_bytes += per_iter[name] * nbytes
+            flow_stream_us += per_iter[name] * us
+    us_per_flow_it = stats["flowSolveMs"] * 1e3 / iters
     line = {
         "metric": METRIC, "value": jobs * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.partitioned else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -302,17 +460,34 @@ def main():
         "gpu_launches": int(stats["kernelLaunches"]),
         "roofline": {"bound": "hbm", "kernel": "k_spmv_dot (the fp64 SpMV of the flow PCG, y = A d fused with d.y; flow system in the sliced SELL-32 layout, fp64 values / int32 columns)",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
-                     "traffic": traffic, "bytes_per_launch": spmv_bytes, "us_per_launch": spmv_ms * 1e3, "rows": stats["flowRows"], "nnz": stats["flowNnz"]},
+                     "traffic": traffic, "bytes_per_launch": spmv_bytes, "us_per_launch": spmv_ms * 1e3, "rows": stats["flowRows"], "nnz": stats["flowNnz"],
+                     "kernels": kernels,
+                     "flow_iteration_bytes": flow_stream_bytes, "flow_iteration_us_at_peak": flow_stream_bytes / (peak * 1e9) * 1e6,
+                     "flow_iteration_us_streaming_kernels": flow_stream_us, "flow_iteration_us_measured": us_per_flow_it,
+                     "flow_iteration_frac": (flow_stream_bytes / (peak * 1e9) * 1e6) / us_per_flow_it if flow_stream_bytes else None,
+                     "flow_iteration_note": ("bytes = the algorithmic bytes of the kernels listed with a flow_ prefix (fine level and the largest coarse level); the rest of an "
+                                             "iteration is ~40 dependent launches of 4-9 us on the smaller multigrid levels (latency bound), see DESIGN.md §4.2; "
+                                             "with two streams the measured time also contains whatever of the smoothing solve overlapped it")},
         "pcg": {"flow_iterations_per_alignment": stats["flowCgIterations"] / args.steps, "smooth_iterations_per_alignment": stats["smoothCgIterations"] / args.steps,
                 "flow_solve_ms_per_alignment": stats["flowSolveMs"] / args.steps, "smooth_solve_ms_per_alignment": stats["smoothSolveMs"] / args.steps,
                 "us_per_flow_iteration": stats["flowSolveMs"] * 1e3 / iters, "setup_ms_per_alignment": stats["setupMs"] / args.steps,
                 "advect_ms_per_alignment": stats["advectMs"] / args.steps, "halo_entries_rank0": stats["haloEntries"]},
     }
-    if world == 1:
+    if partitioned is not None:
+        line["partitioned"] = partitioned
+    if world == 1 and not args.partitioned:
         with tempfile.TemporaryDirectory() as tmp:
             nv = reference_sample_inputs(tmp)
             sec = time_reference_once(tmp)
-        line["cpu_baseline"] = cpu_baseline_dict(sec, nv, V)
+        base = cpu_baseline_dict(sec, nv, V)
+        if not args.quick:
+            base.update(reference_like_for_like())
+        if like_gpu_s and "like_for_like" in base:
+            lfl = base["like_for_like"]
+            lfl.update({"gpu_s": like_gpu_s, "ratio": lfl["ref_s"] / like_gpu_s,
+                        "what": "the same 65 538-vertex pair and iteration count through both: the reference binary from files to file (wall), this library from host "
+                                "buffers to host buffers (wall, uploads and read-back inside); not extrapolated"})
+        line["cpu_baseline"] = base
     print(json.dumps(line))
     return 0
 

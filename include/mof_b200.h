@@ -31,6 +31,10 @@ typedef struct mof_ctx mof_ctx;
 
 /* Solver parameters: the reference's command-line flags (OpticalFlow.cpp:56-63) with the defaults of
  * _main (:1062-1069), plus the PCG controls that replace the direct factorisation. */
+/* A PCG solve that stagnates above its tolerance but below this TRUE relative residual is accepted (and counted in
+ * mof_stats.solvesAboveTolerance); above it the call fails with MOF_E_NOCONVERGE. north_star's flow tolerance is 1e-8. */
+#define MOF_ACCEPT_RELRES 1e-4
+
 typedef struct mof_params {
     int iterations;        /* --iterations 10 */
     double sSmooth;        /* --sSmooth 3e-3 (float literal in the reference) */
@@ -45,6 +49,7 @@ typedef struct mof_params {
     int maxCgIterations;   /* PCG cap, default 100000 */
     int vfMode;            /* --vfMode 0 Whitney | 1 Conformal | 2 Connection (VectorField.h:3-7); read by mof_set_signals */
     int cMode;             /* --cMode 0 projected barycentric | 1 barycentric dual | 2 inverse cotangent (Connection.inl:1-5) */
+    int logSpace;          /* --log: compare log(max(1, x)) * 255 / log(255) (OpticalFlow.cpp:821); the colours advected at the end stay as given; read by mof_set_signals */
 } mof_params;
 
 /* Counters since mof_create / mof_reset_stats. */
@@ -62,6 +67,9 @@ typedef struct mof_stats {
     double flowSpmvBytes;         /* algorithmic bytes of ONE flow-system SpMV: 12*nnz + 4*(n+1) + 16*n */
     long long flowRows, flowNnz;
     long long haloEntries;        /* partitioned mesh: vector entries this rank receives per halo exchange (0 otherwise) */
+    int solvesAboveTolerance;     /* solves whose TRUE relative residual ended above the requested tolerance: accepted when below
+                                     MOF_ACCEPT_RELRES (a stagnated recurrence, after its restarts), an error (MOF_E_NOCONVERGE) otherwise.
+                                     0 in every configuration the tests and the bench run; the reference's direct solves reach ~1e-14 */
 } mof_stats;
 
 void mof_default_params(mof_params* p);
@@ -120,6 +128,11 @@ int mof_advect_vertices_device(mof_ctx* ctx, double alpha, double* d_outA, doubl
 int mof_set_texture_map(mof_ctx* ctx, int W, int H, const int* srcT, const double* srcP, const double* triUV,
                         const unsigned char* texA, const unsigned char* texB);
 int mof_advect_texels(mof_ctx* ctx, double alpha, int bilinear, double* outA, double* outB);
+/* The frame sequence of the same (InputTextureData::flow(flowData, frames, ...), OpticalFlow.cpp:517-539 — what the reference's
+ * viewer renders as an animation): the texels' sample points are carried along the flow in frames - 1 equal steps of
+ * 1 / (frames - 1) — backwards for the first signal, forwards for the second, minimum step 1e-2 * frames — and the texture is
+ * fetched after every step. out[s]: [frames][W*H][3]; frame 0, and the uncovered texels of every frame, are the flipped input. */
+int mof_advect_texels_frames(mof_ctx* ctx, int frames, int bilinear, double* outA, double* outB);
 
 /* The texture configuration's one-time preparation on the device (the reference runs it serially on the CPU; the
  * outputs are the same, integer for integer and bit for bit: see csrc/texprep_kernels.cu).
@@ -188,6 +201,27 @@ int mof_pcg_solve_csr(mof_ctx* ctx, int n, const int* rowptr, const int* col, co
 /* Times `reps` launches of the flow-system SpMV kernel (y = A d fused with d.y) on the context's
  * current flow matrix; returns average ms per launch. Used by bench.py for the roofline line. */
 int mof_time_flow_spmv(mof_ctx* ctx, int reps, float* msPerLaunch);
+/* The same for the other kernels of a PCG iteration and the walk, each launched `reps` times on its own with the solver's own
+ * grid and the context's current operators (CUDA events on the context's stream): average microseconds per launch and the
+ * ALGORITHMIC bytes one launch moves (every array touched once; 0 where trip counts are data dependent). bench.py builds its
+ * per-kernel roofline table from this. Needs a completed mof_iterate with the Whitney basis; scratch vectors of the solvers
+ * are overwritten (results already computed are not). */
+enum mof_kernel_id {
+    MOF_K_FLOW_SPMV = 0,          /* k_spmv_dot: fp64 y = A p fused with p.y (the PCG's matrix product) */
+    MOF_K_FLOW_FINE_SWEEP = 1,    /* k_fine_apply_flow<float>: one damped-Jacobi sweep of the cycle on the fp32 copy, fused with r.z */
+    MOF_K_FLOW_UPDATE = 2,        /* k_update_xr: x += alpha p, r -= alpha q, r.r, first sweep of the next cycle */
+    MOF_K_FLOW_RESTRICT = 3,      /* k_restrict_flow: fine residual -> level-1 cells (+ their first sweep) */
+    MOF_K_FLOW_PROLONG = 4,       /* k_prolong_flow */
+    MOF_K_FLOW_DIRECTION = 5,     /* k_direction: p = z + beta p */
+    MOF_K_FLOW_LEVEL1 = 6,        /* k_coarse_apply<9,3,.> on the largest coarse level: 27-point stencil of 3x3 blocks */
+    MOF_K_SCALAR_SPMV = 7,        /* fp64 six-channel product of the smoothing PCG, fused with p.q */
+    MOF_K_SCALAR_FINE_SWEEP = 8,  /* fp32 six-channel sweep of the smoothing cycle */
+    MOF_K_SCALAR_UPDATE = 9,
+    MOF_K_SCALAR_LEVEL1 = 10,
+    MOF_K_WALK = 11,              /* k_walk_sample along the current flow (bytes = 0: data-dependent trip counts) */
+    MOF_K_COUNT = 12
+};
+int mof_time_kernel(mof_ctx* ctx, int which, int reps, double* usPerLaunch, double* algorithmicBytes);
 
 /* ---- one mesh over several GPUs (BASELINE.json configs[4]: "vertex-partitioned, NCCL-over-NVLink halo exchange for
  * SpMV and allreduce for the CG dot products"). The reference has no counterpart: its solve is one Eigen

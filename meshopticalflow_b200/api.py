@@ -33,11 +33,15 @@ _ARRAY_SPEC = {
 }
 
 # Every symbol include/mof_b200.h declares (the CPU test tier checks the library exports them all).
+# mof_kernel_id (include/mof_b200.h): kernels mof_time_kernel can time on their own
+KERNELS = {"flow_spmv": 0, "flow_fine_sweep": 1, "flow_update": 2, "flow_restrict": 3, "flow_prolong": 4, "flow_direction": 5, "flow_level1": 6,
+           "scalar_spmv": 7, "scalar_fine_sweep": 8, "scalar_update": 9, "scalar_level1": 10, "walk": 11}
+
 EXPORTED_SYMBOLS = [
     "mof_default_params", "mof_create", "mof_destroy", "mof_last_error", "mof_set_params", "mof_get_stats", "mof_reset_stats", "mof_synchronize",
     "mof_set_mesh", "mof_set_mesh_device", "mof_set_signals", "mof_set_signals_device", "mof_iterate", "mof_get_flow", "mof_get_coeffs", "mof_num_edges", "mof_num_coeffs",
-    "mof_advect_vertices", "mof_advect_vertices_device", "mof_set_texture_map", "mof_advect_texels", "mof_csr_size", "mof_get_csr", "mof_array_bytes",
-    "mof_get_array", "mof_pcg_solve_csr", "mof_time_flow_spmv", "mof_dist_unique_id", "mof_dist_init",
+    "mof_advect_vertices", "mof_advect_vertices_device", "mof_set_texture_map", "mof_advect_texels", "mof_advect_texels_frames", "mof_csr_size", "mof_get_csr", "mof_array_bytes",
+    "mof_get_array", "mof_pcg_solve_csr", "mof_time_flow_spmv", "mof_time_kernel", "mof_dist_unique_id", "mof_dist_init",
     "mof_subdivide", "mof_get_subdivision", "mof_build_texture_map", "mof_get_texture_map", "mof_sample_textures_to_vertices",
 ]
 
@@ -45,14 +49,14 @@ EXPORTED_SYMBOLS = [
 class Params(ctypes.Structure):
     _fields_ = [("iterations", c_int), ("sSmooth", c_double), ("sMultiply", c_double), ("vfSmooth", c_double), ("vMultiply", c_double),
                 ("vfSThreshold", c_double), ("dogWeight", c_double), ("dogSmooth", c_double), ("flowTol", c_double), ("smoothTol", c_double),
-                ("maxCgIterations", c_int), ("vfMode", c_int), ("cMode", c_int)]
+                ("maxCgIterations", c_int), ("vfMode", c_int), ("cMode", c_int), ("logSpace", c_int)]
 
 
 class Stats(ctypes.Structure):
     _fields_ = [("kernelLaunches", c_longlong), ("flowCgIterations", c_longlong), ("smoothCgIterations", c_longlong), ("flowSolves", c_int),
                 ("smoothSolves", c_int), ("lastFlowResidual", c_double), ("lastSmoothResidual", c_double), ("flowSolveMs", c_float),
                 ("smoothSolveMs", c_float), ("advectMs", c_float), ("setupMs", c_float), ("flowSpmvBytes", c_double), ("flowRows", c_longlong),
-                ("flowNnz", c_longlong), ("haloEntries", c_longlong)]
+                ("flowNnz", c_longlong), ("haloEntries", c_longlong), ("solvesAboveTolerance", c_int)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -107,6 +111,7 @@ def load_library():
     lib.mof_advect_vertices_device.argtypes = [c_void_p, c_double, c_void_p, c_void_p]
     lib.mof_set_texture_map.argtypes = [c_void_p, c_int, c_int, I, D, D, POINTER(c_ubyte), POINTER(c_ubyte)]
     lib.mof_advect_texels.argtypes = [c_void_p, c_double, c_int, D, D]
+    lib.mof_advect_texels_frames.argtypes = [c_void_p, c_int, c_int, D, D]
     lib.mof_subdivide.argtypes = [c_void_p, POINTER(ctypes.c_float), c_int, I, D, c_int, c_double, I, I]
     lib.mof_get_subdivision.argtypes = [c_void_p, POINTER(ctypes.c_float), I, D]
     lib.mof_build_texture_map.argtypes = [c_void_p, c_int, c_int, c_int, D, POINTER(c_ubyte), POINTER(c_ubyte), I]
@@ -119,6 +124,7 @@ def load_library():
     lib.mof_get_array.argtypes = [c_void_p, c_int, c_void_p]
     lib.mof_pcg_solve_csr.argtypes = [c_void_p, c_int, I, I, D, D, D, c_double, c_int, I, D]
     lib.mof_time_flow_spmv.argtypes = [c_void_p, c_int, POINTER(c_float)]
+    lib.mof_time_kernel.argtypes = [c_void_p, c_int, c_int, POINTER(c_double), POINTER(c_double)]
     lib.mof_dist_unique_id.argtypes = [POINTER(c_ubyte)]
     lib.mof_dist_init.argtypes = [c_void_p, c_int, c_int, POINTER(c_ubyte)]
     _lib = lib
@@ -301,6 +307,13 @@ class Aligner:
         self._check(self._lib.mof_advect_texels(self._ctx, alpha, 1 if bilinear else 0, _d(a), _d(b)))
         return a, b
 
+    def advect_texels_frames(self, frames: int, bilinear: bool = True):
+        """InputTextureData::flow(frames): two arrays [frames, W*H, 3]."""
+        W, H = self._tex
+        a, b = np.empty((frames, W * H, 3)), np.empty((frames, W * H, 3))
+        self._check(self._lib.mof_advect_texels_frames(self._ctx, frames, 1 if bilinear else 0, _d(a), _d(b)))
+        return a, b
+
     # --- debug taps
     def csr(self, which: int):
         import scipy.sparse as sp
@@ -328,6 +341,12 @@ class Aligner:
         iters, relres = c_int(), c_double()
         self._check(self._lib.mof_pcg_solve_csr(self._ctx, b.size, _i(rowptr), _i(col), _d(val), _d(b), _d(x), tol, max_iters, byref(iters), byref(relres)))
         return x, iters.value, relres.value
+
+    def time_kernel(self, which: int, reps: int = 20):
+        """(microseconds per launch, algorithmic bytes per launch) of one kernel of the solvers / the walk (mof_kernel_id)."""
+        us, nbytes = c_double(), c_double()
+        self._check(self._lib.mof_time_kernel(self._ctx, which, reps, byref(us), byref(nbytes)))
+        return us.value, nbytes.value
 
     def time_flow_spmv(self, reps: int = 20) -> float:
         ms = c_float()

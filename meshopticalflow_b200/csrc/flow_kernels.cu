@@ -111,6 +111,8 @@ static int smooth_solve(mof_ctx* ctx, double weight, const double* in6, double* 
         else if (mrc != MOF_E_NOCONVERGE) rc = mrc;
     }
     if (rc == MOF_OK && !solved) {
+        // a multigrid solve that broke down may have left NaN in out6: the Jacobi solve starts from the signal again
+        if (mg_scalar_usable(ctx)) MOF_CUDA(cudaMemcpyAsync(out6, in6, sizeof(double) * 6 * V, cudaMemcpyDeviceToDevice, ctx->stream));
         int jIters = 0;
         rc = pcg_solve_csr6(ctx, V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, ctx->sDinv.p, ctx->rhs6.p, out6, false, tol, ctx->params.maxCgIterations, &jIters,
                             &relres);
@@ -270,9 +272,22 @@ __global__ void k_dog_blend(const double* __restrict__ raw, double w, long long 
 // Difference-of-Gaussians normalisation, OpticalFlow.cpp:822-857 (3-channel branch), all six
 // channels at once. getIntegral (FEM.inl:2081-2098) is the dot product with the barycentric
 // vertex areas m0: sum_t sum_j x[v_j] * sqrt(det g_t)/6.
+// OpticalFlow.cpp:821: log(max(1, x)) * 255 / log(255)
+__global__ void k_log_space(const double* __restrict__ in, long long n, double* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = log(fmax(1., in[i])) * 255. / log(255.);
+}
+
 int dog_preprocess(mof_ctx* ctx) {
     const int V = ctx->V;
     double* sc = ctx->scalars.p + SC_DOG;
+    // --log (OpticalFlow.cpp:821) transforms the COMPARISON signals only; the colours that are advected at the end stay raw6
+    const double* cmp = ctx->raw6.p;
+    if (ctx->params.logSpace) {
+        MOF_CUDA(ctx->log6.alloc(6ull * V));
+        MOF_LAUNCH(k_log_space, blocks_for(6ll * V, B), B, 0, ctx->raw6.p, 6ll * V, ctx->log6.p);
+        cmp = ctx->log6.p;
+    }
     MOF_CUDA(ctx->sig6.alloc(6ull * V));
     MOF_CUDA(ctx->smoothed6.alloc(6ull * V));
     MOF_CUDA(ctx->resampled6.alloc(6ull * V));
@@ -284,21 +299,21 @@ int dog_preprocess(mof_ctx* ctx) {
         MOF_CUDA(ctx->resampledLo6.alloc(6ull * V));
     }
     if (!(ctx->params.dogWeight > 0)) {
-        MOF_CUDA(cudaMemcpyAsync(ctx->sig6.p, ctx->raw6.p, sizeof(double) * 6 * V, cudaMemcpyDeviceToDevice, ctx->stream));
+        MOF_CUDA(cudaMemcpyAsync(ctx->sig6.p, cmp, sizeof(double) * 6 * V, cudaMemcpyDeviceToDevice, ctx->stream));
         return MOF_OK;
     }
     double* x = ctx->smoothed6.p;  // scratch during setup
     double* mb = ctx->resampled6.p;
-    MOF_LAUNCH(k_spmv6, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sMass.p, ctx->raw6.p, V, mb);
-    MOF_TRY(dot6(ctx, ctx->raw6.p, nullptr, ctx->m0.p, V, sc + 0, 4));
-    MOF_TRY(dot6(ctx, ctx->raw6.p, mb, nullptr, V, sc + 1, 4));
-    MOF_TRY(smooth_solve(ctx, ctx->params.dogSmooth, ctx->raw6.p, x, ctx->params.smoothTol));
-    MOF_LAUNCH(k_sub, blocks_for(6ll * V, B), B, 0, ctx->raw6.p, x, 6ll * V, x);
+    MOF_LAUNCH(k_spmv6, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sMass.p, cmp, V, mb);
+    MOF_TRY(dot6(ctx, cmp, nullptr, ctx->m0.p, V, sc + 0, 4));
+    MOF_TRY(dot6(ctx, cmp, mb, nullptr, V, sc + 1, 4));
+    MOF_TRY(smooth_solve(ctx, ctx->params.dogSmooth, cmp, x, ctx->params.smoothTol));
+    MOF_LAUNCH(k_sub, blocks_for(6ll * V, B), B, 0, cmp, x, 6ll * V, x);
     MOF_LAUNCH(k_spmv6, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sMass.p, x, V, mb);
     MOF_TRY(dot6(ctx, x, nullptr, ctx->m0.p, V, sc + 2, 4));
     MOF_TRY(dot6(ctx, x, mb, nullptr, V, sc + 3, 4));
     MOF_LAUNCH(k_dog_finish, blocks_for(6ll * V, B), B, 0, x, sc, V, ctx->sig6.p);
-    if (ctx->blend) MOF_LAUNCH(k_dog_blend, blocks_for(6ll * V, B), B, 0, ctx->raw6.p, ctx->params.dogWeight, 6ll * V, ctx->sig6.p, ctx->sigLo6.p);
+    if (ctx->blend) MOF_LAUNCH(k_dog_blend, blocks_for(6ll * V, B), B, 0, cmp, ctx->params.dogWeight, 6ll * V, ctx->sig6.p, ctx->sigLo6.p);
     return MOF_OK;
 }
 
@@ -408,6 +423,21 @@ int advect_vertices(mof_ctx* ctx, const double* in6, double lenA, double lenB, d
     float ms = 0;
     MOF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.advectMs += ms;
+    return MOF_OK;
+}
+
+// mof_time_kernel(MOF_K_WALK): the walk kernel alone, along the current flow, sampling the comparison signals.
+int time_walk_kernel(mof_ctx* ctx, int reps, float* ms) {
+    WalkMesh m = {ctx->opp.p, ctx->xlin.p, ctx->xcst.p, ctx->g.p, ctx->tfield.p};
+    MOF_CUDA(ctx->tsample6.reserve(6ull * ctx->T));
+    for (int i = 0; i < reps + 2; i++) {
+        if (i == 2) MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        MOF_LAUNCH(k_walk_sample, blocks_for(2ll * ctx->T, B), B, 0, m, ctx->tri.p, ctx->sig6.p, ctx->T, -0.5, 0.5, ctx->tsample6.p);
+    }
+    MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    MOF_CUDA(cudaEventSynchronize(ctx->ev1));
+    MOF_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    *ms /= reps;
     return MOF_OK;
 }
 
@@ -668,6 +698,52 @@ int advect_texels(mof_ctx* ctx, double alpha, int bilinear) {
     MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     MOF_LAUNCH(k_advect_texels, blocks_for(2ll * n, B), B, 0, m, ctx->srcT.p, ctx->srcP.p, ctx->triUV.p, ctx->tex[0].p, ctx->tex[1].p, ctx->texW, ctx->texH, -alpha,
                1. - alpha, bilinear, ctx->texOut.p);
+    MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    MOF_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    MOF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.advectMs += ms;
+    return MOF_OK;
+}
+
+// InputTextureData::flow(frames), OpticalFlow.cpp:517-539: thread (texel, s) carries its sample point along the flow in frames - 1
+// equal steps (signal 0 backwards, signal 1 forwards; minimum step 1e-2 * frames) and fetches the texture after each; frame 0
+// and uncovered texels are the vertically flipped input. out: [2][frames][W*H][3].
+__global__ void k_advect_texels_frames(WalkMesh m, const int* __restrict__ srcT, const double* __restrict__ srcP, const double* __restrict__ triUV,
+                                       const unsigned char* __restrict__ texA, const unsigned char* __restrict__ texB, int W, int H, int frames, int bilinear,
+                                       double* __restrict__ out) {
+    const int n = W * H;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    const int s = i / n, texel = i - s * n;
+    const unsigned char* tex = s ? texB : texA;
+    double* dst = out + ((size_t)s * frames * n + texel) * 3;
+    const int y = texel / W, x = texel - y * W;
+    double raw[3];
+    for (int k = 0; k < 3; k++) raw[k] = (double)tex[3 * ((H - y - 1) * W + x) + k];
+    int t = srcT[texel];
+    const int covered = t != -1;
+    for (int f = 0; f < (covered ? 1 : frames); f++)
+        for (int k = 0; k < 3; k++) dst[(size_t)f * n * 3 + k] = raw[k];
+    if (!covered) return;
+    double p0 = srcP[2 * texel], p1 = srcP[2 * texel + 1];
+    const double length = (s ? 1. : -1.) / (frames - 1);
+    for (int f = 1; f < frames; f++) {
+        flow_point(m, length, t, p0, p1, 1e-2 * frames);
+        const double* uv = triUV + 6 * (size_t)t;
+        double w0 = 1. - p0 - p1;
+        double qu = uv[0] * w0 + uv[2] * p0 + uv[4] * p1, qv = uv[1] * w0 + uv[3] * p0 + uv[5] * p1;
+        sample_texture(tex, W, H, qu, qv, bilinear, dst + (size_t)f * n * 3);
+    }
+}
+
+int advect_texels_frames(mof_ctx* ctx, int frames, int bilinear) {
+    WalkMesh m = {ctx->opp.p, ctx->xlin.p, ctx->xcst.p, ctx->g.p, ctx->tfield.p};
+    const int n = ctx->texW * ctx->texH;
+    MOF_CUDA(ctx->texOut.alloc(6ull * n * frames));
+    MOF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    MOF_LAUNCH(k_advect_texels_frames, blocks_for(2ll * n, B), B, 0, m, ctx->srcT.p, ctx->srcP.p, ctx->triUV.p, ctx->tex[0].p, ctx->tex[1].p, ctx->texW, ctx->texH, frames,
+               bilinear, ctx->texOut.p);
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     MOF_CUDA(cudaEventSynchronize(ctx->ev1));
     float ms = 0;

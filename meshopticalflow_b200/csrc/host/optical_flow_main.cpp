@@ -75,10 +75,11 @@ int main(int argc, char* argv[]) {
     }
 
     const bool processTexture = opt.meshSet;
-    // MOF_GPU_TEXPREP=1: the texture configuration's one-time preparation (Subdivide, SampleTextureToVertices,
-    // GetTextureSource) runs on the GPU (csrc/texprep_kernels.cu) instead of in host/texture_prep.cpp; same outputs.
+    // The texture configuration's one-time preparation (Subdivide, SampleTextureToVertices, GetTextureSource) runs on the GPU
+    // (csrc/texprep_kernels.cu). MOF_GPU_TEXPREP=0 selects the serial host restatement in host/texture_prep.cpp instead — same
+    // outputs, bit for bit; kept as a cross-check.
     const char* gpuPrepEnv = getenv("MOF_GPU_TEXPREP");
-    const bool gpuPrep = processTexture && gpuPrepEnv && *gpuPrepEnv && *gpuPrepEnv != '0';
+    const bool gpuPrep = processTexture && !(gpuPrepEnv && *gpuPrepEnv == '0');
     mof_ctx* ctx = nullptr;
     auto ensure_context = [&]() {
         if (ctx) return true;
@@ -204,6 +205,7 @@ int main(int argc, char* argv[]) {
     const double vfSmoothDefault[3] = {3e-6, 5e-7, 1e4};  // _main, OpticalFlow.cpp:1064-1069
     params.vfSmooth = opt.vfSmoothSet ? (double)opt.vfSmooth : vfSmoothDefault[opt.vfMode];
     params.vfMode = opt.vfMode, params.cMode = opt.cMode;
+    params.logSpace = opt.logSpace ? 1 : 0;  // :821 — the comparison signals only; the colours advected at the end stay raw (:482-489, :1049-1054)
     params.vMultiply = (double)opt.vMultiply, params.vfSThreshold = (double)opt.vfSThreshold;
     params.dogWeight = (double)opt.dogWeight, params.dogSmooth = (double)opt.dogSmooth;
     params.flowTol = opt.flowTol, params.smoothTol = opt.smoothTol;
@@ -235,9 +237,6 @@ int main(int argc, char* argv[]) {
         }
         if (!mof_ok(ctx, mof_set_texture_map(ctx, tW, tH, srcT.data(), srcP.data(), tmesh.uv.data(), textures[0].data(), textures[1].data()))) return EXIT_FAILURE;
     }
-    if (opt.logSpace)  // :821
-        for (int s = 0; s < 2; s++)
-            for (double& x : signal[s]) x = std::log(std::max(1., x)) * 255. / std::log(255.);
     {
         Stopwatch t;
         if (!mof_ok(ctx, mof_set_signals(ctx, signal[0].data(), signal[1].data(), 3))) return EXIT_FAILURE;

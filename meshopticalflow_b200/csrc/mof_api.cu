@@ -35,7 +35,8 @@ __global__ void k_deinterleave(const double* __restrict__ in6, int V, double* __
 // half-edge table 8 slots per triangle. Beyond these sizes an index would wrap (and one B200 could not hold the operators).
 int check_mesh_size(mof_ctx* ctx, int V, int T, const char* who) {
     if (V < 3 || T < 1) return fail(ctx, MOF_E_INVALID, std::string(who) + ": empty mesh");
-    if (V > 60000000 || T > 120000000) return fail(ctx, MOF_E_INVALID, std::string(who) + ": more than 60M vertices / 120M triangles do not fit 32-bit matrix indices");
+    // ~33 entries per vertex, up to ~20 % slice padding on irregular meshes: 48M vertices keep the padded count below 2^31 (checked again after the scan)
+    if (V > 48000000 || T > 96000000) return fail(ctx, MOF_E_INVALID, std::string(who) + ": more than 48M vertices / 96M triangles do not fit 32-bit matrix indices");
     return MOF_OK;
 }
 
@@ -104,6 +105,7 @@ void mof_default_params(mof_params* p) {
     p->maxCgIterations = 100000;
     p->vfMode = 0;                    // WHITNEY_VECTOR_FIELD, OpticalFlow.cpp:58
     p->cMode = 0;                     // PROJECTED_BARICENTRIC_WEIGHTS
+    p->logSpace = 0;
 }
 
 int mof_create(int device, void* stream, mof_ctx** out) {
@@ -146,7 +148,7 @@ void mof_destroy(mof_ctx* ctx) {
     smooth_ahead_destroy(ctx);
     cudaStreamSynchronize(ctx->stream);
     DBuf<double>* dbl[] = {&ctx->pos, &ctx->g, &ctx->area, &ctx->xlin, &ctx->xcst, &ctx->sMass, &ctx->sStiff, &ctx->sSys, &ctx->sDinv, &ctx->P, &ctx->m0, &ctx->m1,
-                           &ctx->wS, &ctx->wA, &ctx->wDinv, &ctx->raw6, &ctx->sig6, &ctx->smoothed6, &ctx->rhs6, &ctx->resampled6, &ctx->tsample6, &ctx->dataD,
+                           &ctx->wS, &ctx->wA, &ctx->wDinv, &ctx->raw6, &ctx->log6, &ctx->sig6, &ctx->smoothed6, &ctx->rhs6, &ctx->resampled6, &ctx->tsample6, &ctx->dataD,
                            &ctx->dataRhs, &ctx->coeffs, &ctx->tfield, &ctx->fb, &ctx->fx, &ctx->scalars, &ctx->pcg.r, &ctx->pcg.d, &ctx->pcg.q, &ctx->pcg.partial,
                            &ctx->pcg.result, &ctx->dtmp0, &ctx->dtmp1, &ctx->dtmp2, &ctx->srcP, &ctx->triUV, &ctx->texOut, &ctx->sigLo6, &ctx->smoothedLo6, &ctx->resampledLo6};
     for (auto* b : dbl) b->release();
@@ -337,6 +339,20 @@ int mof_advect_texels(mof_ctx* ctx, double alpha, int bilinear, double* outA, do
     StreamScope scope(ctx);
     MOF_TRY(advect_texels(ctx, alpha, bilinear));
     size_t n = (size_t)ctx->texW * ctx->texH;
+    MOF_CUDA(cudaMemcpyAsync(outA, ctx->texOut.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaMemcpyAsync(outB, ctx->texOut.p + 3 * n, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MOF_OK;
+}
+
+int mof_advect_texels_frames(mof_ctx* ctx, int frames, int bilinear, double* outA, double* outB) {
+    if (!ctx || !outA || !outB) return MOF_E_INVALID;
+    if (frames < 2 || frames > 4096) return fail(ctx, MOF_E_INVALID, "mof_advect_texels_frames: 2 <= frames <= 4096");
+    MOF_TRY(require_mesh(ctx));
+    if (!ctx->haveTexture) return fail(ctx, MOF_E_INVALID, "call mof_set_texture_map first");
+    StreamScope scope(ctx);
+    MOF_TRY(advect_texels_frames(ctx, frames, bilinear));
+    size_t n = (size_t)ctx->texW * ctx->texH * frames;
     MOF_CUDA(cudaMemcpyAsync(outA, ctx->texOut.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
     MOF_CUDA(cudaMemcpyAsync(outB, ctx->texOut.p + 3 * n, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
     MOF_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -587,6 +603,22 @@ int mof_time_flow_spmv(mof_ctx* ctx, int reps, float* msPerLaunch) {
     StreamScope scope(ctx);
     MOF_CUDA(ctx->pcg.q.reserve(ctx->E));
     return time_spmv_sell(ctx, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, ctx->fx.p, ctx->pcg.q.p, reps, msPerLaunch);
+}
+
+int mof_time_kernel(mof_ctx* ctx, int which, int reps, double* usPerLaunch, double* algorithmicBytes) {
+    if (!ctx || reps < 1 || !usPerLaunch || !algorithmicBytes || which < 0 || which >= MOF_K_COUNT) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    if (!ctx->haveFlowSystem) return fail(ctx, MOF_E_INVALID, "no flow system yet: call mof_iterate first");
+    if (vf_active(ctx)) return fail(ctx, MOF_E_UNSUPPORTED, "mof_time_kernel times the kernels of the Whitney basis");
+    if (dist_active(ctx)) return fail(ctx, MOF_E_UNSUPPORTED, "mof_time_kernel: not on a partitioned mesh");
+    StreamScope scope(ctx);
+    smooth_ahead_drain(ctx);
+    float ms = 0;
+    double bytes = 0;
+    if (which == MOF_K_WALK) MOF_TRY(time_walk_kernel(ctx, reps, &ms));
+    else MOF_TRY(mg_time_kernel(ctx, which, reps, &ms, &bytes));
+    *usPerLaunch = ms * 1e3, *algorithmicBytes = bytes;
+    return MOF_OK;
 }
 
 }  // extern "C"

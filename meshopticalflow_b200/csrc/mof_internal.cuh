@@ -112,7 +112,7 @@ struct mof_ctx {
     mof::DBuf<int> reduced, expanded, positive, wRowptr, wSliceBase, wCol;  // wCol/wS/wA: sliced layout (sell_pos), wPadded entries
     mof::DBuf<double> P, m0, m1, wS, wA, wDinv;
     // signals, (A rgb, B rgb) interleaved per vertex
-    mof::DBuf<double> raw6, sig6, smoothed6, rhs6, resampled6, tsample6, dataD, dataRhs;
+    mof::DBuf<double> raw6, log6, sig6, smoothed6, rhs6, resampled6, tsample6, dataD, dataRhs;  // log6: --log transform of raw6 (comparison only)
     // flow unknowns
     mof::DBuf<double> coeffs, tfield, fb, fx;
     mof::DBuf<double> scalars;
@@ -241,7 +241,8 @@ int mg_flow_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double*
 bool mg_scalar_usable(const mof_ctx* ctx);
 int mg_scalar_update(mof_ctx* ctx);   // per scalar system: coarse operators of the current sSys (sDinv = its inverse diagonal)
 int mg_scalar_solve(mof_ctx* ctx, const double* b6, double* x6, double tol, int maxIters, int* itersOut, double* relresOut);  // x6 = initial guess
-int mg_scalar_cycle(mof_ctx* ctx, const double* r6, double* z6);  // z6 = one cycle applied to r6 (approximate inverse of the current sSys)
+int mg_scalar_cycle(mof_ctx* ctx, const double* r6, double* z6);
+int mg_time_kernel(mof_ctx* ctx, int which, int reps, float* ms, double* bytes);  // mof_time_kernel for the solver kernels  // z6 = one cycle applied to r6 (approximate inverse of the current sSys)
 
 // dist.cu — one mesh over several GPUs: row blocks of the flow system, halo exchange, all-reduce (NCCL on ctx->stream)
 int dist_unique_id(unsigned char* id128);
@@ -276,6 +277,8 @@ void smooth_ahead_destroy(mof_ctx* ctx);
 int update_flow(mof_ctx* ctx, double sWeight, double vfWeight);
 int advect_vertices(mof_ctx* ctx, const double* in6, double lenA, double lenB, double* out6);
 int advect_texels(mof_ctx* ctx, double alpha, int bilinear);
+int advect_texels_frames(mof_ctx* ctx, int frames, int bilinear);  // ctx->texOut: [2][frames][W*H][3]
+int time_walk_kernel(mof_ctx* ctx, int reps, float* ms);
 
 // texprep_kernels.cu — the texture configuration's one-time preparation (MeshFlow.inl:158-467)
 int subdivide_mesh(mof_ctx* ctx, double edgeLength, int* addedOut);                 // ctx->subXyz / subTri / subUv in place

@@ -390,7 +390,8 @@ static int pcg_run(mof_ctx* ctx, PcgArgs<N>& args, bool zeroGuess, double tol, i
         args.zeroGuess = 0;
     }
     *itersOut = total, *relresOut = relres;
-    if (!(relres <= tol * 1.0001) && (total >= maxIters || !(relres <= 1e-4))) {
+    if (!(relres <= tol * 1.0001)) ctx->stats.solvesAboveTolerance++;  // accepted below MOF_ACCEPT_RELRES, or about to fail: visible either way
+    if (!(relres <= tol * 1.0001) && (total >= maxIters || !(relres <= MOF_ACCEPT_RELRES))) {
         char msg[160];
         snprintf(msg, sizeof(msg), "[ERROR] PCG did not reach %g in %d iterations (relative residual %g)", tol, total, relres);
         return fail(ctx, MOF_E_NOCONVERGE, msg);
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(PCG_T, 5) k_spmv_dot(int n, const int* __restr
 }
 
 int spmv_dot_launch(mof_ctx* ctx, int n, const int* sliceBase, const int* col, const double* val, const double* x, double* y, double* partial, int* partials) {
-    static int grid = 0;
+    int& grid = ctx->pcg.gridBlocks;  // per context (per device), computed once
     if (!grid) MOF_TRY(pcg_grid<1>(ctx, &grid));
     MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, n, sliceBase, col, val, x, y, partial);
     *partials = grid;

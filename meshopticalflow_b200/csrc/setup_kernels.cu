@@ -597,6 +597,8 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_TRY(exclusive_scan_int(ctx, ctx->itmp0.p, ctx->wSliceBase.p, slices + 1, nullptr));
     int padded = 0;
     MOF_CUDA(read_back(ctx, &padded, ctx->wSliceBase.p + slices));
+    if (padded < 0 || (long long)padded < nnzW)  // the padded entry count (a 32-bit scan) wrapped: the mesh is beyond what int offsets index
+        return fail(ctx, MOF_E_INVALID, "mof_set_mesh: the padded Whitney pattern does not fit 32-bit offsets (mesh too large)");
     ctx->wPadded = padded;
     MOF_CUDA(ctx->wCol.alloc((size_t)padded));
     MOF_CUDA(ctx->wS.alloc((size_t)padded));

@@ -441,6 +441,17 @@ def advect_texels(W, H, srcT, srcP, opp, lin, cst, g, tfield, tri_uv, texture, l
     return out
 
 
+def advect_texels_frames(W, H, frames, srcT, srcP, opp, lin, cst, g, tfield, tri_uv, texture, sign, bilinear=True):
+    """InputTextureData::flow(frames), OpticalFlow.cpp:517-539: [frames, W*H, 3]; sign -1 for the first signal, +1 for the second."""
+    tex = np.ascontiguousarray(texture, dtype=np.uint8)
+    out = np.empty((frames, W * H, 3), dtype=np.float64)
+    uv = np.ascontiguousarray(tri_uv, dtype=np.float64)
+    tf = np.ascontiguousarray(tfield, dtype=np.float64)
+    _lib().mof_oracle_advect_texels_frames(_I(W), _I(H), _I(frames), _p(srcT, _I), _p(srcP, _D), _p(opp, _I), _p(lin, _D), _p(cst, _D), _p(g, _D), _p(tf, _D), _p(uv, _D),
+                                           _p(tex, _U8), _D(sign), _I(1 if bilinear else 0), _p(out, _D))
+    return out
+
+
 def sample_texture(texture, uv, bilinear=True):
     """Sample, MeshFlow.inl:66-84."""
     tex = np.ascontiguousarray(texture, dtype=np.uint8)
@@ -495,6 +506,7 @@ class Params:
     pad: int = 2
     vfMode: int = 0   # 0 Whitney, 1 Conformal, 2 Connection (VectorField.h:3-7); vfSmooth defaults 3e-6 / 5e-7 / 1e4 (:1067-1069)
     cMode: int = 0    # Connection.inl:1-5
+    logSpace: bool = False  # --log, OpticalFlow.cpp:821: the comparison signals only
 
     def __post_init__(self):
         if self.vfSmooth is None:
@@ -532,6 +544,8 @@ def init(vertices, triangles, sig_a, sig_b, params: Params) -> State:
     lin, cst = np.ascontiguousarray(lin), np.ascontiguousarray(cst)
     M, S = scalar_matrices(g, triangles, nv)
     signals = [np.asarray(sig_a, dtype=np.float64).copy(), np.asarray(sig_b, dtype=np.float64).copy()]
+    if params.logSpace:  # OpticalFlow.cpp:821 (before the DoG; the colours advected at the end, :482-489, stay raw)
+        signals = [np.log(np.maximum(1.0, s)) * 255.0 / np.log(255.0) for s in signals]
     if params.dogWeight > 0:
         dog = [dog_preprocess(M, S, g, triangles, s, params.dogSmooth) for s in signals]
         signals = dog if params.dogWeight >= 1 else [dog_blend(s, d, params.dogWeight) for s, d in zip(signals, dog)]

@@ -143,6 +143,32 @@ void mof_oracle_advect_texels(int W, int H, const int* srcT, const double* srcP,
     }
 }
 
+/* InputTextureData::flow(frames), OpticalFlow.cpp:517-539: the sample points are carried along the flow in `frames - 1`
+ * equal steps of 1 / (frames - 1) (minimum step 1e-2 * frames), each frame fetching the texture where the points stand;
+ * frame 0 and the uncovered texels of every frame are the vertically flipped input. out: [frames][W*H][3]. */
+void mof_oracle_advect_texels_frames(int W, int H, int frames, const int* srcT, const double* srcP, const int* opp, const double* lin, const double* cst,
+                                     const double* g, const double* vf, const double* triUV, const unsigned char* tex, double sign, int bilinear, double* out) {
+    WalkMesh m = {opp, lin, cst, g};
+    const int n = W * H;
+    const double length = sign / (frames - 1);
+    for (int f = 0; f < frames; f++)
+        for (int j = 0; j < H; j++)
+            for (int i = 0; i < W; i++)
+                for (int k = 0; k < 3; k++) out[3 * ((size_t)f * n + j * W + i) + k] = (double)tex[3 * ((H - j - 1) * W + i) + k];
+    for (int i = 0; i < n; i++) {
+        if (srcT[i] == -1) continue;
+        int t = srcT[i];
+        double p[2] = {srcP[2 * i], srcP[2 * i + 1]};
+        for (int f = 1; f < frames; f++) {
+            flow_point(&m, vf, length, &t, p, 1e-2 * frames, 0.);
+            const double* uv = triUV + 6 * t;
+            double w0 = 1. - p[0] - p[1];
+            double qu = uv[0] * w0 + uv[2] * p[0] + uv[4] * p[1], qv = uv[1] * w0 + uv[3] * p[0] + uv[5] * p[1];
+            sample_texture(tex, W, H, qu, qv, bilinear, out + 3 * ((size_t)f * n + i));
+        }
+    }
+}
+
 /* RiemannianMesh::exp, FEM.inl:835-899: straight line from p with initial velocity v (consumed as
  * it goes), unfolded across edges. Returns 0 on success, 1 if the ray misses the triangle (the
  * reference prints an error and exits), 2 on the iteration cap. */

@@ -8,7 +8,7 @@ seeded inputs and stores inputs + selected reference outputs as compressed .npz:
   torus_texture.npz    --mesh m.ply --in A.png B.png --out r.png --eLength 0.08 on a 24x12 uv torus, 48x48 texels
   sample_texture_tool.npz  oracle/_ref/SampleTextureToVertices_ref on the uv torus (ascii, subdivided, binary): files in, files out
   sphere3_modes.npz    the 258-vertex sphere again with 4 iterations of --vfMode 1, --vfMode 2 --cMode 0|1|2 (taps) and of
-                       --dogWeight 0.5 (the 6-channel blend: output colours only, the tap build is 3-channel)
+                       --dogWeight 0.5 (the 6-channel blend: output colours only, the tap build is 3-channel) and of --log (comparison signals, last flow, advected and output colours)
 
   sphere7_vertex.npz / sphere8_vertex.npz   the 65 538- and 262 146-vertex spheres (BASELINE.json configs[2]'s generator at the two
                        sizes below the headline one that the reference finishes in minutes), 3 iterations: per-iteration flow on
@@ -143,6 +143,11 @@ def modes():
         subprocess.check_call([REF, "--in", "A.ply", "B.ply", "--out", "blend.ply", "--iterations", "4", "--dogWeight", "0.5"], cwd=d, stdout=subprocess.DEVNULL)
         out = synthetic.read_ply(os.path.join(d, "blend.ply"))
         data["blend.output_rgb"] = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.uint8)
+        subprocess.check_call([REF, "--in", "A.ply", "B.ply", "--out", "log.ply", "--iterations", "4", "--log", "--tap", "tap_log"], cwd=d, stdout=subprocess.DEVNULL)
+        out = synthetic.read_ply(os.path.join(d, "log.ply"))
+        data["log.output_rgb"] = np.stack([out["vertex"][k] for k in ("red", "green", "blue")], 1).astype(np.uint8)
+        taps = load_taps(os.path.join(d, "tap_log"))
+        data["log.signals0"], data["log.advected0"], data["log.it03.tFlowField"] = taps["signals0"], taps["advected0"], taps["it03.tFlowField"]
     np.savez_compressed(os.path.join(HERE, "sphere3_modes.npz"), **data)
     print("sphere3_modes.npz", os.path.getsize(os.path.join(HERE, "sphere3_modes.npz")) // 1024, "KiB")
 

@@ -121,6 +121,26 @@ def test_six_channel_blend(aligner, golden_modes):
     assert np.abs(out.astype(int) - g["blend.output_rgb"].astype(int)).max() <= 1
 
 
+def test_log_space_comparison(aligner, golden_modes):
+    """mof_params.logSpace (--log): the comparison signals are log-transformed inside the library, the colours advected at the end
+    are the raw ones — the reference's golden output, and the oracle stage by stage."""
+    g = golden_modes
+    v, t, a, b = _golden_inputs(g)
+    al = aligner
+    p = _params(4)
+    p.logSpace = 1
+    al.set_params(p)
+    al.set_mesh(v, t)
+    al.set_signals(a, b)
+    assert rel(al.array(api.ARR_SIGNALS)[:, :3], g["log.signals0"]) < 1e-7
+    al.iterate(4)
+    assert rel(al.flow(), g["log.it03.tFlowField"]) < FLOW_TOL
+    ca, cb = al.advect_vertices(0.5)
+    assert np.abs(ca - g["log.advected0"]).max() < COLOUR_TOL
+    out = O.to_uchar_ply((ca + cb) / 2.0)
+    assert np.abs(out.astype(int) - g["log.output_rgb"].astype(int)).max() <= 1
+
+
 def test_switching_bases_on_one_context(aligner):
     """Whitney -> Connection -> Whitney on the same mesh: the second Whitney run reproduces the first bit for bit, and
     a basis change without new signals is refused."""
@@ -147,7 +167,7 @@ def test_switching_bases_on_one_context(aligner):
     assert np.array_equal(al.flow(), first)
 
 
-@pytest.mark.parametrize("flags,name", [(["--vfMode", "2", "--cMode", "1"], "connection1"), (["--vfMode", "1"], "conformal"), (["--dogWeight", "0.5"], "blend")])
+@pytest.mark.parametrize("flags,name", [(["--vfMode", "2", "--cMode", "1"], "connection1"), (["--vfMode", "1"], "conformal"), (["--dogWeight", "0.5"], "blend"), (["--log"], "log")])
 def test_command_line_flags(tmp_path, golden_modes, flags, name):
     g = golden_modes
     synthetic.write_ply_colored(str(tmp_path / "A.ply"), g["input_vertices_f32"], g["input_a"], g["triangles"], True)

@@ -226,6 +226,35 @@ def test_multigrid_and_jacobi_preconditioned_solves_agree():
     assert iters["1"][0] * 3 < iters["0"][0] and iters["1"][1] * 3 < iters["0"][1], iters
 
 
+def test_texel_frame_sequence_matches_the_oracle(aligner, golden_torus):
+    """InputTextureData::flow(frames) (OpticalFlow.cpp:517-539): the sample points carried along the flow in frames - 1 steps, a
+    texture fetch after each; frame 0 and uncovered texels are the flipped input; the last frame of a 2-frame sequence is the
+    whole flow walked in one go with the coarser minimum step."""
+    g = golden_torus
+    ta, tb = g["input_tex_a"], g["input_tex_b"]
+    v, t, uv = g["vertices"], g["triangles"], g["triangleTextures"].reshape(-1, 6)
+    sig = [O.sample_texture_to_vertices(t, uv, v.shape[0], tex) for tex in (ta, tb)]
+    al = aligner
+    al.set_mesh(v, t)
+    al.set_signals(sig[0], sig[1])
+    al.iterate(4)
+    srcT, srcP = g["textureSource_tIdx"], g["textureSource_p"]
+    al.set_texture_map(48, 48, srcT, srcP, uv, ta, tb)
+    flow = al.flow()
+    opp, lin, cst, gm = (al.array(k) for k in (api.ARR_OPPOSITE, api.ARR_XFORM_LINEAR, api.ARR_XFORM_CONSTANT, api.ARR_METRIC))
+    for frames, bilinear in ((5, True), (2, False)):
+        fa, fb = al.advect_texels_frames(frames, bilinear)
+        for mine, tex, sign in ((fa, ta, -1.0), (fb, tb, 1.0)):
+            ref = O.advect_texels_frames(48, 48, frames, srcT, srcP, opp, lin, cst, gm, flow, uv, tex, sign, bilinear)
+            assert mine.shape == ref.shape == (frames, 48 * 48, 3)
+            assert np.array_equal(mine[0], tex[::-1].reshape(-1, 3).astype(np.float64))
+            assert np.array_equal(mine[:, srcT == -1], ref[:, srcT == -1])
+            assert colour_outliers(mine, ref, 1e-6) < 2e-3  # walk ties aside, the same numbers
+    with pytest.raises(api.MofError) as e:
+        al.advect_texels_frames(1)
+    assert e.value.code == api.MOF_E_INVALID
+
+
 def test_irregular_mesh_matches_the_oracle(aligner):
     """Vertices jittered along the surface (triangle areas vary by ~10x, no flips; aggregates become ragged)."""
     v, t = synthetic.octahedron_sphere(4)

@@ -267,6 +267,16 @@ def test_gpu_tier_error_paths_and_symmetries(aligner):
     test_gpu_parity.test_identical_signals_give_zero_flow_and_swapping_flips_it(aligner)
 
 
+def test_gpu_tier_texel_frame_sequence(aligner, golden_torus):
+    import test_gpu_parity
+    test_gpu_parity.test_texel_frame_sequence_matches_the_oracle(aligner, golden_torus)
+
+
+def test_gpu_tier_log_space_comparison(aligner, golden_modes):
+    import test_gpu_modes
+    test_gpu_modes.test_log_space_comparison(aligner, golden_modes)
+
+
 def test_gpu_tier_switching_bases_on_one_context(aligner):
     import test_gpu_modes
     test_gpu_modes.test_switching_bases_on_one_context(aligner)

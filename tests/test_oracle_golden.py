@@ -121,6 +121,22 @@ def test_six_channel_dog_blend_matches_reference(golden_modes):
     assert np.abs(O.to_uchar_ply(blended).astype(int) - g["blend.output_rgb"].astype(int)).max() <= 1
 
 
+def test_log_space_comparison_matches_reference(golden_modes):
+    """--log (OpticalFlow.cpp:821) transforms the comparison signals only: the flow follows the log signals, the output is the
+    RAW colours advected along it (:482-489, :1049-1054)."""
+    g = golden_modes
+    v, t = g["input_vertices_f32"].astype(np.float64), g["triangles"]
+    a, b = g["input_a"].astype(np.float64), g["input_b"].astype(np.float64)
+    st, out = O.align_vertices(v, t, a, b, O.Params(iterations=4, logSpace=True))
+    assert rel(st.signals[0], g["log.signals0"]) < 1e-9
+    assert rel(st.tfield, g["log.it03.tFlowField"]) < 1e-9
+    assert np.abs(O.to_uchar_ply(out).astype(int) - g["log.output_rgb"].astype(int)).max() <= 1
+    plain, _ = O.align_vertices(v, t, a, b, O.Params(iterations=4))
+    assert rel(st.tfield, plain.tfield) > 1e-2  # the flag matters on this input: another flow ...
+    logged = np.log(np.maximum(1.0, a)) * 255.0 / np.log(255.0)
+    assert np.abs(out - a).mean() < 0.25 * np.abs(out - logged).mean()  # ... and an output in the raw colours' range, not the logarithms'
+
+
 def test_walk_edge_cases():
     """flow() on a tiny closed mesh: zero field, zero time, and a walk long enough to wrap around."""
     v = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]], dtype=np.float64)
