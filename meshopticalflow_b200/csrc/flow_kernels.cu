@@ -150,7 +150,12 @@ struct SmoothAhead {
 
 static bool smooth_ahead_enabled() {  // read per iteration: tests flip it inside one process
     const char* e = getenv("MOF_SMOOTH_AHEAD");
-    return !(e && *e == '0');
+    if (e && *e) return *e != '0';
+    // Under Nsight Compute (its injection variables are in the environment) the second stream's worker thread is left out unless asked
+    // for: ncu 2025.2 crashed the process (SIGSEGV inside the injected library) when two threads captured CUDA graphs at the same
+    // time (profiles/README.md, r2i). Results are bit-identical either way.
+    static const bool profiled = getenv("NV_NSIGHT_INJECTION_PORT_BASE") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
+    return !profiled;
 }
 
 static void smooth_ahead_join(mof_ctx* ctx) {
@@ -214,6 +219,7 @@ static void smooth_ahead_start(mof_ctx* ctx, double weight) {
     v.device = ctx->device, v.params = ctx->params, v.pinned = ctx->pinned;
     v.V = ctx->V, v.T = ctx->T, v.E = ctx->E, v.nnzS = ctx->nnzS;
     v.sRowptr = ctx->sRowptr, v.sCol = ctx->sCol, v.sHe = ctx->sHe, v.sMass = ctx->sMass, v.sStiff = ctx->sStiff, v.sSys = ctx->sSys, v.sDinv = ctx->sDinv, v.rhs6 = ctx->rhs6;
+    v.sSliceBase = ctx->sSliceBase, v.sColSell = ctx->sColSell, v.sSysSell = ctx->sSysSell, v.sPadded = ctx->sPadded;
     v.mgs = ctx->mgs, v.mg = nullptr, v.dist = nullptr, v.vf = nullptr, v.ahead = nullptr;
     // the view's stream starts after everything queued on the owner's (the signals, the previous smoothing's readers)
     if (cudaEventRecord(a->fence, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(a->view.stream, a->fence, 0) != cudaSuccess) return;

@@ -73,6 +73,7 @@ int finish_signals(mof_ctx* ctx) {
     smooth_ahead_drain(ctx);
     if (ctx->params.vfMode != 0 && dist_active(ctx))
         return fail(ctx, MOF_E_UNSUPPORTED, "[ERROR] a partitioned mesh (mof_dist_init) supports the Whitney vector field only");
+    mg_new_pair(ctx);  // same inputs -> same bits: nothing carried over from the previous pair's systems
     MOF_TRY(dog_preprocess(ctx));
     MOF_TRY(vf_init(ctx));  // VectorField::Init for --vfMode 1|2 (OpticalFlow.cpp:862-871); Whitney was built with the mesh
     MOF_CUDA(cudaMemsetAsync(ctx->coeffs.p, 0, sizeof(double) * vf_unknowns(ctx), ctx->stream));
@@ -147,12 +148,12 @@ void mof_destroy(mof_ctx* ctx) {
     StreamScope scope(ctx);
     smooth_ahead_destroy(ctx);
     cudaStreamSynchronize(ctx->stream);
-    DBuf<double>* dbl[] = {&ctx->pos, &ctx->g, &ctx->area, &ctx->xlin, &ctx->xcst, &ctx->sMass, &ctx->sStiff, &ctx->sSys, &ctx->sDinv, &ctx->P, &ctx->m0, &ctx->m1,
+    DBuf<double>* dbl[] = {&ctx->pos, &ctx->g, &ctx->area, &ctx->xlin, &ctx->xcst, &ctx->sMass, &ctx->sStiff, &ctx->sSys, &ctx->sSysSell, &ctx->sDinv, &ctx->P, &ctx->m0, &ctx->m1,
                            &ctx->wS, &ctx->wA, &ctx->wDinv, &ctx->raw6, &ctx->log6, &ctx->sig6, &ctx->smoothed6, &ctx->rhs6, &ctx->resampled6, &ctx->tsample6, &ctx->dataD,
                            &ctx->dataRhs, &ctx->coeffs, &ctx->tfield, &ctx->fb, &ctx->fx, &ctx->scalars, &ctx->pcg.r, &ctx->pcg.d, &ctx->pcg.q, &ctx->pcg.partial,
                            &ctx->pcg.result, &ctx->dtmp0, &ctx->dtmp1, &ctx->dtmp2, &ctx->srcP, &ctx->triUV, &ctx->texOut, &ctx->sigLo6, &ctx->smoothedLo6, &ctx->resampledLo6};
     for (auto* b : dbl) b->release();
-    DBuf<int>* ints[] = {&ctx->tri, &ctx->opp, &ctx->sRowptr, &ctx->sCol, &ctx->sHe, &ctx->reduced, &ctx->expanded, &ctx->positive, &ctx->wRowptr, &ctx->wSliceBase, &ctx->wCol,
+    DBuf<int>* ints[] = {&ctx->tri, &ctx->opp, &ctx->sRowptr, &ctx->sCol, &ctx->sSliceBase, &ctx->sColSell, &ctx->sHe, &ctx->reduced, &ctx->expanded, &ctx->positive, &ctx->wRowptr, &ctx->wSliceBase, &ctx->wCol,
                          &ctx->itmp0, &ctx->itmp1, &ctx->itmp2, &ctx->flags, &ctx->srcT};
     for (auto* b : ints) b->release();
     ctx->hashKeys.release(), ctx->tex[0].release(), ctx->tex[1].release();

@@ -108,6 +108,10 @@ struct mof_ctx {
     // scalar (V x V) operators, one pattern
     mof::DBuf<int> sRowptr, sCol, sHe;
     mof::DBuf<double> sMass, sStiff, sSys, sDinv;
+    // ... and the system matrix once more in the sliced layout (SELL-32) for the solver's kernels: pattern per mesh, values per system
+    mof::DBuf<int> sSliceBase, sColSell;
+    mof::DBuf<double> sSysSell;
+    long long sPadded = 0;
     // Whitney
     mof::DBuf<int> reduced, expanded, positive, wRowptr, wSliceBase, wCol;  // wCol/wS/wA: sliced layout (sell_pos), wPadded entries
     mof::DBuf<double> P, m0, m1, wS, wA, wDinv;
@@ -235,6 +239,7 @@ int spmv_dot_launch(mof_ctx* ctx, int n, const int* sliceBase, const int* col, c
 // multigrid.cu
 int mg_setup_mesh(mof_ctx* ctx);      // per mesh, both hierarchies; leaves one unusable (Jacobi-PCG stays) when the mesh does not fit
 void mg_destroy(mof_ctx* ctx);
+void mg_new_pair(mof_ctx* ctx);       // forget what the previous signal pair's systems left behind (warm starts of the set-up)
 bool mg_flow_usable(const mof_ctx* ctx);
 int mg_flow_update(mof_ctx* ctx);     // per flow system: coarse operators of the current wA
 int mg_flow_solve(mof_ctx* ctx, double tol, int maxIters, int* itersOut, double* relresOut);   // wA fx = fb

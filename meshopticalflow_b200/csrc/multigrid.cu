@@ -36,7 +36,7 @@ namespace mof {
 namespace {
 
 constexpr int B = 256;
-constexpr int NBLK = kSMs * 4;   // fixed grid of the reduction-producing kernels (deterministic partials)
+constexpr int NBLK = kSMs * 8;   // fixed grid of the reduction-producing kernels (deterministic partials): full occupancy at 256 threads
 constexpr int MAXL = 9;          // finest admissible grid level (512^3 cells)
 constexpr int SLOT_CENTER = 13;
 constexpr int COARSEST_CELLS = 64;
@@ -94,6 +94,7 @@ struct Multigrid {
     DBuf<signed char> slotOf;       // per matrix entry: stencil slot at level 1 (-1 for padding)
     DBuf<creal> cinv;               // dense inverse on the coarsest level
     DBuf<creal> fval, fdinv;        // fine matrix values (layout of wA / sSys) and inverse diagonal in cycle precision
+    DBuf<creal> fvalSell;           // SCALAR: the same values in the sliced layout of ctx->sSysSell (what the solver's kernels read)
     DBuf<creal> fz, fz2, ft;        // fine-level vectors of the cycle, nFine * nrhs each
     DBuf<double> fr, fp, fq;        // ... and of PCG
     DBuf<double> partial, scal;
@@ -102,6 +103,8 @@ struct Multigrid {
     // Damping factors as the kernels read them (device): [0] fine level, [1 + l] coarse level l, two constants. By pointer
     // rather than by value so that a captured PCG graph stays valid when the next system changes them.
     DBuf<double> domega;
+    DBuf<creal> eig;                // power-iteration iterates of the last system: fine level, then the coarse levels
+    bool eigValid = false;
     const double* om(int slot) const { return domega.p + slot; }
     double hostOmega[16];
     // Cycle shape: `gamma` coarse corrections per visit on the first `gammaLevels` coarse levels, one below. Default
@@ -617,6 +620,98 @@ __global__ void __launch_bounds__(B) k_fine_apply_scalar_row(int n, const int* _
     }
     if (mode == 0 || (mode == 2 && f.partial)) cta_partial(dot, f.partial, f.slot, f.scal, f.counter);
 }
+// SCALAR, sliced layout (SELL-32, like the E x E operators): warp = slice of 32 rows, lane = row, the six channels of the row in
+// registers. Entry j of the 32 rows is 32 consecutive words, so every val / col load is one coalesced request, and the slice's
+// common length lets the loads of a row be issued in batches ahead of the gathers they feed (the CSR row kernel above walks
+// its row entry by entry: rowptr -> col -> gather, one dependent chain per entry; 3.0-3.7 TB/s against 5-6 here). The entries of
+// a row keep their CSR order, so the sums are the same bits. Modes as k_fine_apply_scalar_row.
+constexpr int SBATCH = 4;
+template <class TV, class TX>
+__global__ void __launch_bounds__(B, 4) k_fine_apply_scalar_sell(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const TV* __restrict__ val,
+                                                                const double* __restrict__ b, const creal* __restrict__ dinv, const double* __restrict__ omegaP,
+                                                                const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f) {
+    using P2 = typename Pair<TX>::type;
+    const double omega = *omegaP;
+    const int lane = threadIdx.x & 31;
+    const int slices = (n + 31) >> 5;
+    const int warps = gridDim.x * (B / 32);
+    double dot = 0;
+    for (int s = blockIdx.x * (B / 32) + (threadIdx.x >> 5); s < slices; s += warps) {
+        const int base = sliceBase[s];
+        const int len = (sliceBase[s + 1] - base) >> 5;
+        const TV* v0 = val + (size_t)base + lane;
+        const int* c0 = col + (size_t)base + lane;
+        const int row = 32 * s + lane;
+        TX acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int j0 = 0; j0 < len; j0 += SBATCH) {
+            TV v[SBATCH];
+            int c[SBATCH];
+            P2 x[SBATCH][3];
+#pragma unroll
+            for (int u = 0; u < SBATCH; u++) {
+                const bool ok = j0 + u < len;
+                v[u] = ok ? __ldcs(v0 + 32 * (size_t)(j0 + u)) : (TV)0;
+                c[u] = ok ? __ldcs(c0 + 32 * (size_t)(j0 + u)) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < SBATCH; u++) {
+                const P2* src = reinterpret_cast<const P2*>(in + 6 * (size_t)c[u]);
+                x[u][0] = src[0], x[u][1] = src[1], x[u][2] = src[2];
+            }
+#pragma unroll
+            for (int u = 0; u < SBATCH; u++)
+                if (j0 + u < len) {
+                    const TX w = (TX)v[u];
+                    acc[0] += w * x[u][0].x, acc[1] += w * x[u][0].y, acc[2] += w * x[u][1].x, acc[3] += w * x[u][1].y, acc[4] += w * x[u][2].x, acc[5] += w * x[u][2].y;
+                }
+        }
+        if (row >= n) continue;
+        const P2* self = reinterpret_cast<const P2*>(in + 6 * (size_t)row);
+        TX o[6];
+        if (mode == 0) {
+            const P2 s0 = self[0], s1 = self[1], s2 = self[2];
+            const TX sv[6] = {s0.x, s0.y, s1.x, s1.y, s2.x, s2.y};
+#pragma unroll
+            for (int c2 = 0; c2 < 6; c2++) o[c2] = acc[c2], dot += (double)sv[c2] * (double)acc[c2];
+        } else {
+            const double2* bp = reinterpret_cast<const double2*>(b + 6 * (size_t)row);
+            const double2 b0 = bp[0], b1 = bp[1], b2 = bp[2];
+            const double bv[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+            if (mode == 1) {
+#pragma unroll
+                for (int c2 = 0; c2 < 6; c2++) o[c2] = (TX)(bv[c2] - (double)acc[c2]);
+            } else {
+                const P2 s0 = self[0], s1 = self[1], s2 = self[2];
+                const TX sv[6] = {s0.x, s0.y, s1.x, s1.y, s2.x, s2.y};
+                const double wd = omega * (double)dinv[row];
+#pragma unroll
+                for (int c2 = 0; c2 < 6; c2++) {
+                    o[c2] = (TX)((double)sv[c2] + wd * (bv[c2] - (double)acc[c2]));
+                    dot += bv[c2] * (double)o[c2];
+                }
+            }
+        }
+        P2* dst = reinterpret_cast<P2*>(out + 6 * (size_t)row);
+        P2 w0, w1, w2;
+        w0.x = o[0], w0.y = o[1], w1.x = o[2], w1.y = o[3], w2.x = o[4], w2.y = o[5];
+        dst[0] = w0, dst[1] = w1, dst[2] = w2;
+    }
+    if (mode == 0 || (mode == 2 && f.partial)) cta_partial(dot, f.partial, f.slot, f.scal, f.counter);
+}
+// CSR values -> the sliced layout, in both precisions (once per scalar system; the pattern's slice offsets are per mesh).
+__global__ void k_scalar_vals_to_sell(const int* __restrict__ rowptr, const double* __restrict__ val, const int* __restrict__ sliceBase, int n, int slices,
+                                      double* __restrict__ sVal, creal* __restrict__ cVal) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= 32 * slices) return;
+    const int longest = (sliceBase[(r >> 5) + 1] - sliceBase[r >> 5]) >> 5;
+    const int k0 = r < n ? rowptr[r] : 0, len = r < n ? rowptr[r + 1] - k0 : 0;
+    for (int j = 0; j < longest; j++) {
+        const double v = j < len ? val[k0 + j] : 0.;
+        const size_t p = sell_pos(sliceBase, r, j);
+        sVal[p] = v, cVal[p] = (creal)v;
+    }
+}
+
 // SCALAR: CSR with six interleaved right-hand sides, one thread per (row, channel). mode 0: out = A in with the CTA's
 // partial of in.out ; modes 1, 2 as above.
 // PART (one mesh over several GPUs): only the rows [r0, r1) of this rank.
@@ -1248,12 +1343,26 @@ __global__ void k_update_xr(const double* __restrict__ p, const double* __restri
                             const creal* __restrict__ dinv, const double* __restrict__ omegaP, int nrhs, creal* __restrict__ z, Fold f) {
     const double alpha = f.scal[S_ALPHA], omega = *omegaP;
     double s = 0;
-    for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < n; i += (long long)gridDim.x * B) {
-        double rv = r[i] - alpha * q[i];
-        x[i] += alpha * p[i];
-        r[i] = rv;
-        z[i] = (creal)(omega * (double)dinv[i / nrhs] * rv);
-        s += rv * rv;
+    const long long stride = (long long)gridDim.x * B;
+    // two elements per trip, all ten loads issued before the first store (the sum keeps the order of the one-element loop)
+    for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < n; i += 2 * stride) {
+        const long long j = i + stride;
+        const bool two = j < n;
+        const double r0 = r[i], q0 = q[i], x0 = x[i], p0 = p[i], d0 = (double)dinv[i / nrhs];
+        double r1 = 0, q1 = 0, x1 = 0, p1 = 0, d1 = 0;
+        if (two) r1 = r[j], q1 = q[j], x1 = x[j], p1 = p[j], d1 = (double)dinv[j / nrhs];
+        const double rv0 = r0 - alpha * q0;
+        x[i] = x0 + alpha * p0;
+        r[i] = rv0;
+        z[i] = (creal)(omega * d0 * rv0);
+        s += rv0 * rv0;
+        if (two) {
+            const double rv1 = r1 - alpha * q1;
+            x[j] = x1 + alpha * p1;
+            r[j] = rv1;
+            z[j] = (creal)(omega * d1 * rv1);
+            s += rv1 * rv1;
+        }
     }
     cta_partial(s, f.partial, f.slot, f.scal, f.counter);
 }
@@ -1310,8 +1419,8 @@ void release_mg(Multigrid* mg) {
             l.z.release(), l.t.release();
     }
     mg->evec.release(), mg->cevec.release(), mg->agg.release(), mg->aggPtr.release(), mg->aggList.release(), mg->slotOf.release(), mg->cinv.release();
-    mg->fval.release(), mg->fdinv.release();
-    mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release(), mg->counter.release(), mg->domega.release();
+    mg->fval.release(), mg->fdinv.release(), mg->fvalSell.release();
+    mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release(), mg->counter.release(), mg->domega.release(), mg->eig.release();
     delete mg;
 }
 
@@ -1446,6 +1555,7 @@ int alloc_common(mof_ctx* ctx, Multigrid& mg) {
     MOF_CUDA(mg.fq.alloc(len));
     MOF_CUDA(mg.fval.alloc(mg.kind == MG_FLOW ? (size_t)ctx->wPadded : (size_t)ctx->nnzS));
     MOF_CUDA(mg.fdinv.alloc((size_t)mg.nFine));
+    if (mg.kind == MG_SCALAR && ctx->sPadded > 0) MOF_CUDA(mg.fvalSell.alloc((size_t)ctx->sPadded));
     const int nc = (mg.kind == MG_FLOW ? 3 : 1) * mg.lev.back().N;
     MOF_CUDA(mg.cinv.alloc((size_t)nc * nc));
     if (mg.kind == MG_FLOW) {
@@ -1470,6 +1580,7 @@ Multigrid* new_mg(mof_ctx* ctx, Multigrid* old, MgKind kind, int nFine, int* rcO
     Multigrid* mg = old ? old : new Multigrid();
     mg->usable = false, mg->K = 0;
     drop_graphs(*mg);  // captured for the previous mesh's buffers
+    mg->eigValid = false;
     mg->tailStart = -1;
     mg->kind = kind, mg->nFine = nFine, mg->nrhs = kind == MG_FLOW ? 1 : 6;
     mg->gamma = std::max(1, std::min(2, env_int("MOF_MG_GAMMA", 2)));
@@ -1492,6 +1603,11 @@ Multigrid* new_mg(mof_ctx* ctx, Multigrid* old, MgKind kind, int nFine, int* rcO
 void mg_destroy(mof_ctx* ctx) {
     release_mg(ctx->mg), release_mg(ctx->mgs);
     ctx->mg = ctx->mgs = nullptr;
+}
+
+void mg_new_pair(mof_ctx* ctx) {
+    if (ctx->mg) ctx->mg->eigValid = false;
+    if (ctx->mgs) ctx->mgs->eigValid = false;
 }
 
 // Mesh-dependent part of both hierarchies.
@@ -1583,9 +1699,18 @@ bool scalar_row_kernel() {
     static const bool on = env_int("MOF_SCALAR_ROWKERNEL", 1) != 0;
     return on;
 }
+// MOF_SCALAR_SELL=0: the V x V operators stay in CSR inside the solver (A/B timing; the partitioned path always does)
+bool scalar_sell(const mof_ctx* ctx) {
+    static const bool on = env_int("MOF_SCALAR_SELL", 1) != 0;
+    return on && ctx->sPadded > 0;
+}
 
 int fine_apply(mof_ctx* ctx, Multigrid& mg, const double* b, const double* omega, const creal* in, creal* out, int mode, int dotSlot = -1) {
     const Fold f = dotSlot >= 0 ? fold_into(mg, dotSlot) : NO_FOLD;
+    if (mg.kind != MG_FLOW && scalar_sell(ctx)) {
+        MOF_LAUNCH((k_fine_apply_scalar_sell<creal, creal>), FINE_GRID, B, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, mg.fvalSell.p, b, mg.fdinv.p, omega, in, out, mode, f);
+        return MOF_OK;
+    }
     if (mg.kind != MG_FLOW && scalar_row_kernel()) {
         MOF_LAUNCH((k_fine_apply_scalar_row<creal, creal>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, f);
         return MOF_OK;
@@ -1601,6 +1726,9 @@ int fine_residual(mof_ctx* ctx, Multigrid& mg, const double* b, const double* in
     if (mg.kind == MG_FLOW)
         MOF_LAUNCH((k_fine_apply_flow<double, double>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, b, (const creal*)nullptr, mg.om(OM_ZERO), in, out, 1,
                    NO_FOLD);
+    else if (scalar_sell(ctx))
+        MOF_LAUNCH((k_fine_apply_scalar_sell<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, ctx->sSysSell.p, b, (const creal*)nullptr,
+                   mg.om(OM_ZERO), in, out, 1, NO_FOLD);
     else
         MOF_LAUNCH((k_fine_apply_scalar<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, b, (const creal*)nullptr, mg.om(OM_ZERO), in, out, 1,
                    NO_FOLD);
@@ -1637,20 +1765,31 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
     // Damping of the Jacobi smoothers: omega_l = 1.4 / rho_l with rho_l the spectral radius of Minv A on that level,
     // estimated by power iteration on I + Minv A (all eigenvalues of Minv A are positive). omega * rho < 2 keeps the
     // cycle positive definite; should an estimate ever be too low, PCG stalls and the caller falls back to Jacobi-PCG.
-    const int powerIts = 10;
+    // The iterate of the previous system on this mesh is kept (Multigrid::eig): consecutive systems differ little (the data term moves
+    // with the flow, eps shrinks by 4), so from the second system on 3 steps from there replace 10 from a pseudo-random start —
+    // the estimates only improve, and the set-up of the ~20 systems of an alignment drops from ~45 ms to ~20 ms at 1M vertices.
+    const bool warm = mg.eigValid && env_int("MOF_MG_POWER_WARM", 1) != 0;
+    const int powerIts = std::max(1, std::min(50, warm ? env_int("MOF_MG_POWER_ITS_WARM", 3) : env_int("MOF_MG_POWER_ITS", 10)));
     const char* pinvEnv = getenv("MOF_MG_PINV_TOL");
     const double pinvTol = pinvEnv && *pinvEnv ? atof(pinvEnv) : 1e-3;
+    size_t eigOffset = 0;
     {
+        MOF_CUDA(mg.eig.alloc(len + (size_t)D * [&] { size_t n = 0; for (int l = 0; l < mg.K; l++) n += mg.lev[l].N; return n; }()));
         MOF_CUDA(cudaMemsetAsync(mg.fq.p, 0, sizeof(double) * len, ctx->stream));  // the zero right-hand side
-        MOF_LAUNCH(k_pseudo_random, blocks_for((long long)len, B), B, 0, (long long)len, mg.fz.p);
+        creal* v = mg.fz.p;
+        creal* w = mg.fz2.p;
+        if (warm) MOF_CUDA(cudaMemcpyAsync(v, mg.eig.p, sizeof(creal) * len, cudaMemcpyDeviceToDevice, ctx->stream));
+        else MOF_LAUNCH(k_pseudo_random, blocks_for((long long)len, B), B, 0, (long long)len, v);
         for (int it = 0; it <= powerIts; it++) {
-            MOF_LAUNCH((k_dot_partial<creal, creal>), NBLK, B, 0, mg.fz.p, mg.fz.p, (long long)len, mg.partial.p);
+            MOF_LAUNCH((k_dot_partial<creal, creal>), NBLK, B, 0, v, v, (long long)len, mg.partial.p);
             MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, 16, mg.scal.p);
             if (it == powerIts) break;
-            MOF_LAUNCH(k_normalise, blocks_for((long long)len, B), B, 0, mg.fz.p, mg.scal.p, 16, (long long)len, mg.fz.p);
-            MOF_TRY(fine_apply(ctx, mg, mg.fq.p, mg.om(OM_MINUS_ONE), mg.fz.p, mg.fz2.p, 2));
-            std::swap(mg.fz.p, mg.fz2.p);
+            MOF_LAUNCH(k_normalise, blocks_for((long long)len, B), B, 0, v, mg.scal.p, 16, (long long)len, v);
+            MOF_TRY(fine_apply(ctx, mg, mg.fq.p, mg.om(OM_MINUS_ONE), v, w, 2));
+            std::swap(v, w);
         }
+        MOF_CUDA(cudaMemcpyAsync(mg.eig.p, v, sizeof(creal) * len, cudaMemcpyDeviceToDevice, ctx->stream));
+        eigOffset = len;
     }
     for (int l = 0; l < mg.K; l++) {
         MgLevel& lv = mg.lev[l];
@@ -1660,7 +1799,10 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
         if (l == mg.K - 1) break;
         const long long nd = (long long)D * lv.N;
         MOF_CUDA(cudaMemsetAsync(lv.r.p, 0, sizeof(creal) * nd, ctx->stream));
-        MOF_LAUNCH(k_pseudo_random, blocks_for(nd, B), B, 0, nd, lv.z.p);
+        creal* const z0 = lv.z.p;  // coarse_apply reads lv.z: the iterate has to be there, so the two buffers trade places and are put back
+        creal* const t0 = lv.t.p;
+        if (warm) MOF_CUDA(cudaMemcpyAsync(lv.z.p, mg.eig.p + eigOffset, sizeof(creal) * nd, cudaMemcpyDeviceToDevice, ctx->stream));
+        else MOF_LAUNCH(k_pseudo_random, blocks_for(nd, B), B, 0, nd, lv.z.p);
         for (int it = 0; it <= powerIts; it++) {
             MOF_LAUNCH((k_dot_partial<creal, creal>), NBLK, B, 0, lv.z.p, lv.z.p, nd, mg.partial.p);
             MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, NBLK, 17 + l, mg.scal.p);
@@ -1669,7 +1811,11 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
             MOF_TRY(coarse_apply(ctx, mg, lv, mg.om(OM_MINUS_ONE), 2, lv.t.p));
             std::swap(lv.z.p, lv.t.p);
         }
+        MOF_CUDA(cudaMemcpyAsync(mg.eig.p + eigOffset, lv.z.p, sizeof(creal) * nd, cudaMemcpyDeviceToDevice, ctx->stream));
+        lv.z.p = z0, lv.t.p = t0;
+        eigOffset += nd;
     }
+    mg.eigValid = true;
     // coarsest level: dense matrix on the host, Cholesky inverse, back to the device
     MgLevel& lc = mg.lev.back();
     const int Kc = mg.comps(), bs = mg.kind == MG_FLOW ? 3 : 1;
@@ -1996,7 +2142,10 @@ int apply_dot(mof_ctx* ctx, Multigrid& mg, const double* p, double* q) {
         MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, np, S_PQ, mg.scal.p);
         return MOF_OK;
     }
-    if (scalar_row_kernel())
+    if (scalar_sell(ctx))
+        MOF_LAUNCH((k_fine_apply_scalar_sell<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, ctx->sSysSell.p, (const double*)nullptr,
+                   (const creal*)nullptr, mg.om(OM_ZERO), p, q, 0, fold_into(mg, S_PQ));
+    else if (scalar_row_kernel())
         MOF_LAUNCH((k_fine_apply_scalar_row<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, (const double*)nullptr,
                    (const creal*)nullptr, mg.om(OM_ZERO), p, q, 0, fold_into(mg, S_PQ));
     else
@@ -2458,6 +2607,10 @@ int mg_scalar_update(mof_ctx* ctx) {
     MOF_LAUNCH(k_level1_scalar, blocks_for(27ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, ctx->sRowptr.p, ctx->sSys.p, mg.slotOf.p, l1.nbr.p, l1.N, coarse_scale(mg, 0), l1.blocks.p);
     MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->sSys.p, ctx->nnzS, mg.fval.p);
     MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, ctx->sDinv.p, (long long)ctx->V, mg.fdinv.p);
+    if (ctx->sPadded > 0) {
+        const int slices = (ctx->V + 31) / 32;
+        MOF_LAUNCH(k_scalar_vals_to_sell, blocks_for(32ll * slices, B), B, 0, ctx->sRowptr.p, ctx->sSys.p, ctx->sSliceBase.p, ctx->V, slices, ctx->sSysSell.p, mg.fvalSell.p);
+    }
     return finish_values(ctx, mg);
 }
 // One cycle of the SCALAR hierarchy as an approximate solve of sSys Z = R from a zero guess (six channels, [V][6]): a fixed,

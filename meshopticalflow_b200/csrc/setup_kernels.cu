@@ -557,6 +557,10 @@ int build_mesh_operators(mof_ctx* ctx) {
     MOF_LAUNCH(k_sort_rows, blocks_for(V, B), B, 0, ctx->sRowptr.p, V, ctx->sCol.p, ctx->sHe.p);
     MOF_LAUNCH(k_scalar_values, blocks_for(V, B), B, 0, ctx->sRowptr.p, ctx->sHe.p, ctx->opp.p, ctx->g.p, V, ctx->sMass.p, ctx->sStiff.p, ctx->flags.p);
 
+    {  // the scalar pattern once more, sliced (SELL-32): slice offsets and columns per mesh, values per system (multigrid.cu)
+        MOF_TRY(csr_to_sell(ctx, V, ctx->sRowptr.p, ctx->sCol.p, ctx->sMass.p, ctx->sSliceBase, ctx->sColSell, ctx->sSysSell));
+        ctx->sPadded = (long long)ctx->sColSell.n;
+    }
     pt.mark("  scalar operators");
     // a6: Whitney dof numbering
     MOF_CUDA(ctx->itmp0.alloc(nH + 1));
