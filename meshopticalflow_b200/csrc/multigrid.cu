@@ -115,6 +115,8 @@ struct Multigrid {
     // count; the smoothing systems are better conditioned (most of their solves take ~15 iterations) and want one
     // W level less.
     int gamma = 2, gammaLevels = -1;
+    int coarseSweeps[MAXL + 1];     // damped-Jacobi sweeps before / after the correction per coarse level (MOF_MG_COARSE_SWEEPS[_SCALAR]="a,b,...", default 1)
+    int fullDepth = 0;              // levels of the hierarchy before any are skipped (MOF_MG_SKIP_CELLS): the W levels are counted on it
     int fineSweeps = 1;             // damped-Jacobi sweeps on the fine level before and after the coarse correction (MOF_MG_FINE_SWEEPS[_SCALAR])
     double* hostRR = nullptr;       // pinned (a slice of ctx->pinned): what a solve reports back (PCG scalars)
     // The small levels as one kernel on one cluster (k_coarse_tail): first level handled there (-1: none), CTAs of the cluster.
@@ -250,13 +252,15 @@ __global__ void k_neighbours(const int* __restrict__ code, const int* __restrict
     }
     nbr[i] = out;
 }
-__global__ void k_parents(const int* __restrict__ code, const int* __restrict__ rankParent, int N, int Nparent, int* __restrict__ parent, int* __restrict__ firstChild) {
+// `shift` = 3 x (grid levels between a level and the next coarser one of the hierarchy: 1, or 2 where a level is skipped)
+__global__ void k_parents(const int* __restrict__ code, const int* __restrict__ rankParent, int N, int Nparent, int shift, int* __restrict__ parent,
+                          int* __restrict__ firstChild) {
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I > N) return;
     if (I == N) { firstChild[Nparent] = N; return; }
-    int p = rankParent[(unsigned)code[I] >> 3];
+    int p = rankParent[(unsigned)code[I] >> shift];
     parent[I] = p;
-    if (I == 0 || rankParent[(unsigned)code[I - 1] >> 3] != p) firstChild[p] = I;
+    if (I == 0 || rankParent[(unsigned)code[I - 1] >> shift] != p) firstChild[p] = I;
 }
 __global__ void k_point_aggregate(GridMap gm, const double* __restrict__ pts, const int* __restrict__ rank, int n, int L, int* __restrict__ agg, int* __restrict__ count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -912,6 +916,76 @@ __global__ void __launch_bounds__(27 / SLOTS * 32) k_coarse_apply(const creal* _
         u = bi[0] * s;
     out[(size_t)D * Ic + c] = zi + omega * u;
 }
+// Residual of a small level AND its restriction to the next one (with that level's first sweep) in one launch: a CTA takes four
+// coarse cells, whose children are at most 32 consecutive cells of the fine level — one chunk of k_coarse_apply<K, D, 1>'s layout
+// (warp = stencil slot, lane = cell) — computes their residuals r - A z into shared memory instead of global memory, and adds
+// them up per parent. Same arithmetic and summation orders as k_coarse_apply<K, D, 1> (mode 1) followed by k_restrict_coarse;
+// one launch less per level and visit, which is what the latency-bound levels are made of.
+constexpr int FUSE_G = 4;
+template <int K, int D>
+__global__ void __launch_bounds__(27 * 32) k_residual_restrict(const creal* __restrict__ blocks, const int* __restrict__ nbr, const creal* __restrict__ r,
+                                                              const creal* __restrict__ z, int N, const int* __restrict__ firstChild, const creal* __restrict__ binvC,
+                                                              const double* __restrict__ omegaP, int Nc, creal* __restrict__ rc, creal* __restrict__ zc) {
+    __shared__ creal part[27][32 * D];
+    __shared__ creal resid[32 * D];
+    __shared__ creal sums[FUSE_G * D];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+    const int c0 = blockIdx.x * FUSE_G, c1 = min(c0 + FUSE_G, Nc);
+    const int f0 = firstChild[c0], f1 = firstChild[c1];
+    const int I = f0 + lane;
+    const int ln = t / D, c = t - D * ln;
+    const int Ic = f0 + ln;
+    const bool live = t < 32 * D && Ic < f1;
+    const creal rv = live ? r[(size_t)D * Ic + c] : (creal)0;
+    creal o[D];
+#pragma unroll
+    for (int c2 = 0; c2 < D; c2++) o[c2] = 0;
+    if (I < f1) {
+        creal m[K], zj[D];
+        int J = nbr[I * 27 + w];
+#pragma unroll
+        for (int k = 0; k < K; k++) m[k] = blocks[blk<K>(N, I, w, k)];
+        J = J < 0 ? I : J;
+#pragma unroll
+        for (int c2 = 0; c2 < D; c2++) zj[c2] = z[(size_t)D * J + c2];
+        if (K == 9) {
+            creal t3[3];
+            mat3_vec(m, zj, t3);
+#pragma unroll
+            for (int c2 = 0; c2 < 3; c2++) o[c2] += t3[c2];
+        } else {
+#pragma unroll
+            for (int c2 = 0; c2 < D; c2++) o[c2] += m[0] * zj[c2];
+        }
+    }
+#pragma unroll
+    for (int c2 = 0; c2 < D; c2++) part[w][lane * D + c2] = o[c2];
+    __syncthreads();
+    if (live) {
+        creal sres = 0;
+#pragma unroll
+        for (int q = 0; q < 27; q++) sres += part[q][t];
+        resid[t] = rv - sres;
+    }
+    __syncthreads();
+    const int ci = t / D, cc = t - D * ci;
+    const int cell = c0 + ci;
+    const bool mine = t < FUSE_G * D && cell < c1;
+    creal a = 0;
+    if (mine) {
+        for (int Ich = firstChild[cell]; Ich < firstChild[cell + 1]; Ich++) a += resid[(Ich - f0) * D + cc];
+        sums[t] = a;
+    }
+    __syncthreads();
+    if (!mine) return;
+    const creal omega = (creal)*omegaP;
+    creal u;
+    if (K == 9) u = binvC[(size_t)(3 * cc) * Nc + cell] * sums[ci * D] + binvC[(size_t)(3 * cc + 1) * Nc + cell] * sums[ci * D + 1] + binvC[(size_t)(3 * cc + 2) * Nc + cell] * sums[ci * D + 2];
+    else u = binvC[cell] * a;
+    rc[(size_t)D * cell + cc] = a;
+    zc[(size_t)D * cell + cc] = omega * u;
+}
+
 // Restriction between coarse levels (children of a cell are contiguous) with the first sweep of the coarser level.
 // One thread per coarse cell.
 template <int K, int D>
@@ -1477,7 +1551,17 @@ int build_octree(mof_ctx* ctx, Multigrid& mg, const double* pts, int n, double m
     int Lc = L1;
     while (Lc > 1 && counts[Lc] > COARSEST_CELLS) Lc--;
     if (counts[Lc] > 2 * COARSEST_CELLS) { freeAll(); return MOF_OK; }
-    const int K = L1 - Lc + 1;
+    // The grid levels of the hierarchy. MOF_MG_SKIP_CELLS (default 0: none): below that many cells every other octree level is left
+    // out (cells coarsen 64-fold in volume, ~16-fold in number on a surface) — the small levels cost a fixed 4-9 us per kernel whatever
+    // their size, and a cycle visits them 4-16 times. The cycle's shape (W levels) is that of the full hierarchy.
+    const int skipCells = env_int(mg.kind == MG_FLOW ? "MOF_MG_SKIP_CELLS" : "MOF_MG_SKIP_CELLS_SCALAR", 0);
+    std::vector<int> gridLevels(1, L1);
+    for (int L = L1; L > Lc;) {
+        L -= (counts[L] <= skipCells && L - 2 >= Lc) ? 2 : 1;
+        gridLevels.push_back(L);
+    }
+    mg.fullDepth = L1 - Lc + 1;
+    const int K = (int)gridLevels.size();
     for (size_t l = K; l < mg.lev.size(); l++) {  // a previous, deeper hierarchy: give the extra levels back
         MgLevel& o = mg.lev[l];
         o.code.release(), o.nbr.release(), o.parent.release(), o.firstChild.release(), o.blocks.release(), o.cblocks.release(), o.binv.release(), o.r.release(),
@@ -1486,7 +1570,7 @@ int build_octree(mof_ctx* ctx, Multigrid& mg, const double* pts, int n, double m
     mg.lev.resize(K);
     for (int l = 0; l < K; l++) {
         MgLevel& lv = mg.lev[l];
-        int L = L1 - l;
+        int L = gridLevels[l];
         lv.gridLevel = L, lv.N = counts[L];
         long long cells = 1ll << (3 * L);
         MOF_CUDA(lv.code.alloc(lv.N));
@@ -1505,7 +1589,7 @@ int build_octree(mof_ctx* ctx, Multigrid& mg, const double* pts, int n, double m
         MgLevel& up = mg.lev[l + 1];
         MOF_CUDA(lv.parent.alloc(lv.N));
         MOF_CUDA(up.firstChild.alloc(up.N + 1));
-        MOF_LAUNCH(k_parents, blocks_for(lv.N + 1, B), B, 0, lv.code.p, rank[up.gridLevel].p, lv.N, up.N, lv.parent.p, up.firstChild.p);
+        MOF_LAUNCH(k_parents, blocks_for(lv.N + 1, B), B, 0, lv.code.p, rank[up.gridLevel].p, lv.N, up.N, 3 * (lv.gridLevel - up.gridLevel), lv.parent.p, up.firstChild.p);
     }
     MgLevel& l1 = mg.lev[0];
     MOF_CUDA(mg.agg.alloc(n));
@@ -1584,6 +1668,15 @@ Multigrid* new_mg(mof_ctx* ctx, Multigrid* old, MgKind kind, int nFine, int* rcO
     mg->tailStart = -1;
     mg->kind = kind, mg->nFine = nFine, mg->nrhs = kind == MG_FLOW ? 1 : 6;
     mg->gamma = std::max(1, std::min(2, env_int("MOF_MG_GAMMA", 2)));
+    {
+        for (int& c : mg->coarseSweeps) c = 1;
+        const char* e = getenv(kind == MG_FLOW ? "MOF_MG_COARSE_SWEEPS" : "MOF_MG_COARSE_SWEEPS_SCALAR");
+        for (int l = 0; e && *e && l <= MAXL; l++) {
+            mg->coarseSweeps[l] = std::max(1, std::min(4, atoi(e)));
+            e = strchr(e, ',');
+            if (e) e++;
+        }
+    }
     mg->fineSweeps = std::max(1, std::min(4, env_int(kind == MG_FLOW ? "MOF_MG_FINE_SWEEPS" : "MOF_MG_FINE_SWEEPS_SCALAR", 1)));
     mg->gammaLevels = env_int(kind == MG_FLOW ? "MOF_MG_GAMMA_LEVELS" : "MOF_MG_GAMMA_LEVELS_SCALAR", -1);  // < 0: by depth, see coarse_cycle
     cudaError_t e = mg->partial.alloc(8192);  // per-CTA partials: NBLK of ours, or the persistent-grid size of k_spmv_dot
@@ -1895,8 +1988,10 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
     return MOF_OK;
 }
 
+bool fuse_residual_restrict() { return env_int("MOF_MG_FUSE_RESTRICT", 1) != 0; }  // (0: the two stand-alone kernels, for A/B timing)
+
 int cycle_passes(const Multigrid& mg, int l) {
-    const int wLevels = mg.gammaLevels >= 0 ? mg.gammaLevels : mg.K - (mg.kind == MG_FLOW ? 4 : 5);
+    const int wLevels = mg.gammaLevels >= 0 ? mg.gammaLevels : mg.fullDepth - (mg.kind == MG_FLOW ? 4 : 5);
     return l < wLevels ? mg.gamma : 1;
 }
 
@@ -2075,7 +2170,22 @@ int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
     MgLevel& up = mg.lev[l + 1];
     const bool upDense = l + 1 == mg.K - 1;
     const int passes = cycle_passes(mg, l);
+    const bool fused = !upDense && mg.tailStart != l + 1 && lv.N < 16384 && lv.gridLevel - up.gridLevel == 1 && fuse_residual_restrict();
+    const int sweeps = l < (int)(sizeof(mg.coarseSweeps) / sizeof(int)) ? mg.coarseSweeps[l] : 1;
+    for (int extra = 1; extra < sweeps; extra++) {  // further pre-smoothing sweeps (the first is the restriction's)
+        MOF_TRY(coarse_apply(ctx, mg, lv, mg.om(1 + l), 2, lv.t.p));
+        std::swap(lv.z.p, lv.t.p);
+    }
     for (int g = 0; g < passes; g++) {
+        if (fused) {  // residual and restriction in one launch (small levels)
+            if (flow)
+                MOF_LAUNCH((k_residual_restrict<9, 3>), blocks_for(up.N, FUSE_G), 27 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.r.p, lv.z.p, lv.N, up.firstChild.p, up.binv.p, mg.om(2 + l),
+                           up.N, up.r.p, up.z.p);
+            else
+                MOF_LAUNCH((k_residual_restrict<1, 6>), blocks_for(up.N, FUSE_G), 27 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.r.p, lv.z.p, lv.N, up.firstChild.p, up.binv.p, mg.om(2 + l),
+                           up.N, up.r.p, up.z.p);
+            MOF_TRY(coarse_cycle(ctx, mg, l + 1));
+        } else {
         MOF_TRY(coarse_apply(ctx, mg, lv, mg.om(1 + l), 1, lv.t.p));
         if (mg.tailStart == l + 1) MOF_TRY(launch_tail(ctx, mg, l + 1, true));
         else {
@@ -2089,6 +2199,7 @@ int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
                 MOF_LAUNCH((k_restrict_coarse<1, 6>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, mg.om(2 + l), up.r.p, up.z.p);
             MOF_TRY(coarse_cycle(ctx, mg, l + 1));
         }
+        }
         if (g + 1 < passes) {  // W-cycle: the correction has to be in z before the next residual
             if (flow) MOF_LAUNCH(k_prolong_coarse<3>, blocks_for(3ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p);
             else MOF_LAUNCH(k_prolong_coarse<6>, blocks_for(6ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p);
@@ -2096,6 +2207,10 @@ int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
     }
     MOF_TRY(coarse_apply(ctx, mg, lv, mg.om(1 + l), 2, lv.t.p, up.z.p));
     std::swap(lv.z.p, lv.t.p);
+    for (int extra = 1; extra < sweeps; extra++) {  // ... and as many more after the correction (symmetry)
+        MOF_TRY(coarse_apply(ctx, mg, lv, mg.om(1 + l), 2, lv.t.p));
+        std::swap(lv.z.p, lv.t.p);
+    }
     return MOF_OK;
 }
 
