@@ -35,6 +35,7 @@ struct DistState {
     bool meshReady = false;
     std::vector<int> sliceStart;            // FLOW: world + 1 (32-row slices)
     Partition part[2];
+    std::vector<Partition*> extra;          // further partitions made by the solvers (multigrid levels dealt in cell ranges): dist_add_partition
     DBuf<double> sendBuf, recvBuf;          // sized for the widest exchange in fp64, reused for fp32
 };
 
@@ -90,10 +91,9 @@ __global__ void k_unpack(const T* __restrict__ buf, const int* __restrict__ idx,
 }
 
 template <class T>
-int halo_exchange(mof_ctx* ctx, int kind, T* vec, ncclDataType_t type) {
+int halo_exchange(mof_ctx* ctx, Partition& p, T* vec, ncclDataType_t type) {
     DistState& d = *ctx->dist;
     if (d.world == 1) return MOF_OK;
-    Partition& p = d.part[kind];
     const int w = p.width;
     T* sb = (T*)d.sendBuf.p;
     T* rb = (T*)d.recvBuf.p;
@@ -192,6 +192,7 @@ void dist_destroy(mof_ctx* ctx) {
     if (!ctx->dist) return;
     DistState& d = *ctx->dist;
     for (Partition& p : d.part) p.sendIdx.release(), p.recvIdx.release();
+    dist_clear_partitions(ctx);
     d.sendBuf.release(), d.recvBuf.release();
     if (d.comm) {
         cudaStreamSynchronize(ctx->stream);
@@ -206,6 +207,7 @@ int dist_setup_mesh(mof_ctx* ctx) {
     if (!ctx->dist || !ctx->dist->comm) return MOF_OK;
     DistState& d = *ctx->dist;
     d.meshReady = false;
+    dist_clear_partitions(ctx);
     const int N = d.world, E = ctx->E, V = ctx->V, S = ctx->wSlices;
     d.sliceStart.assign(N + 1, 0);
     d.part[0].rowStart.assign(N + 1, 0), d.part[1].rowStart.assign(N + 1, 0);
@@ -250,8 +252,58 @@ int dist_setup_mesh(mof_ctx* ctx) {
     return MOF_OK;
 }
 
-int dist_halo_f64(mof_ctx* ctx, int kind, double* vec) { return halo_exchange<double>(ctx, kind, vec, ncclDouble); }
-int dist_halo_f32(mof_ctx* ctx, int kind, float* vec) { return halo_exchange<float>(ctx, kind, vec, ncclFloat); }
+int dist_halo_f64(mof_ctx* ctx, int kind, double* vec) { return halo_exchange<double>(ctx, ctx->dist->part[kind], vec, ncclDouble); }
+int dist_halo_f32(mof_ctx* ctx, int kind, float* vec) { return halo_exchange<float>(ctx, ctx->dist->part[kind], vec, ncclFloat); }
+
+// ---- partitions made by the solvers: any index set dealt to the ranks in contiguous ranges (multigrid levels by cell ranges, the
+// fine rows a rank's aggregates reach into). The caller flags, in ctx->itmp0[0 .. n), the indices outside its own range that it
+// reads; the lists are exchanged like those of the two matrix patterns.
+int dist_add_partition(mof_ctx* ctx, int width, const int* rangeStart, int n, int* idOut) {
+    DistState& d = *ctx->dist;
+    Partition* p = new Partition();
+    p->width = width;
+    p->rowStart.assign(rangeStart, rangeStart + d.world + 1);
+    d.extra.push_back(p);
+    *idOut = (int)d.extra.size() - 1;
+    if (d.world > 1) MOF_TRY(build_lists(ctx, *p, n));
+    else p->sendCount.assign(1, 0), p->sendOff.assign(1, 0), p->recvCount.assign(1, 0), p->recvOff.assign(1, 0);
+    const size_t most = (size_t)std::max(p->nSend, p->nRecv) * width;  // (in doubles: twice what the fp32 exchanges need)
+    if (most > d.sendBuf.n) {
+        MOF_CUDA(d.sendBuf.reserve(most));
+        MOF_CUDA(d.recvBuf.reserve(most));
+    }
+    return MOF_OK;
+}
+void dist_clear_partitions(mof_ctx* ctx) {
+    if (!ctx->dist) return;
+    for (Partition* p : ctx->dist->extra) {
+        p->sendIdx.release(), p->recvIdx.release();
+        delete p;
+    }
+    ctx->dist->extra.clear();
+}
+long long dist_partition_halo(const mof_ctx* ctx, int id) { return ctx->dist->extra[id]->nRecv; }
+int dist_halo_part_f32(mof_ctx* ctx, int id, float* vec) { return halo_exchange<float>(ctx, *ctx->dist->extra[id], vec, ncclFloat); }
+// Every rank's own range of each of `count` vectors to all ranks, one group.
+int dist_allgather_part_f32(mof_ctx* ctx, int id, float* const* vecs, int count) {
+    DistState& d = *ctx->dist;
+    if (d.world == 1) return MOF_OK;
+    const Partition& p = *d.extra[id];
+    MOF_NCCL(ncclGroupStart());
+    for (int v = 0; v < count; v++)
+        for (int k = 0; k < d.world; k++) {
+            const size_t n = (size_t)(p.rowStart[k + 1] - p.rowStart[k]) * p.width;
+            float* at = vecs[v] + (size_t)p.rowStart[k] * p.width;
+            if (n > 0) MOF_NCCL(ncclBroadcast(at, at, n, ncclFloat, k, d.comm, ctx->stream));
+        }
+    MOF_NCCL(ncclGroupEnd());
+    return MOF_OK;
+}
+int dist_rank(const mof_ctx* ctx) { return ctx->dist ? ctx->dist->rank : 0; }
+void dist_row_starts(const mof_ctx* ctx, int kind, int* out) {
+    const std::vector<int>& r = ctx->dist->part[kind].rowStart;
+    std::copy(r.begin(), r.end(), out);
+}
 
 int dist_allreduce_f64(mof_ctx* ctx, double* v, int count) {
     DistState& d = *ctx->dist;

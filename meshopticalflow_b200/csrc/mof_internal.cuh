@@ -263,6 +263,15 @@ int dist_halo_f32(mof_ctx* ctx, int kind, float* vec);
 int dist_allreduce_f64(mof_ctx* ctx, double* v, int count);
 int dist_allreduce_f32(mof_ctx* ctx, float* v, int count);
 int dist_allgather_rows(mof_ctx* ctx, int kind, double* vec);  // every rank's rows to every rank
+// further partitions (any index set dealt in contiguous ranges; the indices outside the own range that this rank reads are flagged in ctx->itmp0[0..n))
+int dist_add_partition(mof_ctx* ctx, int width, const int* rangeStart, int n, int* idOut);
+void dist_clear_partitions(mof_ctx* ctx);
+long long dist_partition_halo(const mof_ctx* ctx, int id);
+int dist_halo_part_f32(mof_ctx* ctx, int id, float* vec);
+int dist_allgather_part_f32(mof_ctx* ctx, int id, float* const* vecs, int count);
+int dist_rank(const mof_ctx* ctx);
+void dist_row_starts(const mof_ctx* ctx, int kind, int* out);  // world + 1 entries
+int mg_dist_setup(mof_ctx* ctx);  // multigrid.cu: which coarse levels are dealt to the ranks, their cell ranges and halo lists (after dist_setup_mesh)
 
 // vector_fields.cu — the Conformal and Connection bases (--vfMode 1|2): matrix-free block-Jacobi PCG
 int vf_init(mof_ctx* ctx);                 // per signal pair, for ctx->params.vfMode / cMode (mode 0 releases the state)

@@ -115,6 +115,14 @@ struct Multigrid {
     // count; the smoothing systems are better conditioned (most of their solves take ~15 iterations) and want one
     // W level less.
     int gamma = 2, gammaLevels = -1;
+    // One mesh over several GPUs: the first distLevels coarse levels are dealt to the ranks in cell ranges (cellStart[l], world + 1
+    // entries, a rank's range on level l being the children of its range on level l + 1), the rest is replicated. Halo lists
+    // (dist.cu partitions): levelPart[l] = cells of level l outside the own range that the own cells' stencils — and, on level 0, the
+    // own fine rows' aggregates — read; memberPart = fine rows outside the own row block that belong to the own level-0 cells.
+    int distLevels = 0;
+    std::vector<std::vector<int>> cellStart;
+    std::vector<int> levelPart;
+    int memberPart = -1, gatherPart = -1;
     int coarseSweeps[MAXL + 1];     // damped-Jacobi sweeps before / after the correction per coarse level (MOF_MG_COARSE_SWEEPS[_SCALAR]="a,b,...", default 1)
     int fullDepth = 0;              // levels of the hierarchy before any are skipped (MOF_MG_SKIP_CELLS): the W levels are counted on it
     int fineSweeps = 1;             // damped-Jacobi sweeps on the fine level before and after the coarse correction (MOF_MG_FINE_SWEEPS[_SCALAR])
@@ -767,9 +775,10 @@ __device__ __forceinline__ void apply_binv(const creal* __restrict__ binv, int N
 // zc = omega * Binv * rc.
 // FLOW restriction: rc[I] = sum over the edges of aggregate I of v_e * r_e (P1^T r). One warp per aggregate.
 __global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ evec, const creal* __restrict__ r, int N,
-                                const creal* __restrict__ binv, const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1) {
-    int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (I >= N) return;
+                                const creal* __restrict__ binv, const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1,
+                                int c0 = 0, int c1 = -1) {  // [c0, c1): the cells of this launch (a rank's own cells when level 1 is dealt to the ranks)
+    int I = c0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (I >= (c1 < 0 ? N : c1)) return;
     const creal omega = (creal)*omegaP;
     const creal bk = lane < 9 ? binv[(size_t)lane * N + I] : (creal)0;  // the cell's block inverse, fetched alongside the sums
     creal a0 = 0, a1 = 0, a2 = 0;
@@ -800,9 +809,9 @@ __global__ void k_prolong_flow(const int* __restrict__ agg, const creal* __restr
 }
 // SCALAR restriction / prolongation: sums and copies per channel. One thread per (cell, channel) / (vertex, channel).
 __global__ void k_restrict_scalar(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ r, int N, const creal* __restrict__ binv,
-                                  const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 6 * N) return;
+                                  const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1, int c0 = 0, int c1 = -1) {
+    int i = 6 * c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6 * (c1 < 0 ? N : c1)) return;
     const creal omega = (creal)*omegaP;
     int I = i / 6, c = i - 6 * I;
     creal a = 0;
@@ -830,18 +839,20 @@ __global__ void k_prolong_scalar(const int* __restrict__ agg, const creal* __res
 template <int K, int D, int SLOTS>
 __global__ void __launch_bounds__(27 / SLOTS * 32) k_coarse_apply(const creal* __restrict__ blocks, const int* __restrict__ nbr, const creal* __restrict__ binv,
                                                                  const creal* __restrict__ r, const creal* __restrict__ z, const double* __restrict__ omegaP, int N,
-                                                                 int mode, creal* __restrict__ out, const int* __restrict__ parent, const creal* __restrict__ zc) {
+                                                                 int mode, creal* __restrict__ out, const int* __restrict__ parent, const creal* __restrict__ zc,
+                                                                 int c0 = 0, int c1 = -1) {  // [c0, c1): the cells of this launch (all, or a rank's own)
     constexpr int WARPS = 27 / SLOTS;
     const creal omega = (creal)*omegaP;
     __shared__ creal part[WARPS][32 * D];
     __shared__ creal resS[32 * D];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int I = blockIdx.x * 32 + lane;
+    const int I = c0 + blockIdx.x * 32 + lane;
+    const int cellEnd = c1 < 0 ? N : c1;
     // operands of the finishing step (thread t finishes component c of cell Ic), fetched ahead of the barrier
     const int t = threadIdx.x;
     const int ln = t / D, c = t - D * ln;
-    const int Ic = blockIdx.x * 32 + ln;
-    const bool live = t < 32 * D && Ic < N;
+    const int Ic = c0 + blockIdx.x * 32 + ln;
+    const bool live = t < 32 * D && Ic < cellEnd;
     creal rv = 0, zi = 0, bi[3] = {0, 0, 0};
     if (live) {
         rv = r[(size_t)D * Ic + c];
@@ -858,7 +869,7 @@ __global__ void __launch_bounds__(27 / SLOTS * 32) k_coarse_apply(const creal* _
     creal o[D];
 #pragma unroll
     for (int c2 = 0; c2 < D; c2++) o[c2] = 0;
-    if (I < N) {
+    if (I < cellEnd) {
         int J[SLOTS], P[SLOTS];
         creal m[SLOTS][K], zj[SLOTS][D];
 #pragma unroll
@@ -990,9 +1001,9 @@ __global__ void __launch_bounds__(27 * 32) k_residual_restrict(const creal* __re
 // One thread per coarse cell.
 template <int K, int D>
 __global__ void k_restrict_coarse(const int* __restrict__ firstChild, const creal* __restrict__ rFine, int Ncoarse, const creal* __restrict__ binv,
-                                  const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc) {
-    int Ip = blockIdx.x * blockDim.x + threadIdx.x;
-    if (Ip >= Ncoarse) return;
+                                  const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int c0 = 0, int c1 = -1) {
+    int Ip = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (Ip >= (c1 < 0 ? Ncoarse : c1)) return;
     const creal omega = (creal)*omegaP;
     creal a[D], o[D];
 #pragma unroll
@@ -1018,9 +1029,9 @@ __global__ void k_level_presmooth(const creal* __restrict__ binv, const creal* _
     for (int c = 0; c < D; c++) z[(size_t)D * I + c] = omega * o[c];
 }
 template <int D>
-__global__ void k_prolong_coarse(const int* __restrict__ parent, const creal* __restrict__ zc, int N, creal* __restrict__ z) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= D * N) return;
+__global__ void k_prolong_coarse(const int* __restrict__ parent, const creal* __restrict__ zc, int N, creal* __restrict__ z, int c0 = 0, int c1 = -1) {
+    int i = D * c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D * (c1 < 0 ? N : c1)) return;
     z[i] += zc[(size_t)D * parent[i / D] + i % D];
 }
 // Coarsest level: restriction into shared memory (every CTA repeats it, it is tiny), then z = M r with the dense inverse
@@ -2530,6 +2541,134 @@ __global__ void k_derive(int raw, double* __restrict__ scal) {
     else if (raw == R_RZNEW) scal[S_BETA] = scal[S_RZ] != 0 ? v / scal[S_RZ] : 0., scal[S_RZ] = v;
 }
 
+// ---- coarse levels dealt to the ranks
+// The replicated coarse levels are what limits a partitioned mesh (16.8M vertices: level 1 alone is 1.17M cells, 1.1 GB of stencil
+// coefficients per sweep on EVERY rank, and its restricted residual a 14 MB all-reduce per cycle). Levels of more than
+// MOF_DIST_LEVEL_CELLS cells (default 100 000) are therefore dealt to the ranks like the fine rows: contiguous cell ranges in
+// Morton order, aligned through the octree (a rank's cells on level l are the children of its cells on level l + 1), so that
+// restriction and prolongation between dealt levels stay inside a rank and only the 27-point stencils (one layer of cells) and
+// the aggregates that straddle a row-block boundary need an exchange. The first replicated level is gathered once per visit.
+__global__ void k_mark_stencil_halo(const int* __restrict__ nbr, int c0, int c1, int* __restrict__ flags) {
+    int i = 27 * c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 27 * c1) return;
+    const int J = nbr[i];
+    if (J >= 0 && (J < c0 || J >= c1)) flags[J] = 1;
+}
+__global__ void k_mark_aggregate_halo(const int* __restrict__ agg, int r0, int r1, int c0, int c1, int* __restrict__ flags) {
+    int e = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r1) return;
+    const int a = agg[e];
+    if (a < c0 || a >= c1) flags[a] = 1;
+}
+__global__ void k_mark_member_halo(const int* __restrict__ aggPtr, const int* __restrict__ aggList, int c0, int c1, int r0, int r1, int* __restrict__ flags) {
+    int q = aggPtr[c0] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= aggPtr[c1]) return;
+    const int e = aggList[q];
+    if (e < r0 || e >= r1) flags[e] = 1;
+}
+
+int mg_dist_setup_one(mof_ctx* ctx, Multigrid& mg) {
+    mg.distLevels = 0, mg.cellStart.clear(), mg.levelPart.clear(), mg.memberPart = mg.gatherPart = -1;
+    const int world = dist_world(ctx), rank = dist_rank(ctx);
+    if (!mg.usable || !std::is_same<creal, float>::value) return MOF_OK;
+    const int threshold = env_int("MOF_DIST_LEVEL_CELLS", 100000);
+    int P = 0;
+    while (P + 2 < mg.K && mg.lev[P].N > threshold) P++;  // (the level below the last dealt one is a stencil level: it is gathered, then replicated)
+    if (P == 0 || threshold <= 0) return MOF_OK;
+    const bool flow = mg.kind == MG_FLOW;
+    const int kind = flow ? 0 : 1, D = mg.dofs();
+    int s0, s1, r0, r1;
+    dist_range(ctx, kind, &s0, &s1, &r0, &r1);
+    // cell ranges, top down
+    mg.cellStart.assign(P + 1, std::vector<int>(world + 1, 0));
+    for (int k = 0; k <= world; k++) mg.cellStart[P][k] = (int)((long long)mg.lev[P].N * k / world);
+    for (int l = P - 1; l >= 0; l--)
+        for (int k = 0; k <= world; k++) MOF_CUDA(read_back(ctx, &mg.cellStart[l][k], mg.lev[l + 1].firstChild.p + mg.cellStart[l + 1][k]));
+    size_t most = (size_t)mg.nFine + 1;
+    for (int l = 0; l < P; l++) most = std::max(most, (size_t)mg.lev[l].N + 1);
+    MOF_CUDA(ctx->itmp0.reserve(most));
+    MOF_CUDA(ctx->itmp1.reserve(most));
+    mg.levelPart.assign(P, -1);
+    for (int l = 0; l < P; l++) {
+        MgLevel& lv = mg.lev[l];
+        const int c0 = mg.cellStart[l][rank], c1 = mg.cellStart[l][rank + 1];
+        MOF_CUDA(cudaMemsetAsync(ctx->itmp0.p, 0, sizeof(int) * ((size_t)lv.N + 1), ctx->stream));
+        if (c1 > c0) MOF_LAUNCH(k_mark_stencil_halo, blocks_for(27ll * (c1 - c0), B), B, 0, lv.nbr.p, c0, c1, ctx->itmp0.p);
+        if (l == 0 && r1 > r0) MOF_LAUNCH(k_mark_aggregate_halo, blocks_for(r1 - r0, B), B, 0, mg.agg.p, r0, r1, c0, c1, ctx->itmp0.p);
+        MOF_TRY(dist_add_partition(ctx, D, mg.cellStart[l].data(), lv.N, &mg.levelPart[l]));
+    }
+    {  // fine rows of my level-0 cells that other ranks own
+        const int c0 = mg.cellStart[0][rank], c1 = mg.cellStart[0][rank + 1];
+        int q0 = 0, q1 = 0;
+        MOF_CUDA(read_back(ctx, &q0, mg.aggPtr.p + c0));
+        MOF_CUDA(read_back(ctx, &q1, mg.aggPtr.p + c1));
+        MOF_CUDA(cudaMemsetAsync(ctx->itmp0.p, 0, sizeof(int) * ((size_t)mg.nFine + 1), ctx->stream));
+        if (q1 > q0) MOF_LAUNCH(k_mark_member_halo, blocks_for(q1 - q0, B), B, 0, mg.aggPtr.p, mg.aggList.p, c0, c1, r0, r1, ctx->itmp0.p);
+        std::vector<int> rowStart(world + 1);
+        dist_row_starts(ctx, kind, rowStart.data());  // the row blocks of this system, as dist.cu dealt them
+        MOF_TRY(dist_add_partition(ctx, mg.nrhs, rowStart.data(), mg.nFine, &mg.memberPart));
+    }
+    {  // the first replicated level: every rank computes its range of it, all ranks get all of it
+        MOF_CUDA(cudaMemsetAsync(ctx->itmp0.p, 0, sizeof(int) * ((size_t)mg.lev[P].N + 1), ctx->stream));
+        MOF_TRY(dist_add_partition(ctx, D, mg.cellStart[P].data(), mg.lev[P].N, &mg.gatherPart));
+    }
+    mg.distLevels = P;
+    drop_graphs(mg);
+    if (env_int("MOF_MG_VERBOSE", 0)) {
+        fprintf(stderr, "[mg %s] rank %d of %d: levels 1..%d dealt to the ranks;", flow ? "flow" : "scalar", rank, world, P);
+        for (int l = 0; l < P; l++)
+            fprintf(stderr, " level %d cells [%d, %d) of %d, halo %lld;", l + 1, mg.cellStart[l][rank], mg.cellStart[l][rank + 1], mg.lev[l].N, dist_partition_halo(ctx, mg.levelPart[l]));
+        fprintf(stderr, " fine rows of my aggregates elsewhere: %lld\n", dist_partition_halo(ctx, mg.memberPart));
+    }
+    return MOF_OK;
+}
+
+// One visit of dealt level l (see coarse_cycle for the replicated form): lev[l].r and the pre-smoothed lev[l].z are valid on the own
+// cells; so is lev[l].z afterwards.
+int coarse_cycle_dist(mof_ctx* ctx, Multigrid& mg, int l) {
+    if (l >= mg.distLevels) return coarse_cycle(ctx, mg, l);
+    const bool flow = mg.kind == MG_FLOW;
+    const int rank = dist_rank(ctx);
+    MgLevel& lv = mg.lev[l];
+    MgLevel& up = mg.lev[l + 1];
+    const int c0 = mg.cellStart[l][rank], c1 = mg.cellStart[l][rank + 1], nc = c1 - c0;
+    const int u0 = mg.cellStart[l + 1][rank], u1 = mg.cellStart[l + 1][rank + 1], nu = u1 - u0;
+    auto apply = [&](int mode, creal* out) -> int {
+        if (nc <= 0) return MOF_OK;
+        if (flow) MOF_LAUNCH((k_coarse_apply<9, 3, 3>), blocks_for(nc, 32), 9 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, mg.om(1 + l), lv.N, mode, out, (const int*)nullptr,
+                             (const creal*)nullptr, c0, c1);
+        else MOF_LAUNCH((k_coarse_apply<1, 6, 3>), blocks_for(nc, 32), 9 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, mg.om(1 + l), lv.N, mode, out, (const int*)nullptr,
+                        (const creal*)nullptr, c0, c1);
+        return MOF_OK;
+    };
+    auto prolong = [&]() -> int {  // z += P zc on the own cells (their parents are own cells of the next level, or the next level is complete)
+        if (nc <= 0) return MOF_OK;
+        if (flow) MOF_LAUNCH(k_prolong_coarse<3>, blocks_for(3ll * nc, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p, c0, c1);
+        else MOF_LAUNCH(k_prolong_coarse<6>, blocks_for(6ll * nc, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p, c0, c1);
+        return MOF_OK;
+    };
+    const int passes = cycle_passes(mg, l);
+    for (int g = 0; g < passes; g++) {
+        MOF_TRY(dist_halo_part_f32(ctx, mg.levelPart[l], (float*)lv.z.p));
+        MOF_TRY(apply(1, lv.t.p));
+        if (nu > 0) {
+            if (flow) MOF_LAUNCH((k_restrict_coarse<9, 3>), blocks_for(nu, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, mg.om(2 + l), up.r.p, up.z.p, u0, u1);
+            else MOF_LAUNCH((k_restrict_coarse<1, 6>), blocks_for(nu, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, mg.om(2 + l), up.r.p, up.z.p, u0, u1);
+        }
+        if (l + 1 == mg.distLevels) {
+            float* both[2] = {(float*)up.r.p, (float*)up.z.p};
+            MOF_TRY(dist_allgather_part_f32(ctx, mg.gatherPart, both, 2));
+        }
+        MOF_TRY(coarse_cycle_dist(ctx, mg, l + 1));
+        if (g + 1 < passes) MOF_TRY(prolong());
+    }
+    MOF_TRY(prolong());
+    MOF_TRY(dist_halo_part_f32(ctx, mg.levelPart[l], (float*)lv.z.p));
+    MOF_TRY(apply(2, lv.t.p));
+    std::swap(lv.z.p, lv.t.p);
+    return MOF_OK;
+}
+
 // The multigrid-PCG of either hierarchy with the fine level row-partitioned over the ranks. Every rank runs this with
 // the same b (and the same initial x unless zeroGuess); vectors are full length, a rank computes the rows [r0, r1) of
 // each (FLOW: = slices [s0, s1); SCALAR: six values per row). Per iteration: three halo exchanges (p in fp64, the
@@ -2572,6 +2711,22 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
         if (!presmoothed && len) MOF_LAUNCH(k_fine_presmooth<creal>, blocks_for(len, B), B, 0, r + e0, mg.fdinv.p + r0, mg.om(0), len, W, mg.fz.p + e0);
         MOF_TRY(dist_halo(ctx, kind, mg.fz.p));
         MOF_TRY(spmv((const creal*)mg.fval.p, r, mg.om(0), (const creal*)mg.fz.p, mg.ft.p, 1, NO_FOLD));
+        if (mg.distLevels > 0) {
+            // level 1 is dealt to the ranks: a rank restricts ALL the rows of its own cells (those that other ranks own arrive by an
+            // exchange of the residual), which is also the level's first sweep — no all-reduce over the level
+            const int c0 = mg.cellStart[0][dist_rank(ctx)], c1 = mg.cellStart[0][dist_rank(ctx) + 1];
+            MOF_TRY(dist_halo_part_f32(ctx, mg.memberPart, (float*)mg.ft.p));
+            if (c1 > c0) {
+                if (flow)
+                    MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * (c1 - c0), B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0,
+                               mg.nFine, c0, c1);
+                else
+                    MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * (c1 - c0), B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine,
+                               c0, c1);
+            }
+            MOF_TRY(coarse_cycle_dist(ctx, mg, 0));
+            MOF_TRY(dist_halo_part_f32(ctx, mg.levelPart[0], (float*)l1.z.p));  // the cells of my rows' aggregates that other ranks own
+        } else {
         if (flow)
             MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, r0, r1);
         else
@@ -2584,6 +2739,7 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
             else MOF_LAUNCH(k_dense_restrict_apply<6>, DENSE_CTAS, B, 0, (const int*)nullptr, l1.r.p, mg.cinv.p, l1.N, l1.z.p);
         }
         MOF_TRY(coarse_cycle(ctx, mg, 0));
+        }
         if (rows) {
             if (flow) MOF_LAUNCH(k_prolong_flow, blocks_for(rows, B), B, 0, mg.agg.p + r0, mg.cevec.p + 3 * (size_t)r0, l1.z.p, rows, mg.fz.p + e0);
             else MOF_LAUNCH(k_prolong_scalar, blocks_for(len, B), B, 0, mg.agg.p + r0, l1.z.p, rows, mg.fz.p + e0);
@@ -2698,6 +2854,17 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
 }
 
 }  // namespace
+
+int mg_dist_setup(mof_ctx* ctx) {
+    if (!dist_active(ctx) || dist_world(ctx) < 2) {
+        if (ctx->mg) ctx->mg->distLevels = 0;
+        if (ctx->mgs) ctx->mgs->distLevels = 0;
+        return MOF_OK;
+    }
+    if (ctx->mg) MOF_TRY(mg_dist_setup_one(ctx, *ctx->mg));
+    if (ctx->mgs) MOF_TRY(mg_dist_setup_one(ctx, *ctx->mgs));
+    return MOF_OK;
+}
 
 // FLOW: coarse operators of the current wA, then the solve wA x = fb into fx.
 int mg_flow_update(mof_ctx* ctx) {

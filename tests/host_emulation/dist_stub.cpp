@@ -17,4 +17,11 @@ int dist_halo_f32(mof_ctx*, int, float*) { return MOF_OK; }
 int dist_allreduce_f64(mof_ctx*, double*, int) { return MOF_OK; }
 int dist_allreduce_f32(mof_ctx*, float*, int) { return MOF_OK; }
 int dist_allgather_rows(mof_ctx*, int, double*) { return MOF_OK; }
+int dist_add_partition(mof_ctx*, int, const int*, int, int* id) { *id = 0; return MOF_OK; }
+void dist_clear_partitions(mof_ctx*) {}
+long long dist_partition_halo(const mof_ctx*, int) { return 0; }
+int dist_halo_part_f32(mof_ctx*, int, float*) { return MOF_OK; }
+int dist_allgather_part_f32(mof_ctx*, int, float* const*, int) { return MOF_OK; }
+int dist_rank(const mof_ctx*) { return 0; }
+void dist_row_starts(const mof_ctx*, int, int* out) { out[0] = out[1] = 0; }
 }  // namespace mof
