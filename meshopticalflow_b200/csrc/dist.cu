@@ -37,6 +37,28 @@ struct DistState {
     Partition part[2];
     std::vector<Partition*> extra;          // further partitions made by the solvers (multigrid levels dealt in cell ranges): dist_add_partition
     DBuf<double> sendBuf, recvBuf;          // sized for the widest exchange in fp64, reused for fp32
+    // MOF_DIST_TRACE=1 (with MOF_DIST_GRAPH=0): device time and count per kind of exchange, printed by rank 0 when the context closes
+    bool trace = false;
+    double traceMs[4] = {0, 0, 0, 0};
+    long long traceN[4] = {0, 0, 0, 0};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+enum { TR_HALO = 0, TR_ALLREDUCE = 1, TR_ALLGATHER = 2, TR_HALO_BYTES = 3 };
+struct TraceScope {
+    mof_ctx* ctx;
+    DistState& d;
+    int cat;
+    TraceScope(mof_ctx* c, int category) : ctx(c), d(*c->dist), cat(category) {
+        if (d.trace) cudaEventRecord(d.t0, ctx->stream);
+    }
+    ~TraceScope() {
+        if (!d.trace) return;
+        cudaEventRecord(d.t1, ctx->stream);
+        cudaEventSynchronize(d.t1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, d.t0, d.t1);
+        d.traceMs[cat] += ms, d.traceN[cat]++;
+    }
 };
 
 namespace {
@@ -94,6 +116,8 @@ template <class T>
 int halo_exchange(mof_ctx* ctx, Partition& p, T* vec, ncclDataType_t type) {
     DistState& d = *ctx->dist;
     if (d.world == 1) return MOF_OK;
+    TraceScope ts(ctx, TR_HALO);
+    if (d.trace) d.traceMs[TR_HALO_BYTES] += (double)(p.nSend + p.nRecv) * p.width * sizeof(T), d.traceN[TR_HALO_BYTES]++;
     const int w = p.width;
     T* sb = (T*)d.sendBuf.p;
     T* rb = (T*)d.recvBuf.p;
@@ -185,12 +209,22 @@ int dist_init(mof_ctx* ctx, int world, int rank, const unsigned char* id128) {
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     MOF_NCCL(ncclCommInitRank(&d.comm, world, id, rank));
+    const char* tr = getenv("MOF_DIST_TRACE");
+    d.trace = tr && *tr && *tr != '0';
+    if (d.trace) cudaEventCreate(&d.t0), cudaEventCreate(&d.t1);
     return MOF_OK;
 }
 
 void dist_destroy(mof_ctx* ctx) {
     if (!ctx->dist) return;
     DistState& d = *ctx->dist;
+    if (d.trace && d.rank == 0)
+        fprintf(stderr, "[dist trace] halo exchanges %lld: %.1f ms (%.1f us each, %.0f bytes each way on average); all-reduces %lld: %.1f ms (%.1f us each); gathers %lld: %.1f ms (%.1f us each)\n",
+                d.traceN[TR_HALO], d.traceMs[TR_HALO], 1e3 * d.traceMs[TR_HALO] / std::max(1ll, d.traceN[TR_HALO]),
+                d.traceMs[TR_HALO_BYTES] / std::max(1ll, d.traceN[TR_HALO_BYTES]) / 2, d.traceN[TR_ALLREDUCE], d.traceMs[TR_ALLREDUCE],
+                1e3 * d.traceMs[TR_ALLREDUCE] / std::max(1ll, d.traceN[TR_ALLREDUCE]), d.traceN[TR_ALLGATHER], d.traceMs[TR_ALLGATHER],
+                1e3 * d.traceMs[TR_ALLGATHER] / std::max(1ll, d.traceN[TR_ALLGATHER]));
+    if (d.t0) cudaEventDestroy(d.t0), cudaEventDestroy(d.t1);
     for (Partition& p : d.part) p.sendIdx.release(), p.recvIdx.release();
     dist_clear_partitions(ctx);
     d.sendBuf.release(), d.recvBuf.release();
@@ -289,6 +323,7 @@ int dist_allgather_part_f32(mof_ctx* ctx, int id, float* const* vecs, int count)
     DistState& d = *ctx->dist;
     if (d.world == 1) return MOF_OK;
     const Partition& p = *d.extra[id];
+    TraceScope ts(ctx, TR_ALLGATHER);
     MOF_NCCL(ncclGroupStart());
     for (int v = 0; v < count; v++)
         for (int k = 0; k < d.world; k++) {
@@ -308,12 +343,14 @@ void dist_row_starts(const mof_ctx* ctx, int kind, int* out) {
 int dist_allreduce_f64(mof_ctx* ctx, double* v, int count) {
     DistState& d = *ctx->dist;
     if (d.world == 1) return MOF_OK;
+    TraceScope ts(ctx, TR_ALLREDUCE);
     MOF_NCCL(ncclAllReduce(v, v, (size_t)count, ncclDouble, ncclSum, d.comm, ctx->stream));
     return MOF_OK;
 }
 int dist_allreduce_f32(mof_ctx* ctx, float* v, int count) {
     DistState& d = *ctx->dist;
     if (d.world == 1) return MOF_OK;
+    TraceScope ts(ctx, TR_ALLREDUCE);
     MOF_NCCL(ncclAllReduce(v, v, (size_t)count, ncclFloat, ncclSum, d.comm, ctx->stream));
     return MOF_OK;
 }

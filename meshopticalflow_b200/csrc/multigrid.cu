@@ -2571,7 +2571,9 @@ int mg_dist_setup_one(mof_ctx* ctx, Multigrid& mg) {
     mg.distLevels = 0, mg.cellStart.clear(), mg.levelPart.clear(), mg.memberPart = mg.gatherPart = -1;
     const int world = dist_world(ctx), rank = dist_rank(ctx);
     if (!mg.usable || !std::is_same<creal, float>::value) return MOF_OK;
-    const int threshold = env_int("MOF_DIST_LEVEL_CELLS", 100000);
+    // (the smoothing systems' levels stay replicated by default: on 8 B200s at 16.8M vertices dealing them cost 709 ms against 644 ms
+    //  replicated — their cycle has one W level less and their exchanges are six values wide; profiles/r2o_partitioned_16M_8gpu.json)
+    const int threshold = mg.kind == MG_FLOW ? env_int("MOF_DIST_LEVEL_CELLS", 100000) : env_int("MOF_DIST_LEVEL_CELLS_SCALAR", 0);
     int P = 0;
     while (P + 2 < mg.K && mg.lev[P].N > threshold) P++;  // (the level below the last dealt one is a stencil level: it is gathered, then replicated)
     if (P == 0 || threshold <= 0) return MOF_OK;

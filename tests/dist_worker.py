@@ -43,11 +43,20 @@ def main():
     uid = sharding.broadcast_bytes(uid, 128, 0, dev)
     al = api.Aligner(local_rank)
     al.dist_init(world, rank, uid)
+    extra = {}
+    if len(sys.argv) > 3 and sys.argv[3] == "ab":  # also with every coarse level replicated (the round-1 scheme), same process, same mesh
+        os.environ["MOF_DIST_LEVEL_CELLS"] = "2000000000"
+        run(al, v, t, a, b, iterations)
+        _, s_r, wall_r = run(al, v, t, a, b, iterations)
+        extra = {"replicated_coarse_levels": {"flow_solve_ms": sharding.max_over_ranks(s_r["flowSolveMs"], dev), "smooth_solve_ms": sharding.max_over_ranks(s_r["smoothSolveMs"], dev),
+                                              "wall_s": sharding.max_over_ranks(wall_r, dev), "flow_iterations": s_r["flowCgIterations"]}}
+        os.environ.pop("MOF_DIST_LEVEL_CELLS")
     flow_d, s_d, wall_d = run(al, v, t, a, b, iterations)
     flow_d2, s_d2, wall_d2 = run(al, v, t, a, b, iterations)  # steady state (pool warm)
     col_a, col_b = al.advect_vertices(0.5)
     al.close()
 
+    os.environ["MOF_SMOOTH_AHEAD"] = "0"  # one stream on both sides of the comparison (the partitioned path has one)
     single = api.Aligner(local_rank)
     run(single, v, t, a, b, iterations)
     flow_s, s_s, wall_s = run(single, v, t, a, b, iterations)
@@ -68,7 +77,8 @@ def main():
             "smooth_solve_ms_partitioned": s_d2["smoothSolveMs"], "smooth_solve_ms_single_gpu": s_s["smoothSolveMs"],
             "smooth_iterations_partitioned": s_d2["smoothCgIterations"], "smooth_iterations_single_gpu": s_s["smoothCgIterations"],
             "last_smooth_residual": s_d2["lastSmoothResidual"],
-            "last_flow_residual": s_d2["lastFlowResidual"], "wall_s_partitioned": wall_d2, "wall_s_single_gpu": wall_s}
+            "last_flow_residual": s_d2["lastFlowResidual"], "wall_s_partitioned": sharding.max_over_ranks(wall_d2, dev), "wall_s_single_gpu": wall_s}
+    line.update(extra)
     sharding.barrier()
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -117,6 +117,7 @@ def test_coarse_levels_dealt_to_the_ranks(emulated, world, threshold, monkeypatc
     single = _align(emulated, v, t, a, b, 1)
     assert "error" not in single, single
     monkeypatch.setenv("MOF_DIST_LEVEL_CELLS", str(threshold))
+    monkeypatch.setenv("MOF_DIST_LEVEL_CELLS_SCALAR", str(threshold))  # (replicated by default)
     out = _run_world(emulated, world, v, t, a, b, 1)
     for r, res in enumerate(out):
         assert rel(res["flow"], single["flow"]) < 1e-6, (world, r)
@@ -128,6 +129,7 @@ def test_coarse_levels_dealt_to_the_ranks(emulated, world, threshold, monkeypatc
     # fewer launches per rank than with replicated coarse levels would not show here (same kernels on fewer cells); what shows is
     # that the level-1 all-reduce is gone: the exchanged halo of the flow system's level partitions is not empty
     monkeypatch.setenv("MOF_DIST_LEVEL_CELLS", "100000000")
+    monkeypatch.setenv("MOF_DIST_LEVEL_CELLS_SCALAR", "0")
     replicated = _run_world(emulated, world, v, t, a, b, 1)
     assert rel(replicated[0]["flow"], out[0]["flow"]) < 1e-9
     assert replicated[0]["stats"]["flowCgIterations"] == its[0]
