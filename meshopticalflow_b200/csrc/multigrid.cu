@@ -103,6 +103,7 @@ struct Multigrid {
     // Damping factors as the kernels read them (device): [0] fine level, [1 + l] coarse level l, two constants. By pointer
     // rather than by value so that a captured PCG graph stays valid when the next system changes them.
     DBuf<double> domega;
+    DBuf<double> chebD, chebR, chebC;  // SCALAR: vectors of mg_scalar_cheb
     DBuf<creal> eig;                // power-iteration iterates of the last system: fine level, then the coarse levels
     bool eigValid = false;
     const double* om(int slot) const { return domega.p + slot; }
@@ -1505,7 +1506,7 @@ void release_mg(Multigrid* mg) {
     }
     mg->evec.release(), mg->cevec.release(), mg->agg.release(), mg->aggPtr.release(), mg->aggList.release(), mg->slotOf.release(), mg->cinv.release();
     mg->fval.release(), mg->fdinv.release(), mg->fvalSell.release();
-    mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release(), mg->counter.release(), mg->domega.release(), mg->eig.release();
+    mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release(), mg->counter.release(), mg->domega.release(), mg->eig.release(), mg->chebD.release(), mg->chebR.release(), mg->chebC.release();
     delete mg;
 }
 
@@ -2907,6 +2908,103 @@ int mg_scalar_cycle(mof_ctx* ctx, const double* r6, double* z6) {
     MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 1, z6);
     return MOF_OK;
 }
+// d = alpha d + beta c ; z += d (one step of the Chebyshev recurrence below)
+__global__ void k_cheb_update(double alpha, double beta, const double* __restrict__ c, long long n, double* __restrict__ d, double* __restrict__ z, int first) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double dn = first ? beta * c[i] : alpha * d[i] + beta * c[i];
+    d[i] = dn;
+    z[i] = first ? dn : z[i] + dn;
+}
+// A sharper approximate inverse of the current sSys than one cycle: `degree` steps of the Chebyshev iteration for sSys Z = R
+// preconditioned by the cycle C (degree 1 = one cycle, scaled). The eigenvalues of C sSys lie in (0, 1] for a symmetric cycle
+// with convergent smoothers (its error propagator is sSys-self-adjoint and non-negative); [lo, 1.05] is what the polynomial is
+// built for — below lo it merely reduces less. Fixed coefficients, no inner products: the result is a FIXED symmetric positive
+// definite operator applied to R, so plain PCG may use it as (part of) a preconditioner. Used by the Conformal basis, whose
+// bi-Laplacian preconditioner squares the inverse's error (vector_fields.cu).
+int mg_scalar_cheb(mof_ctx* ctx, const double* r6, double* z6, int degree, double lo) {
+    Multigrid& mg = *ctx->mgs;
+    const long long len = (long long)mg.fineLen();
+    if (degree <= 1) return mg_scalar_cycle(ctx, r6, z6);
+    degree = std::min(degree, 32);
+    MOF_CUDA(mg.chebD.reserve((size_t)len));
+    MOF_CUDA(mg.chebR.reserve((size_t)len));
+    MOF_CUDA(mg.chebC.reserve((size_t)len));
+    const double hi = 1.05, theta = 0.5 * (hi + lo), delta = 0.5 * (hi - lo), sigma1 = theta / delta;
+    double rho = 1. / sigma1;
+    MOF_TRY(mg_scalar_cycle(ctx, r6, mg.chebC.p));
+    MOF_LAUNCH(k_cheb_update, blocks_for(len, B), B, 0, 0., 1. / theta, mg.chebC.p, len, mg.chebD.p, z6, 1);
+    for (int k = 1; k < degree; k++) {
+        MOF_TRY(fine_residual(ctx, mg, r6, z6, mg.chebR.p));
+        MOF_TRY(mg_scalar_cycle(ctx, mg.chebR.p, mg.chebC.p));
+        const double rhoNew = 1. / (2. * sigma1 - rho);
+        MOF_LAUNCH(k_cheb_update, blocks_for(len, B), B, 0, rhoNew * rho, 2. * rhoNew / delta, mg.chebC.p, len, mg.chebD.p, z6, 0);
+        rho = rhoNew;
+    }
+    return MOF_OK;
+}
+
+// How good an inverse of the current sSys one cycle C is: the smallest eigenvalue of C sSys (the largest is <= 1 for a symmetric cycle
+// with convergent smoothers), from the Lanczos tridiagonal that `steps` iterations of cycle-preconditioned CG on a pseudo-random
+// right-hand side carry in their alpha / beta (diagonal 1/alpha_j + beta_{j-1}/alpha_{j-1}, off-diagonal sqrt(beta_j)/alpha_j): its
+// smallest Ritz value approaches the smallest eigenvalue from above, and — unlike a power iteration on I - C sSys, which returned 0.917
+// for a cycle that really contracts by 0.99 at 1M vertices — does so quickly at the ends of the spectrum.
+__global__ void k_pseudo_random_f64(long long n, double* __restrict__ v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned h = (unsigned)i * 2654435761u + 12345u;
+    h ^= h >> 15, h *= 2246822519u, h ^= h >> 13;
+    v[i] = (double)(h & 0xffff) / 32768. - 1.;
+}
+int mg_scalar_smallest_eigenvalue(mof_ctx* ctx, int steps, double* lambdaMin) {
+    Multigrid& mg = *ctx->mgs;
+    const long long len = (long long)mg.fineLen();
+    MOF_CUDA(mg.chebD.reserve((size_t)len));
+    double* x = mg.chebD.p;  // (the iterate itself is of no interest)
+    double* r = mg.fr.p;
+    double* p = mg.fp.p;
+    double* q = mg.fq.p;
+    MOF_LAUNCH(k_pseudo_random_f64, blocks_for(len, B), B, 0, len, r);
+    MOF_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * len, ctx->stream));
+    MOF_TRY(fine_cycle(ctx, mg, r, false, S_RZ));
+    MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 1, p);
+    std::vector<double> alpha, beta;
+    for (int it = 0; it < steps; it++) {
+        MOF_TRY(apply_dot(ctx, mg, p, q));
+        MOF_LAUNCH(k_update_xr, NBLK, B, 0, p, q, len, x, r, mg.fdinv.p, mg.om(0), mg.nrhs, mg.fz.p, fold_into(mg, S_RR));
+        MOF_TRY(fold_after(ctx, mg, NBLK, S_RR));
+        MOF_TRY(fine_cycle(ctx, mg, r, true, S_RZNEW));
+        MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 0, p);
+        double ab[2] = {0, 0};
+        MOF_CUDA(read_back(ctx, ab, mg.scal.p + S_ALPHA, 2));  // S_ALPHA, S_BETA are adjacent
+        if (!(ab[0] > 0) || !(ab[1] >= 0) || !std::isfinite(ab[0]) || !std::isfinite(ab[1])) break;
+        alpha.push_back(ab[0]), beta.push_back(ab[1]);
+    }
+    const int m = (int)alpha.size();
+    if (m < 2) { *lambdaMin = 0.1; return MOF_OK; }
+    std::vector<double> d(m), e(m, 0.);
+    for (int j = 0; j < m; j++) {
+        d[j] = 1. / alpha[j] + (j ? beta[j - 1] / alpha[j - 1] : 0.);
+        if (j + 1 < m) e[j] = std::sqrt(beta[j]) / alpha[j];
+    }
+    // smallest eigenvalue of the tridiagonal (d, e) by bisection on the Sturm count
+    double lo = 0., hi = d[0];
+    for (int j = 0; j < m; j++) hi = std::min(hi, d[j]);  // the smallest diagonal entry bounds the smallest eigenvalue from above
+    for (int round = 0; round < 60; round++) {
+        const double mid = 0.5 * (lo + hi);
+        int below = 0;
+        double piv = d[0] - mid;
+        if (piv < 0) below++;
+        for (int j = 1; j < m; j++) {
+            piv = d[j] - mid - e[j - 1] * e[j - 1] / (piv != 0 ? piv : 1e-300);
+            if (piv < 0) below++;
+        }
+        if (below >= 1) hi = mid; else lo = mid;
+    }
+    *lambdaMin = hi;
+    return MOF_OK;
+}
+
 // mof_time_kernel: one kernel of a PCG iteration, launched `reps` times on its own with the solver's grid on the solver's own
 // buffers (scratch: fr, fp, fq, fz, ft are re-initialised by every solve). *bytes = the algorithmic bytes of one launch.
 int mg_time_kernel(mof_ctx* ctx, int which, int reps, float* ms, double* bytes) {

@@ -47,6 +47,8 @@ struct VfState {
     bool mgPrec = false;             // the scalar hierarchy is there and MOF_CONFORMAL_MG != 0
     bool mgNow = false;              // ... and set up for the system being solved
     double stiffTrace = 0, kappa = 1;
+    int chebDegree = 3;            // Chebyshev steps around the cycle per approximate inverse of the two-cycle preconditioner, and the
+    double chebLo = 0.12;          // lower end of the interval the polynomial is built for (per system, vf_update_flow)
     DBuf<double> r6, z6;             // [V][6]
     void release() {
         DBuf<double>* all[] = {&connDiag, &connOff, &minv, &blk, &w, &u, &binv, &b, &x, &r, &z, &p, &q, &partial, &sc, &r6, &z6};
@@ -135,11 +137,21 @@ static int vf_dot(mof_ctx* ctx, const double* a, const double* b, long long n, d
 static int vf_two_cycle_preconditioner(mof_ctx* ctx, double* rz) {
     VfState& s = *ctx->vf;
     const int V = ctx->V;
+    // each inverse: MOF_CONFORMAL_CHEB (default 3) Chebyshev steps around the cycle — the preconditioner squares the inverse's error, and
+    // one unsmoothed-aggregation cycle of a nearly pure Laplacian (eps grows with refinement) is a rough inverse: 875 outer
+    // iterations at 65 538 vertices with one cycle per inverse, no finish at 1M (profiles/r1e_modes_1M.txt)
+    // (degree and lower bound are chosen per system from the cycle's measured contraction: vf_update_flow)
     MOF_LAUNCH(k_conformal_pack, blocks_for(V, B), B, 0, s.r.p, V, s.r6.p);
-    MOF_TRY(mg_scalar_cycle(ctx, s.r6.p, s.z6.p));
+    MOF_TRY(mg_scalar_cheb(ctx, s.r6.p, s.z6.p, s.chebDegree, s.chebLo));
     MOF_LAUNCH(k_conformal_weight, blocks_for(V, B), B, 0, s.z6.p, ctx->m0.p, V, s.r6.p);
-    MOF_TRY(mg_scalar_cycle(ctx, s.r6.p, s.z6.p));
+    MOF_TRY(mg_scalar_cheb(ctx, s.r6.p, s.z6.p, s.chebDegree, s.chebLo));
     MOF_LAUNCH(k_conformal_unpack, blocks_for(V, B), B, 0, s.z6.p, s.kappa, V, s.z.p);
+    // The operator annihilates the constants of either potential, and this preconditioner amplifies them by (eps K / M)^2 relative to
+    // everything else — 1e10 at 1M vertices, enough for the rounding of the fp32 cycles to take the iteration over (no convergence in
+    // 1 800 iterations): keep z in the complement (an orthogonal projector after a symmetric operator: still symmetric, PCG applies).
+    MOF_TRY(reduce_sum(ctx, s.z.p, V, ctx->scalars.p + SC_TMP));
+    MOF_TRY(reduce_sum(ctx, s.z.p + V, V, ctx->scalars.p + SC_TMP + 1));
+    MOF_LAUNCH(k_conformal_remove_means, blocks_for(V, B), B, 0, ctx->scalars.p + SC_TMP, V, s.z.p);
     MOF_LAUNCH(k_dot_partial, RED, B, 0, s.r.p, s.z.p, s.N, rz);
     return MOF_OK;
 }
@@ -160,7 +172,7 @@ static int vf_pcg(mof_ctx* ctx, double weight, double tol, int maxIters, int* it
     *itersOut = 0, *relresOut = 0;
     if (!(bb > 0)) return MOF_OK;  // zero right-hand side: x = 0
     int iters = 0;
-    double relres = 1;
+    double relres = 1, previous = 1;
     for (int restart = 0; restart < 8; restart++) {
         int cur = 0;
         double* rzrr = s.partial.p + RED;
@@ -181,6 +193,8 @@ static int vf_pcg(mof_ctx* ctx, double weight, double tol, int maxIters, int* it
             MOF_CUDA(read_back(ctx, &rr, sc + S_RR));
             if (!(rr == rr)) return fail(ctx, MOF_E_NOCONVERGE, "flow PCG (matrix-free) produced a NaN residual");
             converged = rr <= tol * tol * bb;
+            static const bool verbose = getenv("MOF_VF_VERBOSE") && *getenv("MOF_VF_VERBOSE") != '0';
+            if (verbose && (iters % 50 == 0 || converged)) fprintf(stderr, "[vf pcg] %d iterations, recurrence residual %.3e\n", iters, sqrt(rr / bb));
         }
         // true residual
         MOF_TRY(vf_apply(ctx, weight, s.x.p, s.q.p));
@@ -189,10 +203,25 @@ static int vf_pcg(mof_ctx* ctx, double weight, double tol, int maxIters, int* it
         double rr = 0;
         MOF_CUDA(read_back(ctx, &rr, sc + S_RR));
         relres = sqrt(rr / bb);
+        {
+            static const bool verbose = getenv("MOF_VF_VERBOSE") && *getenv("MOF_VF_VERBOSE") != '0';
+            if (verbose) fprintf(stderr, "[vf pcg] %d iterations, TRUE residual %.3e (restart %d)\n", iters, relres, restart);
+        }
         if (relres <= tol || iters >= maxIters) break;
+        // The true residual has a floor: the operator itself (K M^-1 K, entries ~ h^-4) is evaluated with a rounding error of ~2e-8 |b| at
+        // 1M vertices, and a restart that gains less than a factor 2 has reached it. Below MOF_ACCEPT_RELRES that is an accepted
+        // solve, counted in mof_stats.solvesAboveTolerance like a stagnated solve of the other bases.
+        if (restart > 0 && relres > 0.5 * previous && relres <= MOF_ACCEPT_RELRES) break;
+        previous = relres;
     }
     *itersOut = iters, *relresOut = relres;
-    if (!(relres <= tol)) return fail(ctx, MOF_E_NOCONVERGE, "flow PCG (matrix-free) hit its iteration cap");
+    if (!(relres <= tol)) {
+        if (iters < maxIters && relres <= MOF_ACCEPT_RELRES) {
+            ctx->stats.solvesAboveTolerance++;
+            return MOF_OK;
+        }
+        return fail(ctx, MOF_E_NOCONVERGE, "flow PCG (matrix-free) hit its iteration cap");
+    }
     return MOF_OK;
 }
 
@@ -236,11 +265,41 @@ int vf_update_flow(mof_ctx* ctx, double vfWeight) {
             MOF_TRY(scalar_system_set(ctx, eps));
             s.kappa = 2. * eps * eps / vfWeight;
             s.mgNow = mg_scalar_usable(ctx);
+            if (s.mgNow) {
+                // How sharp an inverse one cycle is on THIS system (eps — the weight of the Laplacian — grows with refinement, and an
+                // unsmoothed-aggregation cycle of a nearly pure Laplacian contracts by 0.8-0.95 only), and from it the Chebyshev
+                // polynomial around the cycle: the lower spectral bound from a short Lanczos run with a margin (a Ritz value approaches
+                // it from above), the degree from the Chebyshev bound. MOF_CONFORMAL_CHEB /
+                // MOF_CONFORMAL_CHEB_MIN fix them instead.
+                const char* eDeg = getenv("MOF_CONFORMAL_CHEB");
+                const char* eLo = getenv("MOF_CONFORMAL_CHEB_MIN");
+                double lambdaMin = 0.1;
+                if (!(eDeg && *eDeg && eLo && *eLo)) MOF_TRY(mg_scalar_smallest_eigenvalue(ctx, 50, &lambdaMin));
+                const double rho = std::min(0.9999, std::max(0.3, 1. - lambdaMin));
+                s.chebLo = eLo && *eLo ? atof(eLo) : std::max(1e-4, 0.8 * (1. - rho));
+                // the degree that minimises (cycles per inverse) x (outer iterations ~ (1 + f) / (1 - f), f = the polynomial's error bound)
+                const double kap = 1.05 / s.chebLo, q = (std::sqrt(kap) - 1.) / (std::sqrt(kap) + 1.);
+                int degree = 2;
+                double best = 1e300;
+                for (int k = 2; k <= 32; k++) {
+                    const double f = 2. * std::pow(q, k) / (1. + std::pow(q, 2 * k)), cost = k * (1. + f) / (1. - f);
+                    if (cost < best) best = cost, degree = k;
+                }
+                s.chebDegree = eDeg && *eDeg ? std::max(1, std::min(32, atoi(eDeg))) : degree;
+                if (getenv("MOF_MG_VERBOSE") && *getenv("MOF_MG_VERBOSE") != '0')
+                    fprintf(stderr, "[conformal] eps %.3g: one cycle contracts by %.3f; Chebyshev degree %d over [%.3f, 1.05]\n", eps, rho, s.chebDegree, s.chebLo);
+            }
         }
     }
     int rc = MOF_E_NOCONVERGE, mgIters = 0;
     if (s.mgNow) {
-        rc = vf_pcg(ctx, vfWeight, ctx->params.flowTol, std::min(ctx->params.maxCgIterations, 3000), &mgIters, &relres);
+        // a solve that is not done within 600 iterations had too optimistic an interval: widen it (more Chebyshev steps per inverse) and go on
+        for (int attempt = 0; attempt < 3 && rc == MOF_E_NOCONVERGE; attempt++) {
+            int its = 0;
+            rc = vf_pcg(ctx, vfWeight, ctx->params.flowTol, std::min(ctx->params.maxCgIterations, 600), &its, &relres);
+            mgIters += its;
+            if (rc == MOF_E_NOCONVERGE) s.chebLo *= 0.4, s.chebDegree = std::min(32, s.chebDegree * 3 / 2 + 1);
+        }
         s.mgNow = false;
     }
     // no hierarchy — or a stalled solve, which is not an error: block Jacobi always converges

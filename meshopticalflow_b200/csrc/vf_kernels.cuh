@@ -401,6 +401,12 @@ __global__ void k_conformal_unpack(const double* __restrict__ z6, double kappa, 
     if (v >= V) return;
     z[v] = kappa * z6[6 * (size_t)v], z[v + V] = kappa * z6[6 * (size_t)v + 1];
 }
+// z -= mean(z) on each half: the projector onto the complement of the operator's null space (the constants of either potential)
+__global__ void k_conformal_remove_means(const double* __restrict__ sums, int V, double* __restrict__ z) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    z[v] -= sums[0] / V, z[v + V] -= sums[1] / V;
+}
 // the diagonal of the stiffness matrix / the trace of a vertex's diagonal block of P^T D P (to balance eps)
 __global__ void k_stiffness_diagonal(const int* __restrict__ rowptr, const int* __restrict__ he, const double* __restrict__ stiff, int V, double* __restrict__ out) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
