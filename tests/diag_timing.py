@@ -14,10 +14,17 @@ def main():
     level = int(sys.argv[1]) if len(sys.argv) > 1 else 7
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     t0 = time.time()
-    v, t = synthetic.octahedron_sphere(level)
+    numbering = os.environ.get("MOF_SYNTH_NUMBERING", "morton")  # morton | subdivision (the generator's own order) | random
+    v, t = synthetic.octahedron_sphere(level, spatial_sort=numbering == "morton")
+    if numbering == "random":
+        rng = np.random.default_rng(1)
+        order = rng.permutation(v.shape[0])
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        v, t = np.ascontiguousarray(v[order]), np.ascontiguousarray(rank[t][rng.permutation(t.shape[0])].astype(np.int32))
     ca, cb = synthetic.smooth_rgb_pair(v, 0)
     ca, cb = ca.astype(np.float64), cb.astype(np.float64)
-    print(f"level {level}: V={v.shape[0]} T={t.shape[0]} (generated in {time.time() - t0:.1f}s)", flush=True)
+    print(f"level {level}: V={v.shape[0]} T={t.shape[0]} numbering {numbering} (generated in {time.time() - t0:.1f}s)", flush=True)
     al = api.Aligner(0)
     vf_mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     p = api.default_params()

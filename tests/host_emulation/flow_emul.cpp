@@ -115,6 +115,8 @@ bool mg_scalar_usable(const mof_ctx*) { return false; }
 int mg_scalar_update(mof_ctx*) { return MOF_E_INVALID; }
 int mg_scalar_solve(mof_ctx*, const double*, double*, double, int, int*, double*) { return MOF_E_INVALID; }
 int mg_scalar_cycle(mof_ctx*, const double*, double*) { return MOF_E_INVALID; }
+int mg_scalar_smallest_eigenvalue(mof_ctx*, int, double*) { return MOF_E_INVALID; }
+int mg_scalar_cheb(mof_ctx*, const double*, double*, int, double) { return MOF_E_INVALID; }
 // dist.cu
 bool dist_active(const mof_ctx*) { return false; }
 
