@@ -94,6 +94,21 @@ int mof_synchronize(mof_ctx* ctx);
 int mof_set_mesh(mof_ctx* ctx, const double* xyz, int V, const int* tri, int T);
 int mof_set_mesh_device(mof_ctx* ctx, const double* d_xyz, int V, const int* d_tri, int T);
 
+/* Numbering. The reference's solver applies a fill-reducing ordering of its own inside the factorisation
+ * (Eigen::SimplicialLDLT, LinearSolvers.h:277, AMD by default), so it is indifferent to how the PLY file numbers
+ * vertices and triangles; a gather-based GPU path is not (1M vertices: 46 ms per UpdateFlow numbered along a space-filling
+ * curve, 71 ms in creation order, 83 ms shuffled). mof_set_mesh therefore renumbers a mesh of >= 65 536 vertices whose
+ * numbering is not local (mean index span of a triangle, or mean jump between consecutive triangles, above V/16) along the
+ * Morton curve of positions / centroids, and mof_set_signals, mof_get_flow and mof_advect_vertices translate at the
+ * boundary: the caller only ever sees its own numbering. mode: -1 (default) decide by that measure, 0 never, 1 always;
+ * takes effect at the next mof_set_mesh. What stays in the library's numbering: the debug taps (mof_get_csr,
+ * mof_get_array, mof_get_coeffs) - mof_get_permutation returns the two orders (new index -> caller's index; identity when
+ * nothing was renumbered). The texture-map entries (mof_set_texture_map, mof_build_texture_map) follow the caller's
+ * triangle ORDER (first-writer rule of RasterizeTriangle, MeshFlow.inl:281-337) and refuse a renumbered mesh: call
+ * mof_set_reorder(ctx, 0) first, as the command line does for --mesh. */
+int mof_set_reorder(mof_ctx* ctx, int mode);
+int mof_get_permutation(mof_ctx* ctx, int* reordered, int* vertexOrder, int* triangleOrder);
+
 /* The two signals to align, V x channels each (channels must be 3), as in flowData.signals
  * (OpticalFlow.cpp:745-751, 772-779), followed by the difference-of-Gaussians normalisation of
  * OpticalFlow.cpp:822-857 when params.dogWeight > 0. The raw values are kept for
@@ -113,6 +128,16 @@ int mof_get_flow(mof_ctx* ctx, double* tField);
 int mof_get_coeffs(mof_ctx* ctx, double* coeffs);
 int mof_num_edges(mof_ctx* ctx);
 long long mof_num_coeffs(mof_ctx* ctx);
+
+/* The reference's sibling tool `Spectrum` (Spectrum/Spectrum.cpp:184-190): the `count` lowest eigenpairs of the vector Laplacian of
+ * the basis in params.vfMode / cMode, S x = lambda M x with M = R (g area) P — ComputeSpectrum, include/Src/VectorLaplacianSpectrum.inl:5-39,
+ * which factorises S - 1e-8 M and runs ARPACK's shift-invert Lanczos (EigenvalueSolver.h:177-219). Here: LOBPCG on the operators the
+ * context already holds (csrc/spectrum.cu), no factorisation. Needs the mesh only; afterwards mof_set_signals has to be called again
+ * before an alignment. eigenvalues[count] ascending; fields[count][T][2] = the prolonged eigenvectors P x (what the tool writes to
+ * eigenvector-%03d.bin), x normalised to x^T M x = 1 like ARPACK's, sign free; inside a multiple eigenvalue only the span is defined.
+ * Converged when every pair has ||S x - lambda M x|| <= tol (||S x|| + lambda ||M x||); MOF_E_NOCONVERGE after maxIterations.
+ * count <= 25 (a block of count + max(4, count/4) <= 32 vectors). */
+int mof_spectrum(mof_ctx* ctx, int count, double tol, int maxIterations, double* eigenvalues, double* fields, int* iterations, double* residual);
 
 /* InputGeometryData::flow (OpticalFlow.cpp:482-489): the raw signals resampled along -alpha and
  * 1-alpha of the flow (ResampleSignal, :198-216). outA/outB: V x 3. */

@@ -39,7 +39,7 @@ KERNELS = {"flow_spmv": 0, "flow_fine_sweep": 1, "flow_update": 2, "flow_restric
 
 EXPORTED_SYMBOLS = [
     "mof_default_params", "mof_create", "mof_destroy", "mof_last_error", "mof_set_params", "mof_get_stats", "mof_reset_stats", "mof_synchronize",
-    "mof_set_mesh", "mof_set_mesh_device", "mof_set_signals", "mof_set_signals_device", "mof_iterate", "mof_get_flow", "mof_get_coeffs", "mof_num_edges", "mof_num_coeffs",
+    "mof_set_mesh", "mof_set_mesh_device", "mof_set_reorder", "mof_get_permutation", "mof_spectrum", "mof_set_signals", "mof_set_signals_device", "mof_iterate", "mof_get_flow", "mof_get_coeffs", "mof_num_edges", "mof_num_coeffs",
     "mof_advect_vertices", "mof_advect_vertices_device", "mof_set_texture_map", "mof_advect_texels", "mof_advect_texels_frames", "mof_csr_size", "mof_get_csr", "mof_array_bytes",
     "mof_get_array", "mof_pcg_solve_csr", "mof_time_flow_spmv", "mof_time_kernel", "mof_dist_unique_id", "mof_dist_init",
     "mof_subdivide", "mof_get_subdivision", "mof_build_texture_map", "mof_get_texture_map", "mof_sample_textures_to_vertices",
@@ -99,6 +99,9 @@ def load_library():
     lib.mof_synchronize.argtypes = [c_void_p]
     lib.mof_set_mesh.argtypes = [c_void_p, D, c_int, I, c_int]
     lib.mof_set_mesh_device.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int]
+    lib.mof_set_reorder.argtypes = [c_void_p, c_int]
+    lib.mof_get_permutation.argtypes = [c_void_p, I, I, I]
+    lib.mof_spectrum.argtypes = [c_void_p, c_int, c_double, c_int, D, D, I, D]
     lib.mof_set_signals.argtypes = [c_void_p, D, D, c_int]
     lib.mof_set_signals_device.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
     lib.mof_iterate.argtypes = [c_void_p, c_int]
@@ -195,6 +198,26 @@ class Aligner:
 
     def synchronize(self):
         self._check(self._lib.mof_synchronize(self._ctx))
+
+    # --- numbering (include/mof_b200.h: mof_set_reorder): -1 decide by the locality of the caller's numbering, 0 never, 1 always
+    def set_reorder(self, mode: int):
+        self._check(self._lib.mof_set_reorder(self._ctx, mode))
+
+    def permutation(self):
+        """(reordered, vertex order, triangle order): new index -> the caller's index (identity if nothing was renumbered)."""
+        flag = c_int(0)
+        vo, to = np.empty(self.V, dtype=np.int32), np.empty(self.T, dtype=np.int32)
+        self._check(self._lib.mof_get_permutation(self._ctx, byref(flag), _i(vo), _i(to)))
+        return bool(flag.value), vo, to
+
+    # --- the Spectrum tool (Spectrum.cpp, VectorLaplacianSpectrum.inl): lowest eigenpairs of the basis' vector Laplacian
+    def spectrum(self, count: int = 20, tol: float = 1e-8, max_iterations: int = 2000):
+        """(eigenvalues [count], fields [count, T, 2], iterations, residual)."""
+        ev = np.empty(count, dtype=np.float64)
+        fields = np.empty((count, self.T, 2), dtype=np.float64)
+        its, res = c_int(0), c_double(0)
+        self._check(self._lib.mof_spectrum(self._ctx, count, tol, max_iterations, _d(ev), _d(fields), byref(its), byref(res)))
+        return ev, fields, its.value, res.value
 
     # --- one mesh over several GPUs (no reference counterpart): call before set_mesh, on every rank
     def dist_init(self, world: int, rank: int, unique_id: bytes):

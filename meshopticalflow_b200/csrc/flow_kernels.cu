@@ -654,6 +654,34 @@ int update_flow(mof_ctx* ctx, double sWeight, double vfWeight) {
     return MOF_OK;
 }
 
+// The mass operator of the Whitney basis, M = R (g area) P (VectorLaplacianSpectrum.inl:9-19: vfMass, then restriction * vfMass * prolongation),
+// on the pattern of S and in its sliced layout: the flow assembly above with D_t = g_t area_t. Overwrites the data term of the alignment.
+__global__ void k_metric_mass(const double* __restrict__ g, const double* __restrict__ area, int T, double* __restrict__ D) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const double a = area[t];
+    D[3 * t] = g[3 * t] * a, D[3 * t + 1] = g[3 * t + 1] * a, D[3 * t + 2] = g[3 * t + 2] * a;
+}
+int metric_mass_blocks(mof_ctx* ctx) {
+    MOF_LAUNCH(k_metric_mass, blocks_for(ctx->T, B), B, 0, ctx->g.p, ctx->area.p, ctx->T, ctx->dataD.p);
+    MOF_CUDA(cudaMemsetAsync(ctx->dataRhs.p, 0, sizeof(double) * 2 * ctx->T, ctx->stream));
+    ctx->haveFlowSystem = false;
+    return MOF_OK;
+}
+int whitney_mass_operator(mof_ctx* ctx, double* wM) {
+    const int E = ctx->E;
+    MOF_TRY(metric_mass_blocks(ctx));
+    MOF_CUDA(ctx->dtmp0.reserve((size_t)E));
+    MOF_LAUNCH(k_flow_rows, blocks_for(E, B), B, 0, ctx->expanded.p, ctx->reduced.p, ctx->opp.p, ctx->P.p, ctx->dataD.p, ctx->dataRhs.p, ctx->wRowptr.p,
+               ctx->wSliceBase.p, ctx->wCol.p, E, wM, ctx->fb.p, ctx->dtmp0.p);
+    return MOF_OK;
+}
+// tField = P coeffs for any coefficient vector of the Whitney basis (GetTriangleVectorField, VectorField.h:107-112).
+int whitney_triangle_field(mof_ctx* ctx, const double* coeffs, double* tfield) {
+    MOF_LAUNCH(k_triangle_field, blocks_for(ctx->T, B), B, 0, ctx->reduced.p, ctx->P.p, coeffs, ctx->T, tfield);
+    return MOF_OK;
+}
+
 // ---------------------------------------------------------------------- texel advection (a15)
 
 // Sample, MeshFlow.inl:66-84.

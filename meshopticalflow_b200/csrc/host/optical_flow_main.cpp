@@ -210,6 +210,9 @@ int main(int argc, char* argv[]) {
     params.dogWeight = (double)opt.dogWeight, params.dogSmooth = (double)opt.dogSmooth;
     params.flowTol = opt.flowTol, params.smoothTol = opt.smoothTol;
     if (!mof_ok(ctx, mof_set_params(ctx, &params))) return EXIT_FAILURE;
+    // The texture configuration's map follows the file's triangle order (first-writer rule, MeshFlow.inl:281-337) and --debug dumps the
+    // library's per-vertex arrays: both keep the caller's numbering; otherwise the library may renumber a badly ordered mesh (mof_set_reorder).
+    if (!mof_ok(ctx, mof_set_reorder(ctx, processTexture || opt.debug ? 0 : -1))) return EXIT_FAILURE;
 
     {
         Stopwatch t;

@@ -40,6 +40,18 @@ int check_mesh_size(mof_ctx* ctx, int V, int T, const char* who) {
     return MOF_OK;
 }
 
+// mof_set_reorder, overridden by MOF_REORDER=0|1 in the environment (A/B timing, tests).
+int reorder_mode(const mof_ctx* ctx) {
+    const char* e = getenv("MOF_REORDER");
+    if (e && (*e == '0' || *e == '1')) return *e - '0';
+    return ctx->reorderMode;
+}
+int require_callers_numbering(mof_ctx* ctx, const char* who) {
+    if (!ctx->reordered) return MOF_OK;
+    return fail(ctx, MOF_E_UNSUPPORTED, std::string(who) + ": the texture map follows the caller's triangle order (the first-writer rule of MeshFlow.inl:281-337); "
+                                                            "call mof_set_reorder(ctx, 0) before mof_set_mesh");
+}
+
 int require_mesh(mof_ctx* ctx) { return ctx->haveMesh ? MOF_OK : fail(ctx, MOF_E_INVALID, "call mof_set_mesh first"); }
 int require_signals(mof_ctx* ctx) { return ctx->haveSignals ? MOF_OK : fail(ctx, MOF_E_INVALID, "call mof_set_signals first"); }
 
@@ -122,6 +134,10 @@ int mof_create(int device, void* stream, mof_ctx** out) {
     ctx->device = device;
     mof_default_params(&ctx->params);
     memset(&ctx->stats, 0, sizeof(ctx->stats));
+    {
+        const char* pd = getenv("MOF_PDL");  // programmatic dependent launches in the solvers (mof_internal.cuh); MOF_PDL=0: plain stream order
+        ctx->pdl = !(pd && *pd == '0');
+    }
     if (stream) ctx->stream = (cudaStream_t)stream;
     else {
         // The context's own stream carries the critical path (the flow solves); the smoothing solves that run ahead on a
@@ -160,6 +176,7 @@ void mof_destroy(mof_ctx* ctx) {
     for (auto* b : ints) b->release();
     ctx->hashKeys.release(), ctx->tex[0].release(), ctx->tex[1].release();
     ctx->subXyz.release(), ctx->subTri.release(), ctx->subUv.release();
+    ctx->vOrder.release(), ctx->vRank.release(), ctx->tOrder.release();
     mg_destroy(ctx);
     dist_destroy(ctx);
     vf_destroy(ctx);
@@ -203,6 +220,47 @@ int mof_synchronize(mof_ctx* ctx) {
     return MOF_OK;
 }
 
+int mof_set_reorder(mof_ctx* ctx, int mode) {
+    if (!ctx || mode < -1 || mode > 1) return MOF_E_INVALID;
+    ctx->reorderMode = mode;
+    return MOF_OK;
+}
+int mof_get_permutation(mof_ctx* ctx, int* reordered, int* vertexOrder, int* triangleOrder) {
+    if (!ctx) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    if (reordered) *reordered = ctx->reordered ? 1 : 0;
+    if (!ctx->reordered) {
+        if (vertexOrder) for (int i = 0; i < ctx->V; i++) vertexOrder[i] = i;
+        if (triangleOrder) for (int i = 0; i < ctx->T; i++) triangleOrder[i] = i;
+        return MOF_OK;
+    }
+    if (vertexOrder) MOF_CUDA(read_back(ctx, vertexOrder, ctx->vOrder.p, (size_t)ctx->V));
+    if (triangleOrder) MOF_CUDA(read_back(ctx, triangleOrder, ctx->tOrder.p, (size_t)ctx->T));
+    return MOF_OK;
+}
+
+int mof_spectrum(mof_ctx* ctx, int count, double tol, int maxIterations, double* eigenvalues, double* fields, int* iterations, double* residual) {
+    if (!ctx || !eigenvalues || !fields) return MOF_E_INVALID;
+    MOF_TRY(require_mesh(ctx));
+    if (dist_active(ctx)) return fail(ctx, MOF_E_UNSUPPORTED, "mof_spectrum: not on a partitioned mesh");
+    if (!(tol > 0) || maxIterations < 1) return fail(ctx, MOF_E_INVALID, "mof_spectrum: bad tolerance / iteration limit");
+    StreamScope scope(ctx);
+    smooth_ahead_drain(ctx);
+    const int T = ctx->T;
+    int rc = spectrum_lowest(ctx, count, tol, maxIterations, eigenvalues, fields, iterations, residual);
+    if (rc == MOF_OK && ctx->reordered) {  // rows of every field back into the caller's triangle order
+        std::vector<double> tmp(2 * (size_t)T);
+        std::vector<int> order((size_t)T);
+        MOF_CUDA(read_back(ctx, order.data(), ctx->tOrder.p, (size_t)T));
+        for (int j = 0; j < count; j++) {
+            double* f = fields + 2 * (size_t)T * j;
+            for (int t = 0; t < T; t++) tmp[2 * (size_t)order[t]] = f[2 * (size_t)t], tmp[2 * (size_t)order[t] + 1] = f[2 * (size_t)t + 1];
+            memcpy(f, tmp.data(), sizeof(double) * 2 * T);
+        }
+    }
+    return rc;
+}
+
 int mof_dist_unique_id(unsigned char id128[128]) { return id128 ? dist_unique_id(id128) : MOF_E_INVALID; }
 int mof_dist_init(mof_ctx* ctx, int world, int rank, const unsigned char id128[128]) {
     if (!ctx) return MOF_E_INVALID;
@@ -223,6 +281,7 @@ int mof_set_mesh(mof_ctx* ctx, const double* xyz, int V, const int* tri, int T) 
     MOF_CUDA(ctx->tri.alloc(3ull * T));
     MOF_CUDA(cudaMemcpyAsync(ctx->pos.p, xyz, sizeof(double) * 3 * V, cudaMemcpyHostToDevice, ctx->stream));
     MOF_CUDA(cudaMemcpyAsync(ctx->tri.p, tri, sizeof(int) * 3 * T, cudaMemcpyHostToDevice, ctx->stream));
+    MOF_TRY(reorder_mesh(ctx, reorder_mode(ctx)));
     return finish_mesh(ctx);
 }
 
@@ -236,6 +295,7 @@ int mof_set_mesh_device(mof_ctx* ctx, const double* d_xyz, int V, const int* d_t
     MOF_CUDA(ctx->tri.alloc(3ull * T));
     MOF_CUDA(cudaMemcpyAsync(ctx->pos.p, d_xyz, sizeof(double) * 3 * V, cudaMemcpyDeviceToDevice, ctx->stream));
     MOF_CUDA(cudaMemcpyAsync(ctx->tri.p, d_tri, sizeof(int) * 3 * T, cudaMemcpyDeviceToDevice, ctx->stream));
+    MOF_TRY(reorder_mesh(ctx, reorder_mode(ctx)));
     return finish_mesh(ctx);
 }
 
@@ -252,6 +312,12 @@ static int set_signals_common(mof_ctx* ctx, const double* a, const double* b, in
     double* sb = ctx->dtmp0.p + 3ull * V;
     MOF_CUDA(cudaMemcpyAsync(sa, a, sizeof(double) * 3 * V, kind, ctx->stream));
     MOF_CUDA(cudaMemcpyAsync(sb, b, sizeof(double) * 3 * V, kind, ctx->stream));
+    if (ctx->reordered) {  // the caller's rows -> the library's numbering (reorder.cu)
+        MOF_CUDA(ctx->dtmp2.reserve(6ull * V));
+        MOF_TRY(reorder_gather(ctx, 0, sa, 3, ctx->dtmp2.p));
+        MOF_TRY(reorder_gather(ctx, 0, sb, 3, ctx->dtmp2.p + 3ull * V));
+        sa = ctx->dtmp2.p, sb = ctx->dtmp2.p + 3ull * V;
+    }
     MOF_LAUNCH(k_interleave, blocks_for(3ll * V, 256), 256, 0, sa, sb, V, ctx->raw6.p);
     return finish_signals(ctx);
 }
@@ -279,7 +345,14 @@ long long mof_num_coeffs(mof_ctx* ctx) { return ctx && ctx->haveMesh ? vf_unknow
 int mof_get_flow(mof_ctx* ctx, double* tField) {
     if (!ctx || !tField) return MOF_E_INVALID;
     MOF_TRY(require_mesh(ctx));
-    MOF_CUDA(cudaMemcpyAsync(tField, ctx->tfield.p, sizeof(double) * 2 * ctx->T, cudaMemcpyDeviceToHost, ctx->stream));
+    StreamScope scope(ctx);
+    const double* field = ctx->tfield.p;
+    if (ctx->reordered) {  // a triangle keeps its corner order, hence its chart: only the rows move
+        MOF_CUDA(ctx->dtmp2.reserve(2ull * ctx->T));
+        MOF_TRY(reorder_scatter(ctx, 1, ctx->tfield.p, 2, ctx->dtmp2.p));
+        field = ctx->dtmp2.p;
+    }
+    MOF_CUDA(cudaMemcpyAsync(tField, field, sizeof(double) * 2 * ctx->T, cudaMemcpyDeviceToHost, ctx->stream));
     MOF_CUDA(cudaStreamSynchronize(ctx->stream));
     return MOF_OK;
 }
@@ -303,6 +376,12 @@ static int advect_common(mof_ctx* ctx, double alpha, double* outA, double* outB,
     double* sa = ctx->dtmp0.p;
     double* sb = ctx->dtmp0.p + 3ull * V;
     MOF_LAUNCH(k_deinterleave, blocks_for(3ll * V, 256), 256, 0, ctx->resampled6.p, V, sa, sb);
+    if (ctx->reordered) {  // back to the caller's numbering
+        MOF_CUDA(ctx->dtmp2.reserve(6ull * V));
+        MOF_TRY(reorder_scatter(ctx, 0, sa, 3, ctx->dtmp2.p));
+        MOF_TRY(reorder_scatter(ctx, 0, sb, 3, ctx->dtmp2.p + 3ull * V));
+        sa = ctx->dtmp2.p, sb = ctx->dtmp2.p + 3ull * V;
+    }
     MOF_CUDA(cudaMemcpyAsync(outA, sa, sizeof(double) * 3 * V, kind, ctx->stream));
     MOF_CUDA(cudaMemcpyAsync(outB, sb, sizeof(double) * 3 * V, kind, ctx->stream));
     MOF_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -315,6 +394,7 @@ int mof_set_texture_map(mof_ctx* ctx, int W, int H, const int* srcT, const doubl
     if (!ctx) return MOF_E_INVALID;
     MOF_TRY(require_mesh(ctx));
     if (W < 2 || H < 2 || !srcT || !srcP || !triUV || !texA || !texB) return fail(ctx, MOF_E_INVALID, "mof_set_texture_map: bad arguments");
+    MOF_TRY(require_callers_numbering(ctx, "mof_set_texture_map"));
     StreamScope scope(ctx);
     size_t n = (size_t)W * H;
     for (size_t i = 0; i < n; i++)
@@ -399,6 +479,7 @@ int mof_build_texture_map(mof_ctx* ctx, int W, int H, int padRadius, const doubl
     if (!ctx) return MOF_E_INVALID;
     MOF_TRY(require_mesh(ctx));
     if (W < 2 || H < 2 || (long long)W * H > (1ll << 30) || padRadius < 0 || !triUV || !texA || !texB) return fail(ctx, MOF_E_INVALID, "mof_build_texture_map: bad arguments");
+    MOF_TRY(require_callers_numbering(ctx, "mof_build_texture_map"));
     StreamScope scope(ctx);
     size_t n = (size_t)W * H;
     ctx->haveTexture = false;

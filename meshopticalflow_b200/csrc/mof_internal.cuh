@@ -89,6 +89,10 @@ struct mof_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool ownStream = false;
+    int reorderMode = -1;  // mof_set_reorder: -1 by the locality of the caller's numbering, 0 never, 1 always (reorder.cu)
+    bool reordered = false;  // the mesh in ctx->pos / ctx->tri is numbered along a Morton curve; vOrder / tOrder: new -> old, vRank: old -> new
+    mof::DBuf<int> vOrder, vRank, tOrder;
+    bool pdl = false;  // kernels of the solvers are launched with programmatic stream serialisation (MOF_LAUNCH_PDL; MOF_PDL=0 turns it off)
     std::string err;
     mof_params params;
     mof_stats stats;
@@ -213,6 +217,57 @@ struct PhaseTimer {
         if (e__ != cudaSuccess) return mof::cuda_fail(ctx, e__, #kernel);           \
     } while (0)
 #endif
+
+// Programmatic dependent launch (griddepcontrol, sm_90+): a kernel launched through MOF_LAUNCH_PDL may have its CTAs scheduled while the
+// previous kernel on the stream is still draining, which hides most of the ~2 us launch-to-launch gap of the dependent chain of small
+// kernels a multigrid cycle is made of. The contract: such a kernel's FIRST statement is pdl_wait() — it returns when the preceding
+// grids have completed and their writes are visible, so nothing before that point may touch memory (reads or writes); with every
+// kernel of the chain doing so the ordering is that of plain stream order. Without the launch attribute the instruction is a no-op.
+#ifdef MOF_HOST_EMULATION
+inline void pdl_wait() {}
+#else
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+#ifdef MOF_HOST_EMULATION
+#define MOF_LAUNCH_PDL MOF_LAUNCH
+#else
+#define MOF_LAUNCH_PDL(kernel, grid, block, smem, ...)                                                  \
+    do {                                                                                                \
+        cudaError_t e__;                                                                                \
+        if (ctx->pdl) {                                                                                 \
+            cudaLaunchConfig_t cfg__ = {};                                                              \
+            cfg__.gridDim = dim3((unsigned)(grid)), cfg__.blockDim = dim3((unsigned)(block));           \
+            cfg__.dynamicSmemBytes = (smem), cfg__.stream = ctx->stream;                                \
+            cudaLaunchAttribute attr__[1];                                                              \
+            attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                          \
+            attr__[0].val.programmaticStreamSerializationAllowed = 1;                                   \
+            cfg__.attrs = attr__, cfg__.numAttrs = 1;                                                   \
+            e__ = cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);                                      \
+        } else {                                                                                        \
+            kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                              \
+            e__ = cudaGetLastError();                                                                   \
+        }                                                                                               \
+        ctx->stats.kernelLaunches++;                                                                    \
+        if (e__ != cudaSuccess) return mof::cuda_fail(ctx, e__, #kernel);                               \
+    } while (0)
+#endif
+
+// spectrum.cu and what it borrows from the alignment path
+int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, double* eigenvalues, double* fields, int* iterationsOut, double* residualOut);
+int metric_mass_blocks(mof_ctx* ctx);                       // flow_kernels.cu: ctx->dataD = g_t area_t
+int whitney_mass_operator(mof_ctx* ctx, double* wM);        // flow_kernels.cu
+int whitney_triangle_field(mof_ctx* ctx, const double* coeffs, double* tfield);
+int vf_apply_operator(mof_ctx* ctx, double dataScale, double weight, const double* x, double* y);  // vector_fields.cu
+int vf_smooth_diagonal(mof_ctx* ctx, double* out);
+int vf_triangle_field(mof_ctx* ctx, const double* coeffs, double* tfield);
+
+// reorder.cu
+int reorder_mesh(mof_ctx* ctx, int mode);
+int reorder_gather(mof_ctx* ctx, int kind, const double* callerRows, int width, double* libraryRows);   // kind 0: per vertex, 1: per triangle
+int reorder_scatter(mof_ctx* ctx, int kind, const double* libraryRows, int width, double* callerRows);
 
 // setup_kernels.cu
 int build_mesh_operators(mof_ctx* ctx);

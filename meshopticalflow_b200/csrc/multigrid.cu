@@ -31,6 +31,12 @@
 
 #include "mof_internal.cuh"
 
+// Every kernel of this file starts with pdl_wait(), so every launch of this file may be a programmatic dependent launch.
+#ifndef MOF_HOST_EMULATION
+#undef MOF_LAUNCH
+#define MOF_LAUNCH MOF_LAUNCH_PDL
+#endif
+
 namespace mof {
 
 namespace {
@@ -172,7 +178,7 @@ __host__ __device__ __forceinline__ unsigned morton3(unsigned x, unsigned y, uns
 
 // Edge vectors, midpoints and squared lengths of the Whitney unknowns.
 __global__ void k_edge_geometry(const double* __restrict__ pos, const int* __restrict__ tri, const int* __restrict__ expanded, int E, double* __restrict__ evec,
-                                double* __restrict__ emid, double* __restrict__ len2) {
+                                double* __restrict__ emid, double* __restrict__ len2) { pdl_wait();
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     int h = expanded[e], t = h / 3, j = h - 3 * t;
@@ -187,7 +193,7 @@ __global__ void k_edge_geometry(const double* __restrict__ pos, const int* __res
 }
 
 // min (mode 0) / max (mode 1) of a strided array, two stages.
-__global__ void k_minmax_partial(const double* __restrict__ in, long long n, int stride, int offset, int mode, double* __restrict__ partial) {
+__global__ void k_minmax_partial(const double* __restrict__ in, long long n, int stride, int offset, int mode, double* __restrict__ partial) { pdl_wait();
     __shared__ double sh[B];
     double s = mode ? -1e300 : 1e300;
     for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < n; i += (long long)gridDim.x * B) {
@@ -202,7 +208,7 @@ __global__ void k_minmax_partial(const double* __restrict__ in, long long n, int
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
-__global__ void k_minmax_final(const double* __restrict__ partial, int np, int mode, double* __restrict__ out) {
+__global__ void k_minmax_final(const double* __restrict__ partial, int np, int mode, double* __restrict__ out) { pdl_wait();
     __shared__ double sh[B];
     double s = mode ? -1e300 : 1e300;
     for (int i = threadIdx.x; i < np; i += B) s = mode ? fmax(s, partial[i]) : fmin(s, partial[i]);
@@ -235,19 +241,19 @@ __device__ __forceinline__ unsigned cell_code(const GridMap& gm, const double* p
     }
     return morton3(c[0], c[1], c[2]);
 }
-__global__ void k_mark_cells(GridMap gm, const double* __restrict__ pts, int n, int L, int* __restrict__ occ) {
+__global__ void k_mark_cells(GridMap gm, const double* __restrict__ pts, int n, int L, int* __restrict__ occ) { pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) occ[cell_code(gm, pts + 3 * (size_t)i, L)] = 1;
 }
-__global__ void k_mark_parents(const int* __restrict__ occ, long long cells, int* __restrict__ occParent) {
+__global__ void k_mark_parents(const int* __restrict__ occ, long long cells, int* __restrict__ occParent) { pdl_wait();
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < cells && occ[c]) occParent[c >> 3] = 1;
 }
-__global__ void k_node_codes(const int* __restrict__ occ, const int* __restrict__ rank, long long cells, int* __restrict__ code) {
+__global__ void k_node_codes(const int* __restrict__ occ, const int* __restrict__ rank, long long cells, int* __restrict__ code) { pdl_wait();
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < cells && occ[c]) code[rank[c]] = (int)c;
 }
-__global__ void k_neighbours(const int* __restrict__ code, const int* __restrict__ occ, const int* __restrict__ rank, int N, int L, int* __restrict__ nbr) {
+__global__ void k_neighbours(const int* __restrict__ code, const int* __restrict__ occ, const int* __restrict__ rank, int N, int L, int* __restrict__ nbr) { pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * 27) return;
     int I = i / 27, s = i - 27 * I;
@@ -263,7 +269,7 @@ __global__ void k_neighbours(const int* __restrict__ code, const int* __restrict
 }
 // `shift` = 3 x (grid levels between a level and the next coarser one of the hierarchy: 1, or 2 where a level is skipped)
 __global__ void k_parents(const int* __restrict__ code, const int* __restrict__ rankParent, int N, int Nparent, int shift, int* __restrict__ parent,
-                          int* __restrict__ firstChild) {
+                          int* __restrict__ firstChild) { pdl_wait();
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I > N) return;
     if (I == N) { firstChild[Nparent] = N; return; }
@@ -271,19 +277,19 @@ __global__ void k_parents(const int* __restrict__ code, const int* __restrict__ 
     parent[I] = p;
     if (I == 0 || rankParent[(unsigned)code[I - 1] >> shift] != p) firstChild[p] = I;
 }
-__global__ void k_point_aggregate(GridMap gm, const double* __restrict__ pts, const int* __restrict__ rank, int n, int L, int* __restrict__ agg, int* __restrict__ count) {
+__global__ void k_point_aggregate(GridMap gm, const double* __restrict__ pts, const int* __restrict__ rank, int n, int L, int* __restrict__ agg, int* __restrict__ count) { pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int a = rank[cell_code(gm, pts + 3 * (size_t)i, L)];
     agg[i] = a;
     atomicAdd(&count[a], 1);
 }
-__global__ void k_aggregate_fill(const int* __restrict__ agg, int n, int* cursor, int* __restrict__ list) {
+__global__ void k_aggregate_fill(const int* __restrict__ agg, int n, int* cursor, int* __restrict__ list) { pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) list[atomicAdd(&cursor[agg[i]], 1)] = i;
 }
 // Ascending member ids within every aggregate (fixed summation order). One warp per aggregate, rank sort.
-__global__ void k_aggregate_sort(const int* __restrict__ ptr, int N, const int* __restrict__ in, int* __restrict__ out) {
+__global__ void k_aggregate_sort(const int* __restrict__ ptr, int N, const int* __restrict__ in, int* __restrict__ out) { pdl_wait();
     int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (I >= N) return;
     int b = ptr[I], n = ptr[I + 1] - b;
@@ -304,7 +310,7 @@ __device__ __forceinline__ signed char slot_between(unsigned ci, unsigned cf, in
 }
 // Stencil slot of every entry (e,f) of the sliced FLOW matrix.
 __global__ void k_entry_slots_flow(const int* __restrict__ wRowptr, const int* __restrict__ sliceBase, const int* __restrict__ wCol, const int* __restrict__ agg,
-                                   const int* __restrict__ code, int E, int slices, signed char* __restrict__ slotOf, int* __restrict__ flags) {
+                                   const int* __restrict__ code, int E, int slices, signed char* __restrict__ slotOf, int* __restrict__ flags) { pdl_wait();
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= 32 * slices) return;
     const int longest = (sliceBase[(e >> 5) + 1] - sliceBase[e >> 5]) >> 5;
@@ -317,7 +323,7 @@ __global__ void k_entry_slots_flow(const int* __restrict__ wRowptr, const int* _
 }
 // ... and of every entry (v,u) of the SCALAR CSR pattern.
 __global__ void k_entry_slots_scalar(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ agg, const int* __restrict__ code, int V,
-                                     signed char* __restrict__ slotOf, int* __restrict__ flags) {
+                                     signed char* __restrict__ slotOf, int* __restrict__ flags) { pdl_wait();
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
     unsigned ci = (unsigned)code[agg[v]];
@@ -330,7 +336,7 @@ __global__ void k_entry_slots_scalar(const int* __restrict__ rowptr, const int* 
 // A_ef * v_e v_f^T. One thread per (I, slot); the 27 threads of a cell walk the same entries (broadcast).
 __global__ void k_level1_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const int* __restrict__ wRowptr, const int* __restrict__ sliceBase,
                               const int* __restrict__ wCol, const double* __restrict__ wA, const signed char* __restrict__ slotOf, const double* __restrict__ evec,
-                              const int* __restrict__ nbr, int N, double scale, double* __restrict__ blocks) {
+                              const int* __restrict__ nbr, int N, double scale, double* __restrict__ blocks) { pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * 27) return;
     int I = i / 27, s = i - 27 * I;
@@ -354,7 +360,7 @@ __global__ void k_level1_flow(const int* __restrict__ aggPtr, const int* __restr
 }
 // SCALAR level-1 weight (I, slot) = sum over vertices v of I of the entries of row v that fall in that cell.
 __global__ void k_level1_scalar(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const int* __restrict__ rowptr, const double* __restrict__ val,
-                                const signed char* __restrict__ slotOf, const int* __restrict__ nbr, int N, double scale, double* __restrict__ blocks) {
+                                const signed char* __restrict__ slotOf, const int* __restrict__ nbr, int N, double scale, double* __restrict__ blocks) { pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * 27) return;
     int I = i / 27, s = i - 27 * I;
@@ -371,7 +377,7 @@ __global__ void k_level1_scalar(const int* __restrict__ aggPtr, const int* __res
 // Coarser coefficient (I', slot') = sum of the finer ones (I, s) with parent(I) = I' and parent(nbr(I, s)) = nbr'(I', slot').
 template <int K>
 __global__ void k_coarsen_blocks(const int* __restrict__ firstChild, const int* __restrict__ nbrFine, const int* __restrict__ parentFine, const double* __restrict__ blocksFine,
-                                 int Nfine, const int* __restrict__ nbrCoarse, int Ncoarse, double scale, double* __restrict__ blocksCoarse) {
+                                 int Nfine, const int* __restrict__ nbrCoarse, int Ncoarse, double scale, double* __restrict__ blocksCoarse) { pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ncoarse * 27) return;
     int Ip = i / 27, sp = i - 27 * Ip;
@@ -397,7 +403,7 @@ __global__ void k_coarsen_blocks(const int* __restrict__ firstChild, const int* 
 //    with relTol = 1e-3 rho stays at 1.8 on every level and size (and 4M vertices need 164 iterations, not 194).
 // An explicit cofactor inverse of such a block is NOT good enough: its error in the well-conditioned directions scales
 // with the condition number and the smoother stops being positive definite.
-__global__ void k_block_pinv(const double* __restrict__ blocks, int N, double relTol, creal* __restrict__ binv) {
+__global__ void k_block_pinv(const double* __restrict__ blocks, int N, double relTol, creal* __restrict__ binv) { pdl_wait();
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= N) return;
     double m[9];
@@ -434,14 +440,14 @@ __global__ void k_block_pinv(const double* __restrict__ blocks, int N, double re
     }
     for (int k = 0; k < 9; k++) binv[(size_t)k * N + I] = (creal)inv[k];
 }
-__global__ void k_scalar_inv(const double* __restrict__ blocks, int N, creal* __restrict__ binv) {
+__global__ void k_scalar_inv(const double* __restrict__ blocks, int N, creal* __restrict__ binv) { pdl_wait();
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= N) return;
     double w = blocks[blk<1>(N, I, SLOT_CENTER, 0)];
     binv[I] = (creal)(w > 0 ? 1. / w : 0.);
 }
 // fp64 -> cycle precision (matrix values, inverse diagonals, coarse coefficients, edge vectors)
-__global__ void k_to_creal(const double* __restrict__ src, long long n, creal* __restrict__ dst) {
+__global__ void k_to_creal(const double* __restrict__ src, long long n, creal* __restrict__ dst) { pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = (creal)src[i];
 }
 
@@ -450,7 +456,7 @@ __global__ void k_to_creal(const double* __restrict__ src, long long n, creal* _
 // z = omega * dinv[row] * r, flat over nrhs interleaved right-hand sides
 template <class TZ>
 __global__ void k_fine_presmooth(const double* __restrict__ r, const creal* __restrict__ dinv, const double* __restrict__ omegaP, long long len, int nrhs,
-                                 TZ* __restrict__ z) {
+                                 TZ* __restrict__ z) { pdl_wait();
     const double omega = *omegaP;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < len) z[i] = (TZ)(omega * (double)dinv[i / nrhs] * r[i]);
@@ -532,7 +538,7 @@ constexpr int BATCH = 6;
 template <class TV, class TX, bool PART = false>
 __global__ void __launch_bounds__(B, 8) k_fine_apply_flow(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const TV* __restrict__ val,
                                                       const double* __restrict__ b, const creal* __restrict__ dinv, const double* __restrict__ omegaP,
-                                                      const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f, int s0 = 0, int s1 = 0) {
+                                                      const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f, int s0 = 0, int s1 = 0) { pdl_wait();
     const double omega = *omegaP;
     const int lane = threadIdx.x & 31;
     const int slices = PART ? s1 : (n + 31) >> 5;
@@ -588,7 +594,7 @@ template <> struct Pair<double> { using type = double2; };
 template <class TV, class TX>
 __global__ void __launch_bounds__(B) k_fine_apply_scalar_row(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const TV* __restrict__ val,
                                                             const double* __restrict__ b, const creal* __restrict__ dinv, const double* __restrict__ omegaP,
-                                                            const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f) {
+                                                            const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f) { pdl_wait();
     const double omega = *omegaP;
     using P2 = typename Pair<TX>::type;
     double dot = 0;
@@ -642,7 +648,7 @@ constexpr int SBATCH = 4;
 template <class TV, class TX>
 __global__ void __launch_bounds__(B, 4) k_fine_apply_scalar_sell(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const TV* __restrict__ val,
                                                                 const double* __restrict__ b, const creal* __restrict__ dinv, const double* __restrict__ omegaP,
-                                                                const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f) {
+                                                                const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f) { pdl_wait();
     using P2 = typename Pair<TX>::type;
     const double omega = *omegaP;
     const int lane = threadIdx.x & 31;
@@ -713,7 +719,7 @@ __global__ void __launch_bounds__(B, 4) k_fine_apply_scalar_sell(int n, const in
 }
 // CSR values -> the sliced layout, in both precisions (once per scalar system; the pattern's slice offsets are per mesh).
 __global__ void k_scalar_vals_to_sell(const int* __restrict__ rowptr, const double* __restrict__ val, const int* __restrict__ sliceBase, int n, int slices,
-                                      double* __restrict__ sVal, creal* __restrict__ cVal) {
+                                      double* __restrict__ sVal, creal* __restrict__ cVal) { pdl_wait();
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= 32 * slices) return;
     const int longest = (sliceBase[(r >> 5) + 1] - sliceBase[r >> 5]) >> 5;
@@ -731,7 +737,7 @@ __global__ void k_scalar_vals_to_sell(const int* __restrict__ rowptr, const doub
 template <class TV, class TX, bool PART = false>
 __global__ void __launch_bounds__(B, 8) k_fine_apply_scalar(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const TV* __restrict__ val,
                                                         const double* __restrict__ b, const creal* __restrict__ dinv, const double* __restrict__ omegaP,
-                                                        const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f, int r0 = 0, int r1 = 0) {
+                                                        const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f, int r0 = 0, int r1 = 0) { pdl_wait();
     const double omega = *omegaP;
     const long long len = PART ? 6ll * r1 : 6ll * n;
     double dot = 0;
@@ -777,7 +783,7 @@ __device__ __forceinline__ void apply_binv(const creal* __restrict__ binv, int N
 // FLOW restriction: rc[I] = sum over the edges of aggregate I of v_e * r_e (P1^T r). One warp per aggregate.
 __global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ evec, const creal* __restrict__ r, int N,
                                 const creal* __restrict__ binv, const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1,
-                                int c0 = 0, int c1 = -1) {  // [c0, c1): the cells of this launch (a rank's own cells when level 1 is dealt to the ranks)
+                                int c0 = 0, int c1 = -1) { pdl_wait();  // [c0, c1): the cells of this launch (a rank's own cells when level 1 is dealt to the ranks)
     int I = c0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (I >= (c1 < 0 ? N : c1)) return;
     const creal omega = (creal)*omegaP;
@@ -802,7 +808,7 @@ __global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __res
     }
 }
 // FLOW prolongation: z_e += v_e . zc[agg(e)]
-__global__ void k_prolong_flow(const int* __restrict__ agg, const creal* __restrict__ evec, const creal* __restrict__ zc, int E, creal* __restrict__ z) {
+__global__ void k_prolong_flow(const int* __restrict__ agg, const creal* __restrict__ evec, const creal* __restrict__ zc, int E, creal* __restrict__ z) { pdl_wait();
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     const creal* c = zc + 3 * (size_t)agg[e];
@@ -810,7 +816,7 @@ __global__ void k_prolong_flow(const int* __restrict__ agg, const creal* __restr
 }
 // SCALAR restriction / prolongation: sums and copies per channel. One thread per (cell, channel) / (vertex, channel).
 __global__ void k_restrict_scalar(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ r, int N, const creal* __restrict__ binv,
-                                  const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1, int c0 = 0, int c1 = -1) {
+                                  const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1, int c0 = 0, int c1 = -1) { pdl_wait();
     int i = 6 * c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 6 * (c1 < 0 ? N : c1)) return;
     const creal omega = (creal)*omegaP;
@@ -823,7 +829,7 @@ __global__ void k_restrict_scalar(const int* __restrict__ aggPtr, const int* __r
     rc[i] = a;
     zc[i] = omega * binv[I] * a;
 }
-__global__ void k_prolong_scalar(const int* __restrict__ agg, const creal* __restrict__ zc, int V, creal* __restrict__ z) {
+__global__ void k_prolong_scalar(const int* __restrict__ agg, const creal* __restrict__ zc, int V, creal* __restrict__ z) { pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 6ll * V) return;
     long long v = i / 6;
@@ -841,7 +847,7 @@ template <int K, int D, int SLOTS>
 __global__ void __launch_bounds__(27 / SLOTS * 32) k_coarse_apply(const creal* __restrict__ blocks, const int* __restrict__ nbr, const creal* __restrict__ binv,
                                                                  const creal* __restrict__ r, const creal* __restrict__ z, const double* __restrict__ omegaP, int N,
                                                                  int mode, creal* __restrict__ out, const int* __restrict__ parent, const creal* __restrict__ zc,
-                                                                 int c0 = 0, int c1 = -1) {  // [c0, c1): the cells of this launch (all, or a rank's own)
+                                                                 int c0 = 0, int c1 = -1) { pdl_wait();  // [c0, c1): the cells of this launch (all, or a rank's own)
     constexpr int WARPS = 27 / SLOTS;
     const creal omega = (creal)*omegaP;
     __shared__ creal part[WARPS][32 * D];
@@ -937,7 +943,7 @@ constexpr int FUSE_G = 4;
 template <int K, int D>
 __global__ void __launch_bounds__(27 * 32) k_residual_restrict(const creal* __restrict__ blocks, const int* __restrict__ nbr, const creal* __restrict__ r,
                                                               const creal* __restrict__ z, int N, const int* __restrict__ firstChild, const creal* __restrict__ binvC,
-                                                              const double* __restrict__ omegaP, int Nc, creal* __restrict__ rc, creal* __restrict__ zc) {
+                                                              const double* __restrict__ omegaP, int Nc, creal* __restrict__ rc, creal* __restrict__ zc) { pdl_wait();
     __shared__ creal part[27][32 * D];
     __shared__ creal resid[32 * D];
     __shared__ creal sums[FUSE_G * D];
@@ -1002,7 +1008,7 @@ __global__ void __launch_bounds__(27 * 32) k_residual_restrict(const creal* __re
 // One thread per coarse cell.
 template <int K, int D>
 __global__ void k_restrict_coarse(const int* __restrict__ firstChild, const creal* __restrict__ rFine, int Ncoarse, const creal* __restrict__ binv,
-                                  const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int c0 = 0, int c1 = -1) {
+                                  const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int c0 = 0, int c1 = -1) { pdl_wait();
     int Ip = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (Ip >= (c1 < 0 ? Ncoarse : c1)) return;
     const creal omega = (creal)*omegaP;
@@ -1018,7 +1024,7 @@ __global__ void k_restrict_coarse(const int* __restrict__ firstChild, const crea
 }
 // z = omega * Binv * r on a level (partitioned mesh: the first sweep of level 1, after the restriction was all-reduced)
 template <int K, int D>
-__global__ void k_level_presmooth(const creal* __restrict__ binv, const creal* __restrict__ r, const double* __restrict__ omegaP, int N, creal* __restrict__ z) {
+__global__ void k_level_presmooth(const creal* __restrict__ binv, const creal* __restrict__ r, const double* __restrict__ omegaP, int N, creal* __restrict__ z) { pdl_wait();
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     if (I >= N) return;
     const creal omega = (creal)*omegaP;
@@ -1030,7 +1036,7 @@ __global__ void k_level_presmooth(const creal* __restrict__ binv, const creal* _
     for (int c = 0; c < D; c++) z[(size_t)D * I + c] = omega * o[c];
 }
 template <int D>
-__global__ void k_prolong_coarse(const int* __restrict__ parent, const creal* __restrict__ zc, int N, creal* __restrict__ z, int c0 = 0, int c1 = -1) {
+__global__ void k_prolong_coarse(const int* __restrict__ parent, const creal* __restrict__ zc, int N, creal* __restrict__ z, int c0 = 0, int c1 = -1) { pdl_wait();
     int i = D * c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D * (c1 < 0 ? N : c1)) return;
     z[i] += zc[(size_t)D * parent[i / D] + i % D];
@@ -1041,7 +1047,7 @@ constexpr int DENSE_MAX = 6 * 2 * COARSEST_CELLS;
 constexpr int DENSE_CTAS = 8;
 template <int D>
 __global__ void __launch_bounds__(B) k_dense_restrict_apply(const int* __restrict__ firstChild, const creal* __restrict__ rFine, const creal* __restrict__ m, int n,
-                                                           creal* __restrict__ z) {
+                                                           creal* __restrict__ z) { pdl_wait();
     constexpr int C = D == 3 ? 1 : 6;  // FLOW: n = 3 * cells, one right-hand side; SCALAR: n = cells, six
     __shared__ creal r[DENSE_MAX];
     const int total = n * C;  // = D * cells
@@ -1153,7 +1159,7 @@ __device__ __forceinline__ int tail_pack(int I, int cpc) {
 }
 
 template <int K, int D>
-__global__ void __launch_bounds__(TAIL_T, 1) k_coarse_tail(const TailArgs a) {
+__global__ void __launch_bounds__(TAIL_T, 1) k_coarse_tail(const TailArgs a) { pdl_wait();
     constexpr int C = D == 3 ? 1 : 6;
     constexpr int PROW = TAIL_BATCH * D;  // part[slot][cell of the batch][component]
 #ifdef MOF_HOST_EMULATION
@@ -1409,7 +1415,7 @@ __global__ void __launch_bounds__(TAIL_T, 1) k_coarse_tail(const TailArgs a) {
 // ------------------------------------------------------------------------------------- PCG kernels
 
 template <class TA, class TB>
-__global__ void k_dot_partial(const TA* __restrict__ a, const TB* __restrict__ b, long long n, double* __restrict__ partial) {
+__global__ void k_dot_partial(const TA* __restrict__ a, const TB* __restrict__ b, long long n, double* __restrict__ partial) { pdl_wait();
     __shared__ double sh[B];
     double s = 0;
     for (long long i = (long long)blockIdx.x * B + threadIdx.x; i < n; i += (long long)gridDim.x * B) s += (double)a[i] * (double)b[i];
@@ -1422,11 +1428,11 @@ __global__ void k_dot_partial(const TA* __restrict__ a, const TB* __restrict__ b
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 // Folds the partials (fixed order) into scal[slot] and derives the PCG scalar that depends on it.
-__global__ void k_fold(const double* __restrict__ partial, int np, int slot, double* __restrict__ scal) { fold_partials(partial, np, slot, scal); }
+__global__ void k_fold(const double* __restrict__ partial, int np, int slot, double* __restrict__ scal) { pdl_wait(); fold_partials(partial, np, slot, scal); }
 // x += alpha p ; r -= alpha q ; partial(r.r) ; and the cycle's pre-smoothing of the new residual, z = omega * dinv * r
 // (the last CTA folds r.r into scal[S_RR])
 __global__ void k_update_xr(const double* __restrict__ p, const double* __restrict__ q, long long n, double* __restrict__ x, double* __restrict__ r,
-                            const creal* __restrict__ dinv, const double* __restrict__ omegaP, int nrhs, creal* __restrict__ z, Fold f) {
+                            const creal* __restrict__ dinv, const double* __restrict__ omegaP, int nrhs, creal* __restrict__ z, Fold f) { pdl_wait();
     const double alpha = f.scal[S_ALPHA], omega = *omegaP;
     double s = 0;
     const long long stride = (long long)gridDim.x * B;
@@ -1452,18 +1458,18 @@ __global__ void k_update_xr(const double* __restrict__ p, const double* __restri
     }
     cta_partial(s, f.partial, f.slot, f.scal, f.counter);
 }
-__global__ void k_direction(const creal* __restrict__ z, const double* __restrict__ scal, long long n, int first, double* __restrict__ p) {
+__global__ void k_direction(const creal* __restrict__ z, const double* __restrict__ scal, long long n, int first, double* __restrict__ p) { pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = first ? (double)z[i] : (double)z[i] + scal[S_BETA] * p[i];
 }
 // Loop control of a captured solve, one thread each.
 // Before a solve: the threshold from b.b (already in scal), the counters.
-__global__ void k_pcg_begin(double* __restrict__ scal, double tol2, int maxIters) {
+__global__ void k_pcg_begin(double* __restrict__ scal, double tol2, int maxIters) { pdl_wait();
     scal[S_THR] = tol2 * scal[S_BB], scal[S_IT] = 0, scal[S_MAXIT] = maxIters, scal[S_RR0] = 0;
 }
 // In front of the loop (enter = 1): run it at all? At the end of a pass of two iterations (enter = 0): another one? The
 // same test the host made between graph replays: both residual norms of the pass above the threshold, finite, iterations left.
-__global__ void k_pcg_continue(cudaGraphConditionalHandle loop, double* __restrict__ scal, int enter) {
+__global__ void k_pcg_continue(cudaGraphConditionalHandle loop, double* __restrict__ scal, int enter) { pdl_wait();
     const double thr = scal[S_THR], rr = scal[S_RR];
     bool go = scal[S_BB] > 0 && rr > thr && rr < 1e300;  // (also false for NaN)
     if (!enter) {
@@ -1474,14 +1480,14 @@ __global__ void k_pcg_continue(cudaGraphConditionalHandle loop, double* __restri
     cudaGraphSetConditional(loop, go ? 1u : 0u);
 }
 // Power iteration support (spectral radius of Minv A per level, for the Jacobi damping).
-__global__ void k_pseudo_random(long long n, creal* __restrict__ v) {
+__global__ void k_pseudo_random(long long n, creal* __restrict__ v) { pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned h = (unsigned)i * 2654435761u + 12345u;
     h ^= h >> 15, h *= 2246822519u, h ^= h >> 13;
     v[i] = (creal)((double)(h & 0xffff) / 32768. - 1.);
 }
-__global__ void k_normalise(const creal* __restrict__ t, const double* __restrict__ scal, int slot, long long n, creal* __restrict__ v) {
+__global__ void k_normalise(const creal* __restrict__ t, const double* __restrict__ scal, int slot, long long n, creal* __restrict__ v) { pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s = scal[slot];
@@ -1821,22 +1827,22 @@ int fine_apply(mof_ctx* ctx, Multigrid& mg, const double* b, const double* omega
         return MOF_OK;
     }
     if (mg.kind == MG_FLOW)
-        MOF_LAUNCH((k_fine_apply_flow<creal, creal>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, f);
+        MOF_LAUNCH((k_fine_apply_flow<creal, creal>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, f, 0, 0);
     else
-        MOF_LAUNCH((k_fine_apply_scalar<creal, creal>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, f);
+        MOF_LAUNCH((k_fine_apply_scalar<creal, creal>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, mg.fval.p, b, mg.fdinv.p, omega, in, out, mode, f, 0, 0);
     return MOF_OK;
 }
 // out = b - A in with the fp64 matrix (initial and true residuals of PCG)
 int fine_residual(mof_ctx* ctx, Multigrid& mg, const double* b, const double* in, double* out) {
     if (mg.kind == MG_FLOW)
         MOF_LAUNCH((k_fine_apply_flow<double, double>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, b, (const creal*)nullptr, mg.om(OM_ZERO), in, out, 1,
-                   NO_FOLD);
+                   NO_FOLD, 0, 0);
     else if (scalar_sell(ctx))
         MOF_LAUNCH((k_fine_apply_scalar_sell<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, ctx->sSysSell.p, b, (const creal*)nullptr,
                    mg.om(OM_ZERO), in, out, 1, NO_FOLD);
     else
         MOF_LAUNCH((k_fine_apply_scalar<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, b, (const creal*)nullptr, mg.om(OM_ZERO), in, out, 1,
-                   NO_FOLD);
+                   NO_FOLD, 0, 0);
     return MOF_OK;
 }
 
@@ -1845,9 +1851,9 @@ template <int K, int D>
 int coarse_apply(mof_ctx* ctx, MgLevel& lv, const double* omega, int mode, creal* out, const creal* zc) {
     const int* parent = zc ? lv.parent.p : nullptr;
     if (lv.N >= 16384)
-        MOF_LAUNCH((k_coarse_apply<K, D, 3>), blocks_for(lv.N, 32), 9 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, omega, lv.N, mode, out, parent, zc);
+        MOF_LAUNCH((k_coarse_apply<K, D, 3>), blocks_for(lv.N, 32), 9 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, omega, lv.N, mode, out, parent, zc, 0, -1);
     else
-        MOF_LAUNCH((k_coarse_apply<K, D, 1>), blocks_for(lv.N, 32), 27 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, omega, lv.N, mode, out, parent, zc);
+        MOF_LAUNCH((k_coarse_apply<K, D, 1>), blocks_for(lv.N, 32), 27 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, omega, lv.N, mode, out, parent, zc, 0, -1);
     return MOF_OK;
 }
 int coarse_apply(mof_ctx* ctx, Multigrid& mg, MgLevel& lv, const double* omega, int mode, creal* out, const creal* zc = nullptr) {
@@ -2206,15 +2212,15 @@ int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
                 if (flow) MOF_LAUNCH(k_dense_restrict_apply<3>, DENSE_CTAS, B, 0, up.firstChild.p, lv.t.p, mg.cinv.p, n, up.z.p);
                 else MOF_LAUNCH(k_dense_restrict_apply<6>, DENSE_CTAS, B, 0, up.firstChild.p, lv.t.p, mg.cinv.p, n, up.z.p);
             } else if (flow)
-                MOF_LAUNCH((k_restrict_coarse<9, 3>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, mg.om(2 + l), up.r.p, up.z.p);
+                MOF_LAUNCH((k_restrict_coarse<9, 3>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, mg.om(2 + l), up.r.p, up.z.p, 0, -1);
             else
-                MOF_LAUNCH((k_restrict_coarse<1, 6>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, mg.om(2 + l), up.r.p, up.z.p);
+                MOF_LAUNCH((k_restrict_coarse<1, 6>), blocks_for(up.N, 128), 128, 0, up.firstChild.p, lv.t.p, up.N, up.binv.p, mg.om(2 + l), up.r.p, up.z.p, 0, -1);
             MOF_TRY(coarse_cycle(ctx, mg, l + 1));
         }
         }
         if (g + 1 < passes) {  // W-cycle: the correction has to be in z before the next residual
-            if (flow) MOF_LAUNCH(k_prolong_coarse<3>, blocks_for(3ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p);
-            else MOF_LAUNCH(k_prolong_coarse<6>, blocks_for(6ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p);
+            if (flow) MOF_LAUNCH(k_prolong_coarse<3>, blocks_for(3ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p, 0, -1);
+            else MOF_LAUNCH(k_prolong_coarse<6>, blocks_for(6ll * lv.N, B), B, 0, lv.parent.p, up.z.p, lv.N, lv.z.p, 0, -1);
         }
     }
     MOF_TRY(coarse_apply(ctx, mg, lv, mg.om(1 + l), 2, lv.t.p, up.z.p));
@@ -2238,9 +2244,9 @@ int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed, i
     }
     MOF_TRY(fine_apply(ctx, mg, r, mg.om(0), mg.fz.p, mg.ft.p, 1));
     if (mg.kind == MG_FLOW)
-        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine);
+        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine, 0, -1);
     else
-        MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine);
+        MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine, 0, -1);
     if (mg.K == 1) {  // the aggregates are already the coarsest level
         const bool flow = mg.kind == MG_FLOW;
         const int n = (flow ? 3 : 1) * l1.N;
@@ -2277,7 +2283,7 @@ int apply_dot(mof_ctx* ctx, Multigrid& mg, const double* p, double* q) {
                    (const creal*)nullptr, mg.om(OM_ZERO), p, q, 0, fold_into(mg, S_PQ));
     else
         MOF_LAUNCH((k_fine_apply_scalar<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sRowptr.p, ctx->sCol.p, ctx->sSys.p, (const double*)nullptr,
-                   (const creal*)nullptr, mg.om(OM_ZERO), p, q, 0, fold_into(mg, S_PQ));
+                   (const creal*)nullptr, mg.om(OM_ZERO), p, q, 0, fold_into(mg, S_PQ), 0, 0);
     return fold_after(ctx, mg, FINE_GRID, S_PQ);
 }
 
@@ -2533,7 +2539,7 @@ inline int dist_allreduce(mof_ctx* c, double* v, int n) { return dist_allreduce_
 
 // Raw slots of mg.scal for this rank's partial sums (all-reduced in place), and the scalar each one feeds.
 enum { R_PQ = 8, R_RR = 9, R_RZNEW = 10, R_RZ = 11, R_BB = 12 };  // R_RR and R_RZNEW adjacent: one all-reduce carries both
-__global__ void k_derive(int raw, double* __restrict__ scal) {
+__global__ void k_derive(int raw, double* __restrict__ scal) { pdl_wait();
     const double v = scal[raw];
     if (raw == R_PQ) scal[S_PQ] = v, scal[S_ALPHA] = v != 0 ? scal[S_RZ] / v : 0.;
     else if (raw == R_RR) scal[S_RR] = v;
@@ -2549,19 +2555,19 @@ __global__ void k_derive(int raw, double* __restrict__ scal) {
 // Morton order, aligned through the octree (a rank's cells on level l are the children of its cells on level l + 1), so that
 // restriction and prolongation between dealt levels stay inside a rank and only the 27-point stencils (one layer of cells) and
 // the aggregates that straddle a row-block boundary need an exchange. The first replicated level is gathered once per visit.
-__global__ void k_mark_stencil_halo(const int* __restrict__ nbr, int c0, int c1, int* __restrict__ flags) {
+__global__ void k_mark_stencil_halo(const int* __restrict__ nbr, int c0, int c1, int* __restrict__ flags) { pdl_wait();
     int i = 27 * c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 27 * c1) return;
     const int J = nbr[i];
     if (J >= 0 && (J < c0 || J >= c1)) flags[J] = 1;
 }
-__global__ void k_mark_aggregate_halo(const int* __restrict__ agg, int r0, int r1, int c0, int c1, int* __restrict__ flags) {
+__global__ void k_mark_aggregate_halo(const int* __restrict__ agg, int r0, int r1, int c0, int c1, int* __restrict__ flags) { pdl_wait();
     int e = r0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= r1) return;
     const int a = agg[e];
     if (a < c0 || a >= c1) flags[a] = 1;
 }
-__global__ void k_mark_member_halo(const int* __restrict__ aggPtr, const int* __restrict__ aggList, int c0, int c1, int r0, int r1, int* __restrict__ flags) {
+__global__ void k_mark_member_halo(const int* __restrict__ aggPtr, const int* __restrict__ aggList, int c0, int c1, int r0, int r1, int* __restrict__ flags) { pdl_wait();
     int q = aggPtr[c0] + blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= aggPtr[c1]) return;
     const int e = aggList[q];
@@ -2731,9 +2737,9 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
             MOF_TRY(dist_halo_part_f32(ctx, mg.levelPart[0], (float*)l1.z.p));  // the cells of my rows' aggregates that other ranks own
         } else {
         if (flow)
-            MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, r0, r1);
+            MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, r0, r1, 0, -1);
         else
-            MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, r0, r1);
+            MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, r0, r1, 0, -1);
         MOF_TRY(dist_allreduce(ctx, l1.r.p, D * l1.N));
         if (flow) MOF_LAUNCH((k_level_presmooth<9, 3>), blocks_for(l1.N, B), B, 0, l1.binv.p, l1.r.p, mg.om(1), l1.N, l1.z.p);
         else MOF_LAUNCH((k_level_presmooth<1, 6>), blocks_for(l1.N, B), B, 0, l1.binv.p, l1.r.p, mg.om(1), l1.N, l1.z.p);
@@ -2909,7 +2915,7 @@ int mg_scalar_cycle(mof_ctx* ctx, const double* r6, double* z6) {
     return MOF_OK;
 }
 // d = alpha d + beta c ; z += d (one step of the Chebyshev recurrence below)
-__global__ void k_cheb_update(double alpha, double beta, const double* __restrict__ c, long long n, double* __restrict__ d, double* __restrict__ z, int first) {
+__global__ void k_cheb_update(double alpha, double beta, const double* __restrict__ c, long long n, double* __restrict__ d, double* __restrict__ z, int first) { pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double dn = first ? beta * c[i] : alpha * d[i] + beta * c[i];
@@ -2949,7 +2955,7 @@ int mg_scalar_cheb(mof_ctx* ctx, const double* r6, double* z6, int degree, doubl
 // right-hand side carry in their alpha / beta (diagonal 1/alpha_j + beta_{j-1}/alpha_{j-1}, off-diagonal sqrt(beta_j)/alpha_j): its
 // smallest Ritz value approaches the smallest eigenvalue from above, and — unlike a power iteration on I - C sSys, which returned 0.917
 // for a cycle that really contracts by 0.99 at 1M vertices — does so quickly at the ends of the spectrum.
-__global__ void k_pseudo_random_f64(long long n, double* __restrict__ v) {
+__global__ void k_pseudo_random_f64(long long n, double* __restrict__ v) { pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned h = (unsigned)i * 2654435761u + 12345u;
@@ -3028,7 +3034,7 @@ int mg_time_kernel(mof_ctx* ctx, int which, int reps, float* ms, double* bytes) 
                 MOF_LAUNCH(k_update_xr, NBLK, B, 0, mg.fp.p, mg.fq.p, len, scratchX, mg.fr.p, mg.fdinv.p, mg.om(0), mg.nrhs, mg.fz.p, fold_into(mg, S_RR));
                 return MOF_OK;
             case MOF_K_FLOW_RESTRICT:
-                MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine);
+                MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine, 0, -1);
                 return MOF_OK;
             case MOF_K_FLOW_PROLONG:
                 MOF_LAUNCH(k_prolong_flow, blocks_for(mg.nFine, B), B, 0, mg.agg.p, mg.cevec.p, l1.z.p, mg.nFine, mg.fz.p);

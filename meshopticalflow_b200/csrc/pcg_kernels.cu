@@ -432,6 +432,7 @@ int extract_inverse_diagonal(mof_ctx* ctx, int n, const int* rowptr, const int* 
 // same code, same grid as inside k_pcg<1>.
 __global__ void __launch_bounds__(PCG_T, 5) k_spmv_dot(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const double* __restrict__ val,
                                                        const double* __restrict__ x, double* __restrict__ y, double* __restrict__ partial) {
+    pdl_wait();
     __shared__ double sh[PCG_NW];
     double dot[1] = {0};
     spmv_sell(n, sliceBase, col, val, nullptr, x, y, 0, dot[0]);
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(PCG_T, 5) k_spmv_dot(int n, const int* __restr
 int spmv_dot_launch(mof_ctx* ctx, int n, const int* sliceBase, const int* col, const double* val, const double* x, double* y, double* partial, int* partials) {
     int& grid = ctx->pcg.gridBlocks;  // per context (per device), computed once
     if (!grid) MOF_TRY(pcg_grid<1>(ctx, &grid));
-    MOF_LAUNCH(k_spmv_dot, grid, PCG_T, 0, n, sliceBase, col, val, x, y, partial);
+    MOF_LAUNCH_PDL(k_spmv_dot, grid, PCG_T, 0, n, sliceBase, col, val, x, y, partial);
     *partials = grid;
     return MOF_OK;
 }

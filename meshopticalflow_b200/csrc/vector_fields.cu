@@ -126,6 +126,40 @@ static int vf_apply(mof_ctx* ctx, double weight, const double* x, double* y) {
     return MOF_OK;
 }
 
+// For the Spectrum tool (spectrum.cu): y = (dataScale * P^T D P + weight * S) x with D from ctx->dataD — (0, 1) is the smoothness
+// operator S of the basis, (1, 0) with D_t = g_t area_t its mass operator (VectorLaplacianSpectrum.inl:9-19).
+__global__ void k_set_data_scale(double v, double* __restrict__ scalars) { scalars[SC_DATA_SCALE] = v; }
+int vf_apply_operator(mof_ctx* ctx, double dataScale, double weight, const double* x, double* y) {
+    MOF_LAUNCH(k_set_data_scale, 1, 1, 0, dataScale, ctx->scalars.p);
+    return vf_apply(ctx, weight, x, y);
+}
+// diag(S): Connection — the diagonal of each triangle's 2x2 block; Conformal — (K diag(1/m) K / 2)_vv on both halves.
+__global__ void k_connection_diagonal(const double* __restrict__ diag, int T, double* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) out[2 * t] = diag[3 * t], out[2 * t + 1] = diag[3 * t + 2];
+}
+__global__ void k_conformal_diagonal(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ stiff, const double* __restrict__ minv, int V,
+                                     double* __restrict__ out) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    double d = 0;
+    for (int k = rowptr[v]; k < rowptr[v + 1]; k++) d += stiff[k] * stiff[k] * minv[col[k]];
+    out[v] = out[v + V] = 0.5 * d;
+}
+int vf_smooth_diagonal(mof_ctx* ctx, double* out) {
+    VfState& s = *ctx->vf;
+    if (s.mode == 1) MOF_LAUNCH(k_conformal_diagonal, blocks_for(ctx->V, B), B, 0, ctx->sRowptr.p, ctx->sCol.p, ctx->sStiff.p, s.minv.p, ctx->V, out);
+    else MOF_LAUNCH(k_connection_diagonal, blocks_for(ctx->T, B), B, 0, s.connDiag.p, ctx->T, out);
+    return MOF_OK;
+}
+// tField = P coeffs for any coefficient vector of the basis (Conformal.inl:49-64; Connection: the identity).
+int vf_triangle_field(mof_ctx* ctx, const double* coeffs, double* tfield) {
+    VfState& s = *ctx->vf;
+    if (s.mode == 1) MOF_LAUNCH(k_conformal_field, blocks_for(ctx->T, B), B, 0, ctx->tri.p, ctx->g.p, coeffs, ctx->V, ctx->T, tfield);
+    else MOF_CUDA(cudaMemcpyAsync(tfield, coeffs, sizeof(double) * 2 * ctx->T, cudaMemcpyDeviceToDevice, ctx->stream));
+    return MOF_OK;
+}
+
 static int vf_dot(mof_ctx* ctx, const double* a, const double* b, long long n, double* out) {
     VfState& s = *ctx->vf;
     MOF_LAUNCH(k_dot_partial, RED, B, 0, a, b, n, s.partial.p);

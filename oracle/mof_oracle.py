@@ -326,6 +326,50 @@ def connection_field(g, opp, lin, cst, mode):
     return sp.identity(2 * T, format="csr"), S
 
 
+# ------------------------------------------------------------------------------------ Spectrum tool
+
+def vector_field_mass(g, P):
+    """massOperator = restriction * vfMass * prolongation, VectorLaplacianSpectrum.inl:9-19: vfMass = blockdiag(g_t * area_t)."""
+    area = triangle_areas(g)
+    T = g.shape[0]
+    t = np.arange(T)
+    rows = np.concatenate([2 * t, 2 * t, 2 * t + 1, 2 * t + 1])
+    cols = np.concatenate([2 * t, 2 * t + 1, 2 * t, 2 * t + 1])
+    vals = np.concatenate([g[:, 0] * area, g[:, 1] * area, g[:, 1] * area, g[:, 2] * area])
+    vf_mass = sp.coo_matrix((vals, (rows, cols)), shape=(2 * T, 2 * T)).tocsr()
+    return (P.T @ vf_mass @ P).tocsc()
+
+
+def spectrum(vertices, triangles, count=20, vf_mode=0, c_mode=0, shift=1e-8):
+    """ComputeSpectrum, VectorLaplacianSpectrum.inl:5-39, as Spectrum.cpp:177-184 calls it: the `count` eigenpairs of S x = lambda M x
+    nearest `shift` by shift-invert Lanczos (scipy's eigsh is the same ARPACK driver the reference calls through ARPACK++,
+    EigenvalueSolver.h:177-219, with SuperLU where the reference uses Eigen's LDLT), prolonged to per-triangle fields.
+    Returns (eigenvalues ascending [count], fields [count, T, 2], coefficient vectors [count, N], S, M)."""
+    import scipy.sparse.linalg as spla
+
+    triangles = np.asarray(triangles)
+    nv = vertices.shape[0]
+    g = make_unit_area(metric_from_embedding(vertices, triangles))
+    opp = opposite_half_edges(triangles)
+    if vf_mode == 0:
+        reduced, expanded, positive = whitney_numbering(opp)
+        P = whitney_prolongation(g, reduced, positive)
+        S = whitney_smooth_operator(g, triangles, opp, reduced, expanded, positive, nv)[0]
+    elif vf_mode == 1:
+        K = scalar_matrices(g, triangles, nv)[1]
+        P, S = conformal_field(g, triangles, nv, K)
+    else:
+        lin, cst = edge_xforms(g, opp)
+        P, S = connection_field(g, opp, lin, cst, c_mode)
+    M = vector_field_mass(g, P)
+    vals, vecs = spla.eigsh(S.tocsc(), k=count, M=M, sigma=shift, which="LM")
+    order = np.argsort(vals)
+    vals, vecs = vals[order], vecs[:, order]
+    T = triangles.shape[0]
+    fields = np.stack([(P @ vecs[:, i]).reshape(T, 2) for i in range(count)])
+    return vals, fields, vecs.T.copy(), S, M
+
+
 # -------------------------------------------------------------------------------- solver pieces
 
 def smooth_signal(M, S, signal, weight):

@@ -20,6 +20,10 @@
 #include "../../meshopticalflow_b200/csrc/texprep_kernels.cu"
 #elif EMUL_UNIT == 6
 #include "../../meshopticalflow_b200/csrc/mof_api.cu"
+#elif EMUL_UNIT == 8
+#include "../../meshopticalflow_b200/csrc/reorder.cu"
+#elif EMUL_UNIT == 9
+#include "../../meshopticalflow_b200/csrc/spectrum.cu"
 #elif EMUL_UNIT == 7  // instead of dist_stub.cpp, with -DMOF_EMUL_THREADS: NCCL as threads of this process (nccl.h here)
 #include "../../meshopticalflow_b200/csrc/dist.cu"
 #endif

@@ -17,7 +17,7 @@ from conftest import ROOT, rel  # noqa: F401 (golden_sphere comes from conftest)
 from meshopticalflow_b200 import api, synthetic
 
 EMU_DIR = os.path.join(ROOT, "tests", "host_emulation")
-UNITS = 8  # library_emul.cpp: units 0-6 as in test_library_host_emulation.py, unit 7 = dist.cu
+UNITS = 10  # library_emul.cpp: units 0-6, 8 and 9 as in test_library_host_emulation.py, unit 7 = dist.cu
 
 
 @pytest.fixture(scope="module")

@@ -163,3 +163,45 @@ def test_million_vertex_flow_system_residual_with_scipy(aligner):
     rng = np.random.default_rng(0)
     for y in (x, rng.standard_normal(x.shape[0])):
         assert y @ (A @ y) > 0
+
+
+@pytest.mark.timeout(600)
+def test_badly_numbered_mesh_is_renumbered_and_gives_the_same_alignment(aligner):
+    """mof_set_reorder (csrc/reorder.cu): the 65 538-vertex sphere with its vertices and triangles shuffled. The library renumbers it
+    on its own (its numbering is not local), the results come back in the caller's numbering and equal those of the sorted mesh; with
+    the renumbering switched off the same results, only slower."""
+    v, t = synthetic.octahedron_sphere(7)
+    a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(v, 3))
+    rng = np.random.default_rng(11)
+    vo, to = rng.permutation(v.shape[0]), rng.permutation(t.shape[0])  # shuffled index -> original index
+    rank = np.empty_like(vo)
+    rank[vo] = np.arange(vo.size)
+    vs, ts = np.ascontiguousarray(v[vo]), np.ascontiguousarray(rank[t][to].astype(np.int32))
+    al = aligner
+    p = api.default_params()
+    p.iterations = 3
+    al.set_params(p)
+
+    def run(vertices, triangles, sa, sb):
+        al.set_mesh(vertices, triangles)
+        al.set_signals(sa, sb)
+        al.iterate(3)
+        return al.flow(), al.advect_vertices(0.5), al.permutation()[0]
+
+    f0, (a0, b0), on0 = run(v, t, a, b)
+    assert not on0  # numbered along a Morton curve by the generator: left alone
+    f1, (a1, b1), on1 = run(vs, ts, a[vo], b[vo])
+    assert on1
+    back = np.empty_like(f1)
+    back[to] = f1
+    assert rel(back, f0) < 1e-5
+    ca, cb = np.empty_like(a1), np.empty_like(b1)
+    ca[vo], cb[vo] = a1, b1
+    assert colour_outliers(ca, a0, 1e-3) < TIE_FRACTION and colour_outliers(cb, b0, 1e-3) < TIE_FRACTION
+    al.set_reorder(0)
+    f2, (a2, b2), on2 = run(vs, ts, a[vo], b[vo])
+    assert not on2
+    back[to] = f2
+    assert rel(back, f0) < 1e-5
+    ca[vo], cb[vo] = a2, b2
+    assert colour_outliers(ca, a0, 1e-3) < TIE_FRACTION and colour_outliers(cb, b0, 1e-3) < TIE_FRACTION

@@ -21,7 +21,7 @@ from meshopticalflow_b200 import api, synthetic
 from oracle import mof_oracle as O
 
 EMU_DIR = os.path.join(ROOT, "tests", "host_emulation")
-UNITS = 7  # library_emul.cpp: one translation unit per .cu file
+UNITS = [0, 1, 2, 3, 4, 5, 6, 8, 9]  # library_emul.cpp: one translation unit per .cu file (7 = dist.cu, stubbed here)
 
 
 @pytest.fixture(scope="module")
@@ -32,7 +32,7 @@ def emulated(tmp_path_factory):
     # buffer overrun of every kernel into a test failure: "device" memory is malloc'd
     extra = os.environ.get("MOF_EMUL_CXXFLAGS", "-O2").split()
     base = ["g++"] + extra + ["-std=c++17", "-fPIC", "-c", "-x", "c++", "-DMOF_HOST_EMULATION", "-fno-gnu-unique", "-I.", "-w"]
-    jobs = [base + ["-DEMUL_UNIT=%d" % u, "-o", str(out / ("unit%d.o" % u)), "library_emul.cpp"] for u in range(UNITS)]
+    jobs = [base + ["-DEMUL_UNIT=%d" % u, "-o", str(out / ("unit%d.o" % u)), "library_emul.cpp"] for u in UNITS]
     jobs += [base + ["-o", str(out / "dist_stub.o"), "dist_stub.cpp"], base + ["-o", str(out / "runtime.o"), "emul_runtime.cpp"]]
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         list(pool.map(lambda cmd: subprocess.check_call(cmd, cwd=EMU_DIR), jobs))
@@ -85,6 +85,91 @@ def test_vertex_alignment_matches_the_reference_golden(aligner, golden_sphere):
     assert np.abs(out.astype(int) - g["output_rgb"].astype(int)).max() <= 1
     s = al.stats()
     assert s["flowSolves"] == 10 and s["lastFlowResidual"] <= 1.01e-8 and s["kernelLaunches"] > 0
+
+
+def test_renumbered_mesh_gives_the_callers_numbering_back(aligner, golden_sphere, emulated):
+    """mof_set_reorder (reorder.cu): the golden sphere with its vertices and triangles shuffled, renumbering forced — the flow and the
+    advected colours come back in the caller's (shuffled) numbering and are the golden's; the texture entries refuse the mesh."""
+    g = golden_sphere
+    v, t = g["input_vertices_f32"].astype(np.float64), g["triangles"]
+    rng = np.random.default_rng(5)
+    vo, to = rng.permutation(v.shape[0]), rng.permutation(t.shape[0])  # shuffled index -> original index
+    rank = np.empty_like(vo)
+    rank[vo] = np.arange(vo.size)
+    vs, ts = np.ascontiguousarray(v[vo]), np.ascontiguousarray(rank[t][to].astype(np.int32))
+    al = aligner
+    al.set_reorder(1)
+    al.set_mesh(vs, ts)
+    on, vorder, torder = al.permutation()
+    assert on and sorted(vorder.tolist()) == list(range(v.shape[0])) and sorted(torder.tolist()) == list(range(t.shape[0]))
+    al.set_signals(g["input_a"].astype(np.float64)[vo], g["input_b"].astype(np.float64)[vo])
+    for i in range(10):
+        al.iterate(1)
+        f = np.empty_like(g["it%02d.tFlowField" % i])
+        f[to] = al.flow()
+        assert rel(f, g["it%02d.tFlowField" % i]) < 1e-6, i
+    ca, cb = al.advect_vertices(0.5)
+    a0, b0 = np.empty_like(ca), np.empty_like(cb)
+    a0[vo], b0[vo] = ca, cb
+    assert np.abs(a0 - g["advected0"]).max() < 1e-4 and np.abs(b0 - g["advected1"]).max() < 1e-4
+    with pytest.raises(api.MofError, match="mof_set_reorder"):
+        al.set_texture_map(4, 4, np.zeros(16, np.int32), np.zeros((16, 2)), np.zeros((t.shape[0], 6)), np.zeros((4, 4, 3), np.uint8), np.zeros((4, 4, 3), np.uint8))
+    al.set_reorder(-1)
+    al.set_mesh(vs, ts)  # small mesh: left alone
+    assert not al.permutation()[0]
+    # the decision itself, on a context whose first mesh this is: shuffled -> renumbered, the file's own order -> left alone
+    os.environ["MOF_REORDER_MIN_VERTICES"] = "100"
+    try:
+        fresh = emulated.Aligner(0)
+        fresh.set_mesh(vs, ts)
+        assert fresh.permutation()[0]
+        v5, t5 = synthetic.octahedron_sphere(5)  # numbered along a Morton curve by the generator (mean index span of a triangle: V/30)
+        fresh.set_mesh(v5, t5)
+        assert not fresh.permutation()[0]
+        v5, t5 = synthetic.octahedron_sphere(5, spatial_sort=False)  # ... in the order the subdivision created the vertices (V/2)
+        fresh.set_mesh(v5, t5)
+        assert fresh.permutation()[0]
+        fresh.close()
+    finally:
+        del os.environ["MOF_REORDER_MIN_VERTICES"]
+
+
+@pytest.mark.parametrize("mode,cmode,count", [(0, 0, 6), (2, 0, 6), (2, 2, 6), (1, 0, 6)])
+def test_spectrum_matches_the_shift_invert_lanczos_of_the_checker(aligner, mode, cmode, count):
+    """mof_spectrum (csrc/spectrum.cu: LOBPCG) against ComputeSpectrum as the checker restates it (ARPACK shift-invert through scipy):
+    eigenvalues, and the span of the prolonged eigenvectors cluster by cluster (a sphere's eigenvalues are multiple)."""
+    v, t = synthetic.octahedron_sphere(3)
+    al = aligner
+    p = api.default_params()
+    p.vfMode, p.cMode = mode, cmode
+    al.set_params(p)
+    al.set_mesh(v, t)
+    ev, fields, its, res = al.spectrum(count, 1e-9, 3000)
+    if mode == 1:  # S and M share a null space (constants of either potential): ARPACK's shift-invert answer is not defined there;
+        import scipy.linalg as sla  # the checker is the dense generalised problem on the complement of the constants
+
+        vals, _, _, S, M = O.spectrum(v, t, 2, mode, cmode)
+        nv = v.shape[0]
+        Q = np.linalg.qr(np.kron(np.eye(2), np.ones((nv, 1))), mode="complete")[0][:, 2:]
+        w, U = sla.eigh(Q.T @ S.toarray() @ Q, Q.T @ M.toarray() @ Q)
+        ref_ev = w[:count]
+        g = O.make_unit_area(O.metric_from_embedding(v, t))
+        K = O.scalar_matrices(g, t, nv)[1]
+        P = O.conformal_field(g, t, nv, K)[0]
+        ref_fields = np.stack([(P @ (Q @ U[:, i])).reshape(-1, 2) for i in range(count)])
+    else:
+        ref_ev, ref_fields, _, _, _ = O.spectrum(v, t, count, mode, cmode)
+    assert res <= 1e-9 and its > 0
+    assert np.abs(ev - ref_ev).max() <= 1e-7 * np.abs(ref_ev).max(), (ev, ref_ev)
+    # <f, h> = sum_t f_t^T (g_t area_t) h_t = x^T M y: both sets are orthonormal in it; on whole clusters the cross-Gram matrix is orthogonal
+    g = O.make_unit_area(O.metric_from_embedding(v, t))
+    area = O.triangle_areas(g)
+
+    def weighted(f):
+        return np.stack([(g[:, 0] * f[:, 0] + g[:, 1] * f[:, 1]) * area, (g[:, 1] * f[:, 0] + g[:, 2] * f[:, 1]) * area], 1)
+
+    G = np.array([[np.sum(fields[i] * weighted(ref_fields[j])) for j in range(count)] for i in range(count)])
+    assert np.abs(G @ G.T - np.eye(count)).max() < 1e-5, G
 
 
 def test_multigrid_and_jacobi_solves_agree_with_the_checker(emulated):
