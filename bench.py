@@ -259,6 +259,42 @@ def partitioned_record(api, sharding, synthetic, torch, dev, stream, rank, local
     return out
 
 
+def concurrent_record(api, torch, dev, verts, tris, pairs_h, contexts=2, pairs_each=2):
+    """`contexts` solver contexts on this ONE GPU, one host thread each, aligning independent pairs at the same time from host buffers
+    (the batched configuration, configs[3], per GPU): the latency-bound part of one pair's solves is filled by another's. Wall clock
+    between device-wide synchronisations (several streams: no single stream's events bracket it)."""
+    als = [api.Aligner(dev.index) for _ in range(contexts)]
+    outs = [(np.empty((verts.shape[0], 3)), np.empty((verts.shape[0], 3))) for _ in range(contexts)]
+    p = api.default_params()
+
+    def work(k, n):
+        al = als[k]
+        a, b = pairs_h[k % len(pairs_h)]
+        for _ in range(n):
+            al.set_mesh(verts, tris)
+            al.set_signals(a, b)
+            al.iterate(p.iterations)
+            al.advect_vertices(0.5, *outs[k])
+
+    try:
+        for k in range(contexts):
+            work(k, 1)  # warm-up: pools, graphs
+        torch.cuda.synchronize(dev)
+        threads = [threading.Thread(target=work, args=(k, pairs_each)) for k in range(contexts)]
+        t0 = time.perf_counter()
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+    finally:
+        for al in als:
+            al.close()
+    return {"contexts_per_gpu": contexts, "alignments": contexts * pairs_each, "seconds": dt, "value": contexts * pairs_each / dt, "unit": UNIT,
+            "what": "independent pairs aligned at the same time by several contexts on one GPU, host buffers in and out, wall clock; `value` above is one pair at a time"}
+
+
 def run_single(al, p, verts, tris, a, b, torch, dev, stream):
     al.set_params(p)
     ms = []
@@ -289,7 +325,7 @@ def main():
 
     V = 4 * 4 ** args.level + 2
     config = {"workload": f"synthetic subdivided-octahedron sphere, {V} vertices / {2 * V - 4} triangles / {3 * V - 6} Whitney unknowns, vertices and triangles "
-                          "numbered along a Morton curve by the generator (outside the timed region; the library does not reorder), smooth random RGB "
+                          "numbered along a Morton curve by the generator (outside the timed region; the library's own renumbering of badly ordered meshes, mof_set_reorder, measures it as local and leaves it), smooth random RGB "
                           "per-vertex signals (B = A rotated 4 deg), reference defaults (10 iterations), one pair per GPU per step",
               "numbering": "Morton-sorted (synthetic.octahedron_sphere spatial_sort=True)",
               "vertices": V, "pairs_per_step": 1 if args.partitioned else args.gpus,
@@ -404,6 +440,7 @@ def main():
                     kernel_rows.append((name, None, str(e)))
         like_gpu_s = gpu_like_for_like(al, api) if (rank == 0 and world == 1 and not args.partitioned and not args.quick) else None
         al.close()
+        concurrent = concurrent_record(api, torch, dev, verts, tris, pairs_h) if (world == 1 and not args.partitioned and not args.quick) else None
 
         # N > 1: BASELINE.json configs[4] next to the sharded pairs — one mesh, its solves row-partitioned over all ranks, against rank 0 alone
         partitioned = None
@@ -475,6 +512,8 @@ def main():
     }
     if partitioned is not None:
         line["partitioned"] = partitioned
+    if concurrent is not None:
+        line["concurrent_contexts"] = concurrent
     if world == 1 and not args.partitioned:
         with tempfile.TemporaryDirectory() as tmp:
             nv = reference_sample_inputs(tmp)

@@ -136,7 +136,8 @@ long long mof_num_coeffs(mof_ctx* ctx);
  * before an alignment. eigenvalues[count] ascending; fields[count][T][2] = the prolonged eigenvectors P x (what the tool writes to
  * eigenvector-%03d.bin), x normalised to x^T M x = 1 like ARPACK's, sign free; inside a multiple eigenvalue only the span is defined.
  * Converged when every pair has ||S x - lambda M x|| <= tol (||S x|| + lambda ||M x||); MOF_E_NOCONVERGE after maxIterations.
- * count <= 25 (a block of count + max(4, count/4) <= 32 vectors). */
+ * count <= 28 (a block of min(32, count + max(4, count/2 + 2)) vectors: the guard keeps the block from ending inside the cluster of the
+ * last wanted eigenvalue). */
 int mof_spectrum(mof_ctx* ctx, int count, double tol, int maxIterations, double* eigenvalues, double* fields, int* iterations, double* residual);
 
 /* InputGeometryData::flow (OpticalFlow.cpp:482-489): the raw signals resampled along -alpha and

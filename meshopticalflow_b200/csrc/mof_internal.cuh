@@ -302,6 +302,8 @@ bool mg_scalar_usable(const mof_ctx* ctx);
 int mg_scalar_update(mof_ctx* ctx);   // per scalar system: coarse operators of the current sSys (sDinv = its inverse diagonal)
 int mg_scalar_solve(mof_ctx* ctx, const double* b6, double* x6, double tol, int maxIters, int* itersOut, double* relresOut);  // x6 = initial guess
 int mg_scalar_cycle(mof_ctx* ctx, const double* r6, double* z6);
+bool mg_flow_try_update(mof_ctx* ctx);  // mg_flow_update for a matrix other than an alignment's; false: the hierarchy cannot take it
+int mg_flow_cycle(mof_ctx* ctx, const double* r, double* z);  // one cycle of the flow hierarchy on the matrix of the last mg_flow_update
 int mg_scalar_cheb(mof_ctx* ctx, const double* r6, double* z6, int degree, double lo);  // ... sharpened by `degree` Chebyshev steps around the cycle (fixed SPD operator)
 int mg_scalar_smallest_eigenvalue(mof_ctx* ctx, int steps, double* lambdaMin);  // of (one cycle) x (current sSys), from the Lanczos tridiagonal of `steps` PCG iterations
 int mg_time_kernel(mof_ctx* ctx, int which, int reps, float* ms, double* bytes);  // mof_time_kernel for the solver kernels  // z6 = one cycle applied to r6 (approximate inverse of the current sSys)

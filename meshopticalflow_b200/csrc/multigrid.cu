@@ -2914,6 +2914,24 @@ int mg_scalar_cycle(mof_ctx* ctx, const double* r6, double* z6) {
     MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 1, z6);
     return MOF_OK;
 }
+// mg_flow_update for a matrix that is not an alignment's (spectrum.cu): whether the hierarchy took it (positive definite coarsest level);
+// either way the hierarchy stays available to the next alignment, whose own system re-values it.
+bool mg_flow_try_update(mof_ctx* ctx) {
+    if (!mg_flow_usable(ctx)) return false;
+    const int rc = mg_flow_update(ctx);
+    const bool ok = rc == MOF_OK && ctx->mg->usable;
+    ctx->mg->usable = true;
+    return ok;
+}
+// The same for the FLOW hierarchy: Z = cycle(R) for the matrix in ctx->wA whose coarse operators mg_flow_update built last — the
+// preconditioner of the Spectrum tool's block iteration (spectrum.cu), where wA = S + tau M.
+int mg_flow_cycle(mof_ctx* ctx, const double* r, double* z) {
+    Multigrid& mg = *ctx->mg;
+    MOF_TRY(fine_cycle(ctx, mg, r, false, S_RZ));
+    const long long len = (long long)mg.fineLen();
+    MOF_LAUNCH(k_direction, blocks_for(len, B), B, 0, mg.fz.p, mg.scal.p, len, 1, z);
+    return MOF_OK;
+}
 // d = alpha d + beta c ; z += d (one step of the Chebyshev recurrence below)
 __global__ void k_cheb_update(double alpha, double beta, const double* __restrict__ c, long long n, double* __restrict__ d, double* __restrict__ z, int first) { pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -7,7 +7,7 @@
 // the operators the alignment path already has on the device:
 //   Whitney     S = ctx->wS (sliced layout), M assembled once on the same pattern by the flow assembly with D_t = g_t area_t;
 //   Conformal / Connection   S and M applied matrix-free by the kernels of vector_fields.cu ((0, 1) and (1, 0) of s P^T D P + w S).
-// Per iteration, for a block of m = count + guard vectors: the residuals R = S X - M X diag(theta), W = T R (T = the inverse
+// Per iteration, for a block of m = count + guard vectors (guard = max(4, count/2 + 2), m <= 32): the residuals R = S X - M X diag(theta), W = T R (T = the inverse
 // diagonal of S), a Rayleigh-Ritz step on span[X, W, P] — two Gram matrices of 3m x 3m by a tiled kernel with per-CTA partials
 // folded in a fixed order (deterministic), the dense generalised eigenproblem of that size on the host (Cholesky + cyclic Jacobi,
 // <= 96 x 96), and the new X, P, S X, M X, S P, M P as block combinations (one kernel). Vectors are column-major (each column
@@ -33,6 +33,8 @@ constexpr int GRAM_CTAS = 296;    // per-CTA partials of the Gram kernel (2 per 
 struct Ops {
     int mode = 0;
     long long n = 0;
+    bool cycle = false;  // Whitney on a mesh with a flow hierarchy: T = one multigrid cycle on S + tau M instead of the inverse diagonal
+    double tau = 0;
     DBuf<double> wM, tinv;
 };
 
@@ -61,6 +63,22 @@ __global__ void k_sell_inverse_diagonal(int n, const int* __restrict__ sliceBase
         if (col[k] == r) d += val[k];
     }
     out[r] = d > 0 ? 1. / d : 0.;
+}
+// A = S + tau M on the padded sliced layout, with its inverse diagonal (the matrix the multigrid preconditioner is built for).
+__global__ void k_shifted_operator(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const double* __restrict__ S, const double* __restrict__ M,
+                                   double tau, double* __restrict__ A, double* __restrict__ dinv) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int s = r >> 5;
+    const int len = (sliceBase[s + 1] - sliceBase[s]) >> 5;
+    double d = 0;
+    for (int j = 0; j < len; j++) {
+        const size_t k = sell_pos(sliceBase, r, j);
+        const double v = S[k] + tau * M[k];
+        A[k] = v;
+        if (col[k] == r) d += v;
+    }
+    dinv[r] = d > 0 ? 1. / d : 0.;
 }
 __global__ void k_invert_positive(long long n, double* __restrict__ v) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -327,7 +345,10 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
         MOF_TRY(metric_mass_blocks(ctx));
     }
     const long long n = ops.n = vf_unknowns(ctx);
-    const int guard = std::max(4, count / 4);
+    // Block size: the wanted pairs plus a guard. A pair converges at a rate set by the gap to the first eigenvalue OUTSIDE the block, and a
+    // closed surface's eigenvalues come in clusters (a sphere's: 3, 3, 5, 5, 7, 7 ...): a block that ends inside the cluster of the last wanted
+    // pair leaves that gap at zero (65 538 vertices, 20 pairs: 545 iterations with a guard of 5, which ends inside the 7 + 7 cluster at 75.4).
+    const int guard = std::max(4, count / 2 + 2);
     const int m = std::min<long long>(std::min(MAXM, count + guard), n);
     if (count < 1 || count > m) return fail(ctx, MOF_E_INVALID, "mof_spectrum: between 1 and 28 eigenvectors (and no more than unknowns)");
     MOF_CUDA(ops.tinv.alloc((size_t)n));
@@ -336,6 +357,27 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
         MOF_CUDA(cudaMemsetAsync(ops.wM.p, 0, sizeof(double) * ctx->wS.n, ctx->stream));  // (the assembly writes a row's own entries; the slices' padding stays 0)
         MOF_TRY(whitney_mass_operator(ctx, ops.wM.p));
         MOF_LAUNCH(k_sell_inverse_diagonal, blocks_for(n, B), B, 0, (int)n, ctx->wSliceBase.p, ctx->wCol.p, ctx->wS.p, ops.tinv.p);
+        const char* e = getenv("MOF_SPECTRUM_MG");
+        if (mg_flow_usable(ctx) && !(e && *e == '0')) {
+            // The flow hierarchy (multigrid.cu) re-valued for S + tau M. tau > 0 keeps the matrix definite on any genus (harmonic fields are in
+            // the null space of S); what it should be is the size of the WANTED eigenvalues — T (S - theta M) then has the spectrum
+            // (lambda - theta) / (lambda + tau), clustered at 1 for the bulk and of order one for the wanted pairs — which is not known
+            // yet: start from tr S / tr M / 1e3 (far below the bulk whatever the units) and follow the Ritz values down (retune below).
+            MOF_CUDA(ctx->dtmp0.reserve((size_t)n));
+            MOF_LAUNCH(k_shifted_operator, blocks_for(n, B), B, 0, (int)n, ctx->wSliceBase.p, ctx->wCol.p, ctx->wS.p, ops.wM.p, 0., ctx->wA.p, ctx->wDinv.p);
+            MOF_LAUNCH(k_invert_positive, blocks_for(n, B), B, 0, n, ctx->wDinv.p);  // diag S
+            MOF_TRY(reduce_sum(ctx, ctx->wDinv.p, n, ctx->scalars.p + SC_TMP));
+            MOF_LAUNCH(k_sell_inverse_diagonal, blocks_for(n, B), B, 0, (int)n, ctx->wSliceBase.p, ctx->wCol.p, ops.wM.p, ctx->dtmp0.p);
+            MOF_LAUNCH(k_invert_positive, blocks_for(n, B), B, 0, n, ctx->dtmp0.p);  // diag M
+            MOF_TRY(reduce_sum(ctx, ctx->dtmp0.p, n, ctx->scalars.p + SC_TMP + 1));
+            double tr[2] = {0, 0};
+            MOF_CUDA(read_back(ctx, tr, ctx->scalars.p + SC_TMP, 2));
+            const double tau = ops.tau = tr[1] > 0 ? 1e-3 * tr[0] / tr[1] : 0.;
+            MOF_LAUNCH(k_shifted_operator, blocks_for(n, B), B, 0, (int)n, ctx->wSliceBase.p, ctx->wCol.p, ctx->wS.p, ops.wM.p, tau, ctx->wA.p, ctx->wDinv.p);
+            ctx->haveFlowSystem = false;
+            ops.cycle = mg_flow_try_update(ctx);
+            if (getenv("MOF_SPECTRUM_VERBOSE")) fprintf(stderr, "[spectrum] multigrid preconditioner on S + %.3g M: %s\n", tau, ops.cycle ? "yes" : "no (inverse diagonal)");
+        }
     } else {
         MOF_TRY(vf_smooth_diagonal(ctx, ops.tinv.p));
         MOF_LAUNCH(k_invert_positive, blocks_for(n, B), B, 0, n, ops.tinv.p);
@@ -401,6 +443,8 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
             MOF_CUDA(cudaMemcpyAsync(dtheta.p, theta.data(), sizeof(double) * m, cudaMemcpyHostToDevice, ctx->stream));
             MOF_LAUNCH(k_residual_block, blocks_for((long long)blk, B), B, 0, n, m, SX, MX, dtheta.p, ops.tinv.p, T0, W);
             if (mode == 1) MOF_LAUNCH(k_remove_half_means, 2 * m, B, 0, n / 2, W);
+            if (ops.cycle)
+                for (int j = 0; j < m; j++) MOF_TRY(mg_flow_cycle(ctx, T0 + (size_t)j * n, W + (size_t)j * n));
             std::vector<double> rr((size_t)m * m), ss((size_t)m * m), mm((size_t)m * m);
             MOF_TRY(gram(ctx, w, T0, T0, n, m, m, rr.data()));
             MOF_TRY(gram(ctx, w, SX, SX, n, m, m, ss.data()));
@@ -413,6 +457,15 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
             if (getenv("MOF_SPECTRUM_VERBOSE") && it % 20 == 0) fprintf(stderr, "[spectrum] iteration %d: residual %.3g, theta[0] %.10g theta[%d] %.10g\n", it, worst, theta[0], count - 1, theta[count - 1]);
             if (!(worst > tol)) break;
             if (!std::isfinite(worst)) return fail(ctx, MOF_E_NOCONVERGE, "mof_spectrum: the iteration broke down");
+            // follow the Ritz values down with the preconditioner's shift (see above): re-value the hierarchy when the largest wanted one
+            // has fallen below half the shift in use; the directions of the old preconditioner are dropped with it
+            if (ops.cycle && it >= 3 && theta[count - 1] > 0 && theta[count - 1] < 0.5 * ops.tau) {
+                ops.tau = theta[count - 1];
+                MOF_LAUNCH(k_shifted_operator, blocks_for(n, B), B, 0, (int)n, ctx->wSliceBase.p, ctx->wCol.p, ctx->wS.p, ops.wM.p, ops.tau, ctx->wA.p, ctx->wDinv.p);
+                ops.cycle = mg_flow_try_update(ctx);
+                haveP = false;
+                if (getenv("MOF_SPECTRUM_VERBOSE")) fprintf(stderr, "[spectrum] iteration %d: preconditioner re-valued for S + %.3g M (%s)\n", it, ops.tau, ops.cycle ? "cycle" : "inverse diagonal");
+            }
             // W against X in the M inner product: W <- W - X (X^T M W)   (X is M-orthonormal)
             MOF_TRY(gram(ctx, w, MX, W, n, m, m, G.data()));
             {

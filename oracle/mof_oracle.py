@@ -362,8 +362,13 @@ def spectrum(vertices, triangles, count=20, vf_mode=0, c_mode=0, shift=1e-8):
         lin, cst = edge_xforms(g, opp)
         P, S = connection_field(g, opp, lin, cst, c_mode)
     M = vector_field_mass(g, P)
-    vals, vecs = spla.eigsh(S.tocsc(), k=count, M=M, sigma=shift, which="LM")
-    order = np.argsort(vals)
+    # A single-vector Lanczos process can miss copies of a multiple eigenvalue (a sphere's come in clusters of 3-6): ask for a few
+    # more pairs than wanted, in a Krylov space four times that, from a fixed start vector, and keep the lowest `count`.
+    n = S.shape[0]
+    k = min(count + 8, n - 2)
+    v0 = np.random.default_rng(0).standard_normal(n)
+    vals, vecs = spla.eigsh(S.tocsc(), k=k, M=M, sigma=shift, which="LM", ncv=min(n - 1, max(4 * k, 80)), v0=v0)
+    order = np.argsort(vals)[:count]
     vals, vecs = vals[order], vecs[:, order]
     T = triangles.shape[0]
     fields = np.stack([(P @ vecs[:, i]).reshape(T, 2) for i in range(count)])

@@ -110,6 +110,8 @@ int pcg_solve_sell(mof_ctx* ctx, int n, const int* sliceBase, const int* col, co
 // multigrid.cu: no hierarchies on the host
 bool mg_flow_usable(const mof_ctx*) { return false; }
 int mg_flow_update(mof_ctx*) { return MOF_E_INVALID; }
+bool mg_flow_try_update(mof_ctx*) { return false; }
+int mg_flow_cycle(mof_ctx*, const double*, double*) { return MOF_E_INVALID; }
 int mg_flow_solve(mof_ctx*, double, int, int*, double*) { return MOF_E_INVALID; }
 bool mg_scalar_usable(const mof_ctx*) { return false; }
 int mg_scalar_update(mof_ctx*) { return MOF_E_INVALID; }

@@ -349,3 +349,31 @@ def test_smoothing_ahead_on_a_second_stream_changes_nothing(monkeypatch):
     assert np.array_equal(runs["1"][1], runs["0"][1]) and np.array_equal(runs["1"][2], runs["0"][2])
     assert runs["1"][3:] == runs["0"][3:]
     assert runs["1"][5] == 2 * (1 + 5)
+
+
+def test_programmatic_dependent_launches_change_nothing(monkeypatch):
+    """MOF_PDL (mof_internal.cuh: every solver kernel starts with griddepcontrol.wait and is launched with programmatic stream
+    serialisation, inside the captured PCG graph too) only changes WHEN a kernel's CTAs are scheduled: with it and without it the
+    flows, the advected colours and the iteration counts are identical, bit for bit — also through the replay loop (MOF_MG_WHILE=0)."""
+    v, t = synthetic.octahedron_sphere(7)
+    a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(v, 8))
+    runs = {}
+    for mode in ("pdl", "plain", "pdl-replay"):
+        monkeypatch.setenv("MOF_PDL", "0" if mode == "plain" else "1")
+        monkeypatch.setenv("MOF_MG_WHILE", "0" if mode == "pdl-replay" else "1")
+        al = api.Aligner(0)
+        try:
+            p = api.default_params()
+            p.iterations = 4
+            al.set_params(p)
+            al.set_mesh(v, t)
+            al.set_signals(a, b)
+            al.iterate(4)
+            s = al.stats()
+            runs[mode] = (al.flow(), al.advect_vertices(0.5), s["flowCgIterations"], s["smoothCgIterations"])
+        finally:
+            al.close()
+    for mode in ("plain", "pdl-replay"):
+        assert np.array_equal(runs["pdl"][0], runs[mode][0]), mode
+        assert np.array_equal(runs["pdl"][1][0], runs[mode][1][0]) and np.array_equal(runs["pdl"][1][1], runs[mode][1][1]), mode
+        assert runs["pdl"][2:] == runs[mode][2:], mode
