@@ -196,7 +196,9 @@ static int vf_pcg(mof_ctx* ctx, double weight, double tol, int maxIters, int* it
     VfState& s = *ctx->vf;
     const long long N = s.N, half = N / 2;
     const int split = s.mode == 1 ? 1 : 0;
-    const int kCheck = s.mgNow ? 5 : 25;  // iterations between convergence read-backs (a two-cycle iteration is ~20x a block-Jacobi one)
+    // iterations between convergence read-backs (a two-cycle iteration is ~20x a block-Jacobi one); even, so that a batch leaves the
+    // ping-pong slot `cur` where it found it and ONE captured graph of a batch serves the whole solve
+    const int kCheck = s.mgNow ? 6 : 26;
     double* sc = s.sc.p;
     MOF_CUDA(cudaMemsetAsync(s.x.p, 0, sizeof(double) * N, ctx->stream));
     MOF_CUDA(cudaMemcpyAsync(s.r.p, s.b.p, sizeof(double) * N, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -207,29 +209,77 @@ static int vf_pcg(mof_ctx* ctx, double weight, double tol, int maxIters, int* it
     if (!(bb > 0)) return MOF_OK;  // zero right-hand side: x = 0
     int iters = 0;
     double relres = 1, previous = 1;
-    for (int restart = 0; restart < 8; restart++) {
+    double* rzrr = s.partial.p + RED;
+    auto iteration = [&](int& cur) -> int {
+        MOF_TRY(vf_apply(ctx, weight, s.p.p, s.q.p));
+        MOF_LAUNCH(k_pcg_step, RED, B, 0, s.mgNow ? (const double*)nullptr : s.binv.p, sc, S_RZ0 + cur, s.partial.p, RED, s.p.p, s.q.p, half, split, s.x.p, s.r.p,
+                   s.z.p, rzrr);
+        if (s.mgNow) MOF_TRY(vf_two_cycle_preconditioner(ctx, rzrr));
+        MOF_LAUNCH(k_pcg_direction, RED, B, 0, sc, S_RZ0 + (cur ^ 1), S_RZ0 + cur, rzrr, RED, s.z.p, N, s.p.p);
+        cur ^= 1;
+        return MOF_OK;
+    };
+    // An iteration is 3 launches (Connection), 4 (Conformal, block Jacobi) or ~80 (Conformal, two-cycle preconditioner): below ~300 k
+    // unknowns the host cannot issue them as fast as the GPU retires them. The first batch runs eagerly (it also sizes every scratch
+    // buffer), then the same batch is captured once and replayed: one graph launch and one read-back per batch. MOF_VF_GRAPH=0: eager.
+    struct BatchGraph {  // destroyed on every way out of the solve
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        void reset() {
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            exec = nullptr, graph = nullptr;
+        }
+        ~BatchGraph() { reset(); }
+    } batch;
+    cudaGraph_t& graph = batch.graph;
+    cudaGraphExec_t& exec = batch.exec;
+    long long launchesPerBatch = 0;
+    bool triedCapture = false;
+    {
+        const char* e = getenv("MOF_VF_GRAPH");
+        if (e && *e == '0') triedCapture = true;
+    }
+    auto drop_graph = [&]() { batch.reset(); };
+    int rcLoop = MOF_OK;
+    for (int restart = 0; restart < 8 && rcLoop == MOF_OK; restart++) {
         int cur = 0;
-        double* rzrr = s.partial.p + RED;
         MOF_LAUNCH(k_pcg_start, RED, B, 0, s.binv.p, s.r.p, half, split, s.z.p, rzrr);  // z = block Jacobi, r.z, r.r
         if (s.mgNow) MOF_TRY(vf_two_cycle_preconditioner(ctx, rzrr));                  // ... replaced
         MOF_LAUNCH(k_pcg_direction, RED, B, 0, sc, S_RZ0 + cur, -1, rzrr, RED, s.z.p, N, s.p.p);
         bool converged = false;
         while (iters < maxIters && !converged) {
-            for (int k = 0; k < kCheck && iters < maxIters; k++, iters++) {
-                MOF_TRY(vf_apply(ctx, weight, s.p.p, s.q.p));
-                MOF_LAUNCH(k_pcg_step, RED, B, 0, s.mgNow ? (const double*)nullptr : s.binv.p, sc, S_RZ0 + cur, s.partial.p, RED, s.p.p, s.q.p, half, split, s.x.p,
-                           s.r.p, s.z.p, rzrr);
-                if (s.mgNow) MOF_TRY(vf_two_cycle_preconditioner(ctx, rzrr));
-                MOF_LAUNCH(k_pcg_direction, RED, B, 0, sc, S_RZ0 + (cur ^ 1), S_RZ0 + cur, rzrr, RED, s.z.p, N, s.p.p);
-                cur ^= 1;
+            if (exec) {
+                cudaError_t ce = cudaGraphLaunch(exec, ctx->stream);
+                if (ce != cudaSuccess) { drop_graph(); return cuda_fail(ctx, ce, "cudaGraphLaunch(vf pcg batch)"); }
+                ctx->stats.kernelLaunches += launchesPerBatch;
+                iters += kCheck;
+            } else {
+                for (int k = 0; k < kCheck && rcLoop == MOF_OK; k++, iters++) rcLoop = iteration(cur);
+                if (rcLoop != MOF_OK) break;
+                if (!triedCapture) {
+                    triedCapture = true;
+                    const long long before = ctx->stats.kernelLaunches;
+                    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                        int c2 = cur, crc = MOF_OK;
+                        for (int k = 0; k < kCheck && crc == MOF_OK; k++) crc = iteration(c2);
+                        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                        launchesPerBatch = ctx->stats.kernelLaunches - before;
+                        if (crc == MOF_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
+                        if (crc != MOF_OK || ce != cudaSuccess || !exec) drop_graph(), cudaGetLastError();
+                    }
+                    ctx->stats.kernelLaunches = before;
+                }
             }
             double rr = 0;
-            MOF_CUDA(read_back(ctx, &rr, sc + S_RR));
-            if (!(rr == rr)) return fail(ctx, MOF_E_NOCONVERGE, "flow PCG (matrix-free) produced a NaN residual");
+            cudaError_t re = read_back(ctx, &rr, sc + S_RR);
+            if (re != cudaSuccess) { drop_graph(); return cuda_fail(ctx, re, "read_back(vf pcg residual)"); }
+            if (!(rr == rr)) { drop_graph(); return fail(ctx, MOF_E_NOCONVERGE, "flow PCG (matrix-free) produced a NaN residual"); }
             converged = rr <= tol * tol * bb;
             static const bool verbose = getenv("MOF_VF_VERBOSE") && *getenv("MOF_VF_VERBOSE") != '0';
-            if (verbose && (iters % 50 == 0 || converged)) fprintf(stderr, "[vf pcg] %d iterations, recurrence residual %.3e\n", iters, sqrt(rr / bb));
+            if (verbose && (iters % 50 < kCheck || converged)) fprintf(stderr, "[vf pcg] %d iterations, recurrence residual %.3e\n", iters, sqrt(rr / bb));
         }
+        if (rcLoop != MOF_OK) break;
         // true residual
         MOF_TRY(vf_apply(ctx, weight, s.x.p, s.q.p));
         MOF_LAUNCH(k_residual, blocks_for(N, B), B, 0, s.b.p, s.q.p, N, s.r.p);
