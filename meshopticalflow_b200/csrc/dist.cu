@@ -27,6 +27,24 @@ struct Partition {
     std::vector<int> sendCount, sendOff, recvCount, recvOff;    // per peer, in indices
     int nSend = 0, nRecv = 0;
     DBuf<int> sendIdx, recvIdx;
+    DBuf<int> offs;  // device copy for the peer-memory exchange: sendOff[0 .. world], then recvOff[0 .. world]
+};
+
+// Peer-memory halo exchange (MOF_DIST_P2P, default on where the GPUs can map each other's memory): every rank owns a WINDOW of device
+// memory (cudaMalloc, shared through cudaIpc handles) that its peers write into directly over NVLink — one region per (source rank,
+// slot) plus one arrival flag each. An exchange is two kernels and no library call: k_halo_put packs the values a peer needs straight
+// into that peer's window and, from its last CTA, raises the flag with the pair's sequence number; k_halo_wait polls the flags of the
+// ranks it expects data from and unpacks. Two slots per pair, used alternately, are enough: the next message to a peer is only sent
+// after that peer's message of the current exchange has arrived, which it sends before it unpacks — so it can be at most one message
+// behind (pairs exchange in both directions or not at all: an empty message still raises the flag). Sequence numbers live in device
+// memory, so the two kernels can sit in a replayed CUDA graph.
+struct PeerWindow {
+    bool on = false;
+    unsigned char* base = nullptr;
+    size_t bytes = 0, flagBytes = 0, haloCap = 0;
+    std::vector<unsigned char*> peer;      // peer[j]: rank j's window mapped into this process (peer[rank] = base)
+    DBuf<unsigned char*> table;            // the same on the device
+    DBuf<unsigned long long> seq;          // [0, w) messages sent to j; [w, 2w) received from j; [2w], [2w+1] CTA counters; [2w+2] time-out flag
 };
 
 struct DistState {
@@ -37,6 +55,7 @@ struct DistState {
     Partition part[2];
     std::vector<Partition*> extra;          // further partitions made by the solvers (multigrid levels dealt in cell ranges): dist_add_partition
     DBuf<double> sendBuf, recvBuf;          // sized for the widest exchange in fp64, reused for fp32
+    PeerWindow win;
     // MOF_DIST_TRACE=1 (with MOF_DIST_GRAPH=0): device time and count per kind of exchange, printed by rank 0 when the context closes
     bool trace = false;
     double traceMs[4] = {0, 0, 0, 0};
@@ -112,6 +131,226 @@ __global__ void k_unpack(const T* __restrict__ buf, const int* __restrict__ idx,
     vec[(size_t)idx[e] * width + c] = buf[i];
 }
 
+#ifdef MOF_HOST_EMULATION
+inline unsigned long long p2p_clock() { return 0; }
+template <class T> inline T p2p_load(const T* p) { return *(const volatile T*)p; }
+#else
+__device__ __forceinline__ unsigned long long p2p_clock() { return (unsigned long long)clock64(); }
+template <class T> __device__ __forceinline__ T p2p_load(const T* p) { return __ldcv(p); }  // written by another GPU: never from L1
+#endif
+constexpr unsigned long long P2P_SPIN_LIMIT = 20000000000ull;  // ~10 s of SM clock: a peer that never arrives is an error, not a hang
+
+// offs: sendOff[0 .. world], recvOff[0 .. world]. A pair is active in an exchange when either direction carries entries.
+__device__ __forceinline__ bool p2p_active(const int* offs, int world, int j) { return offs[j + 1] > offs[j] || offs[world + 1 + j + 1] > offs[world + 1 + j]; }
+
+template <class T>
+__global__ void k_halo_put(const T* __restrict__ vec, const int* __restrict__ sendIdx, const int* __restrict__ offs, int world, int me, int width,
+                           unsigned char* const* __restrict__ peer, size_t flagBytes, size_t haloCap, unsigned long long* seq) {
+    const long long total = (long long)offs[world] * width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i / width), c = (int)(i - (long long)e * width);
+        int j = 0;
+        while (e >= offs[j + 1]) j++;
+        const unsigned long long s = seq[j] + 1;  // (raised by the last CTA below, after every CTA has read it)
+        T* dst = reinterpret_cast<T*>(peer[j] + flagBytes + ((size_t)me * 2 + (size_t)(s & 1)) * haloCap) + (size_t)(e - offs[j]) * width + c;
+        *dst = vec[(size_t)sendIdx[e] * width + c];
+    }
+    __threadfence_system();
+    __shared__ int last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&seq[2 * world], 1ull) == (unsigned long long)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    for (int j = threadIdx.x; j < world; j += blockDim.x)
+        if (j != me && p2p_active(offs, world, j)) {
+            const unsigned long long s = seq[j] + 1;
+            seq[j] = s;
+            volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(peer[j]) + ((size_t)me * 2 + (size_t)(s & 1));
+            *flag = s;
+        }
+    if (threadIdx.x == 0) seq[2 * world] = 0;
+}
+
+template <class T>
+__global__ void k_halo_wait(T* __restrict__ vec, const int* __restrict__ recvIdx, const int* __restrict__ offs, int world, int me, int width,
+                            const unsigned char* __restrict__ mine, size_t flagBytes, size_t haloCap, unsigned long long* seq) {
+    const int* recvOff = offs + world + 1;
+    if ((int)threadIdx.x < world) {
+        const int j = threadIdx.x;
+        if (j != me && p2p_active(offs, world, j)) {
+            const unsigned long long s = seq[world + j] + 1;
+            const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(mine) + ((size_t)j * 2 + (size_t)(s & 1));
+            const unsigned long long t0 = p2p_clock();
+            while (*flag < s)
+                if (p2p_clock() - t0 > P2P_SPIN_LIMIT) {
+                    seq[2 * world + 2] = 1;
+                    break;
+                }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    const long long total = (long long)recvOff[world] * width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i / width), c = (int)(i - (long long)e * width);
+        int j = 0;
+        while (e >= recvOff[j + 1]) j++;
+        const unsigned long long s = seq[world + j] + 1;
+        const T* src = reinterpret_cast<const T*>(mine + flagBytes + ((size_t)j * 2 + (size_t)(s & 1)) * haloCap) + (size_t)(e - recvOff[j]) * width + c;
+        vec[(size_t)recvIdx[e] * width + c] = p2p_load(src);
+    }
+    __shared__ int last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&seq[2 * world + 1], 1ull) == (unsigned long long)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    for (int j = threadIdx.x; j < world; j += blockDim.x)
+        if (j != me && p2p_active(offs, world, j)) seq[world + j] += 1;
+    if (threadIdx.x == 0) seq[2 * world + 1] = 0;
+}
+
+// The two as ONE launch: a CTA writes its share of the outgoing entries, the last one to finish raises the flags, and every CTA goes on to
+// poll for the peers' messages and unpack its share of them. Waiting depends on the PEER's writes, not on this grid's, and the grid is small
+// enough to be resident as a whole (<= 2 CTAs per SM), so no CTA ever waits for one that cannot run.
+template <class T>
+__global__ void k_halo_exchange(T* __restrict__ vec, const int* __restrict__ sendIdx, const int* __restrict__ recvIdx, const int* __restrict__ offs, int world, int me,
+                                int width, unsigned char* const* __restrict__ peer, const unsigned char* __restrict__ mine, size_t flagBytes, size_t haloCap,
+                                unsigned long long* seq) {
+    __shared__ int last;
+    {
+        const long long total = (long long)offs[world] * width;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int e = (int)(i / width), c = (int)(i - (long long)e * width);
+            int j = 0;
+            while (e >= offs[j + 1]) j++;
+            const unsigned long long s = seq[j] + 1;
+            T* dst = reinterpret_cast<T*>(peer[j] + flagBytes + ((size_t)me * 2 + (size_t)(s & 1)) * haloCap) + (size_t)(e - offs[j]) * width + c;
+            *dst = vec[(size_t)sendIdx[e] * width + c];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(&seq[2 * world], 1ull) == (unsigned long long)gridDim.x - 1;
+        __syncthreads();
+        if (last) {
+            __threadfence_system();
+            for (int j = threadIdx.x; j < world; j += blockDim.x)
+                if (j != me && p2p_active(offs, world, j)) {
+                    const unsigned long long s = seq[j] + 1;
+                    seq[j] = s;
+                    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(peer[j]) + ((size_t)me * 2 + (size_t)(s & 1));
+                    *flag = s;
+                }
+            if (threadIdx.x == 0) seq[2 * world] = 0;
+        }
+        __syncthreads();
+    }
+    const int* recvOff = offs + world + 1;
+    if ((int)threadIdx.x < world) {
+        const int j = threadIdx.x;
+        if (j != me && p2p_active(offs, world, j)) {
+            const unsigned long long s = seq[world + j] + 1;
+            const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(mine) + ((size_t)j * 2 + (size_t)(s & 1));
+            const unsigned long long t0 = p2p_clock();
+            while (*flag < s)
+                if (p2p_clock() - t0 > P2P_SPIN_LIMIT) {
+                    seq[2 * world + 2] = 1;
+                    break;
+                }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    const long long total = (long long)recvOff[world] * width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(i / width), c = (int)(i - (long long)e * width);
+        int j = 0;
+        while (e >= recvOff[j + 1]) j++;
+        const unsigned long long s = seq[world + j] + 1;
+        const T* src = reinterpret_cast<const T*>(mine + flagBytes + ((size_t)j * 2 + (size_t)(s & 1)) * haloCap) + (size_t)(e - recvOff[j]) * width + c;
+        vec[(size_t)recvIdx[e] * width + c] = p2p_load(src);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&seq[2 * world + 1], 1ull) == (unsigned long long)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    for (int j = threadIdx.x; j < world; j += blockDim.x)
+        if (j != me && p2p_active(offs, world, j)) seq[world + j] += 1;
+    if (threadIdx.x == 0) seq[2 * world + 1] = 0;
+}
+
+// All-gather of every rank's own range of up to two fp32 vectors through the same windows: a message to EVERY peer (so every pair is
+// active), laid out [vector][own range]; the receiver copies each peer's range into place.
+struct GatherVecs {
+    float* v[2];
+    int count;
+};
+__global__ void k_gather_put(GatherVecs vs, const int* __restrict__ rowStart, int world, int me, int width, unsigned char* const* __restrict__ peer, size_t flagBytes,
+                             size_t haloCap, unsigned long long* seq) {
+    const long long own = (long long)(rowStart[me + 1] - rowStart[me]) * width, first = (long long)rowStart[me] * width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < own * vs.count; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i / own);
+        const float x = vs.v[v][first + (i - (long long)v * own)];
+        for (int j = 0; j < world; j++) {
+            if (j == me) continue;
+            const unsigned long long s = seq[j] + 1;
+            reinterpret_cast<float*>(peer[j] + flagBytes + ((size_t)me * 2 + (size_t)(s & 1)) * haloCap)[i] = x;
+        }
+    }
+    __threadfence_system();
+    __shared__ int last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&seq[2 * world], 1ull) == (unsigned long long)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    for (int j = threadIdx.x; j < world; j += blockDim.x)
+        if (j != me) {
+            const unsigned long long s = seq[j] + 1;
+            seq[j] = s;
+            volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(peer[j]) + ((size_t)me * 2 + (size_t)(s & 1));
+            *flag = s;
+        }
+    if (threadIdx.x == 0) seq[2 * world] = 0;
+}
+__global__ void k_gather_wait(GatherVecs vs, const int* __restrict__ rowStart, int world, int me, int width, const unsigned char* __restrict__ mine, size_t flagBytes,
+                              size_t haloCap, unsigned long long* seq) {
+    if ((int)threadIdx.x < world && (int)threadIdx.x != me) {
+        const int j = threadIdx.x;
+        const unsigned long long s = seq[world + j] + 1;
+        const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(mine) + ((size_t)j * 2 + (size_t)(s & 1));
+        const unsigned long long t0 = p2p_clock();
+        while (*flag < s)
+            if (p2p_clock() - t0 > P2P_SPIN_LIMIT) {
+                seq[2 * world + 2] = 1;
+                break;
+            }
+    }
+    __syncthreads();
+    __threadfence_system();
+    // element i of the concatenation of the peers' messages (my own range is already in place)
+    const long long all = (long long)rowStart[world] * width, mineLen = (long long)(rowStart[me + 1] - rowStart[me]) * width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (all - mineLen) * vs.count; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i / (all - mineLen));
+        long long r = i - (long long)v * (all - mineLen);  // position among the rows that are not mine
+        if (r >= (long long)rowStart[me] * width) r += mineLen;
+        int j = 0;
+        while (r >= (long long)rowStart[j + 1] * width) j++;
+        const long long len = (long long)(rowStart[j + 1] - rowStart[j]) * width, at = r - (long long)rowStart[j] * width;
+        const unsigned long long s = seq[world + j] + 1;
+        const float* src = reinterpret_cast<const float*>(mine + flagBytes + ((size_t)j * 2 + (size_t)(s & 1)) * haloCap) + (long long)v * len + at;
+        vs.v[v][r] = p2p_load(src);
+    }
+    __shared__ int last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&seq[2 * world + 1], 1ull) == (unsigned long long)gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    for (int j = threadIdx.x; j < world; j += blockDim.x)
+        if (j != me) seq[world + j] += 1;
+    if (threadIdx.x == 0) seq[2 * world + 1] = 0;
+}
+
 template <class T>
 int halo_exchange(mof_ctx* ctx, Partition& p, T* vec, ncclDataType_t type) {
     DistState& d = *ctx->dist;
@@ -119,6 +358,27 @@ int halo_exchange(mof_ctx* ctx, Partition& p, T* vec, ncclDataType_t type) {
     TraceScope ts(ctx, TR_HALO);
     if (d.trace) d.traceMs[TR_HALO_BYTES] += (double)(p.nSend + p.nRecv) * p.width * sizeof(T), d.traceN[TR_HALO_BYTES]++;
     const int w = p.width;
+    if (d.win.on) {
+        const PeerWindow& win = d.win;
+        static const bool fused = !(getenv("MOF_DIST_P2P_FUSED") && *getenv("MOF_DIST_P2P_FUSED") == '0');
+        const int putGrid = std::max(1, std::min(kSMs * 2, blocks_for((long long)p.nSend * w, B)));
+        const int waitGrid = std::max(1, std::min(kSMs * 2, blocks_for((long long)p.nRecv * w, B)));
+        if (fused) {
+#ifdef MOF_HOST_EMULATION
+            const int grid = 1;  // (the emulator runs CTAs one after the other: a CTA polling for a peer would keep the flag-raising one from running)
+#else
+            const int grid = std::max(putGrid, waitGrid);
+#endif
+            MOF_LAUNCH(k_halo_exchange<T>, grid, B, 0, vec, (const int*)p.sendIdx.p, (const int*)p.recvIdx.p, (const int*)p.offs.p, d.world, d.rank, w,
+                       (unsigned char* const*)win.table.p, (const unsigned char*)win.base, win.flagBytes, win.haloCap, win.seq.p);
+            return MOF_OK;
+        }
+        MOF_LAUNCH(k_halo_put<T>, putGrid, B, 0, (const T*)vec, (const int*)p.sendIdx.p, (const int*)p.offs.p, d.world, d.rank, w, (unsigned char* const*)win.table.p,
+                   win.flagBytes, win.haloCap, win.seq.p);
+        MOF_LAUNCH(k_halo_wait<T>, waitGrid, B, 0, vec, (const int*)p.recvIdx.p, (const int*)p.offs.p, d.world, d.rank, w, (const unsigned char*)win.base,
+                   win.flagBytes, win.haloCap, win.seq.p);
+        return MOF_OK;
+    }
     T* sb = (T*)d.sendBuf.p;
     T* rb = (T*)d.recvBuf.p;
     if (p.nSend) MOF_LAUNCH(k_pack<T>, blocks_for((long long)p.nSend * w, B), B, 0, vec, p.sendIdx.p, p.nSend, w, sb);
@@ -182,6 +442,8 @@ int build_lists(mof_ctx* ctx, Partition& p, int n) {
 
 }  // namespace
 
+static void p2p_release(mof_ctx* ctx);
+
 bool dist_active(const mof_ctx* ctx) { return ctx->dist && ctx->dist->comm && ctx->dist->meshReady; }
 int dist_world(const mof_ctx* ctx) { return ctx->dist ? ctx->dist->world : 1; }
 
@@ -225,9 +487,11 @@ void dist_destroy(mof_ctx* ctx) {
                 1e3 * d.traceMs[TR_ALLREDUCE] / std::max(1ll, d.traceN[TR_ALLREDUCE]), d.traceN[TR_ALLGATHER], d.traceMs[TR_ALLGATHER],
                 1e3 * d.traceMs[TR_ALLGATHER] / std::max(1ll, d.traceN[TR_ALLGATHER]));
     if (d.t0) cudaEventDestroy(d.t0), cudaEventDestroy(d.t1);
-    for (Partition& p : d.part) p.sendIdx.release(), p.recvIdx.release();
+    for (Partition& p : d.part) p.sendIdx.release(), p.recvIdx.release(), p.offs.release();
     dist_clear_partitions(ctx);
     d.sendBuf.release(), d.recvBuf.release();
+    if (d.comm) cudaStreamSynchronize(ctx->stream);
+    p2p_release(ctx);
     if (d.comm) {
         cudaStreamSynchronize(ctx->stream);
         ncclCommDestroy(d.comm);
@@ -241,6 +505,7 @@ int dist_setup_mesh(mof_ctx* ctx) {
     if (!ctx->dist || !ctx->dist->comm) return MOF_OK;
     DistState& d = *ctx->dist;
     d.meshReady = false;
+    d.win.on = false;  // until dist_p2p_setup has seen the new mesh's partitions
     dist_clear_partitions(ctx);
     const int N = d.world, E = ctx->E, V = ctx->V, S = ctx->wSlices;
     d.sliceStart.assign(N + 1, 0);
@@ -286,6 +551,129 @@ int dist_setup_mesh(mof_ctx* ctx) {
     return MOF_OK;
 }
 
+// ---- the peer-memory window (see PeerWindow): after every partition of the mesh exists (the matrix patterns' and the multigrid levels').
+static void p2p_release(mof_ctx* ctx) {
+    DistState& d = *ctx->dist;
+    PeerWindow& w = d.win;
+    for (int j = 0; j < (int)w.peer.size(); j++)
+        if (j != d.rank && w.peer[j]) cudaIpcCloseMemHandle(w.peer[j]);
+    w.peer.clear();
+    if (w.base) cudaFree(w.base);
+    w.base = nullptr, w.bytes = 0, w.on = false;
+    w.table.release(), w.seq.release();
+}
+
+int dist_p2p_setup(mof_ctx* ctx) {
+    if (!ctx->dist || !ctx->dist->comm || ctx->dist->world == 1) return MOF_OK;
+    DistState& d = *ctx->dist;
+    const int N = d.world;
+    const char* e = getenv("MOF_DIST_P2P");
+    const bool wanted = !(e && *e == '0');
+    // what the widest message of any partition needs (fp64 bytes), the same number on every rank
+    std::vector<Partition*> parts = {&d.part[0], &d.part[1]};
+    for (Partition* q : d.extra) parts.push_back(q);
+    long long need = 0;
+    for (Partition* q : parts)
+        for (int j = 0; j < N; j++) need = std::max(need, (long long)std::max(q->recvCount[j], q->sendCount[j]) * q->width * 8);
+    // the solvers' own partitions are also all-gathered (a rank's range of two fp32 vectors per message): room for those of up to 4 MB,
+    // larger ones keep going through NCCL (dist_allgather_part_f32 checks)
+    for (Partition* q : d.extra)
+        for (int j = 0; j < N; j++) {
+            const long long bytes = (long long)(q->rowStart[j + 1] - q->rowStart[j]) * q->width * 8;
+            if (bytes <= (4ll << 20)) need = std::max(need, bytes);
+        }
+    // (all-gathers of ints, reduced on the host: the message sizes are bytes of one halo message and fit an int)
+    DBuf<int> agreeSend, agreeAll;
+    MOF_CUDA(agreeSend.alloc(2));
+    MOF_CUDA(agreeAll.alloc(2 * (size_t)N));
+    std::vector<int> gathered(2 * (size_t)N);
+    auto agree = [&](int a, int b, long long* maxA, long long* minB) -> int {
+        const int mine2[2] = {a, b};
+        MOF_CUDA(cudaMemcpyAsync(agreeSend.p, mine2, sizeof(mine2), cudaMemcpyHostToDevice, ctx->stream));
+        MOF_NCCL(ncclAllGather(agreeSend.p, agreeAll.p, 2, ncclInt, d.comm, ctx->stream));
+        MOF_CUDA(read_back(ctx, gathered.data(), agreeAll.p, gathered.size()));
+        *maxA = gathered[0], *minB = gathered[1];
+        for (int j = 1; j < N; j++) *maxA = std::max<long long>(*maxA, gathered[2 * j]), *minB = std::min<long long>(*minB, gathered[2 * j + 1]);
+        return MOF_OK;
+    };
+    long long all[2] = {0, 0};
+    MOF_TRY(agree((int)std::min<long long>(need, 2000000000ll), wanted ? 1 : 0, &all[0], &all[1]));
+    if (!all[1]) {  // switched off on some rank: NCCL everywhere
+        p2p_release(ctx);
+        agreeSend.release(), agreeAll.release();
+        return MOF_OK;
+    }
+    const size_t cap = ((size_t)std::max(all[0], 4096ll) + 255) & ~(size_t)255;
+    PeerWindow& w = d.win;
+    long long ok = 1;
+    if (!w.base || w.haloCap < cap) {
+        // (re)create: every rank gets here together (the all-reduces above), and the stream is idle after the read-back
+        p2p_release(ctx);
+        w.flagBytes = ((size_t)N * 2 * sizeof(unsigned long long) + 255) & ~(size_t)255;
+        w.haloCap = cap;
+        w.bytes = w.flagBytes + (size_t)N * 2 * cap;
+        cudaIpcMemHandle_t handle;
+        DBuf<unsigned char> hsend, hall;
+        std::vector<unsigned char> handles((size_t)N * sizeof(handle));
+        if (cudaMalloc((void**)&w.base, w.bytes) != cudaSuccess || cudaMemset(w.base, 0, w.bytes) != cudaSuccess || cudaIpcGetMemHandle(&handle, w.base) != cudaSuccess) ok = 0;
+        cudaGetLastError();
+        static_assert(sizeof(handle) % sizeof(int) == 0, "the handles travel as ints");
+        MOF_CUDA(hsend.alloc(sizeof(handle)));
+        MOF_CUDA(hall.alloc((size_t)N * sizeof(handle)));
+        if (!ok) memset(&handle, 0, sizeof(handle));
+        MOF_CUDA(cudaMemcpyAsync(hsend.p, &handle, sizeof(handle), cudaMemcpyHostToDevice, ctx->stream));
+        MOF_NCCL(ncclAllGather(hsend.p, hall.p, sizeof(handle) / sizeof(int), ncclInt, d.comm, ctx->stream));
+        MOF_CUDA(read_back(ctx, handles.data(), hall.p, handles.size()));
+        hsend.release(), hall.release();
+        w.peer.assign(N, nullptr);
+        for (int j = 0; j < N && ok; j++) {
+            if (j == d.rank) { w.peer[j] = w.base; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles.data() + (size_t)j * sizeof(h), sizeof(h));
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0, cudaGetLastError();
+            w.peer[j] = (unsigned char*)ptr;
+        }
+        if (ok) {
+            MOF_CUDA(w.table.alloc((size_t)N));
+            MOF_CUDA(w.seq.alloc((size_t)2 * N + 4));
+            MOF_CUDA(cudaMemcpyAsync(w.table.p, w.peer.data(), sizeof(unsigned char*) * N, cudaMemcpyHostToDevice, ctx->stream));
+            MOF_CUDA(cudaMemsetAsync(w.seq.p, 0, sizeof(unsigned long long) * (2 * N + 4), ctx->stream));
+            MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    // every rank mapped every window, or nobody uses them
+    MOF_TRY(agree(0, (int)ok, &all[0], &all[1]));
+    agreeSend.release(), agreeAll.release();
+    if (!all[1]) {
+        p2p_release(ctx);
+        if (getenv("MOF_MG_VERBOSE") && d.rank == 0) fprintf(stderr, "[dist] peer windows could not be mapped: halo exchanges go through NCCL\n");
+        return MOF_OK;
+    }
+    for (Partition* q : parts) {
+        std::vector<int> offs(3 * (size_t)(N + 1));
+        for (int j = 0; j < N; j++) offs[j] = q->sendOff[j], offs[N + 1 + j] = q->recvOff[j];
+        offs[N] = q->nSend, offs[2 * N + 1] = q->nRecv;
+        for (int j = 0; j <= N; j++) offs[2 * (N + 1) + j] = q->rowStart[j];
+        MOF_CUDA(q->offs.alloc(offs.size()));
+        MOF_CUDA(cudaMemcpyAsync(q->offs.p, offs.data(), sizeof(int) * offs.size(), cudaMemcpyHostToDevice, ctx->stream));
+        MOF_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    w.on = true;
+    if (getenv("MOF_MG_VERBOSE") && d.rank == 0)
+        fprintf(stderr, "[dist] halo exchanges through peer memory: %d windows of %.1f MB (%zu bytes per message slot)\n", N, w.bytes / 1048576., w.haloCap);
+    return MOF_OK;
+}
+// A peer that never arrived (k_halo_wait gave up after ~10 s): the solve's result is garbage and says so.
+int dist_p2p_check(mof_ctx* ctx) {
+    if (!ctx->dist || !ctx->dist->win.on) return MOF_OK;
+    DistState& d = *ctx->dist;
+    unsigned long long flag = 0;
+    MOF_CUDA(read_back(ctx, &flag, d.win.seq.p + 2 * d.world + 2));
+    if (flag) return fail(ctx, MOF_E_CUDA, "[ERROR] partitioned mesh: a peer's halo values never arrived (peer-memory exchange timed out)");
+    return MOF_OK;
+}
+
 int dist_halo_f64(mof_ctx* ctx, int kind, double* vec) { return halo_exchange<double>(ctx, ctx->dist->part[kind], vec, ncclDouble); }
 int dist_halo_f32(mof_ctx* ctx, int kind, float* vec) { return halo_exchange<float>(ctx, ctx->dist->part[kind], vec, ncclFloat); }
 
@@ -311,7 +699,7 @@ int dist_add_partition(mof_ctx* ctx, int width, const int* rangeStart, int n, in
 void dist_clear_partitions(mof_ctx* ctx) {
     if (!ctx->dist) return;
     for (Partition* p : ctx->dist->extra) {
-        p->sendIdx.release(), p->recvIdx.release();
+        p->sendIdx.release(), p->recvIdx.release(), p->offs.release();
         delete p;
     }
     ctx->dist->extra.clear();
@@ -324,6 +712,23 @@ int dist_allgather_part_f32(mof_ctx* ctx, int id, float* const* vecs, int count)
     if (d.world == 1) return MOF_OK;
     const Partition& p = *d.extra[id];
     TraceScope ts(ctx, TR_ALLGATHER);
+    if (d.win.on && count <= 2 && p.offs.p) {
+        long long widest = 0;
+        for (int k = 0; k < d.world; k++) widest = std::max(widest, (long long)(p.rowStart[k + 1] - p.rowStart[k]) * p.width * (long long)sizeof(float) * count);
+        if ((size_t)widest <= d.win.haloCap) {  // (the same decision on every rank: the ranges are common knowledge)
+            const PeerWindow& win = d.win;
+            GatherVecs vs;
+            vs.count = count, vs.v[0] = vecs[0], vs.v[1] = count > 1 ? vecs[1] : nullptr;
+            const int* rowStart = p.offs.p + 2 * (d.world + 1);
+            const long long own = (long long)(p.rowStart[d.rank + 1] - p.rowStart[d.rank]) * p.width * count;
+            const long long others = ((long long)p.rowStart[d.world] - (p.rowStart[d.rank + 1] - p.rowStart[d.rank])) * p.width * count;
+            MOF_LAUNCH(k_gather_put, std::max(1, std::min(kSMs * 2, blocks_for(own, B))), B, 0, vs, rowStart, d.world, d.rank, p.width, (unsigned char* const*)win.table.p,
+                       win.flagBytes, win.haloCap, win.seq.p);
+            MOF_LAUNCH(k_gather_wait, std::max(1, std::min(kSMs * 2, blocks_for(others, B))), B, 0, vs, rowStart, d.world, d.rank, p.width, (const unsigned char*)win.base,
+                       win.flagBytes, win.haloCap, win.seq.p);
+            return MOF_OK;
+        }
+    }
     MOF_NCCL(ncclGroupStart());
     for (int v = 0; v < count; v++)
         for (int k = 0; k < d.world; k++) {

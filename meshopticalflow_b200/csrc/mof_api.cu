@@ -70,6 +70,8 @@ int finish_mesh(mof_ctx* ctx) {
     if (rc != MOF_OK) return rc;
     rc = mg_dist_setup(ctx);
     if (rc != MOF_OK) return rc;
+    rc = dist_p2p_setup(ctx);
+    if (rc != MOF_OK) return rc;
     pt.mark("row blocks and halo lists");
     MOF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     MOF_CUDA(cudaEventSynchronize(ctx->ev1));

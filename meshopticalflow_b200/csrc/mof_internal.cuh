@@ -330,6 +330,8 @@ int dist_halo_part_f32(mof_ctx* ctx, int id, float* vec);
 int dist_allgather_part_f32(mof_ctx* ctx, int id, float* const* vecs, int count);
 int dist_rank(const mof_ctx* ctx);
 void dist_row_starts(const mof_ctx* ctx, int kind, int* out);  // world + 1 entries
+int dist_p2p_setup(mof_ctx* ctx);   // after every partition exists: peer-memory windows for the halo exchanges (falls back to NCCL)
+int dist_p2p_check(mof_ctx* ctx);   // after a solve: did every peer's halo arrive
 int mg_dist_setup(mof_ctx* ctx);  // multigrid.cu: which coarse levels are dealt to the ranks, their cell ranges and halo lists (after dist_setup_mesh)
 
 // vector_fields.cu — the Conformal and Connection bases (--vfMode 1|2): matrix-free block-Jacobi PCG

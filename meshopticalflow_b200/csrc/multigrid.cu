@@ -2851,6 +2851,7 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
         if (it >= maxIters || !std::isfinite(rr)) break;
     }
     MOF_TRY(dist_allgather_rows(ctx, kind, x));
+    MOF_TRY(dist_p2p_check(ctx));
     *itersOut = it;
     *relresOut = std::sqrt(rr / bb);
     if (!(*relresOut <= tol * 1.0001)) ctx->stats.solvesAboveTolerance++;

@@ -48,6 +48,15 @@ inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : 2; }
 inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMalloc(void** p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
+// "inter-process" memory handles between the emulated ranks (OS threads of one process): the handle is the pointer
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return *p ? cudaSuccess : 1; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 namespace mof_emul {
 // Stream capture: while a capture is open, launches and stream-ordered copies are RECORDED (with their arguments, by
 // value) instead of run, like on the device; cudaGraphLaunch runs the recorded list.
@@ -219,4 +228,5 @@ template <class T> inline T atomicCAS(T* p, T expected, T desired) { T o = *p; i
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 inline void __threadfence() {}
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __syncwarp(unsigned = 0xffffffffu) {}
