@@ -9,6 +9,8 @@ int dist_unique_id(unsigned char*) { return MOF_E_UNSUPPORTED; }
 int dist_init(mof_ctx* ctx, int, int, const unsigned char*) { return fail(ctx, MOF_E_UNSUPPORTED, "the emulated build has no communicator"); }
 void dist_destroy(mof_ctx*) {}
 int dist_setup_mesh(mof_ctx*) { return MOF_OK; }
+int dist_p2p_setup(mof_ctx*) { return MOF_OK; }
+int dist_p2p_check(mof_ctx*) { return MOF_OK; }
 bool dist_active(const mof_ctx*) { return false; }
 int dist_world(const mof_ctx*) { return 1; }
 void dist_range(const mof_ctx*, int, int* s0, int* s1, int* r0, int* r1) { *s0 = *s1 = *r0 = *r1 = 0; }
