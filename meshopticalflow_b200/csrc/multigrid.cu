@@ -496,14 +496,13 @@ __device__ __forceinline__ void fold_partials(const double* partial, int np, int
 // Sum of one value per thread over the CTA, in a fixed order; thread 0 stores it in partial[blockIdx.x]. With slot >= 0
 // the last CTA of the grid to arrive (a self-resetting counter) also folds all the partials — in index order, so the
 // result does not depend on which CTA that is — which saves a one-CTA launch on the critical path.
-template <int NT = B>  // threads of the CTA (256, or 192 in the three-lanes-per-row scalar sweep)
 __device__ __forceinline__ void cta_partial(double v, double* partial, int slot = -1, double* scal = nullptr, unsigned* counter = nullptr) {
-    __shared__ double sh[NT];
+    __shared__ double sh[B];
     __shared__ bool last;
     sh[threadIdx.x] = v;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {  // (NT <= 256; the pairs of a 256-thread CTA are those of the power-of-two tree)
-        if ((int)threadIdx.x < o && (int)threadIdx.x + o < NT) sh[threadIdx.x] += sh[threadIdx.x + o];
+    for (int o = B / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -717,75 +716,6 @@ __global__ void __launch_bounds__(B, 4) k_fine_apply_scalar_sell(int n, const in
         dst[0] = w0, dst[1] = w1, dst[2] = w2;
     }
     if (mode == 0 || (mode == 2 && f.partial)) cta_partial(dot, f.partial, f.slot, f.scal, f.counter);
-}
-// The same with THREE lanes per row (round 2, after the --set full capture of the kernel above: 64 registers, 49 % occupancy, the L1 pipe
-// at 69 %): a lane of the kernel above gathers a neighbour's six channels as three 16-byte loads, and the 32 lanes of each of those
-// instructions hit 32 different rows - 32 L1 wavefronts per instruction, 21 instructions per slice and batch of seven entries. Here
-// lanes 3r, 3r+1, 3r+2 own the three 16-byte (fp32: 8-byte) pieces of row r: one gather instruction covers ~11 rows with 48
-// contiguous bytes each (a third of the wavefronts), a thread carries two channels instead of six (40 registers, 75 % occupancy),
-// and a row's output is one 48-byte contiguous store across its three lanes. A CTA of 192 threads takes two slices per trip.
-// Entry order per row and channel is unchanged: the same bits per element; the CTA partials of the dot products group differently.
-constexpr int S3T = 192;
-template <class TV, class TX>
-__global__ void __launch_bounds__(S3T, 8) k_fine_apply_scalar_sell3(int n, const int* __restrict__ sliceBase, const int* __restrict__ col, const TV* __restrict__ val,
-                                                                   const double* __restrict__ b, const creal* __restrict__ dinv, const double* __restrict__ omegaP,
-                                                                   const TX* __restrict__ in, TX* __restrict__ out, int mode, Fold f) { pdl_wait();
-    using P2 = typename Pair<TX>::type;
-    const double omega = *omegaP;
-    const int sub = threadIdx.x / 96, t = threadIdx.x - 96 * sub;
-    const int r = t / 3, part = t - 3 * r;
-    const int slices = (n + 31) >> 5;
-    double dot = 0;
-    for (int s = blockIdx.x * 2 + sub; s < slices; s += gridDim.x * 2) {
-        const int base = sliceBase[s];
-        const int len = (sliceBase[s + 1] - base) >> 5;
-        const TV* v0 = val + (size_t)base + r;
-        const int* c0 = col + (size_t)base + r;
-        const int row = 32 * s + r;
-        TX a0 = 0, a1 = 0;
-        for (int j0 = 0; j0 < len; j0 += SBATCH) {
-            TV v[SBATCH];
-            int c[SBATCH];
-            P2 x[SBATCH];
-#pragma unroll
-            for (int u = 0; u < SBATCH; u++) {
-                const bool ok = j0 + u < len;
-                v[u] = ok ? __ldcs(v0 + 32 * (size_t)(j0 + u)) : (TV)0;
-                c[u] = ok ? __ldcs(c0 + 32 * (size_t)(j0 + u)) : 0;
-            }
-#pragma unroll
-            for (int u = 0; u < SBATCH; u++) x[u] = reinterpret_cast<const P2*>(in + 6 * (size_t)c[u])[part];
-#pragma unroll
-            for (int u = 0; u < SBATCH; u++)
-                if (j0 + u < len) {
-                    const TX w = (TX)v[u];
-                    a0 += w * x[u].x, a1 += w * x[u].y;
-                }
-        }
-        if (row >= n) continue;
-        TX o0, o1;
-        if (mode == 0) {
-            const P2 sv = reinterpret_cast<const P2*>(in + 6 * (size_t)row)[part];
-            o0 = a0, o1 = a1;
-            dot += (double)sv.x * (double)a0;
-            dot += (double)sv.y * (double)a1;
-        } else {
-            const double2 bv = reinterpret_cast<const double2*>(b + 6 * (size_t)row)[part];
-            if (mode == 1) {
-                o0 = (TX)(bv.x - (double)a0), o1 = (TX)(bv.y - (double)a1);
-            } else {
-                const P2 sv = reinterpret_cast<const P2*>(in + 6 * (size_t)row)[part];
-                const double wd = omega * (double)dinv[row];
-                o0 = (TX)((double)sv.x + wd * (bv.x - (double)a0)), o1 = (TX)((double)sv.y + wd * (bv.y - (double)a1));
-                dot += bv.x * (double)o0;
-                dot += bv.y * (double)o1;
-            }
-        }
-        P2 w;
-        w.x = o0, w.y = o1;
-        reinterpret_cast<P2*>(out + 6 * (size_t)row)[part] = w;
-    }
-    if (mode == 0 || (mode == 2 && f.partial)) cta_partial<S3T>(dot, f.partial, f.slot, f.scal, f.counter);
 }
 // CSR values -> the sliced layout, in both precisions (once per scalar system; the pattern's slice offsets are per mesh).
 __global__ void k_scalar_vals_to_sell(const int* __restrict__ rowptr, const double* __restrict__ val, const int* __restrict__ sliceBase, int n, int slices,
@@ -1885,16 +1815,11 @@ bool scalar_sell(const mof_ctx* ctx) {
     static const bool on = env_int("MOF_SCALAR_SELL", 1) != 0;
     return on && ctx->sPadded > 0;
 }
-// MOF_SCALAR_SELL3=0: one lane per row (k_fine_apply_scalar_sell) instead of three (k_fine_apply_scalar_sell3); read per call (A/B in one process)
-bool scalar_sell3() { return env_int("MOF_SCALAR_SELL3", 1) != 0; }
 
 int fine_apply(mof_ctx* ctx, Multigrid& mg, const double* b, const double* omega, const creal* in, creal* out, int mode, int dotSlot = -1) {
     const Fold f = dotSlot >= 0 ? fold_into(mg, dotSlot) : NO_FOLD;
     if (mg.kind != MG_FLOW && scalar_sell(ctx)) {
-        if (scalar_sell3())
-            MOF_LAUNCH((k_fine_apply_scalar_sell3<creal, creal>), FINE_GRID, S3T, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, mg.fvalSell.p, b, mg.fdinv.p, omega, in, out, mode, f);
-        else
-            MOF_LAUNCH((k_fine_apply_scalar_sell<creal, creal>), FINE_GRID, B, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, mg.fvalSell.p, b, mg.fdinv.p, omega, in, out, mode, f);
+        MOF_LAUNCH((k_fine_apply_scalar_sell<creal, creal>), FINE_GRID, B, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, mg.fvalSell.p, b, mg.fdinv.p, omega, in, out, mode, f);
         return MOF_OK;
     }
     if (mg.kind != MG_FLOW && scalar_row_kernel()) {
@@ -1912,9 +1837,6 @@ int fine_residual(mof_ctx* ctx, Multigrid& mg, const double* b, const double* in
     if (mg.kind == MG_FLOW)
         MOF_LAUNCH((k_fine_apply_flow<double, double>), FINE_GRID, B, 0, ctx->E, ctx->wSliceBase.p, ctx->wCol.p, ctx->wA.p, b, (const creal*)nullptr, mg.om(OM_ZERO), in, out, 1,
                    NO_FOLD, 0, 0);
-    else if (scalar_sell(ctx) && scalar_sell3())
-        MOF_LAUNCH((k_fine_apply_scalar_sell3<double, double>), FINE_GRID, S3T, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, ctx->sSysSell.p, b, (const creal*)nullptr,
-                   mg.om(OM_ZERO), in, out, 1, NO_FOLD);
     else if (scalar_sell(ctx))
         MOF_LAUNCH((k_fine_apply_scalar_sell<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, ctx->sSysSell.p, b, (const creal*)nullptr,
                    mg.om(OM_ZERO), in, out, 1, NO_FOLD);
@@ -1928,7 +1850,8 @@ int fine_residual(mof_ctx* ctx, Multigrid& mg, const double* b, const double* in
 template <int K, int D>
 int coarse_apply(mof_ctx* ctx, MgLevel& lv, const double* omega, int mode, creal* out, const creal* zc) {
     const int* parent = zc ? lv.parent.p : nullptr;
-    if (lv.N >= 16384)
+    static const int wideFrom = env_int("MOF_MG_WIDE_FROM", 16384);  // cells from which the 9-warp variant (three slots per warp) replaces the 27-warp one
+    if (lv.N >= wideFrom)
         MOF_LAUNCH((k_coarse_apply<K, D, 3>), blocks_for(lv.N, 32), 9 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, omega, lv.N, mode, out, parent, zc, 0, -1);
     else
         MOF_LAUNCH((k_coarse_apply<K, D, 1>), blocks_for(lv.N, 32), 27 * 32, 0, lv.cblocks.p, lv.nbr.p, lv.binv.p, lv.r.p, lv.z.p, omega, lv.N, mode, out, parent, zc, 0, -1);
@@ -2266,7 +2189,7 @@ int coarse_cycle(mof_ctx* ctx, Multigrid& mg, int l) {
     MgLevel& up = mg.lev[l + 1];
     const bool upDense = l + 1 == mg.K - 1;
     const int passes = cycle_passes(mg, l);
-    const bool fused = !upDense && mg.tailStart != l + 1 && lv.N < 16384 && lv.gridLevel - up.gridLevel == 1 && fuse_residual_restrict();
+    const bool fused = !upDense && mg.tailStart != l + 1 && lv.N < env_int("MOF_MG_FUSE_BELOW", 16384) && lv.gridLevel - up.gridLevel == 1 && fuse_residual_restrict();
     const int sweeps = l < (int)(sizeof(mg.coarseSweeps) / sizeof(int)) ? mg.coarseSweeps[l] : 1;
     for (int extra = 1; extra < sweeps; extra++) {  // further pre-smoothing sweeps (the first is the restriction's)
         MOF_TRY(coarse_apply(ctx, mg, lv, mg.om(1 + l), 2, lv.t.p));
@@ -2353,10 +2276,7 @@ int apply_dot(mof_ctx* ctx, Multigrid& mg, const double* p, double* q) {
         MOF_LAUNCH(k_fold, 1, B, 0, mg.partial.p, np, S_PQ, mg.scal.p);
         return MOF_OK;
     }
-    if (scalar_sell(ctx) && scalar_sell3())
-        MOF_LAUNCH((k_fine_apply_scalar_sell3<double, double>), FINE_GRID, S3T, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, ctx->sSysSell.p, (const double*)nullptr,
-                   (const creal*)nullptr, mg.om(OM_ZERO), p, q, 0, fold_into(mg, S_PQ));
-    else if (scalar_sell(ctx))
+    if (scalar_sell(ctx))
         MOF_LAUNCH((k_fine_apply_scalar_sell<double, double>), FINE_GRID, B, 0, ctx->V, ctx->sSliceBase.p, ctx->sColSell.p, ctx->sSysSell.p, (const double*)nullptr,
                    (const creal*)nullptr, mg.om(OM_ZERO), p, q, 0, fold_into(mg, S_PQ));
     else if (scalar_row_kernel())
