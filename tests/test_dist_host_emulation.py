@@ -91,8 +91,11 @@ def workload(emulated):
     return v, t, a, b, single
 
 
-@pytest.mark.parametrize("world", [1, 2, 3, 4])
-def test_partitioned_solves_give_the_single_gpu_result_on_every_rank(emulated, workload, world):
+@pytest.mark.parametrize("world,exchange", [(1, "nccl"), (2, "nccl"), (3, "nccl"), (4, "nccl"), (2, "peer"), (3, "peer"), (4, "peer")])
+def test_partitioned_solves_give_the_single_gpu_result_on_every_rank(emulated, workload, world, exchange, monkeypatch):
+    """exchange = "peer": halo values written straight into the peers' memory windows by one fused kernel per exchange (dist.cu:
+    PeerWindow, MOF_DIST_P2P=1; here the windows are plain pointers between the ranks' OS threads) instead of NCCL send / recv."""
+    monkeypatch.setenv("MOF_DIST_P2P", "1" if exchange == "peer" else "0")
     v, t, a, b, single = workload
     out = _run_world(emulated, world, v, t, a, b, 2)
     for r, res in enumerate(out):
@@ -108,6 +111,7 @@ def test_partitioned_solves_give_the_single_gpu_result_on_every_rank(emulated, w
 
 @pytest.mark.parametrize("world,threshold", [(2, 100), (3, 100), (4, 800)])
 def test_coarse_levels_dealt_to_the_ranks(emulated, world, threshold, monkeypatch):
+    monkeypatch.setenv("MOF_DIST_P2P", "1")  # the levels' halos and the gather of the first replicated level through the peer windows too
     """16 386 vertices, four-level hierarchies. MOF_DIST_LEVEL_CELLS lowered so that the levels of more than `threshold` cells are
     dealt to the ranks in octree-aligned cell ranges (threshold 100: two levels, 800: one): stencil halos per level, the
     aggregates that straddle a row-block boundary (residual rows in, correction cells out), restriction and prolongation inside a
