@@ -23,7 +23,17 @@
 #include "mof_b200.h"
 #include "ply_io.h"
 #include "png_codec.h"
-#include "texture_prep.h"
+#ifdef MOF_WITH_HOST_TEXPREP
+#include "texture_prep.h"  // test builds only (see below)
+#else
+namespace mof {
+struct TexturedMesh {          // the texture configuration's mesh as the files give it (texture_prep.h has the same, with the host restatement)
+    std::vector<float> xyz;    // 3 per vertex, float like the reference's PlyVertex<float>
+    std::vector<int> tri;      // 3 per triangle
+    std::vector<double> uv;    // 6 per triangle: (u,v) of each corner
+};
+}  // namespace mof
+#endif
 
 namespace {
 
@@ -76,10 +86,14 @@ int main(int argc, char* argv[]) {
 
     const bool processTexture = opt.meshSet;
     // The texture configuration's one-time preparation (Subdivide, SampleTextureToVertices, GetTextureSource) runs on the GPU
-    // (csrc/texprep_kernels.cu). MOF_GPU_TEXPREP=0 selects the serial host restatement in host/texture_prep.cpp instead — same
-    // outputs, bit for bit; kept as a cross-check.
+    // (csrc/texprep_kernels.cu). The serial host restatement of it (host/texture_prep.cpp — same outputs, bit for bit) is NOT part of
+    // the product: it is compiled in by the tests only (-DMOF_WITH_HOST_TEXPREP, where MOF_GPU_TEXPREP=0 selects it as the cross-check).
+#ifdef MOF_WITH_HOST_TEXPREP
     const char* gpuPrepEnv = getenv("MOF_GPU_TEXPREP");
     const bool gpuPrep = processTexture && !(gpuPrepEnv && *gpuPrepEnv == '0');
+#else
+    const bool gpuPrep = processTexture;
+#endif
     mof_ctx* ctx = nullptr;
     auto ensure_context = [&]() {
         if (ctx) return true;
@@ -132,8 +146,11 @@ int main(int argc, char* argv[]) {
                 return EXIT_FAILURE;
             tmesh.xyz.resize(3 * (size_t)newV), tmesh.tri.resize(3 * (size_t)newT), tmesh.uv.resize(6 * (size_t)newT);
             if (!mof_ok(ctx, mof_get_subdivision(ctx, tmesh.xyz.data(), tmesh.tri.data(), tmesh.uv.data()))) return EXIT_FAILURE;
-        } else if (eLength > 0)
+        }
+#ifdef MOF_WITH_HOST_TEXPREP
+        else if (eLength > 0)
             mof::subdivide(tmesh, (double)eLength);
+#endif
         printf("Num vertices %d  \n", (int)(tmesh.xyz.size() / 3));
 
         for (int s = 0; s < 2; s++) {
@@ -152,8 +169,10 @@ int main(int argc, char* argv[]) {
                 return EXIT_FAILURE;
             }
         }
+#ifdef MOF_WITH_HOST_TEXPREP
         if (!gpuPrep)
             for (int s = 0; s < 2; s++) mof::sample_texture_to_vertices(tmesh, textures[s].data(), tW, tH, !opt.nearest, signal[s]);
+#endif
         vertices.assign(tmesh.xyz.begin(), tmesh.xyz.end());
         triangles = tmesh.tri;
     } else {
@@ -225,7 +244,9 @@ int main(int argc, char* argv[]) {
         if (!mof_ok(ctx, mof_build_texture_map(ctx, tW, tH, opt.pad, tmesh.uv.data(), textures[0].data(), textures[1].data(), &misses))) return misses ? 0 : EXIT_FAILURE;
         for (int s = 0; s < 2; s++) signal[s].resize(3 * (size_t)V);
         if (!mof_ok(ctx, mof_sample_textures_to_vertices(ctx, opt.nearest ? 0 : 1, signal[0].data(), signal[1].data()))) return EXIT_FAILURE;
-    } else if (processTexture) {
+    }
+#ifdef MOF_WITH_HOST_TEXPREP
+    else if (processTexture) {
         // GetTextureSource (:818) on the host, from the edge transforms the GPU just built
         std::vector<int> opp(3 * (size_t)T), srcT;
         std::vector<double> lin(12 * (size_t)T), cst(6 * (size_t)T), srcP;
@@ -240,6 +261,7 @@ int main(int argc, char* argv[]) {
         }
         if (!mof_ok(ctx, mof_set_texture_map(ctx, tW, tH, srcT.data(), srcP.data(), tmesh.uv.data(), textures[0].data(), textures[1].data()))) return EXIT_FAILURE;
     }
+#endif
     {
         Stopwatch t;
         if (!mof_ok(ctx, mof_set_signals(ctx, signal[0].data(), signal[1].data(), 3))) return EXIT_FAILURE;

@@ -46,10 +46,16 @@ def main():
         Image.fromarray(ta).save(os.path.join(d, "A.png"))
         Image.fromarray(tb).save(os.path.join(d, "B.png"))
         cli = os.path.join(ROOT, "meshopticalflow_b200", "OpticalFlow")
+        # the host restatement is test infrastructure: a checker binary with it compiled in (MOF_GPU_TEXPREP=0 selects it there)
+        host, libdir = os.path.join(ROOT, "meshopticalflow_b200", "csrc", "host"), os.path.join(ROOT, "meshopticalflow_b200")
+        checker = os.path.join(d, "OpticalFlow_hostprep")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DMOF_WITH_HOST_TEXPREP", "-I" + os.path.join(ROOT, "include"), "-o", checker] +
+                              [os.path.join(host, f) for f in ("optical_flow_main.cpp", "ply_io.cpp", "png_codec.cpp", "texture_prep.cpp", "cmdline.cpp")] +
+                              ["-L" + libdir, "-lmof_b200", "-lz", "-Wl,-rpath," + libdir])
         pictures = []
         for mode in ("0", "1", "0", "1"):
             t0 = time.perf_counter()
-            subprocess.check_call([cli, "--mesh", "m.ply", "--in", "A.png", "B.png", "--out", "r%s.png" % mode], cwd=d, stdout=subprocess.DEVNULL,
+            subprocess.check_call([checker if mode == "0" else cli, "--mesh", "m.ply", "--in", "A.png", "B.png", "--out", "r%s.png" % mode], cwd=d, stdout=subprocess.DEVNULL,
                                   env=dict(os.environ, MOF_GPU_TEXPREP=mode))
             print(f"command line, MOF_GPU_TEXPREP={mode}: {time.perf_counter() - t0:.2f} s wall")
             pictures.append(np.asarray(Image.open(os.path.join(d, "r%s.png" % mode))).astype(int))

@@ -123,15 +123,23 @@ def test_error_paths(aligner):
 
 
 def test_command_line_with_device_preparation(tmp_path, golden_torus):
-    """MOF_GPU_TEXPREP=1: the same picture as with the host preparation, and the reference's."""
+    """The command line prepares the texture configuration on the GPU. The serial host restatement of the preparation
+    (csrc/host/texture_prep.cpp) is no longer part of the product: it is compiled into a test binary here (-DMOF_WITH_HOST_TEXPREP, where
+    MOF_GPU_TEXPREP=0 selects it) as the cross-check — the same picture from both, and the reference's."""
     from PIL import Image
     g = golden_torus
     synthetic.write_ply_textured(str(tmp_path / "m.ply"), g["input_vertices_f32"], g["input_triangles"], g["input_uv"])
     open(tmp_path / "A.png", "wb").write(g["png_a"].tobytes())
     open(tmp_path / "B.png", "wb").write(g["png_b"].tobytes())
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host, libdir = os.path.join(root, "meshopticalflow_b200", "csrc", "host"), os.path.join(root, "meshopticalflow_b200")
+    checker = str(tmp_path / "OpticalFlow_hostprep")
+    sources = [os.path.join(host, f) for f in ("optical_flow_main.cpp", "ply_io.cpp", "png_codec.cpp", "texture_prep.cpp", "cmdline.cpp")]
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DMOF_WITH_HOST_TEXPREP", "-I" + os.path.join(root, "include"), "-o", checker] + sources +
+                          ["-L" + libdir, "-lmof_b200", "-lz", "-Wl,-rpath," + libdir])
     outs = []
-    for mode in ("0", "1"):
-        r = subprocess.run([CLI_BIN, "--mesh", "m.ply", "--in", "A.png", "B.png", "--out", "r%s.png" % mode, "--eLength", "0.08"], cwd=tmp_path, capture_output=True,
+    for exe, mode in ((checker, "0"), (CLI_BIN, "1")):
+        r = subprocess.run([exe, "--mesh", "m.ply", "--in", "A.png", "B.png", "--out", "r%s.png" % mode, "--eLength", "0.08"], cwd=tmp_path, capture_output=True,
                            text=True, timeout=300, env=dict(os.environ, MOF_GPU_TEXPREP=mode))
         assert r.returncode == 0, r.stderr
         assert "Num vertices %d" % g["vertices"].shape[0] in r.stdout

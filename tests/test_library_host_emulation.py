@@ -389,7 +389,8 @@ def test_command_line_on_the_emulated_build(emulated, tmp_path, golden_torus):
     lib = emulated.load_library()._name
     exe = str(tmp_path / "OpticalFlow_emul")
     sources = [os.path.join(host, f) for f in ("optical_flow_main.cpp", "ply_io.cpp", "png_codec.cpp", "texture_prep.cpp", "cmdline.cpp")]
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", exe] + sources + [lib, "-lz", "-Wl,-rpath," + os.path.dirname(lib)])
+    # -DMOF_WITH_HOST_TEXPREP: the serial host restatement of the preparation (host/texture_prep.cpp, test infrastructure) as the cross-check
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DMOF_WITH_HOST_TEXPREP", "-I" + os.path.join(ROOT, "include"), "-o", exe] + sources + [lib, "-lz", "-Wl,-rpath," + os.path.dirname(lib)])
     g = golden_torus
     synthetic.write_ply_textured(str(tmp_path / "m.ply"), g["input_vertices_f32"], g["input_triangles"], g["input_uv"])
     open(tmp_path / "A.png", "wb").write(g["png_a"].tobytes())
