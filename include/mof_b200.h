@@ -135,7 +135,8 @@ long long mof_num_coeffs(mof_ctx* ctx);
  * context already holds (csrc/spectrum.cu), no factorisation. Needs the mesh only; afterwards mof_set_signals has to be called again
  * before an alignment. eigenvalues[count] ascending; fields[count][T][2] = the prolonged eigenvectors P x (what the tool writes to
  * eigenvector-%03d.bin), x normalised to x^T M x = 1 like ARPACK's, sign free; inside a multiple eigenvalue only the span is defined.
- * Converged when every pair has ||S x - lambda M x|| <= tol (||S x|| + lambda ||M x||); MOF_E_NOCONVERGE after maxIterations.
+ * Converged when every pair has ||S x - lambda M x|| <= tol (||S x|| + max(|lambda|, lambda_count / 1000) ||M x||) - the floor is for the
+ * harmonic fields of a surface of genus > 0, whose lambda is 0; MOF_E_NOCONVERGE after maxIterations.
  * count <= 28 (a block of min(32, count + max(4, count/2 + 2)) vectors: the guard keeps the block from ending inside the cluster of the
  * last wanted eigenvalue). */
 int mof_spectrum(mof_ctx* ctx, int count, double tol, int maxIterations, double* eigenvalues, double* fields, int* iterations, double* residual);

@@ -12,7 +12,7 @@
 // folded in a fixed order (deterministic), the dense generalised eigenproblem of that size on the host (Cholesky + cyclic Jacobi,
 // <= 96 x 96), and the new X, P, S X, M X, S P, M P as block combinations (one kernel). Vectors are column-major (each column
 // contiguous) so every single-vector kernel of the library applies to a column as it is.
-// Converged when every wanted pair has ||S x - theta M x|| <= tol * (||S x|| + theta ||M x||).
+// Converged when every wanted pair has ||S x - theta M x|| <= tol * (||S x|| + max(|theta|, theta_max / 1000) ||M x||).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -450,8 +450,11 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
             MOF_TRY(gram(ctx, w, SX, SX, n, m, m, ss.data()));
             MOF_TRY(gram(ctx, w, MX, MX, n, m, m, mm.data()));
             worst = 0;
+            // (harmonic fields of a surface of genus > 0 have lambda = 0 and S x -> 0: their residual is measured against the scale of the wanted
+            // eigenvalues instead of against itself)
+            const double floorTheta = 1e-3 * std::fabs(theta[count - 1]);
             for (int j = 0; j < count; j++) {
-                const double den = std::sqrt(ss[j * m + j]) + std::fabs(theta[j]) * std::sqrt(mm[j * m + j]);
+                const double den = std::sqrt(ss[j * m + j]) + std::max(std::fabs(theta[j]), floorTheta) * std::sqrt(mm[j * m + j]);
                 worst = std::max(worst, den > 0 ? std::sqrt(rr[j * m + j]) / den : 0.);
             }
             if (getenv("MOF_SPECTRUM_VERBOSE") && it % 20 == 0) fprintf(stderr, "[spectrum] iteration %d: residual %.3g, theta[0] %.10g theta[%d] %.10g\n", it, worst, theta[0], count - 1, theta[count - 1]);

@@ -87,6 +87,20 @@ def test_conformal_spectrum_on_the_complement_of_the_constants(aligner):
     assert np.abs(G @ G.T - np.eye(count)).max() < 1e-5
 
 
+def test_spectrum_on_a_torus_finds_the_harmonic_fields(aligner, golden_torus):
+    """Genus 1: S is singular (two harmonic fields, lambda = 0 — the reference's shift of 1e-8 is what lets it factorise). The block
+    iteration returns them first, then the pairs of the torus' symmetric spectrum; eigenvalues against the checker's ARPACK values
+    (absolutely, on the scale of the largest: the zeros are zeros to rounding on both sides)."""
+    g = golden_torus
+    v, t = g["vertices"].astype(np.float64), g["triangles"].astype(np.int32)
+    al = aligner
+    al.set_mesh(v, t)
+    ev, fields, its, res = al.spectrum(6, 1e-8, 3000)
+    ref_ev = O.spectrum(v, t, 6, 0, 0)[0]
+    assert res <= 1e-8 and np.abs(ev - ref_ev).max() <= 1e-7 * ref_ev.max(), (ev, ref_ev)
+    assert np.abs(ev[:2]).max() < 1e-9 and ev[2] > 1.0
+
+
 def test_spectrum_of_a_renumbered_mesh(aligner):
     """A shuffled 65 538-vertex sphere is renumbered inside mof_set_mesh (reorder.cu): same eigenvalues, fields back in the caller's
     triangle order (the span of the first cluster equals that of the sorted mesh's)."""

@@ -172,6 +172,20 @@ def test_spectrum_matches_the_shift_invert_lanczos_of_the_checker(aligner, mode,
     assert np.abs(G @ G.T - np.eye(count)).max() < 1e-5, G
 
 
+def test_spectrum_on_a_torus_finds_the_harmonic_fields(aligner, golden_torus):
+    """Genus 1: S is singular (two harmonic fields, lambda = 0 — the reference's shift of 1e-8 is what lets it factorise). The block
+    iteration returns them first, then the pairs of the torus' symmetric spectrum; eigenvalues against the checker's ARPACK values
+    (absolutely, on the scale of the largest: the zeros are zeros to rounding on both sides)."""
+    g = golden_torus
+    v, t = g["vertices"].astype(np.float64), g["triangles"].astype(np.int32)
+    al = aligner
+    al.set_mesh(v, t)
+    ev, fields, its, res = al.spectrum(6, 1e-8, 3000)
+    ref_ev = O.spectrum(v, t, 6, 0, 0)[0]
+    assert res <= 1e-8 and np.abs(ev - ref_ev).max() <= 1e-7 * ref_ev.max(), (ev, ref_ev)
+    assert np.abs(ev[:2]).max() < 1e-9 and ev[2] > 1.0
+
+
 def test_multigrid_and_jacobi_solves_agree_with_the_checker(emulated):
     """4 098 vertices: three-level hierarchies for the flow and the smoothing systems (sliced fine sweeps, 27-point stencil level,
     dense coarsest solve, two iterations per replayed graph); then the same alignment with the Jacobi-PCG kernel."""
