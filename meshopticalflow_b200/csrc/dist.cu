@@ -585,7 +585,7 @@ int dist_p2p_setup(mof_ctx* ctx) {
             if (bytes <= (4ll << 20)) need = std::max(need, bytes);
         }
     // (all-gathers of ints, reduced on the host: the message sizes are bytes of one halo message and fit an int)
-    DBuf<int> agreeSend, agreeAll;
+    ScopedBuf<int> agreeSend, agreeAll;
     MOF_CUDA(agreeSend.alloc(2));
     MOF_CUDA(agreeAll.alloc(2 * (size_t)N));
     std::vector<int> gathered(2 * (size_t)N);
@@ -602,7 +602,6 @@ int dist_p2p_setup(mof_ctx* ctx) {
     MOF_TRY(agree((int)std::min<long long>(need, 2000000000ll), wanted ? 1 : 0, &all[0], &all[1]));
     if (!all[1]) {  // switched off on some rank: NCCL everywhere
         p2p_release(ctx);
-        agreeSend.release(), agreeAll.release();
         return MOF_OK;
     }
     const size_t cap = ((size_t)std::max(all[0], 4096ll) + 255) & ~(size_t)255;
@@ -615,7 +614,7 @@ int dist_p2p_setup(mof_ctx* ctx) {
         w.haloCap = cap;
         w.bytes = w.flagBytes + (size_t)N * 2 * cap;
         cudaIpcMemHandle_t handle;
-        DBuf<unsigned char> hsend, hall;
+        ScopedBuf<unsigned char> hsend, hall;
         std::vector<unsigned char> handles((size_t)N * sizeof(handle));
         if (cudaMalloc((void**)&w.base, w.bytes) != cudaSuccess || cudaMemset(w.base, 0, w.bytes) != cudaSuccess || cudaIpcGetMemHandle(&handle, w.base) != cudaSuccess) ok = 0;
         cudaGetLastError();
@@ -626,7 +625,6 @@ int dist_p2p_setup(mof_ctx* ctx) {
         MOF_CUDA(cudaMemcpyAsync(hsend.p, &handle, sizeof(handle), cudaMemcpyHostToDevice, ctx->stream));
         MOF_NCCL(ncclAllGather(hsend.p, hall.p, sizeof(handle) / sizeof(int), ncclInt, d.comm, ctx->stream));
         MOF_CUDA(read_back(ctx, handles.data(), hall.p, handles.size()));
-        hsend.release(), hall.release();
         w.peer.assign(N, nullptr);
         for (int j = 0; j < N && ok; j++) {
             if (j == d.rank) { w.peer[j] = w.base; continue; }
@@ -646,7 +644,6 @@ int dist_p2p_setup(mof_ctx* ctx) {
     }
     // every rank mapped every window, or nobody uses them
     MOF_TRY(agree(0, (int)ok, &all[0], &all[1]));
-    agreeSend.release(), agreeAll.release();
     if (!all[1]) {
         p2p_release(ctx);
         if (getenv("MOF_MG_VERBOSE") && d.rank == 0) fprintf(stderr, "[dist] peer windows could not be mapped: halo exchanges go through NCCL\n");

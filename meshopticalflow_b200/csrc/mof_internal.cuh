@@ -59,6 +59,14 @@ struct DBuf {
     }
     size_t bytes() const { return n * sizeof(T); }
 };
+// A scratch buffer of one function: handed back to the pool on every way out of the scope, error returns included.
+template <class T>
+struct ScopedBuf : DBuf<T> {
+    ScopedBuf() = default;
+    ScopedBuf(const ScopedBuf&) = delete;
+    ScopedBuf& operator=(const ScopedBuf&) = delete;
+    ~ScopedBuf() { this->release(); }
+};
 
 // Sliced storage of the E x E Whitney operators (SELL-32): rows are grouped by 32 (one warp), every
 // group is padded to its longest row and stored entry-major, i.e. entry j of row r lives at

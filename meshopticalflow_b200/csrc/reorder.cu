@@ -142,9 +142,9 @@ int sort_pairs(mof_ctx* ctx, unsigned long long* code, int* idx, int n) {
     for (int i = 0; i < n; i++) code[i] = p[i].first, idx[i] = p[i].second;
     return MOF_OK;
 #else
-    DBuf<unsigned long long> code2;
-    DBuf<int> idx2;
-    DBuf<unsigned char> scratch;
+    ScopedBuf<unsigned long long> code2;
+    ScopedBuf<int> idx2;
+    ScopedBuf<unsigned char> scratch;
     MOF_CUDA(code2.alloc((size_t)n));
     MOF_CUDA(idx2.alloc((size_t)n));
     size_t bytes = 0;
@@ -152,7 +152,6 @@ int sort_pairs(mof_ctx* ctx, unsigned long long* code, int* idx, int n) {
     MOF_CUDA(scratch.alloc(bytes));
     cudaError_t e = cub::DeviceRadixSort::SortPairs(scratch.p, bytes, code, code2.p, idx, idx2.p, n, 0, 63, ctx->stream);  // (LSD radix sort: stable)
     if (e == cudaSuccess) e = cudaMemcpyAsync(idx, idx2.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream);
-    code2.release(), idx2.release(), scratch.release();
     MOF_CUDA(e);
     return MOF_OK;
 #endif
@@ -179,9 +178,9 @@ int reorder_mesh(mof_ctx* ctx, int mode) {
         const double limit = (double)V / 16.;
         if (sums[0] / T <= limit && sums[1] / T <= limit) return MOF_OK;
     }
-    DBuf<double> box, partial, pos2;
-    DBuf<unsigned long long> code;
-    DBuf<int> tri2;
+    ScopedBuf<double> box, partial, pos2;
+    ScopedBuf<unsigned long long> code;
+    ScopedBuf<int> tri2;
     const int np = std::min(1024, blocks_for(V, B));
     MOF_CUDA(box.alloc(6));
     MOF_CUDA(partial.alloc(6ull * np));
@@ -203,7 +202,6 @@ int reorder_mesh(mof_ctx* ctx, int mode) {
     MOF_LAUNCH(k_gather_triangles, blocks_for(3ll * T, B), B, 0, ctx->tri.p, ctx->tOrder.p, ctx->vRank.p, T, V, tri2.p);
     MOF_CUDA(cudaMemcpyAsync(ctx->pos.p, pos2.p, sizeof(double) * 3 * V, cudaMemcpyDeviceToDevice, ctx->stream));
     MOF_CUDA(cudaMemcpyAsync(ctx->tri.p, tri2.p, sizeof(int) * 3 * T, cudaMemcpyDeviceToDevice, ctx->stream));
-    box.release(), partial.release(), pos2.release(), code.release(), tri2.release();
     ctx->reordered = true;
     return MOF_OK;
 }

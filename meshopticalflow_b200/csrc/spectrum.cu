@@ -35,7 +35,7 @@ struct Ops {
     long long n = 0;
     bool cycle = false;  // Whitney on a mesh with a flow hierarchy: T = one multigrid cycle on S + tau M instead of the inverse diagonal
     double tau = 0;
-    DBuf<double> wM, tinv;
+    ScopedBuf<double> wM, tinv;
 };
 
 // y = A x, A in the sliced layout (padding entries carry value 0 and the row's own column).
@@ -309,7 +309,7 @@ int apply_block(mof_ctx* ctx, Ops& ops, bool mass, const double* X, int m, doubl
 }
 
 struct Work {
-    DBuf<double> partial, gram, coef;
+    ScopedBuf<double> partial, gram, coef;
     std::vector<double> host;
 };
 // G (host, ka x kb, row-major) = A^T B
@@ -383,7 +383,7 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
         MOF_LAUNCH(k_invert_positive, blocks_for(n, B), B, 0, n, ops.tinv.p);
     }
     // blocks: X W P and their images under S and M, plus one spare of each for the combinations
-    DBuf<double> store;
+    ScopedBuf<double> store;
     const size_t blk = (size_t)n * m;
     MOF_CUDA(store.alloc(12 * blk));
     double *X = store.p, *W = X + blk, *P = W + blk, *SX = P + blk, *SW = SX + blk, *SP = SW + blk, *MX = SP + blk, *MW = MX + blk, *MP = MW + blk, *T0 = MP + blk,
@@ -392,9 +392,8 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
     MOF_CUDA(w.partial.alloc((size_t)GRAM_CTAS * MAXM * MAXM));
     MOF_CUDA(w.gram.alloc((size_t)MAXM * MAXM));
     MOF_CUDA(w.coef.alloc((size_t)3 * MAXM * MAXM));
-    DBuf<double> dtheta;
+    ScopedBuf<double> dtheta;
     MOF_CUDA(dtheta.alloc(MAXM));
-    auto release = [&]() { store.release(), w.partial.release(), w.gram.release(), w.coef.release(), dtheta.release(), ops.tinv.release(), ops.wM.release(); };
 
     std::vector<double> theta(m, 0.), G((size_t)m * m), C, th;
     int rc = MOF_OK, it = 0;
@@ -558,8 +557,7 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
         };
         rc = fieldsOut();
     }
-    release();
-    return rc;
+    return rc;  // (the blocks and the operators' scratch go back to the pool with their scopes)
 }
 
 }  // namespace mof
