@@ -35,7 +35,10 @@ struct Ops {
     long long n = 0;
     bool cycle = false;  // Whitney on a mesh with a flow hierarchy: T = one multigrid cycle on S + tau M instead of the inverse diagonal
     double tau = 0;
-    ScopedBuf<double> wM, tinv;
+    bool twoCycle = false;  // Conformal on a mesh with a scalar hierarchy: T = 2 eps^2 C M C (below) instead of the inverse diagonal
+    int chebDegree = 1;
+    double chebLo = 0.1;
+    ScopedBuf<double> wM, tinv, r6, z6;
 };
 
 // y = A x, A in the sliced layout (padding entries carry value 0 and the row's own column).
@@ -117,6 +120,30 @@ __global__ void __launch_bounds__(B) k_remove_half_means(long long half, double*
     }
     const double mean = sh[0] / (double)half;
     for (long long i = threadIdx.x; i < half; i += B) x[i] -= mean;
+}
+
+// Conformal basis, preconditioner T = 2 eps^2 C M C on each half (C ~ (M + eps K)^-1 by the scalar hierarchy, eps = 1/tau: the inverse of
+// (K + tau M) M^-1 (K + tau M) / 2 = S + tau K + tau^2 M / 2, cf. the flow solve's two-cycle preconditioner in vector_fields.cu). The scalar
+// hierarchy carries six channels: THREE columns of the block (two halves each) ride in one application.
+__global__ void k_conformal_pack3(const double* __restrict__ R, long long n, int V, int cols, double* __restrict__ r6) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    double* d = r6 + 6 * (size_t)v;
+    for (int k = 0; k < 3; k++) {
+        d[2 * k] = k < cols ? R[(size_t)k * n + v] : 0.;
+        d[2 * k + 1] = k < cols ? R[(size_t)k * n + V + v] : 0.;
+    }
+}
+__global__ void k_conformal_weight6(const double* __restrict__ z6, const double* __restrict__ m0, int V, double* __restrict__ r6) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6ll * V) return;
+    r6[i] = m0[i / 6] * z6[i];
+}
+__global__ void k_conformal_unpack3(const double* __restrict__ z6, double kappa, long long n, int V, int cols, double* __restrict__ W) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const double* d = z6 + 6 * (size_t)v;
+    for (int k = 0; k < cols; k++) W[(size_t)k * n + v] = kappa * d[2 * k], W[(size_t)k * n + V + v] = kappa * d[2 * k + 1];
 }
 
 // G[i][j] = sum_r A[r + i n] B[r + j n] for i < ka, j < kb: per-CTA partials (tiles of GRAM_ROWS rows through shared memory), folded below.
@@ -308,6 +335,47 @@ int apply_block(mof_ctx* ctx, Ops& ops, bool mass, const double* X, int m, doubl
     return MOF_OK;
 }
 
+// (Re)values the scalar hierarchy for M + K / tau and plans the Chebyshev sharpening of one cycle as the flow solve does (vector_fields.cu):
+// lower end of the spectrum of (cycle x system) from a short Lanczos run, the degree that minimises cycles x predicted outer iterations.
+int conformal_preconditioner_setup(mof_ctx* ctx, Ops& ops, double tau) {
+    ops.tau = tau;
+    MOF_TRY(scalar_system_set(ctx, 1. / tau));
+    if (!mg_scalar_usable(ctx)) {
+        ops.twoCycle = false;
+        return MOF_OK;
+    }
+    double lambdaMin = 0.1;
+    MOF_TRY(mg_scalar_smallest_eigenvalue(ctx, 50, &lambdaMin));
+    const double rho = std::min(0.9999, std::max(0.3, 1. - lambdaMin));
+    ops.chebLo = std::max(1e-4, 0.8 * (1. - rho));
+    const double kap = 1.05 / ops.chebLo, q = (std::sqrt(kap) - 1.) / (std::sqrt(kap) + 1.);
+    double best = 1e300;
+    ops.chebDegree = 2;
+    for (int k = 2; k <= 32; k++) {
+        const double f = 2. * std::pow(q, k) / (1. + std::pow(q, 2 * k)), cost = k * (1. + f) / (1. - f);
+        if (cost < best) best = cost, ops.chebDegree = k;
+    }
+    ops.twoCycle = true;
+    if (getenv("MOF_SPECTRUM_VERBOSE"))
+        fprintf(stderr, "[spectrum] two-cycle preconditioner on (K + %.3g M) M^-1 (K + %.3g M) / 2: one cycle contracts by %.3f, Chebyshev degree %d\n", tau, tau, rho, ops.chebDegree);
+    return MOF_OK;
+}
+// W[:, j] = T R[:, j] for the m columns of a block, three columns per application of the six-channel hierarchy.
+int conformal_precondition_block(mof_ctx* ctx, Ops& ops, const double* R, int m, double* W) {
+    const int V = ctx->V;
+    const long long n = ops.n;
+    const double eps = 1. / ops.tau, kappa = 2. * eps * eps;
+    for (int j0 = 0; j0 < m; j0 += 3) {
+        const int cols = std::min(3, m - j0);
+        MOF_LAUNCH(k_conformal_pack3, blocks_for(V, B), B, 0, R + (size_t)j0 * n, n, V, cols, ops.r6.p);
+        MOF_TRY(mg_scalar_cheb(ctx, ops.r6.p, ops.z6.p, ops.chebDegree, ops.chebLo));
+        MOF_LAUNCH(k_conformal_weight6, blocks_for(6ll * V, B), B, 0, (const double*)ops.z6.p, (const double*)ctx->m0.p, V, ops.r6.p);
+        MOF_TRY(mg_scalar_cheb(ctx, ops.r6.p, ops.z6.p, ops.chebDegree, ops.chebLo));
+        MOF_LAUNCH(k_conformal_unpack3, blocks_for(V, B), B, 0, (const double*)ops.z6.p, kappa, n, V, cols, W + (size_t)j0 * n);
+    }
+    return MOF_OK;
+}
+
 struct Work {
     ScopedBuf<double> partial, gram, coef;
     std::vector<double> host;
@@ -381,6 +449,22 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
     } else {
         MOF_TRY(vf_smooth_diagonal(ctx, ops.tinv.p));
         MOF_LAUNCH(k_invert_positive, blocks_for(n, B), B, 0, n, ops.tinv.p);
+        const char* e = getenv("MOF_SPECTRUM_MG");
+        if (mode == 1 && mg_scalar_usable(ctx) && !(e && *e == '0')) {
+            // The inverse diagonal does nothing about the bi-Laplacian's h^-4 conditioning (65 538 vertices: no convergence in 4 000
+            // iterations). Start the shift at the scale of the bulk of K's spectrum over 1e3 and follow the Ritz values down (below).
+            MOF_CUDA(ops.r6.alloc(6ull * ctx->V));
+            MOF_CUDA(ops.z6.alloc(6ull * ctx->V));
+            MOF_CUDA(ctx->dtmp0.reserve((size_t)n));
+            MOF_TRY(vf_smooth_diagonal(ctx, ctx->dtmp0.p));
+            MOF_TRY(reduce_sum(ctx, ctx->dtmp0.p, n, ctx->scalars.p + SC_TMP));
+            MOF_TRY(reduce_sum(ctx, ctx->m0.p, ctx->V, ctx->scalars.p + SC_TMP + 1));
+            double tr[2] = {0, 0};
+            MOF_CUDA(read_back(ctx, tr, ctx->scalars.p + SC_TMP, 2));
+            // tr S ~ sum_v K_vv^2 / m_v and K_vv ~ lambda_bulk m_v: sqrt(tr S / tr M_lumped) is the bulk of K's generalised spectrum
+            const double bulk = tr[1] > 0 ? std::sqrt(std::max(tr[0], 0.) / (2. * tr[1])) : 1.;
+            MOF_TRY(conformal_preconditioner_setup(ctx, ops, std::max(1e-3 * bulk, 1e-12)));
+        }
     }
     // blocks: X W P and their images under S and M, plus one spare of each for the combinations
     ScopedBuf<double> store;
@@ -444,6 +528,10 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
             if (mode == 1) MOF_LAUNCH(k_remove_half_means, 2 * m, B, 0, n / 2, W);
             if (ops.cycle)
                 for (int j = 0; j < m; j++) MOF_TRY(mg_flow_cycle(ctx, T0 + (size_t)j * n, W + (size_t)j * n));
+            if (ops.twoCycle) {
+                MOF_TRY(conformal_precondition_block(ctx, ops, T0, m, W));
+                MOF_LAUNCH(k_remove_half_means, 2 * m, B, 0, n / 2, W);
+            }
             std::vector<double> rr((size_t)m * m), ss((size_t)m * m), mm((size_t)m * m);
             MOF_TRY(gram(ctx, w, T0, T0, n, m, m, rr.data()));
             MOF_TRY(gram(ctx, w, SX, SX, n, m, m, ss.data()));
@@ -461,6 +549,10 @@ int spectrum_lowest(mof_ctx* ctx, int count, double tol, int maxIterations, doub
             if (!std::isfinite(worst)) return fail(ctx, MOF_E_NOCONVERGE, "mof_spectrum: the iteration broke down");
             // follow the Ritz values down with the preconditioner's shift (see above): re-value the hierarchy when the largest wanted one
             // has fallen below half the shift in use; the directions of the old preconditioner are dropped with it
+            if (ops.twoCycle && it >= 3 && theta[count - 1] > 0 && theta[count - 1] < 0.5 * ops.tau) {
+                MOF_TRY(conformal_preconditioner_setup(ctx, ops, theta[count - 1]));
+                haveP = false;
+            }
             if (ops.cycle && it >= 3 && theta[count - 1] > 0 && theta[count - 1] < 0.5 * ops.tau) {
                 ops.tau = theta[count - 1];
                 MOF_LAUNCH(k_shifted_operator, blocks_for(n, B), B, 0, (int)n, ctx->wSliceBase.p, ctx->wCol.p, ctx->wS.p, ops.wM.p, ops.tau, ctx->wA.p, ctx->wDinv.p);

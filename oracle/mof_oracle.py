@@ -362,14 +362,23 @@ def spectrum(vertices, triangles, count=20, vf_mode=0, c_mode=0, shift=1e-8):
         lin, cst = edge_xforms(g, opp)
         P, S = connection_field(g, opp, lin, cst, c_mode)
     M = vector_field_mass(g, P)
+    # Conformal basis: the constants of either potential are in the null space of S AND of M (P maps them to the zero field), where
+    # the shift-invert problem is not defined (the reference's own answer there is whatever its LDLT makes of a singular pencil). The
+    # checker works on the quotient by the constants: one vertex of each potential is pinned (rows / columns 0 and V removed), which
+    # leaves the eigenvalues and the prolonged fields unchanged.
+    n_full = S.shape[0]
+    keep = np.setdiff1d(np.arange(n_full), [0, nv]) if vf_mode == 1 else np.arange(n_full)
+    Sk, Mk = S.tocsr()[keep][:, keep].tocsc(), M.tocsr()[keep][:, keep].tocsc()
     # A single-vector Lanczos process can miss copies of a multiple eigenvalue (a sphere's come in clusters of 3-6): ask for a few
     # more pairs than wanted, in a Krylov space four times that, from a fixed start vector, and keep the lowest `count`.
-    n = S.shape[0]
+    n = Sk.shape[0]
     k = min(count + 8, n - 2)
     v0 = np.random.default_rng(0).standard_normal(n)
-    vals, vecs = spla.eigsh(S.tocsc(), k=k, M=M, sigma=shift, which="LM", ncv=min(n - 1, max(4 * k, 80)), v0=v0)
+    vals, vk = spla.eigsh(Sk, k=k, M=Mk, sigma=shift, which="LM", ncv=min(n - 1, max(4 * k, 80)), v0=v0)
     order = np.argsort(vals)[:count]
-    vals, vecs = vals[order], vecs[:, order]
+    vals = vals[order]
+    vecs = np.zeros((n_full, count))
+    vecs[keep] = vk[:, order]
     T = triangles.shape[0]
     fields = np.stack([(P @ vecs[:, i]).reshape(T, 2) for i in range(count)])
     return vals, fields, vecs.T.copy(), S, M

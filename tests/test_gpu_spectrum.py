@@ -63,26 +63,20 @@ def test_spectrum_matches_the_checker(aligner, mode, cmode, level, count, cluste
         assert np.linalg.norm(al.flow() - st.tfield) <= 1e-3 * np.linalg.norm(st.tfield)
 
 
-def test_conformal_spectrum_on_the_complement_of_the_constants(aligner):
+@pytest.mark.parametrize("level,count", [(3, 6), (6, 6)])
+def test_conformal_spectrum_on_the_complement_of_the_constants(aligner, level, count):
     """Conformal basis: constants of either potential are in the null space of S and of M, where ARPACK's shift-invert answer is
-    not defined; the checker is the dense generalised problem on their complement."""
-    import scipy.linalg as sla
-
-    v, t = synthetic.octahedron_sphere(3)
-    nv, count = v.shape[0], 6
+    not defined; the checker works on the quotient (oracle.mof_oracle.spectrum). 258 vertices: inverse-diagonal preconditioner;
+    16 386 vertices: the two-cycle preconditioner over the scalar hierarchy (without it the iteration does not converge there)."""
+    v, t = synthetic.octahedron_sphere(level)
     al = aligner
     p = api.default_params()
     p.vfMode = 1
     al.set_params(p)
     al.set_mesh(v, t)
-    ev, fields, its, res = al.spectrum(count, 1e-8, 20000)
-    _, _, _, S, M = O.spectrum(v, t, 2, 1, 0)
-    Q = np.linalg.qr(np.kron(np.eye(2), np.ones((nv, 1))), mode="complete")[0][:, 2:]
-    w, U = sla.eigh(Q.T @ S.toarray() @ Q, Q.T @ M.toarray() @ Q)
-    g = O.make_unit_area(O.metric_from_embedding(v, t))
-    P = O.conformal_field(g, t, nv, O.scalar_matrices(g, t, nv)[1])[0]
-    ref_fields = np.stack([(P @ (Q @ U[:, i])).reshape(-1, 2) for i in range(count)])
-    assert res <= 1e-8 and np.abs(ev - w[:count]).max() <= 1e-7 * w[count - 1]
+    ev, fields, its, res = al.spectrum(count, 1e-8, 3000)
+    ref_ev, ref_fields, _, _, _ = O.spectrum(v, t, count, 1, 0)
+    assert res <= 1e-8 and np.abs(ev - ref_ev).max() <= 1e-7 * ref_ev[-1], (ev, ref_ev)
     G = cross_gram(v, t, fields, ref_fields)
     assert np.abs(G @ G.T - np.eye(count)).max() < 1e-5
 
