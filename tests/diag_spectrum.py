@@ -23,7 +23,7 @@ def main():
         t0 = time.perf_counter()
         try:
             ev, _, its, res = al.spectrum(count, 1e-8, 4000 if mg == "1" else 30000)
-            print(f"level {level} V={v.shape[0]} unknowns={al.num_coeffs} vfMode {p.vfMode} preconditioner {'cycle' if mg == '1' and p.vfMode == 0 else 'diagonal'}: "
+            print(f"level {level} V={v.shape[0]} unknowns={al.num_coeffs} vfMode {p.vfMode} preconditioner {('cycle' if p.vfMode == 0 else 'two-cycle' if p.vfMode == 1 else 'diagonal') if mg == '1' else 'diagonal'}: "
                   f"{its} iterations, {time.perf_counter() - t0:.2f} s, residual {res:.2e}, lambda[0] {ev[0]:.8f} lambda[{count - 1}] {ev[-1]:.8f}", flush=True)
         except api.MofError as e:
             print(f"level {level} MG {mg}: {e} after {time.perf_counter() - t0:.2f} s", flush=True)
