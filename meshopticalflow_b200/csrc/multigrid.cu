@@ -96,6 +96,7 @@ struct Multigrid {
     std::vector<MgLevel> lev;       // lev[0] = level 1 (finest aggregates)
     DBuf<double> evec;              // FLOW: edge vectors [E][3]
     DBuf<creal> cevec;              // ... in cycle precision
+    DBuf<creal> cevecAgg;           // ... and in the order of the aggregates' member lists (aggList): the restriction streams it
     DBuf<int> agg, aggPtr, aggList; // aggregate of every fine unknown; members of every aggregate, ascending
     DBuf<signed char> slotOf;       // per matrix entry: stencil slot at level 1 (-1 for padding)
     DBuf<creal> cinv;               // dense inverse on the coarsest level
@@ -778,9 +779,17 @@ __device__ __forceinline__ void apply_binv(const creal* __restrict__ binv, int N
     }
 }
 
+// The edge vectors in member-list order: evecAgg[q] = evec[aggList[q]] (once per mesh).
+__global__ void k_gather_evec(const int* __restrict__ aggList, const creal* __restrict__ evec, int n, creal* __restrict__ out) { pdl_wait();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3ll * n) return;
+    const long long q = i / 3;
+    out[i] = evec[3 * (size_t)aggList[q] + (i - 3 * q)];
+}
 // Every restriction also performs the first smoothing sweep of the level it lands on (from a zero guess):
 // zc = omega * Binv * rc.
-// FLOW restriction: rc[I] = sum over the edges of aggregate I of v_e * r_e (P1^T r). One warp per aggregate.
+// FLOW restriction: rc[I] = sum over the edges of aggregate I of v_e * r_e (P1^T r). One warp per aggregate; `evec` = the edge vectors in
+// the order of the member lists (Multigrid::cevecAgg), so that only r is gathered.
 __global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __restrict__ aggList, const creal* __restrict__ evec, const creal* __restrict__ r, int N,
                                 const creal* __restrict__ binv, const double* __restrict__ omegaP, creal* __restrict__ rc, creal* __restrict__ zc, int r0, int r1,
                                 int c0 = 0, int c1 = -1) { pdl_wait();  // [c0, c1): the cells of this launch (a rank's own cells when level 1 is dealt to the ranks)
@@ -793,7 +802,7 @@ __global__ void k_restrict_flow(const int* __restrict__ aggPtr, const int* __res
         int e = aggList[q];
         if (e < r0 || e >= r1) continue;  // partitioned mesh: this rank's rows only (the partial sums are all-reduced)
         creal re = r[e];
-        a0 += evec[3 * (size_t)e] * re, a1 += evec[3 * (size_t)e + 1] * re, a2 += evec[3 * (size_t)e + 2] * re;
+        a0 += evec[3 * (size_t)q] * re, a1 += evec[3 * (size_t)q + 1] * re, a2 += evec[3 * (size_t)q + 2] * re;  // (evec in member-list order: coalesced)
     }
     for (int o = 16; o > 0; o >>= 1) {
         a0 += __shfl_xor_sync(0xffffffffu, a0, o), a1 += __shfl_xor_sync(0xffffffffu, a1, o), a2 += __shfl_xor_sync(0xffffffffu, a2, o);
@@ -1510,7 +1519,7 @@ void release_mg(Multigrid* mg) {
         l.code.release(), l.nbr.release(), l.parent.release(), l.firstChild.release(), l.blocks.release(), l.cblocks.release(), l.binv.release(), l.r.release(),
             l.z.release(), l.t.release();
     }
-    mg->evec.release(), mg->cevec.release(), mg->agg.release(), mg->aggPtr.release(), mg->aggList.release(), mg->slotOf.release(), mg->cinv.release();
+    mg->evec.release(), mg->cevec.release(), mg->cevecAgg.release(), mg->agg.release(), mg->aggPtr.release(), mg->aggList.release(), mg->slotOf.release(), mg->cinv.release();
     mg->fval.release(), mg->fdinv.release(), mg->fvalSell.release();
     mg->fz.release(), mg->fz2.release(), mg->ft.release(), mg->fr.release(), mg->fp.release(), mg->fq.release(), mg->partial.release(), mg->scal.release(), mg->counter.release(), mg->domega.release(), mg->eig.release(), mg->chebD.release(), mg->chebR.release(), mg->chebC.release();
     delete mg;
@@ -1663,6 +1672,8 @@ int alloc_common(mof_ctx* ctx, Multigrid& mg) {
     if (mg.kind == MG_FLOW) {
         MOF_CUDA(mg.cevec.alloc(3ull * mg.nFine));
         MOF_LAUNCH(k_to_creal, kSMs * 8, B, 0, mg.evec.p, 3ll * mg.nFine, mg.cevec.p);
+        MOF_CUDA(mg.cevecAgg.alloc(3ull * mg.nFine));
+        MOF_LAUNCH(k_gather_evec, blocks_for(3ll * mg.nFine, B), B, 0, (const int*)mg.aggList.p, (const creal*)mg.cevec.p, mg.nFine, mg.cevecAgg.p);
     }
     return MOF_OK;
 }
@@ -2245,7 +2256,7 @@ int fine_cycle(mof_ctx* ctx, Multigrid& mg, const double* r, bool presmoothed, i
     }
     MOF_TRY(fine_apply(ctx, mg, r, mg.om(0), mg.fz.p, mg.ft.p, 1));
     if (mg.kind == MG_FLOW)
-        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine, 0, -1);
+        MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevecAgg.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine, 0, -1);
     else
         MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine, 0, -1);
     if (mg.K == 1) {  // the aggregates are already the coarsest level
@@ -2728,7 +2739,7 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
             MOF_TRY(dist_halo_part_f32(ctx, mg.memberPart, (float*)mg.ft.p));
             if (c1 > c0) {
                 if (flow)
-                    MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * (c1 - c0), B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0,
+                    MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * (c1 - c0), B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevecAgg.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0,
                                mg.nFine, c0, c1);
                 else
                     MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * (c1 - c0), B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine,
@@ -2738,7 +2749,7 @@ int mg_pcg_dist(mof_ctx* ctx, Multigrid& mg, const double* b, double* x, bool ze
             MOF_TRY(dist_halo_part_f32(ctx, mg.levelPart[0], (float*)l1.z.p));  // the cells of my rows' aggregates that other ranks own
         } else {
         if (flow)
-            MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, r0, r1, 0, -1);
+            MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevecAgg.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, r0, r1, 0, -1);
         else
             MOF_LAUNCH(k_restrict_scalar, blocks_for(6ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, r0, r1, 0, -1);
         MOF_TRY(dist_allreduce(ctx, l1.r.p, D * l1.N));
@@ -3054,7 +3065,7 @@ int mg_time_kernel(mof_ctx* ctx, int which, int reps, float* ms, double* bytes) 
                 MOF_LAUNCH(k_update_xr, NBLK, B, 0, mg.fp.p, mg.fq.p, len, scratchX, mg.fr.p, mg.fdinv.p, mg.om(0), mg.nrhs, mg.fz.p, fold_into(mg, S_RR));
                 return MOF_OK;
             case MOF_K_FLOW_RESTRICT:
-                MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevec.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine, 0, -1);
+                MOF_LAUNCH(k_restrict_flow, blocks_for(32ll * l1.N, B), B, 0, mg.aggPtr.p, mg.aggList.p, mg.cevecAgg.p, mg.ft.p, l1.N, l1.binv.p, mg.om(1), l1.r.p, l1.z.p, 0, mg.nFine, 0, -1);
                 return MOF_OK;
             case MOF_K_FLOW_PROLONG:
                 MOF_LAUNCH(k_prolong_flow, blocks_for(mg.nFine, B), B, 0, mg.agg.p, mg.cevec.p, l1.z.p, mg.nFine, mg.fz.p);
