@@ -406,3 +406,30 @@ def test_command_line_on_the_emulated_build(emulated, tmp_path, golden_torus):
         pictures.append(np.asarray(Image.open(tmp_path / ("r%s.png" % mode))).astype(int))
     assert pictures[0].shape == (48, 48, 3) and np.array_equal(pictures[0], pictures[1])  # same preparation, bit for bit => same file
     assert colour_outliers(pictures[1], g["output_pixels"], 1.0) < 2e-3
+
+
+def test_spectrum_command_line_on_the_emulated_build(emulated, tmp_path):
+    """The Spectrum command line (csrc/host/spectrum_main.cpp) linked against the emulated library: eigenvector-%03d.bin files in the
+    working directory (int count, count x 2 doubles: WriteVector, Src/VectorIO.h:23-31), the reference's eigenvalue listing, the usage
+    text without --mesh."""
+    import struct
+    host = os.path.join(ROOT, "meshopticalflow_b200", "csrc", "host")
+    lib = emulated.load_library()._name
+    exe = str(tmp_path / "Spectrum_emul")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-o", exe, os.path.join(host, "spectrum_main.cpp"), os.path.join(host, "ply_io.cpp"),
+                           lib, "-Wl,-rpath," + os.path.dirname(lib)])
+    v, t = synthetic.octahedron_sphere(3)
+    synthetic.write_ply_colored(str(tmp_path / "m.ply"), v, np.zeros((v.shape[0], 3), np.uint8), t)
+    r = subprocess.run([exe, "--mesh", "m.ply", "--eigenVectors", "6", "--vfMode", "2", "--cMode", "1"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    vf = v.astype(np.float32).astype(np.float64)  # what the tool read from the file
+    ref_ev = O.spectrum(vf, t, 6, 2, 1)[0]
+    listed = np.array([float(x) for x in r.stdout.split("Eigenvalues:")[1].split()])
+    assert np.abs(listed - ref_ev).max() < 2e-8 * ref_ev.max() + 1e-8
+    for i in range(6):
+        raw = (tmp_path / ("eigenvector-%03d.bin" % (i + 1))).read_bytes()
+        assert struct.unpack("<i", raw[:4])[0] == t.shape[0] and len(raw) == 4 + 16 * t.shape[0]
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "--mesh" in r.stdout
+    r = subprocess.run([exe, "--mesh", "m.ply", "--edgeMetric"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "edgeMetric" in r.stderr
