@@ -40,6 +40,7 @@ struct Partition {
 // memory, so the two kernels can sit in a replayed CUDA graph.
 struct PeerWindow {
     bool on = false;
+    bool shared = false;                   // every rank has mapped every window (agreed): releasing them is a collective step
     unsigned char* base = nullptr;
     size_t bytes = 0, flagBytes = 0, haloCap = 0;
     std::vector<unsigned char*> peer;      // peer[j]: rank j's window mapped into this process (peer[rank] = base)
@@ -442,7 +443,7 @@ int build_lists(mof_ctx* ctx, Partition& p, int n) {
 
 }  // namespace
 
-static void p2p_release(mof_ctx* ctx);
+static void p2p_release(mof_ctx* ctx, bool together);
 
 bool dist_active(const mof_ctx* ctx) { return ctx->dist && ctx->dist->comm && ctx->dist->meshReady; }
 int dist_world(const mof_ctx* ctx) { return ctx->dist ? ctx->dist->world : 1; }
@@ -491,7 +492,7 @@ void dist_destroy(mof_ctx* ctx) {
     dist_clear_partitions(ctx);
     d.sendBuf.release(), d.recvBuf.release();
     if (d.comm) cudaStreamSynchronize(ctx->stream);
-    p2p_release(ctx);
+    p2p_release(ctx, d.win.shared);  // (contexts of a communicator are destroyed together, like the communicator itself)
     if (d.comm) {
         cudaStreamSynchronize(ctx->stream);
         ncclCommDestroy(d.comm);
@@ -552,14 +553,23 @@ int dist_setup_mesh(mof_ctx* ctx) {
 }
 
 // ---- the peer-memory window (see PeerWindow): after every partition of the mesh exists (the matrix patterns' and the multigrid levels').
-static void p2p_release(mof_ctx* ctx) {
+// together: every rank of the communicator is making this same call now (common knowledge at the call site, never a local condition).
+static void p2p_release(mof_ctx* ctx, bool together) {
     DistState& d = *ctx->dist;
     PeerWindow& w = d.win;
     for (int j = 0; j < (int)w.peer.size(); j++)
         if (j != d.rank && w.peer[j]) cudaIpcCloseMemHandle(w.peer[j]);
     w.peer.clear();
+    if (together && d.comm && d.world > 1) {
+        // An exported allocation must outlive its mappings in the peers: every rank gets here at the same point of the program (a new
+        // mesh, a failed set-up, the end of the context), closes its mappings above, and only frees its own window once all have.
+        ScopedBuf<int> token;
+        if (token.alloc(1) == cudaSuccess && cudaMemsetAsync(token.p, 0, sizeof(int), ctx->stream) == cudaSuccess &&
+            ncclAllReduce(token.p, token.p, 1, ncclInt, ncclSum, d.comm, ctx->stream) == ncclSuccess)
+            cudaStreamSynchronize(ctx->stream);
+    }
     if (w.base) cudaFree(w.base);
-    w.base = nullptr, w.bytes = 0, w.on = false;
+    w.base = nullptr, w.bytes = 0, w.on = false, w.shared = false;
     w.table.release(), w.seq.release();
 }
 
@@ -601,15 +611,15 @@ int dist_p2p_setup(mof_ctx* ctx) {
     long long all[2] = {0, 0};
     MOF_TRY(agree((int)std::min<long long>(need, 2000000000ll), wanted ? 1 : 0, &all[0], &all[1]));
     if (!all[1]) {  // switched off on some rank: NCCL everywhere
-        p2p_release(ctx);
+        p2p_release(ctx, d.win.shared);
         return MOF_OK;
     }
     const size_t cap = ((size_t)std::max(all[0], 4096ll) + 255) & ~(size_t)255;
     PeerWindow& w = d.win;
     long long ok = 1;
     if (!w.base || w.haloCap < cap) {
-        // (re)create: every rank gets here together (the all-reduces above), and the stream is idle after the read-back
-        p2p_release(ctx);
+        // (re)create: every rank gets here together (the all-gathers above; capacities are common knowledge), and the stream is idle after the read-back
+        p2p_release(ctx, d.win.shared);
         w.flagBytes = ((size_t)N * 2 * sizeof(unsigned long long) + 255) & ~(size_t)255;
         w.haloCap = cap;
         w.bytes = w.flagBytes + (size_t)N * 2 * cap;
@@ -645,7 +655,7 @@ int dist_p2p_setup(mof_ctx* ctx) {
     // every rank mapped every window, or nobody uses them
     MOF_TRY(agree(0, (int)ok, &all[0], &all[1]));
     if (!all[1]) {
-        p2p_release(ctx);
+        p2p_release(ctx, true);
         if (getenv("MOF_MG_VERBOSE") && d.rank == 0) fprintf(stderr, "[dist] peer windows could not be mapped: halo exchanges go through NCCL\n");
         return MOF_OK;
     }
@@ -658,7 +668,7 @@ int dist_p2p_setup(mof_ctx* ctx) {
         MOF_CUDA(cudaMemcpyAsync(q->offs.p, offs.data(), sizeof(int) * offs.size(), cudaMemcpyHostToDevice, ctx->stream));
         MOF_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    w.on = true;
+    w.on = w.shared = true;
     if (getenv("MOF_MG_VERBOSE") && d.rank == 0)
         fprintf(stderr, "[dist] halo exchanges through peer memory: %d windows of %.1f MB (%zu bytes per message slot)\n", N, w.bytes / 1048576., w.haloCap);
     return MOF_OK;
