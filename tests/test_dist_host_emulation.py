@@ -111,11 +111,11 @@ def test_partitioned_solves_give_the_single_gpu_result_on_every_rank(emulated, w
 
 @pytest.mark.parametrize("world,threshold", [(2, 100), (3, 100), (4, 800)])
 def test_coarse_levels_dealt_to_the_ranks(emulated, world, threshold, monkeypatch):
-    monkeypatch.setenv("MOF_DIST_P2P", "1")  # the levels' halos and the gather of the first replicated level through the peer windows too
     """16 386 vertices, four-level hierarchies. MOF_DIST_LEVEL_CELLS lowered so that the levels of more than `threshold` cells are
     dealt to the ranks in octree-aligned cell ranges (threshold 100: two levels, 800: one): stencil halos per level, the
     aggregates that straddle a row-block boundary (residual rows in, correction cells out), restriction and prolongation inside a
     rank, the first replicated level gathered once per visit — against the single-"GPU" run and across ranks."""
+    monkeypatch.setenv("MOF_DIST_P2P", "1")  # the levels' halos and the gather of the first replicated level through the peer windows too
     v, t = synthetic.octahedron_sphere(6)
     a, b = (x.astype(np.float64) for x in synthetic.smooth_rgb_pair(v, 9))
     single = _align(emulated, v, t, a, b, 1)
@@ -187,3 +187,27 @@ def test_cooperative_jacobi_pcg_on_three_ctas(emulated, golden_sphere):
         assert s["lastFlowResidual"] <= 1.01e-8 and s["lastSmoothResidual"] <= 1.01e-10
     finally:
         al.close()
+
+
+def test_partitioned_solves_on_a_renumbered_mesh(emulated, workload, monkeypatch):
+    """A badly numbered mesh is renumbered along a Morton curve inside mof_set_mesh (reorder.cu) BEFORE the rows are dealt to the ranks —
+    contiguous ranges of the library's numbering are compact patches whatever the caller's was — and every rank hands the flow and the
+    colours back in the caller's numbering: a shuffled copy of the workload on two ranks against the sorted single-"GPU" run."""
+    v, t, a, b, single = workload
+    rng = np.random.default_rng(2)
+    vo, to = rng.permutation(v.shape[0]), rng.permutation(t.shape[0])  # shuffled index -> original index
+    rank = np.empty_like(vo)
+    rank[vo] = np.arange(vo.size)
+    vs, ts = np.ascontiguousarray(v[vo]), np.ascontiguousarray(rank[t][to].astype(np.int32))
+    monkeypatch.setenv("MOF_REORDER", "1")
+    monkeypatch.setenv("MOF_DIST_P2P", "0")
+    out = _run_world(emulated, 2, vs, ts, a[vo], b[vo], 2)
+    for r, res in enumerate(out):
+        flow = np.empty_like(res["flow"])
+        flow[to] = res["flow"]
+        colours = np.empty_like(res["colours"])
+        colours[vo] = res["colours"]
+        assert rel(flow, single["flow"]) < 1e-6, r
+        assert np.abs(colours - single["colours"]).max() < 1e-3, r
+        assert res["stats"]["haloEntries"] > 0
+        assert np.array_equal(res["flow"], out[0]["flow"])
