@@ -1889,10 +1889,11 @@ int finish_values(mof_ctx* ctx, Multigrid& mg) {
     // estimated by power iteration on I + Minv A (all eigenvalues of Minv A are positive). omega * rho < 2 keeps the
     // cycle positive definite; should an estimate ever be too low, PCG stalls and the caller falls back to Jacobi-PCG.
     // The iterate of the previous system on this mesh is kept (Multigrid::eig): consecutive systems differ little (the data term moves
-    // with the flow, eps shrinks by 4), so from the second system on 3 steps from there replace 10 from a pseudo-random start —
+    // with the flow, eps shrinks by 4), so from the second system on ONE step from there replaces 10 from a pseudo-random start (3 until the end of round 2: 542 -> 530 ms per
+    // alignment for the same iteration counts; the estimate approaches rho from below and omega = 1.4 / rho leaves a factor 1.43 before omega rho = 2) —
     // the estimates only improve, and the set-up of the ~20 systems of an alignment drops from ~45 ms to ~20 ms at 1M vertices.
     const bool warm = mg.eigValid && env_int("MOF_MG_POWER_WARM", 1) != 0;
-    const int powerIts = std::max(1, std::min(50, warm ? env_int("MOF_MG_POWER_ITS_WARM", 3) : env_int("MOF_MG_POWER_ITS", 10)));
+    const int powerIts = std::max(1, std::min(50, warm ? env_int("MOF_MG_POWER_ITS_WARM", 1) : env_int("MOF_MG_POWER_ITS", 10)));
     const char* pinvEnv = getenv("MOF_MG_PINV_TOL");
     const double pinvTol = pinvEnv && *pinvEnv ? atof(pinvEnv) : 1e-3;
     size_t eigOffset = 0;
